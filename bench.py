@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- structure-tensor loss fwd+bwd throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c5|c1] [--impl reference]
+
+One "step" = one forward + backward pass of the fused ST loss over one batch of synthetic
+SR/HR images (the hot path of SURVEY.md section 8).  Printed: ONE JSON line.
+
+  value      images/s with inputs resident in HBM: the two kernels (forward, backward) are enqueued
+             through the C ABI on one stream, K steps captured in a CUDA graph, timed with CUDA
+             events on that stream, max over ranks.  Every step reads a different batch from a pool
+             larger than the 126 MB L2, so no step sees L2-warm inputs.
+  e2e        the same metric through the public API (StructureTensorLoss()(sr, gt); backward();
+             loss.item()) with each step's inputs copied host->device from pinned memory and the
+             loss read back, as the reference's train.py:119-144 does.
+  roofline   forward kernel (dominant) against the measured HBM copy bandwidth of
+             MEASURED_PEAKS.json; algorithmic bytes = 24 B/pixel forward, 36 B/pixel backward
+             (SURVEY.md section 8d).  The fwd+bwd pair is reported beside it.
+  cpu_baseline  the oracle port (numpy fp32, one process per host core) on a bounded sample.
+
+`--impl reference` times that CPU port alone (the reference is pure Python/ATen; /root/reference
+does not exist on the GPU box, so the timed CPU arm is the oracle's restatement of it).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "st_loss_fwd_bwd_images_per_sec"
+UNIT = "images/s"
+
+# per-rank workloads (weak scaling: every rank processes its own batch)
+WORKLOADS = {
+    # BASELINE.json configs[1]: warmup.py step's loss, batch 64 of 96x96 crops per GPU
+    "c2": dict(B=64, H=96, W=96, desc="ST loss fwd+bwd, batch 64 x 3x96x96 per GPU (configs[1] loss path)"),
+    # configs[4]: DIV2K-shaped validation image, one 1356x2040 image per GPU
+    "c5": dict(B=1, H=1356, W=2040, desc="ST loss fwd+bwd, 1 x 3x1356x2040 per GPU (configs[4])"),
+    # configs[0]/[2]: batch 16 of 96x96 per GPU
+    "c1": dict(B=16, H=96, W=96, desc="ST loss fwd+bwd, batch 16 x 3x96x96 per GPU (configs[0]/[2])"),
+}
+BYTES_FWD, BYTES_BWD = 24, 36  # algorithmic bytes per pixel
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: oracle port, one process per core
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    import numpy as np
+    from oracle import st_oracle as O
+    seed, n, H, W = args
+    rng = np.random.default_rng(seed)
+    taps = (*O.gaussian_taps(0.5, True), O.gaussian_taps(2.0))
+    t = 0.0
+    for _ in range(n):
+        sr = rng.random((1, 3, H, W), dtype=np.float32)
+        hr = rng.random((1, 3, H, W), dtype=np.float32)
+        t0 = time.perf_counter()
+        O.st_loss(sr, hr, taps=taps, dtype=np.float32)
+        t += time.perf_counter() - t0
+    return t
+
+
+def cpu_port_images_per_sec(H, W, n_images, cores=None):
+    """Times oracle/st_oracle.py (fp32 port of the reference's algorithm, fwd + bwd) on
+    `n_images` synthetic images split over `cores` processes.  Returns (images/s, cores)."""
+    import multiprocessing as mp
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    cores = max(1, min(cores or avail, n_images))
+    per = [n_images // cores + (1 if i < n_images % cores else 0) for i in range(cores)]
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(i, 1, min(H, 32), min(W, 32)) for i in range(cores)])  # spin-up
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(100 + i, per[i], H, W) for i in range(cores)])
+        dt = time.perf_counter() - t0
+    return n_images / dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = WORKLOADS[args.workload]
+    H, W = wl["H"], wl["W"]
+    # bounded sample per step: ~1.5 s of CPU work on one core per step and core
+    probe, cores = cpu_port_images_per_sec(H, W, 4 if H * W > 1e6 else 64)
+    budget_s = min(1.5, 150.0 / max(args.steps + args.warmup, 1))  # whole run stays within minutes
+    n_step = max(cores, int(probe * budget_s)) if H * W <= 1e6 else max(2, min(cores, 16))
+    for _ in range(args.warmup):
+        cpu_port_images_per_sec(H, W, max(1, n_step // 4))
+    rates = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, cores = cpu_port_images_per_sec(H, W, n_step)
+        rates.append(r)
+    total = time.perf_counter() - t0
+    value = statistics.median(rates)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "sample_images_per_step": n_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_step} images of 3x{H}x{W} per step, oracle/st_oracle.py fp32 fwd+bwd, "
+                                   f"one process per core"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s in sm if s >= 0.5 * max(sm)]
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_pair(torch, B, H, W, gen, device):
+    """Synthetic DIV2K-like pair: HR = low-passed 8-bit noise, SR = 4x down/up
+    sampled HR + noise, saturated to [0,1]."""
+    import torch.nn.functional as F
+    hr = torch.randint(0, 256, (B, 3, H, W), generator=gen, device=device).float()
+    hr = (F.avg_pool2d(hr, 3, 1, 1, count_include_pad=False).round() / 255).contiguous()
+    lo = F.interpolate(hr, size=(max(H // 4, 1), max(W // 4, 1)), mode="bicubic", align_corners=False)
+    sr = F.interpolate(lo, size=(H, W), mode="bicubic", align_corners=False)
+    sr = (sr + 0.02 * torch.randn(B, 3, H, W, generator=gen, device=device)).clamp_(0, 1).contiguous()
+    return sr, hr
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from srgan_st_b200 import StructureTensorLoss, _cabi, taps as T
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lib = _cabi.lib()
+    g, dg = T.gaussian_taps(0.5)
+    k, _ = T.gaussian_taps(2.0)
+    hbm_peak, peak_src = _peaks()
+
+    def measure(wl_name, K, Wm, with_e2e):
+        wl = WORKLOADS[wl_name]
+        B, H, W = wl["B"], wl["H"], wl["W"]
+        bytes_pair = 2 * B * 3 * H * W * 4
+        pool_n = max(4, min(64, int(300e6 // bytes_pair) + 1))  # > 2x the 126 MB L2
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        pool = [make_pair(torch, B, H, W, gen, dev) for _ in range(pool_n)]
+        ds = torch.empty(B, 3, H, W, device=dev)
+        d_sr = torch.empty(B, 3, H, W, device=dev)
+        loss = torch.zeros((), device=dev)
+        go = torch.ones((), device=dev)
+        nws = lib.srst_st_workspace_bytes(B, H, W)
+        ws = torch.zeros(max(nws, 4096), dtype=torch.uint8, device=dev)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        s = torch.cuda.Stream(device=dev)
+        sp = ctypes.c_void_p(s.cuda_stream)
+
+        def fwd(i):
+            sr, hr = pool[i % pool_n]
+            _cabi.check(lib.srst_st_forward(vp(sr), vp(hr), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8, 1,
+                                            1e-12, vp(loss), vp(ds), None, vp(ws), ws.numel(), sp), "fwd")
+
+        def bwd(i):
+            sr, _ = pool[i % pool_n]
+            _cabi.check(lib.srst_st_backward(vp(sr), vp(ds), vp(go), B, H, W, T.as_c(g), T.as_c(dg), 2,
+                                             T.as_c(k), 8, vp(d_sr), sp), "bwd")
+
+        def graph_of(fn_list, n):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                for i in range(n):
+                    for fn in fn_list:
+                        fn(i)
+            return gr
+
+        def time_graph(gr):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(s):
+                e0.record(s)
+                gr.replay()
+                e1.record(s)
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1))
+
+        with torch.cuda.stream(s):
+            for i in range(max(Wm, 3)):
+                fwd(i); bwd(i)
+        torch.cuda.synchronize()
+        g_pair = graph_of([fwd, bwd], K)
+        g_f = graph_of([fwd], K)
+        g_b = graph_of([bwd], K)
+        for gr in (g_pair, g_f, g_b):  # untimed replay: graph upload + instruction cache
+            with torch.cuda.stream(s):
+                gr.replay()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ms_pair = min(time_graph(g_pair) for _ in range(3))
+        ms_f = min(time_graph(g_f) for _ in range(3))
+        ms_b = min(time_graph(g_b) for _ in range(3))
+        clocks = sampler.stop() if rank == 0 else None
+        loss_val = float(loss.item())
+        res = dict(wl=wl, ms_step=ms_pair / K, ms_fwd=ms_f / K, ms_bwd=ms_b / K, clocks=clocks, pool_n=pool_n,
+                   loss=loss_val, images_per_s=world * B * K / (ms_pair * 1e-3))
+        px = B * H * W
+        res["roofline_fwd"] = BYTES_FWD * px / (res["ms_fwd"] * 1e-3) / 1e9
+        res["roofline_bwd"] = BYTES_BWD * px / (res["ms_bwd"] * 1e-3) / 1e9
+        res["roofline_pair"] = (BYTES_FWD + BYTES_BWD) * px / (res["ms_step"] * 1e-3) / 1e9
+
+        if with_e2e:
+            crit = StructureTensorLoss()
+            n_host = 4
+            host = [(sr.cpu().pin_memory(), hr.cpu().pin_memory()) for sr, hr in pool[:n_host]]
+            sr_d = torch.empty(B, 3, H, W, device=dev)
+            hr_d = torch.empty(B, 3, H, W, device=dev)
+
+            def step(i):
+                sr_h, hr_h = host[i % n_host]
+                sr_d.copy_(sr_h, non_blocking=True)
+                hr_d.copy_(hr_h, non_blocking=True)
+                x = sr_d.detach().requires_grad_(True)
+                l = crit(x, hr_d)
+                l.backward()
+                return l.item()  # device->host read of the step's result, as train.py:141
+
+            for i in range(max(Wm, 3)):
+                step(i)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(K):
+                step(i)
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            res["e2e"] = {"value": world * B * K / (ms * 1e-3), "unit": UNIT,
+                          "h2d_bytes_per_step": bytes_pair, "d2h_bytes_per_step": 4,
+                          "ms_per_step": ms / K}
+        del pool
+        torch.cuda.empty_cache()
+        return res
+
+    K, Wm = args.steps, args.warmup
+    main = measure(args.workload, K, Wm, with_e2e=True)
+    others = {}
+    if not args.no_extra:
+        for name in WORKLOADS:
+            if name != args.workload:
+                r = measure(name, max(20, min(K, 200)), Wm, with_e2e=False)
+                others[name] = {"workload": r["wl"]["desc"], "images_per_s": r["images_per_s"],
+                                "ms_per_step": r["ms_step"], "ms_fwd": r["ms_fwd"], "ms_bwd": r["ms_bwd"],
+                                "hbm_frac_fwd": r["roofline_fwd"] / hbm_peak, "hbm_frac_bwd": r["roofline_bwd"] / hbm_peak,
+                                "hbm_frac_pair": r["roofline_pair"] / hbm_peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        wl = main["wl"]
+        probe, cores = cpu_port_images_per_sec(wl["H"], wl["W"], 4 if wl["H"] * wl["W"] > 1e6 else 128)
+        n = int(min(max(probe * 12, cores), 200000)) if wl["H"] * wl["W"] <= 1e6 else max(cores, 8)
+        v, cores = cpu_port_images_per_sec(wl["H"], wl["W"], n)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} synthetic images of 3x{wl['H']}x{wl['W']}, oracle/st_oracle.py fp32 fwd+bwd, one process per core"}
+
+    if rank == 0:
+        wl = main["wl"]
+        out = {
+            "metric": METRIC, "value": main["images_per_s"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": main["ms_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "per_gpu_batch": wl["B"], "height": wl["H"], "width": wl["W"],
+                       "sigma": 0.5, "rho": 2.0, "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "l2_policy": f"inputs cycle through a pool of {main['pool_n']} batches (> 2x L2) so every step is L2-cold",
+                       "timing": "CUDA graph of K (fwd,bwd) kernel pairs on one stream, CUDA events, max over ranks, best of 3"},
+            "clocks": main["clocks"],
+            "e2e": main.get("e2e"),
+            "gpu_launches": 2 * K,
+            "roofline": {"bound": "hbm", "kernel": "st_forward_kernel", "achieved": main["roofline_fwd"], "peak": hbm_peak,
+                         "unit": "GB/s", "frac": main["roofline_fwd"] / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "bytes_per_pixel": BYTES_FWD,
+                         "backward": {"kernel": "st_backward_kernel", "achieved": main["roofline_bwd"],
+                                      "frac": main["roofline_bwd"] / hbm_peak, "bytes_per_pixel": BYTES_BWD},
+                         "fwd_bwd_pair": {"achieved": main["roofline_pair"], "frac": main["roofline_pair"] / hbm_peak,
+                                          "bytes_per_pixel": BYTES_FWD + BYTES_BWD},
+                         "ms_fwd": main["ms_fwd"], "ms_bwd": main["ms_bwd"]},
+            "cpu_baseline": cpu,
+            "loss_check": main["loss"],
+            "other_workloads": others,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch under torchrun on one node
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,123 @@
+/* srst.h -- C ABI of libsrst.so: the B200-native structure-tensor / Best-Buddy loss hot path.
+ *
+ * This is the drop-in boundary for the loss hot path of SebastianBitsch/SRGAN-ST.  The reference
+ * has no native code: the hot path is a chain of ATen calls behind two nn.Modules
+ * (loss.py:380-413 StructureTensorLoss, loss.py:78-141 BestBuddyLoss).  Each entry point below
+ * names the reference code it replaces.  The Python host (srgan_st_b200/loss.py) binds these with
+ * ctypes from inside a torch.autograd.Function; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, >0 = a cudaError_t value, <0 = an SRST_E_* code.
+ *   - image/gradient buffers are DEVICE pointers to contiguous fp32 NCHW tensors owned by the
+ *     caller; filter taps are HOST pointers (they are copied into kernel parameters).
+ *   - no function allocates, synchronises or keeps state: all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*) and every scratch buffer comes in through `workspace`.
+ *     The library is re-entrant across streams and devices as long as workspaces differ.
+ *   - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef SRST_H_
+#define SRST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRST_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#define SRST_E_INVALID (-1)     /* null pointer / non-positive size / bad enum */
+#define SRST_E_UNSUPPORTED (-2) /* filter radius or patch geometry not compiled in */
+#define SRST_E_WORKSPACE (-3)   /* workspace missing, misaligned or too small */
+#define SRST_E_SHAPE (-4)       /* image shape not usable by this entry point */
+
+int srst_version(void);
+const char* srst_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * Structure-tensor loss.   Replaces, fused into one kernel per direction:
+ *   torchvision Grayscale                        (loss.py:400-401)
+ *   utils.structure_tensor  (10 conv2d / image)  (utils.py:212-233)
+ *   utils.normalize / compute_invS1xS2           (utils.py:236-254)
+ *   utils.compute_eigenvalues / compute_distance (utils.py:257-279)
+ *   .mean() over pixels and batch                (loss.py:409,413)
+ * and the autograd backward of that chain.
+ *
+ * g, dg: 2*r_sigma+1 host floats (utils.get_gaussian_kernel(sigma, also_dg=True), utils.py:194-208)
+ * k    : 2*r_rho+1   host floats (utils.get_gaussian_kernel(rho))
+ * Compiled radius pairs are listed by srst_st_supported(); the reference default
+ * (sigma=0.5, rho=2.0) is (2, 8).
+ * ------------------------------------------------------------------------------------------- */
+
+/* 1 if the (r_sigma, r_rho) pair has a compiled kernel, else 0. */
+int srst_st_supported(int r_sigma, int r_rho);
+
+/* Scratch bytes srst_st_forward needs for a [B,3,H,W] problem (per-CTA partial sums + ticket).
+ * The workspace must be 16-byte aligned and ZERO-FILLED ONCE before its first use; the kernels
+ * leave it zeroed again, so it can be reused by later calls on the same stream. */
+size_t srst_st_workspace_bytes(int B, int H, int W);
+
+/* Forward.  sr, hr: device [B,3,H,W] fp32.  Writes
+ *   loss_out[0]  = mean over B*H*W pixels of the Riemannian distance   (device, 1 float)
+ *   ds_sr        = d(sum of distances)/d(Jxx,Jyy,Jxy of SR), device [B,3,H,W], or NULL to skip
+ *   ds_hr        = same w.r.t. the HR tensor, or NULL (only needed when hr requires grad)
+ * The ds_* planes are the "saved intermediates" the backward pass consumes; they are unscaled
+ * (neither 1/(B*H*W) nor the upstream gradient is applied yet). */
+int srst_st_forward(const float* sr, const float* hr, int B, int H, int W,
+                    const float* g, const float* dg, int r_sigma,
+                    const float* k, int r_rho,
+                    int normalize, float eps,
+                    float* loss_out, float* ds_sr, float* ds_hr,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward for one image tensor.  img: the same [B,3,H,W] tensor the forward saw (sr or hr);
+ * ds: the matching ds_* planes; grad_out: device pointer to the upstream scalar gradient.
+ * Writes d_img[B,3,H,W] = grad_out/(B*H*W) * dLoss_sum/dimg (adjoint smoothing, product rule,
+ * adjoint Gaussian-derivative filters, grayscale weights). */
+int srst_st_backward(const float* img, const float* ds, const float* grad_out,
+                     int B, int H, int W,
+                     const float* g, const float* dg, int r_sigma,
+                     const float* k, int r_rho,
+                     float* d_img, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Best-Buddy loss.   Replaces
+ *   F.unfold x4, torch.cat                        (loss.py:116-130)
+ *   utils.batch_pairwise_distance(...,'l2') x2    (utils.py:173-187; two torch.bmm)
+ *   torch.min(score, dim=2), torch.gather         (loss.py:135-137)
+ *   L1Loss / MSELoss                              (loss.py:139)
+ * for ksize=3, stride=3, pad=0 (27-dim patches).  gt2 / gt4 are the bicubic x1/2 and x1/4
+ * levels of gt ([B,3,H/2,W/2], [B,3,H/4,W/4]); pass NULL to have the library compute them with
+ * the same taps F.interpolate(mode='bicubic', align_corners=False) uses (loss.py:123,127),
+ * in which case `workspace` must also hold them (see srst_bb_workspace_bytes).
+ * H and W must be multiples of 12.
+ * ------------------------------------------------------------------------------------------- */
+#define SRST_BB_L1 0
+#define SRST_BB_L2 1
+
+size_t srst_bb_workspace_bytes(int B, int H, int W);
+
+/* Forward: idx_out[B, N] int64 (N = (H/3)*(W/3)) = argmin over the M = N + N/4 + N/16 candidate
+ * patches of alpha*d(sr_i, cand_j) + beta*d(gt_i, cand_j), first minimal index on ties
+ * (torch.min rule); loss_out[0] = mean |sr_patch - cand[idx]| (L1) or mean square (L2). */
+int srst_bb_forward(const float* sr, const float* gt, const float* gt2, const float* gt4,
+                    int B, int H, int W, float alpha, float beta, int criterion,
+                    int64_t* idx_out, float* loss_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward: only the final criterion is differentiable w.r.t. sr (loss.py:139; argmin is not).
+ * d_sr[B,3,H,W] = grad_out/(B*N*27) * sign(sr_patch - cand[idx])           (L1)
+ *               = grad_out/(B*N*27) * 2*(sr_patch - cand[idx])             (L2)     */
+int srst_bb_backward(const float* sr, const float* gt, const float* gt2, const float* gt4,
+                     const int64_t* idx, const float* grad_out,
+                     int B, int H, int W, int criterion,
+                     float* d_sr, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The HR pyramid on its own (exposed for tests): out2 [B,3,H/2,W/2], out4 [B,3,H/4,W/4]. */
+int srst_bb_pyramid(const float* gt, int B, int H, int W, float* out2, float* out4, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRST_H_ */

@@ -1,0 +1,10 @@
+"""srgan_st_b200 -- B200-native (sm_100a) loss hot path of SebastianBitsch/SRGAN-ST.
+
+Public surface (mirrors reference loss.py): ``StructureTensorLoss``, ``BestBuddyLoss``.
+Importing this package needs ``libsrst.so`` (build: ``python -m srgan_st_b200.build``); there is
+no CPU or PyTorch fallback.
+"""
+from .loss import StructureTensorLoss  # noqa: F401
+
+__all__ = ["StructureTensorLoss"]
+__version__ = "0.1.0"

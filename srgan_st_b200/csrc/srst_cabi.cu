@@ -1,0 +1,185 @@
+// C ABI of libsrst.so (declared in include/srst.h).  Host-side launch logic only: validates
+// arguments, picks a compiled tile configuration and enqueues the sm_100a kernels on the caller's
+// stream.  No allocation, no synchronisation, no global state, no CPU fallback.
+//
+// The same file compiles with g++ -DSRST_EMULATE into tests/emu/_build/libsrst_emu.so, a
+// test-only host emulation used to check kernel index logic in the GPU-less build container.
+#include "../../include/srst.h"
+
+#include <cstdlib>
+#include <cstring>
+
+#include "st_kernels.cuh"
+#include "bb_kernels.cuh"
+
+namespace srst {
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return (s && *s) ? std::atoi(s) : dflt;
+}
+
+// ---- compiled structure-tensor tile configurations ------------------------------------------
+//                         TH  TW  RS  RG RK MINB
+using FwdA = StFwdCfg<40, 64, 10, 2, 8, 2>;  // large images (DIV2K-sized validation)
+using FwdB = StFwdCfg<32, 96, 8, 2, 8, 2>;   // 96-wide training crops: a tile spans the row
+using FwdC = StFwdCfg<48, 48, 12, 2, 8, 2>;  // square quarter of a 96x96 crop
+//                         TH  TW  RS   NT  RG RK MINB
+using BwdA = StBwdCfg<32, 64, 12, 352, 2, 8, 2>;
+using BwdB = StBwdCfg<24, 96, 14, 288, 2, 8, 2>;
+using BwdC = StBwdCfg<44, 48, 12, 288, 2, 8, 2>;
+
+constexpr int kMinFwdTH = 32, kMinFwdTW = 48;  // finest compiled forward tiling (workspace sizing)
+
+// Opt in to > 48 KB of dynamic shared memory once per (kernel, device).
+template <class K>
+static int ensure_smem(K kernel, size_t bytes) {
+#ifdef SRST_EMULATE
+  (void)kernel; (void)bytes;
+  return 0;
+#else
+  static bool done[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev >= 0 && dev < 64 && done[dev]) return 0;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return (int)e;
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return 0;
+#endif
+}
+
+template <int RG, int RK>
+static void fill_taps(StTaps<RG, RK>& t, const float* g, const float* dg, const float* k) {
+  std::memcpy(t.g, g, sizeof(t.g));
+  std::memcpy(t.dg, dg, sizeof(t.dg));
+  std::memcpy(t.k, k, sizeof(t.k));
+}
+
+template <class C>
+static int launch_st_forward(StFwdParams<C::RG, C::RK> P, void* stream) {
+  P.tiles_x = (P.W + C::TW - 1) / C::TW;
+  P.tiles_y = (P.H + C::TH - 1) / C::TH;
+  const long long nblk = (long long)P.B * P.tiles_x * P.tiles_y;
+  if (nblk <= 0 || nblk > 0x7fffffffLL) return SRST_E_SHAPE;
+  int e = ensure_smem(st_forward_kernel<C>, C::SMEM_BYTES);
+  if (e) return e;
+  SRST_LAUNCH(st_forward_kernel<C>, dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  return (int)cudaGetLastError();
+}
+
+template <class C>
+static int launch_st_backward(StBwdParams<C::RG, C::RK> P, void* stream) {
+  P.tiles_x = (P.W + C::TW - 1) / C::TW;
+  P.tiles_y = (P.H + C::TH - 1) / C::TH;
+  const long long nblk = (long long)P.B * P.tiles_x * P.tiles_y;
+  if (nblk <= 0 || nblk > 0x7fffffffLL) return SRST_E_SHAPE;
+  int e = ensure_smem(st_backward_kernel<C>, C::SMEM_BYTES);
+  if (e) return e;
+  SRST_LAUNCH(st_backward_kernel<C>, dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  return (int)cudaGetLastError();
+}
+
+static int pick_fwd_cfg(int H, int W) {
+  const int forced = env_int("SRST_ST_FWD_CFG", -1);
+  if (forced >= 0 && forced <= 2) return forced;
+  if (W <= 96) return 1;
+  return 0;
+}
+static int pick_bwd_cfg(int H, int W) {
+  const int forced = env_int("SRST_ST_BWD_CFG", -1);
+  if (forced >= 0 && forced <= 2) return forced;
+  if (W <= 96) return 1;
+  return 0;
+}
+
+}  // namespace srst
+
+using namespace srst;
+
+extern "C" {
+
+int srst_version(void) { return SRST_VERSION; }
+
+const char* srst_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case SRST_E_INVALID: return "srst: invalid argument (null pointer, non-positive size or bad enum)";
+    case SRST_E_UNSUPPORTED: return "srst: filter radius / patch geometry not compiled into libsrst";
+    case SRST_E_WORKSPACE: return "srst: workspace missing, misaligned or too small";
+    case SRST_E_SHAPE: return "srst: image shape not usable by this entry point";
+    default: break;
+  }
+#ifndef SRST_EMULATE
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+#endif
+  return "srst: unknown error";
+}
+
+int srst_st_supported(int r_sigma, int r_rho) { return (r_sigma == 2 && r_rho == 8) ? 1 : 0; }
+
+size_t srst_st_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  // one float per CTA of the finest compiled tiling + the ticket counter, rounded to 256 bytes
+  const size_t tiles = (size_t)B * ((H + kMinFwdTH - 1) / kMinFwdTH) * ((W + kMinFwdTW - 1) / kMinFwdTW);
+  return ((tiles + 4) * sizeof(float) + 255) / 256 * 256;
+}
+
+int srst_st_forward(const float* sr, const float* hr, int B, int H, int W, const float* g, const float* dg,
+                    int r_sigma, const float* k, int r_rho, int normalize, float eps, float* loss_out,
+                    float* ds_sr, float* ds_hr, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!sr || !hr || !g || !dg || !k || !loss_out || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
+  if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
+  if (!workspace || !aligned16(workspace) || workspace_bytes < srst_st_workspace_bytes(B, H, W))
+    return SRST_E_WORKSPACE;
+  StFwdParams<2, 8> P;
+  P.sr = sr; P.hr = hr; P.ds_sr = ds_sr; P.ds_hr = ds_hr;
+  P.ticket = reinterpret_cast<unsigned int*>(workspace);
+  P.partials = reinterpret_cast<float*>(workspace) + 4;
+  P.loss_out = loss_out;
+  P.B = B; P.H = H; P.W = W; P.tiles_x = P.tiles_y = 0;
+  P.normalize = normalize ? 1 : 0;
+  P.vec4 = (W % 4 == 0 && aligned16(sr) && aligned16(hr) && (!ds_sr || aligned16(ds_sr)) &&
+            (!ds_hr || aligned16(ds_hr))) ? 1 : 0;
+  P.eps = eps;
+  P.inv_count = (float)(1.0 / ((double)B * H * W));
+  fill_taps(P.taps, g, dg, k);
+  switch (pick_fwd_cfg(H, W)) {
+    case 1: return launch_st_forward<FwdB>(P, stream);
+    case 2: return launch_st_forward<FwdC>(P, stream);
+    default: return launch_st_forward<FwdA>(P, stream);
+  }
+}
+
+int srst_st_backward(const float* img, const float* ds, const float* grad_out, int B, int H, int W,
+                     const float* g, const float* dg, int r_sigma, const float* k, int r_rho, float* d_img,
+                     void* stream) {
+  if (!img || !ds || !grad_out || !g || !dg || !k || !d_img || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
+  if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
+  StBwdParams<2, 8> P;
+  P.img = img; P.ds = ds; P.grad_out = grad_out; P.d_img = d_img;
+  P.B = B; P.H = H; P.W = W; P.tiles_x = P.tiles_y = 0;
+  P.vec4 = (W % 4 == 0 && aligned16(img) && aligned16(d_img)) ? 1 : 0;
+  P.inv_count = (float)(1.0 / ((double)B * H * W));
+  fill_taps(P.taps, g, dg, k);
+  switch (pick_bwd_cfg(H, W)) {
+    case 1: return launch_st_backward<BwdB>(P, stream);
+    case 2: return launch_st_backward<BwdC>(P, stream);
+    default: return launch_st_backward<BwdA>(P, stream);
+  }
+}
+
+}  // extern "C"
+
+// ---- Best-Buddy entry points: kernels land in bb_kernels.cuh (placeholder until then) ---------
+extern "C" {
+size_t srst_bb_workspace_bytes(int, int, int) { return 0; }
+int srst_bb_forward(const float*, const float*, const float*, const float*, int, int, int, float, float, int,
+                    int64_t*, float*, void*, size_t, void*) { return SRST_E_UNSUPPORTED; }
+int srst_bb_backward(const float*, const float*, const float*, const float*, const int64_t*, const float*, int,
+                     int, int, int, float*, void*, size_t, void*) { return SRST_E_UNSUPPORTED; }
+int srst_bb_pyramid(const float*, int, int, int, float*, float*, void*) { return SRST_E_UNSUPPORTED; }
+}

@@ -1,0 +1,136 @@
+"""Drop-in loss modules backed by the sm_100a kernels in libsrst.so.
+
+``StructureTensorLoss`` and ``BestBuddyLoss`` keep the reference's constructor signatures,
+attributes and ``criterion(sr, gt) -> 0-dim fp32 tensor`` contract (reference loss.py:380-413 and
+loss.py:78-141; called from train.py:138 and warmup.py:91), so they register through
+``config.add_g_criterion(name, module, weight)`` (config.py:122-125) unchanged.  Underneath, each is
+a ``torch.autograd.Function`` whose forward/backward enqueue hand-written CUDA kernels on the
+current stream through the C ABI of ``include/srst.h``.
+
+No CPU path, no PyTorch fallback: CPU tensors, non-fp32 dtypes and unsupported filter radii raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Tuple
+
+import torch
+from torch import nn
+from torch.autograd.function import once_differentiable
+
+from . import _cabi, taps as _taps
+
+_WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(device: torch.device, stream_ptr: int, nbytes: int) -> torch.Tensor:
+    """Zero-initialised scratch, cached per (device, stream).  The kernels leave it zeroed, so it
+    is safe to reuse for later launches on the same stream (srst.h, srst_st_workspace_bytes)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 4096), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _check_pair(x: torch.Tensor, gt: torch.Tensor, who: str) -> None:
+    if not (isinstance(x, torch.Tensor) and isinstance(gt, torch.Tensor)):
+        raise TypeError(f"{who}: expected two tensors")
+    if not (x.is_cuda and gt.is_cuda):
+        raise RuntimeError(f"{who}: inputs must be CUDA tensors (this build has no CPU fallback)")
+    if x.device != gt.device:
+        raise RuntimeError(f"{who}: inputs are on different devices ({x.device} vs {gt.device})")
+    if x.dtype != torch.float32 or gt.dtype != torch.float32:
+        raise TypeError(f"{who}: inputs must be float32 (got {x.dtype}, {gt.dtype})")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"{who}: expected [B,3,H,W] input, got {tuple(x.shape)}")
+    if x.shape != gt.shape:
+        raise ValueError(f"{who}: shape mismatch {tuple(x.shape)} vs {tuple(gt.shape)}")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _StructureTensorLossFn(torch.autograd.Function):
+    """autograd boundary of the fused ST loss (the reference lets autograd differentiate ~100
+    ATen ops instead; loss.py:399-413)."""
+
+    @staticmethod
+    def forward(ctx, sr, hr, sigma, rho, normalize):
+        lib = _cabi.lib()
+        sr = sr.contiguous()
+        hr = hr.contiguous()
+        B, _, H, W = sr.shape
+        g, dg = _taps.gaussian_taps(float(sigma))
+        k, _ = _taps.gaussian_taps(float(rho))
+        rs, rk = len(g) // 2, len(k) // 2
+        if not lib.srst_st_supported(rs, rk):
+            raise NotImplementedError(
+                f"StructureTensorLoss: filter radii (sigma={sigma} -> {rs}, rho={rho} -> {rk}) are not "
+                "compiled into libsrst.so")
+        need_sr, need_hr = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        with torch.cuda.device(sr.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            loss = torch.empty((), dtype=torch.float32, device=sr.device)
+            ds_sr = torch.empty_like(sr) if need_sr else None
+            ds_hr = torch.empty_like(hr) if need_hr else None
+            nbytes = lib.srst_st_workspace_bytes(B, H, W)
+            ws = _workspace(sr.device, stream, nbytes)
+            rc = lib.srst_st_forward(_ptr(sr), _ptr(hr), B, H, W, _taps.as_c(g), _taps.as_c(dg), rs,
+                                     _taps.as_c(k), rk, int(bool(normalize)), 1e-12, _ptr(loss),
+                                     _ptr(ds_sr), _ptr(ds_hr), _ptr(ws), ws.numel(), ctypes.c_void_p(stream))
+        _cabi.check(rc, "srst_st_forward")
+        ctx.save_for_backward(sr, hr, ds_sr, ds_hr)
+        ctx.taps = (g, dg, k)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        lib = _cabi.lib()
+        sr, hr, ds_sr, ds_hr = ctx.saved_tensors
+        g, dg, k = ctx.taps
+        rs, rk = len(g) // 2, len(k) // 2
+        B, _, H, W = sr.shape
+        grad_out = grad_out.to(torch.float32).contiguous()
+        outs = [None, None]
+        with torch.cuda.device(sr.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            for i, (img, ds) in enumerate(((sr, ds_sr), (hr, ds_hr))):
+                if ds is None or not ctx.needs_input_grad[i]:
+                    continue
+                d_img = torch.empty_like(img)
+                rc = lib.srst_st_backward(_ptr(img), _ptr(ds), _ptr(grad_out), B, H, W, _taps.as_c(g),
+                                          _taps.as_c(dg), rs, _taps.as_c(k), rk, _ptr(d_img),
+                                          ctypes.c_void_p(stream))
+                _cabi.check(rc, "srst_st_backward")
+                outs[i] = d_img
+        return outs[0], outs[1], None, None, None
+
+
+class StructureTensorLoss(nn.Module):
+    """Structure-tensor loss; same signature and semantics as reference loss.py:380-413.
+
+    ``forward(x, gt)``: x = SR ``[B,3,H,W]``, gt = HR, both fp32 CUDA; returns the mean over all
+    pixels of the affine-invariant distance between the det-normalised structure tensors.
+    """
+
+    def __init__(self, sigma: float = 0.5, rho: float = 2.0, normalize: bool = True):
+        super().__init__()
+        self.sigma = sigma
+        self.rho = rho
+        self.normalize = normalize
+        _cabi.lib()  # fail at construction time if the CUDA library is missing
+
+    def st_loss(self, x, gt):
+        """Single-sample form (reference loss.py:399-409): x, gt are [3,H,W]."""
+        return self.forward(x.unsqueeze(0), gt.unsqueeze(0))
+
+    def forward(self, x, gt):
+        _check_pair(x, gt, "StructureTensorLoss")
+        return _StructureTensorLossFn.apply(x, gt, self.sigma, self.rho, self.normalize)
+
+    def extra_repr(self) -> str:
+        return f"sigma={self.sigma}, rho={self.rho}, normalize={self.normalize}"

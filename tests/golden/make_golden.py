@@ -1,0 +1,122 @@
+"""Generate golden fixtures by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+The reference hard-codes ``.cuda()`` in ``utils.py:206,208``; on a CPU-only box the single shim
+``torch.Tensor.cuda = identity`` lets ``loss.py`` run unchanged.  Outputs
+are small ``.npz`` files committed next to this script; ``tests/`` replays them against the
+oracle (CPU) and against the CUDA path (GPU).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("SRST_REFERENCE", "/root/reference")
+
+
+def _import_reference():
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self  # the one shim
+    sys.path.insert(0, REF)
+    import loss as ref_loss  # noqa: E402
+    import utils as ref_utils  # noqa: E402
+    return ref_loss, ref_utils
+
+
+def _inputs(kind, B, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "rand":
+        sr = torch.rand(B, 3, H, W, generator=g)
+        hr = torch.rand(B, 3, H, W, generator=g)
+    elif kind == "srlike":
+        # HR = k/255 low-passed noise, SR = blurred HR + noise, saturated to [0,1] (model.py:150)
+        hr = torch.randint(0, 256, (B, 3, H, W), generator=g).float()
+        hr = torch.nn.functional.avg_pool2d(hr, 3, 1, 1, count_include_pad=False).round() / 255
+        sr = torch.nn.functional.avg_pool2d(hr, 3, 1, 1, count_include_pad=False)
+        sr = (sr + 0.05 * torch.randn(B, 3, H, W, generator=g) + 0.1).clamp(0, 1)
+    elif kind == "same":
+        hr = torch.rand(B, 3, H, W, generator=g)
+        sr = hr.clone()
+    else:
+        raise ValueError(kind)
+    return sr.contiguous(), hr.contiguous()
+
+
+ST_CASES = [
+    # name, kind, B, H, W, seed, sigma, rho, normalize
+    ("st_rand_2x24x36", "rand", 2, 24, 36, 1, 0.5, 2.0, True),
+    ("st_rand_1x96x96", "rand", 1, 96, 96, 2, 0.5, 2.0, True),
+    ("st_srlike_2x40x52", "srlike", 2, 40, 52, 3, 0.5, 2.0, True),
+    ("st_same_1x24x24", "same", 1, 24, 24, 4, 0.5, 2.0, True),
+    ("st_rand_s1_r25_1x32x40", "rand", 1, 32, 40, 5, 1.0, 2.5, True),
+    ("st_rand_nonorm_1x24x36", "rand", 1, 24, 36, 6, 0.5, 2.0, False),
+    ("st_rand_ragged_1x37x53", "rand", 1, 37, 53, 7, 0.5, 2.0, True),
+]
+
+BB_CASES = [
+    # name, kind, B, H, W, seed, alpha, beta, criterion
+    ("bb_rand_2x24x24", "rand", 2, 24, 24, 11, 1.0, 1.0, "l1"),
+    ("bb_rand_1x48x36", "rand", 1, 48, 36, 12, 1.0, 1.0, "l1"),
+    ("bb_srlike_2x48x48", "srlike", 2, 48, 48, 13, 1.0, 1.0, "l1"),
+    ("bb_rand_ab_1x36x36", "rand", 1, 36, 36, 14, 0.5, 2.0, "l2"),
+    ("bb_same_1x24x24", "same", 1, 24, 24, 15, 1.0, 1.0, "l1"),
+]
+
+
+def make_st(ref_loss, ref_utils):
+    for name, kind, B, H, W, seed, sigma, rho, norm in ST_CASES:
+        sr, hr = _inputs(kind, B, H, W, seed)
+        sr.requires_grad_(True)
+        hr.requires_grad_(True)
+        m = ref_loss.StructureTensorLoss(sigma=sigma, rho=rho, normalize=norm)
+        loss = m(sr, hr)
+        loss.backward()
+        g, dg = ref_utils.get_gaussian_kernel(sigma, also_dg=True)
+        k = ref_utils.get_gaussian_kernel(rho)
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            sr=sr.detach().numpy(), hr=hr.detach().numpy(), loss=np.float32(loss.item()),
+            d_sr=sr.grad.numpy(), d_hr=hr.grad.numpy(), g=g.numpy(), dg=dg.numpy(), k=k.numpy(),
+            sigma=np.float64(sigma), rho=np.float64(rho), normalize=np.bool_(norm))
+        print(f"{name}: loss={loss.item():.8g} |d_sr|max={sr.grad.abs().max().item():.4g}")
+
+
+def make_bb(ref_loss, ref_utils):
+    import torch.nn.functional as F
+    for name, kind, B, H, W, seed, alpha, beta, crit in BB_CASES:
+        sr, hr = _inputs(kind, B, H, W, seed)
+        sr.requires_grad_(True)
+        m = ref_loss.BestBuddyLoss(alpha=alpha, beta=beta, criterion=crit)
+        loss = m(sr, hr)
+        loss.backward()
+        # Re-derive the indices and the top-2 score gap with the reference's own helpers
+        # (loss.py:116-135) so the tests can apply the near-tie protocol.
+        with torch.no_grad():
+            unf = lambda t: F.unfold(t, kernel_size=3, padding=0, stride=3).permute(0, 2, 1).contiguous()
+            p1, p2 = unf(sr), unf(hr)
+            hr2 = F.interpolate(hr, scale_factor=0.5, mode="bicubic", align_corners=False)
+            hr4 = F.interpolate(hr, scale_factor=0.25, mode="bicubic", align_corners=False)
+            cat = torch.cat([p2, unf(hr2), unf(hr4)], 1)
+            score = alpha * ref_utils.batch_pairwise_distance(p1, cat, "l2") \
+                + beta * ref_utils.batch_pairwise_distance(p2, cat, "l2")
+            w, ind = torch.min(score, dim=2)
+            top2 = torch.topk(score, 2, dim=2, largest=False).values
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            sr=sr.detach().numpy(), hr=hr.detach().numpy(), loss=np.float32(loss.item()),
+            d_sr=sr.grad.numpy(), ind=ind.numpy(), top2=top2.numpy(),
+            hr2=hr2.numpy(), hr4=hr4.numpy(),
+            alpha=np.float64(alpha), beta=np.float64(beta), criterion=np.str_(crit))
+        print(f"{name}: loss={loss.item():.8g} N={p1.shape[1]} M={cat.shape[1]}")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)  # fixed summation order inside MKL for reproducible fixtures
+    rl, ru = _import_reference()
+    make_st(rl, ru)
+    make_bb(rl, ru)

@@ -1,0 +1,87 @@
+"""Shared test helpers: golden fixtures, error metrics, the test-only host emulation library."""
+import ctypes
+import glob
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_LIB = os.path.join(EMU_DIR, "_build", "libsrst_emu.so")
+CSRC = os.path.join(ROOT, "srgan_st_b200", "csrc")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def golden_names(prefix):
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
+
+
+def rel_err(x, ref):
+    """|x - ref| / |ref| for scalars."""
+    return abs(float(x) - float(ref)) / max(abs(float(ref)), 1e-30)
+
+
+def maxnorm_err(x, ref):
+    """max|x - ref| / max|ref|: the gradient metric of SURVEY.md section 8(c)."""
+    x = np.asarray(x, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def emu_lib():
+    """Build (if stale) and load the host emulation of the kernels.  TEST-ONLY: same sources as
+    libsrst.so compiled with g++ -DSRST_EMULATE; it lets the CPU suite execute the kernels' index
+    logic.  The product package never loads this."""
+    from srgan_st_b200 import _cabi
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(EMU_DIR, "cuda_emu.h"),
+                                                                os.path.join(ROOT, "include", "srst.h")]
+    stale = (not os.path.exists(EMU_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(EMU_LIB) for s in srcs)
+    if stale:
+        os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
+        cmd = ["g++", "-x", "c++", "-std=c++20", "-O2", "-DSRST_EMULATE", "-I" + EMU_DIR, "-I" + CSRC,
+               "-shared", "-fPIC", "-pthread", "-o", EMU_LIB, os.path.join(CSRC, "srst_cabi.cu")]
+        subprocess.run(cmd, check=True, capture_output=True)
+    return _cabi.bind(EMU_LIB)
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def emu_st(lib, sr, hr, taps, normalize=True, want_hr=False, grad_out=1.0):
+    """Run srst_st_forward + srst_st_backward of `lib` on host arrays (emulation library only)."""
+    sr = np.ascontiguousarray(sr, np.float32)
+    hr = np.ascontiguousarray(hr, np.float32)
+    B, _, H, W = sr.shape
+    g, dg, k = [np.ascontiguousarray(t, np.float32) for t in taps]
+    nb = lib.srst_st_workspace_bytes(B, H, W)
+    ws = np.zeros(nb // 4 + 4, np.float32)
+    loss = np.zeros(1, np.float32)
+    ds_sr = np.full_like(sr, np.nan)
+    ds_hr = np.full_like(sr, np.nan) if want_hr else None
+    rc = lib.srst_st_forward(_p(sr), _p(hr), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k), len(k) // 2,
+                             int(normalize), 1e-12, _p(loss), _p(ds_sr), _p(ds_hr), _p(ws), nb, None)
+    assert rc == 0, rc
+    go = np.full(1, grad_out, np.float32)
+    out = dict(loss=float(loss[0]), ds_sr=ds_sr, ws=ws)
+    d_sr = np.full_like(sr, np.nan)
+    rc = lib.srst_st_backward(_p(sr), _p(ds_sr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
+                              len(k) // 2, _p(d_sr), None)
+    assert rc == 0, rc
+    out["d_sr"] = d_sr
+    if want_hr:
+        d_hr = np.full_like(sr, np.nan)
+        rc = lib.srst_st_backward(_p(hr), _p(ds_hr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
+                                  len(k) // 2, _p(d_hr), None)
+        assert rc == 0, rc
+        out["d_hr"] = d_hr
+    return out

@@ -1,0 +1,46 @@
+"""CPU: libsrst.so loads without a GPU and exports every entry point include/srst.h declares."""
+import ctypes
+import os
+import re
+
+from tests.helpers import ROOT
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "srst.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(srst_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_hot_path():
+    names = _declared()
+    for must in ("srst_st_forward", "srst_st_backward", "srst_bb_forward", "srst_bb_backward",
+                 "srst_st_workspace_bytes", "srst_bb_workspace_bytes", "srst_version"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from srgan_st_b200 import _cabi
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    missing = [n for n in _declared() if not hasattr(lib, n)]
+    assert not missing, f"declared in srst.h but not exported: {missing}"
+
+
+def test_binding_table_matches_header():
+    from srgan_st_b200 import _cabi
+    assert sorted(_cabi.SIGNATURES) == _declared()
+
+
+def test_no_compute_entry_points_that_need_no_gpu():
+    """Pure host queries work on the CPU box (no kernel is launched)."""
+    from srgan_st_b200 import _cabi
+    lib = _cabi.lib()
+    assert lib.srst_version() == 100
+    assert lib.srst_st_supported(2, 8) == 1
+    assert lib.srst_st_supported(3, 3) == 0
+    assert lib.srst_st_workspace_bytes(16, 96, 96) >= 16 * 3 * 2 * 4
+    assert lib.srst_st_workspace_bytes(0, 96, 96) == 0
+    assert b"workspace" in lib.srst_error_string(-3)
+    # argument validation happens before any CUDA call
+    assert lib.srst_st_forward(None, None, 1, 8, 8, None, None, 2, None, 8, 1, 1e-12, None, None, None,
+                               None, 0, None) == -1

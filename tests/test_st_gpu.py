@@ -1,0 +1,146 @@
+"""GPU parity of the fused structure-tensor loss (through the nn.Module -> autograd.Function ->
+ctypes -> C ABI -> sm_100a kernels path) against the committed reference outputs, the fp64 oracle
+and size-independent properties at the BASELINE.json sizes.
+
+Tolerances (BASELINE.json north_star): loss rel 1e-5, input gradients 1e-4 (max-norm relative), fp32.
+Gradient note: on inputs where the SR and HR tensors nearly coincide at some pixel the reference's
+own fp32 backward is up to ~4e-4 from the fp64 truth (1/(2 sqrt(disc)) amplification, see
+DESIGN.md); there the CUDA path is held to 1e-4 against the fp64 oracle, and against the
+reference to 1e-4 + the reference's own distance from the oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import st_oracle as O
+from tests.helpers import golden, golden_names, maxnorm_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+DEFAULT_CASES = [n for n in golden_names("st_") if "s1_r25" not in n]
+
+
+def _run(sr, hr, normalize=True, want_hr=True, sigma=0.5, rho=2.0):
+    from srgan_st_b200 import StructureTensorLoss
+    dev = torch.device("cuda:0")
+    x = torch.from_numpy(np.ascontiguousarray(sr)).to(dev).requires_grad_(True)
+    y = torch.from_numpy(np.ascontiguousarray(hr)).to(dev).requires_grad_(want_hr)
+    loss = StructureTensorLoss(sigma=sigma, rho=rho, normalize=normalize)(x, y)
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.item(), x.grad.cpu().numpy(), (y.grad.cpu().numpy() if want_hr else None)
+
+
+@pytest.fixture(params=[-1, 0, 1, 2])
+def tile_cfg(request, monkeypatch):
+    """-1 = the library's own choice; 0..2 force each compiled tile shape."""
+    if request.param >= 0:
+        monkeypatch.setenv("SRST_ST_FWD_CFG", str(request.param))
+        monkeypatch.setenv("SRST_ST_BWD_CFG", str(request.param))
+    return request.param
+
+
+@pytest.mark.parametrize("name", DEFAULT_CASES)
+def test_matches_reference_golden(name, tile_cfg):
+    z = golden(name)
+    norm = bool(z["normalize"])
+    loss, d_sr, d_hr = _run(z["sr"], z["hr"], normalize=norm)
+    ref = O.st_loss(z["sr"], z["hr"], normalize=norm, taps=(z["g"], z["dg"], z["k"]), want_hr_grad=True)
+    if "same" in name:
+        assert rel_err(loss, z["loss"]) < 2e-2 and abs(loss - 1.118e-6) < 2e-8
+        assert np.abs(d_sr).max() < 1e-8
+        return
+    assert rel_err(loss, z["loss"]) < 1e-5, "loss vs reference"
+    assert rel_err(loss, ref["loss"]) < 1e-5, "loss vs fp64 oracle"
+    if "nonorm" in name:
+        assert np.abs(d_sr).max() == 0.0
+        return
+    for ours, orc, refg in ((d_sr, ref["d_sr"], z["d_sr"]), (d_hr, ref["d_hr"], z["d_hr"])):
+        assert maxnorm_err(ours, orc) < 1e-4, "grad vs fp64 oracle"
+        assert maxnorm_err(ours, refg) < 1e-4 + maxnorm_err(refg, orc), "grad vs reference"
+
+
+def test_hr_without_grad_and_no_grad_mode():
+    from srgan_st_b200 import StructureTensorLoss
+    z = golden("st_rand_2x24x36")
+    loss, d_sr, _ = _run(z["sr"], z["hr"], want_hr=False)
+    assert rel_err(loss, z["loss"]) < 1e-5
+    assert maxnorm_err(d_sr, z["d_sr"]) < 2e-4
+    with torch.no_grad():
+        x = torch.from_numpy(z["sr"]).cuda()
+        y = torch.from_numpy(z["hr"]).cuda()
+        l2 = StructureTensorLoss()(x, y)
+    assert rel_err(l2.item(), z["loss"]) < 1e-5 and not l2.requires_grad
+
+
+def test_upstream_gradient_and_determinism():
+    from srgan_st_b200 import StructureTensorLoss
+    z = golden("st_srlike_2x40x52")
+    x = torch.from_numpy(z["sr"]).cuda().requires_grad_(True)
+    y = torch.from_numpy(z["hr"]).cuda()
+    m = StructureTensorLoss()
+    (m(x, y) * (1.0 / 3.0)).backward()          # train.py:138-139: loss * weight
+    g1 = x.grad.clone()
+    x.grad = None
+    l_a = m(x, y)
+    l_b = m(x, y)
+    assert torch.equal(l_a, l_b), "loss reduction must be deterministic"
+    l_a.backward()
+    assert torch.allclose(g1, x.grad / 3.0, rtol=1e-6, atol=0)
+    assert maxnorm_err(x.grad.cpu().numpy(), z["d_sr"]) < 2e-4
+
+
+@pytest.mark.parametrize("shape", [(16, 96, 96), (3, 100, 152), (1, 333, 517), (2, 64, 1024)])
+def test_matches_oracle_on_larger_shapes(shape):
+    rng = np.random.default_rng(shape[1])
+    sr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+    hr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+    loss, d_sr, d_hr = _run(sr, hr)
+    ref = O.st_loss(sr, hr, taps=None, want_hr_grad=True)
+    assert rel_err(loss, ref["loss"]) < 1e-5
+    assert maxnorm_err(d_sr, ref["d_sr"]) < 1e-4
+    assert maxnorm_err(d_hr, ref["d_hr"]) < 1e-4
+
+
+def test_full_size_properties_div2k():
+    """Config 5 size (1356x2040): batch additivity (mean of means), translation of the tiling
+    (crop consistency far from borders is NOT expected -- zero padding -- so use batch splits),
+    gradient of a batch equals per-image gradients scaled by 1/B."""
+    from srgan_st_b200 import StructureTensorLoss
+    torch.manual_seed(0)
+    H, W = 1356, 2040
+    hr = (torch.randint(0, 256, (2, 3, H, W), device="cuda").float() / 255)
+    sr = (hr + 0.05 * torch.randn_like(hr)).clamp(0, 1).requires_grad_(True)
+    m = StructureTensorLoss()
+    l_all = m(sr, hr)
+    l_all.backward()
+    g_all = sr.grad.clone()
+    parts, grads = [], []
+    for i in range(2):
+        s = sr.detach()[i:i + 1].clone().requires_grad_(True)
+        li = m(s, hr[i:i + 1])
+        li.backward()
+        parts.append(li.item())
+        grads.append(s.grad)
+    assert rel_err(l_all.item(), 0.5 * (parts[0] + parts[1])) < 1e-6
+    g_parts = torch.cat(grads) / 2
+    assert (g_all - g_parts).abs().max().item() <= 1e-6 * g_parts.abs().max().item() + 1e-12
+    assert torch.isfinite(g_all).all()
+    # flipping both images left-right flips the gradient field and keeps the loss (symmetric taps)
+    sr_f = sr.detach().flip(-1).clone().requires_grad_(True)
+    l_f = m(sr_f, hr.flip(-1))
+    l_f.backward()
+    assert rel_err(l_f.item(), l_all.item()) < 1e-5
+    assert (sr_f.grad.flip(-1) - g_all).abs().max().item() < 1e-4 * g_all.abs().max().item()
+
+
+def test_rejects_what_the_kernels_cannot_do():
+    from srgan_st_b200 import StructureTensorLoss
+    m = StructureTensorLoss()
+    a = torch.rand(1, 3, 16, 16)
+    with pytest.raises(RuntimeError):
+        m(a, a)                                   # CPU tensors: no fallback
+    with pytest.raises(TypeError):
+        m(a.cuda().half(), a.cuda().half())
+    with pytest.raises(ValueError):
+        m(a.cuda()[:, :2], a.cuda()[:, :2])
