@@ -137,48 +137,58 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons of one GPU in a background thread (NVML, ~2 ms period)
+    while the timed regions run; falls back to `nvidia-smi -lms` when NVML is unavailable."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
+    def __init__(self, torch, local):
+        self.samples, self.reason_bits, self.max_mhz = [], 0, None
+        self._stop = False
+        self._thread = None
+        self._h = None
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            self._nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv, h = self._nv, self._h
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+        if self._nv is None:
+            return
+        import threading
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [s for s in sm if s >= 0.5 * max(sm)]
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self._thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        self._stop = True
+        self._thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+        busy = [x for x in self.samples if x >= 0.5 * max(self.samples)]
+        reasons = sorted(n for b, n in self.REASONS.items() if self.reason_bits & b)
+        return {"sm_mhz": statistics.median(busy), "sm_min_mhz": min(busy), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.samples)}
 
 
 def make_pair(torch, B, H, W, gen, device):
@@ -282,15 +292,14 @@ def run_gpu(args):
             with torch.cuda.stream(s):
                 gr.replay()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local)
+        sampler = ClockSampler(torch, local)
         if rank == 0:
             sampler.start()
         ms_pair = min(time_graph(g_pair) for _ in range(3))
         ms_f = min(time_graph(g_f) for _ in range(3))
         ms_b = min(time_graph(g_b) for _ in range(3))
-        clocks = sampler.stop() if rank == 0 else None
         loss_val = float(loss.item())
-        res = dict(wl=wl, ms_step=ms_pair / K, ms_fwd=ms_f / K, ms_bwd=ms_b / K, clocks=clocks, pool_n=pool_n,
+        res = dict(wl=wl, ms_step=ms_pair / K, ms_fwd=ms_f / K, ms_bwd=ms_b / K, clocks=None, pool_n=pool_n,
                    loss=loss_val, images_per_s=world * B * K / (ms_pair * 1e-3))
         px = B * H * W
         res["roofline_fwd"] = BYTES_FWD * px / (res["ms_fwd"] * 1e-3) / 1e9
@@ -326,6 +335,7 @@ def run_gpu(args):
             res["e2e"] = {"value": world * B * K / (ms * 1e-3), "unit": UNIT,
                           "h2d_bytes_per_step": bytes_pair, "d2h_bytes_per_step": 4,
                           "ms_per_step": ms / K}
+        res["clocks"] = sampler.stop() if rank == 0 else None
         del pool
         torch.cuda.empty_cache()
         return res

@@ -1,0 +1,82 @@
+"""Time every compiled ST tile configuration on the B200 (forward and backward separately).
+    python tools/sweep_st.py > gpurun_out/sweep.log
+Uses the C ABI directly, CUDA events on the launching stream, inputs cycling through a pool > L2."""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from srgan_st_b200 import _cabi, taps as T  # noqa: E402
+
+lib = _cabi.lib()
+g, dg = T.gaussian_taps(0.5)
+k, _ = T.gaussian_taps(2.0)
+dev = torch.device("cuda:0")
+vp = lambda t: ctypes.c_void_p(t.data_ptr())
+HBM = 6539.9
+
+
+def run(B, H, W, iters=40):
+    bytes_pair = 2 * B * 3 * H * W * 4
+    pool_n = max(4, min(64, int(300e6 // bytes_pair) + 1))
+    pool = [(torch.rand(B, 3, H, W, device=dev), torch.rand(B, 3, H, W, device=dev)) for _ in range(pool_n)]
+    ds = torch.empty(B, 3, H, W, device=dev)
+    d_sr = torch.empty(B, 3, H, W, device=dev)
+    loss = torch.zeros((), device=dev)
+    go = torch.ones((), device=dev)
+    ws = torch.zeros(max(lib.srst_st_workspace_bytes(B, H, W), 4096), dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(s.cuda_stream)
+
+    def fwd(i):
+        sr, hr = pool[i % pool_n]
+        _cabi.check(lib.srst_st_forward(vp(sr), vp(hr), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8, 1, 1e-12,
+                                        vp(loss), vp(ds), None, vp(ws), ws.numel(), sp), "fwd")
+
+    def bwd(i):
+        sr, _ = pool[i % pool_n]
+        _cabi.check(lib.srst_st_backward(vp(sr), vp(ds), vp(go), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8,
+                                         vp(d_sr), sp), "bwd")
+
+    def timeit(fn):
+        gr = torch.cuda.CUDAGraph()
+        st = torch.cuda.Stream()
+        nonlocal sp
+        sp_old = sp
+        sp = ctypes.c_void_p(st.cuda_stream)
+        with torch.cuda.graph(gr, stream=st):
+            for i in range(iters):
+                fn(i)
+        sp = sp_old
+        gr.replay()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / iters)
+        return best
+
+    for i in range(3):
+        fwd(i); bwd(i)
+    torch.cuda.synchronize()
+    px = B * H * W
+    for cfg in (0, 1, 2):
+        os.environ["SRST_ST_FWD_CFG"] = str(cfg)
+        os.environ["SRST_ST_BWD_CFG"] = str(cfg)
+        tf, tb = timeit(fwd), timeit(bwd)
+        print(f"B={B:3d} {H}x{W} cfg={cfg}: fwd {tf*1e3:8.1f} us ({24*px/tf/1e6/HBM*100:5.1f}% HBM)  "
+              f"bwd {tb*1e3:8.1f} us ({36*px/tb/1e6/HBM*100:5.1f}% HBM)  pair {60*px/(tf+tb)/1e6/HBM*100:5.1f}%  "
+              f"{B/((tf+tb)*1e-3):.0f} img/s", flush=True)
+    os.environ.pop("SRST_ST_FWD_CFG"); os.environ.pop("SRST_ST_BWD_CFG")
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0))
+    for shape in [(16, 96, 96), (64, 96, 96), (256, 96, 96), (1, 1356, 2040), (4, 1356, 2040), (8, 192, 192)]:
+        run(*shape)
