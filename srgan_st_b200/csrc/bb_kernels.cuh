@@ -1,2 +1,390 @@
+// Best-Buddy loss kernels for sm_100a.
+//
+// Reference (loss.py:115-141, utils.py:173-187): unfold 3x3/stride-3 patches of SR and HR, build an
+// HR candidate set from three pyramid levels, materialise two [B,N,M] fp32 distance matrices with
+// torch.bmm, take torch.min over M, gather, L1.  Here the [B,N,M] matrices never exist:
+//
+//   bb_pyramid_kernel : bicubic x1/2 and x1/4 levels of HR (same taps as F.interpolate(bicubic,
+//                       align_corners=False): t = 0.5 on both levels)                (loss.py:123,127)
+//   bb_pack_kernel    : patches -> k-major fp32 matrices Q1 (SR), Q2 (HR), Y (candidates) + norms
+//   bb_search_kernel  : register-tiled fp32 distance evaluation fused with a running argmin;
+//                       per-thread argmin over its candidates, warp-shuffle argmin across lanes,
+//                       shared-memory argmin across warps; first minimal index wins (torch.min)
+//   bb_loss_kernel    : mean |sr_patch - cand[idx]| (or squared), deterministic reduction
+//   bb_backward_kernel: d_sr = grad/(B*N*27) * sign(sr_patch - cand[idx])  (or 2*diff)
+//
+// The score is evaluated with exactly the reference's expression and rounding points,
+//   alpha * max((xn + yn) - 2*dot1, 0) + beta * max((gn + yn) - 2*dot2, 0),
+// with a fixed fp32 order for the 27-term dot products and norms (sequential FMA, k = 0..26;
+// oracle/bb_oracle.c restates the same order so indices can be compared bit-exactly).
 #pragma once
+#include <cstdint>
+
 #include "srst_device.cuh"
+
+namespace srst {
+
+constexpr int BB_D = 27;   // 3 channels x 3 x 3
+constexpr int BB_QT = 64;  // queries per block
+constexpr int BB_CT = 64;  // candidates per chunk
+constexpr int BB_NT = 256;
+
+struct BbGeom {
+  int B, H, W;
+  int n0x, N0;          // level 0 patch grid
+  int H2, W2, n2x, N2;  // x1/2
+  int H4, W4, n4x, N4;  // x1/4
+  int N, M, Npad, Mpad;
+};
+
+inline BbGeom bb_geom(int B, int H, int W) {
+  BbGeom g;
+  g.B = B; g.H = H; g.W = W;
+  g.n0x = W / 3; g.N0 = (H / 3) * g.n0x;
+  g.H2 = H / 2; g.W2 = W / 2; g.n2x = g.W2 / 3; g.N2 = (g.H2 / 3) * g.n2x;
+  g.H4 = H / 4; g.W4 = W / 4; g.n4x = g.W4 / 3; g.N4 = (g.H4 / 3) * g.n4x;
+  g.N = g.N0;
+  g.M = g.N0 + g.N2 + g.N4;
+  g.Npad = (g.N + BB_QT - 1) / BB_QT * BB_QT;
+  g.Mpad = (g.M + BB_CT - 1) / BB_CT * BB_CT;
+  return g;
+}
+
+// Workspace carve-up (floats).  Per image: Q1[27][Npad] Q2[27][Npad] Y[27][Mpad] xn[Npad] gn[Npad] yn[Mpad]
+struct BbWorkspace {
+  unsigned int* ticket;
+  float* partials;
+  float* mats;
+  float* pyr2;
+  float* pyr4;
+  size_t per_image;  // floats
+  size_t total_bytes;
+};
+
+inline BbWorkspace bb_carve(void* base, const BbGeom& g) {
+  BbWorkspace w;
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  w.ticket = reinterpret_cast<unsigned int*>(p + off);
+  off += 256;
+  const size_t nblk_loss = ((size_t)g.B * g.N + BB_NT - 1) / BB_NT;
+  w.partials = reinterpret_cast<float*>(p + off);
+  off += (nblk_loss * sizeof(float) + 255) / 256 * 256;
+  w.per_image = (size_t)(BB_D + 1) * (2 * (size_t)g.Npad + g.Mpad);
+  w.mats = reinterpret_cast<float*>(p + off);
+  off += (w.per_image * g.B * sizeof(float) + 255) / 256 * 256;
+  w.pyr2 = reinterpret_cast<float*>(p + off);
+  off += ((size_t)g.B * 3 * g.H2 * g.W2 * sizeof(float) + 255) / 256 * 256;
+  w.pyr4 = reinterpret_cast<float*>(p + off);
+  off += ((size_t)g.B * 3 * g.H4 * g.W4 * sizeof(float) + 255) / 256 * 256;
+  w.total_bytes = off;
+  return w;
+}
+
+struct BbPtrs {
+  const float* q1; const float* q2; const float* y; const float* xn; const float* gn; const float* yn;
+};
+SRST_DEV BbPtrs bb_image_ptrs(const float* mats, size_t per_image, int b, int Npad, int Mpad) {
+  const float* m = mats + per_image * b;
+  BbPtrs p;
+  p.q1 = m;
+  p.q2 = p.q1 + (size_t)BB_D * Npad;
+  p.y = p.q2 + (size_t)BB_D * Npad;
+  p.xn = p.y + (size_t)BB_D * Mpad;
+  p.gn = p.xn + Npad;
+  p.yn = p.gn + Npad;
+  return p;
+}
+
+// ---- HR pyramid ---------------------------------------------------------------------------------
+// F.interpolate(gt, scale_factor=s, mode='bicubic', align_corners=False), s = 1/2 and 1/4: the source
+// coordinate (dst + 0.5)/s - 0.5 always has fractional part 0.5, so the cubic-convolution (A=-0.75)
+// weights are the constants below, applied to rows/cols 2i-1..2i+2 (x1/2) or 4i..4i+3 (x1/4) with
+// indices clamped to the image.
+SRST_DEV float bb_cubic4(float a, float b, float c, float d) {
+  constexpr float w0 = -0.09375f, w1 = 0.59375f;
+  return ((a * w0 + b * w1) + c * w1) + d * w0;
+}
+
+__global__ void __launch_bounds__(256)
+bb_pyramid_kernel(const float* __restrict__ gt, float* __restrict__ o2, float* __restrict__ o4, int planes, int H,
+                  int W, int H2, int W2, int H4, int W4) {
+  const size_t n2 = (size_t)planes * H2 * W2, n4 = (size_t)planes * H4 * W4;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n2 + n4) return;
+  const bool lvl4 = t >= n2;
+  const size_t u = lvl4 ? t - n2 : t;
+  const int Ho = lvl4 ? H4 : H2, Wo = lvl4 ? W4 : W2;
+  const int x = (int)(u % Wo);
+  const int y = (int)((u / Wo) % Ho);
+  const int pl = (int)(u / ((size_t)Wo * Ho));
+  const int sy = lvl4 ? 4 * y : 2 * y - 1;
+  const int sx = lvl4 ? 4 * x : 2 * x - 1;
+  const float* src = gt + (size_t)pl * H * W;
+  float r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int yy = min(max(sy + i, 0), H - 1);
+    const float* row = src + (size_t)yy * W;
+    const float a = __ldg(row + min(max(sx, 0), W - 1));
+    const float b = __ldg(row + min(max(sx + 1, 0), W - 1));
+    const float c = __ldg(row + min(max(sx + 2, 0), W - 1));
+    const float d = __ldg(row + min(max(sx + 3, 0), W - 1));
+    r[i] = bb_cubic4(a, b, c, d);
+  }
+  (lvl4 ? o4 : o2)[u] = bb_cubic4(r[0], r[1], r[2], r[3]);
+}
+
+// ---- pack ---------------------------------------------------------------------------------------
+// Patch vector layout (F.unfold, loss.py:116): element c*9 + ky*3 + kx; patch index py*(W/3) + px.
+SRST_DEV void bb_read_patch(const float* __restrict__ img, int H, int W, int nx, int p, float (&v)[BB_D]) {
+  const int py = p / nx, px = p - py * nx;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+        v[c * 9 + ky * 3 + kx] = __ldg(img + ((size_t)c * H + 3 * py + ky) * W + 3 * px + kx);
+}
+SRST_DEV float bb_norm(const float (&v)[BB_D]) {
+  float n = 0.f;
+#pragma unroll
+  for (int k = 0; k < BB_D; ++k) n = fmaf(v[k], v[k], n);
+  return n;
+}
+
+__global__ void __launch_bounds__(256)
+bb_pack_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const float* __restrict__ gt2,
+               const float* __restrict__ gt4, float* __restrict__ mats, size_t per_image, BbGeom g) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  float* m = mats + per_image * b;
+  float* q1 = m;
+  float* q2 = q1 + (size_t)BB_D * g.Npad;
+  float* y = q2 + (size_t)BB_D * g.Npad;
+  float* xn = y + (size_t)BB_D * g.Mpad;
+  float* gn = xn + g.Npad;
+  float* yn = gn + g.Npad;
+  float v[BB_D];
+  if (t < g.Npad) {  // query t
+    if (t < g.N) {
+      bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, t, v);
+#pragma unroll
+      for (int k = 0; k < BB_D; ++k) q1[(size_t)k * g.Npad + t] = v[k];
+      xn[t] = bb_norm(v);
+      bb_read_patch(gt + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, t, v);
+#pragma unroll
+      for (int k = 0; k < BB_D; ++k) q2[(size_t)k * g.Npad + t] = v[k];
+      gn[t] = bb_norm(v);
+    } else {
+#pragma unroll
+      for (int k = 0; k < BB_D; ++k) { q1[(size_t)k * g.Npad + t] = 0.f; q2[(size_t)k * g.Npad + t] = 0.f; }
+      xn[t] = 0.f;
+      gn[t] = 0.f;
+    }
+  }
+  if (t < g.Mpad) {  // candidate t: level 0 | level 1/2 | level 1/4 (torch.cat order, loss.py:130)
+    if (t < g.M) {
+      if (t < g.N0) bb_read_patch(gt + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, t, v);
+      else if (t < g.N0 + g.N2) bb_read_patch(gt2 + (size_t)b * 3 * g.H2 * g.W2, g.H2, g.W2, g.n2x, t - g.N0, v);
+      else bb_read_patch(gt4 + (size_t)b * 3 * g.H4 * g.W4, g.H4, g.W4, g.n4x, t - g.N0 - g.N2, v);
+#pragma unroll
+      for (int k = 0; k < BB_D; ++k) y[(size_t)k * g.Mpad + t] = v[k];
+      yn[t] = bb_norm(v);
+    } else {
+#pragma unroll
+      for (int k = 0; k < BB_D; ++k) y[(size_t)k * g.Mpad + t] = 0.f;
+      yn[t] = __int_as_float(0x7f800000);  // +inf: a padded candidate never wins
+    }
+  }
+}
+
+// ---- search -------------------------------------------------------------------------------------
+SRST_DEV float bb_score(float xn, float gn, float yn, float dot1, float dot2, float alpha, float beta) {
+  // utils.py:183-187 with its rounding points: (x_norm + y_norm) - 2*bmm, clamp(0, inf);
+  // loss.py:132-133: alpha*d1 + beta*d2 (separate multiply and add roundings).
+  float d1 = fmaf(-2.0f, dot1, __fadd_rn(xn, yn));
+  float d2 = fmaf(-2.0f, dot2, __fadd_rn(gn, yn));
+  d1 = fmaxf(d1, 0.0f);
+  d2 = fmaxf(d2, 0.0f);
+  return __fadd_rn(__fmul_rn(alpha, d1), __fmul_rn(beta, d2));
+}
+
+SRST_DEV void bb_argmin_merge(float& s, int& i, float so, int io) {
+  if (so < s || (so == s && io < i)) { s = so; i = io; }
+}
+
+__global__ void __launch_bounds__(BB_NT, 2)
+bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, float alpha, float beta,
+                 int64_t* __restrict__ idx_out) {
+  __shared__ __align__(16) float sQ1[BB_D][BB_QT];
+  __shared__ __align__(16) float sQ2[BB_D][BB_QT];
+  __shared__ __align__(16) float sY[BB_D][BB_CT];
+  __shared__ float sXn[BB_QT], sGn[BB_QT], sYn[BB_CT];
+  __shared__ float sBestS[4][BB_QT];
+  __shared__ int sBestI[4][BB_QT];
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y, qt = blockIdx.x;
+  const BbPtrs P = bb_image_ptrs(mats, per_image, b, g.Npad, g.Mpad);
+  const int qbase = qt * BB_QT;
+
+  for (int it = tid; it < BB_D * (BB_QT / 4); it += BB_NT) {
+    const int k = it / (BB_QT / 4), c4 = it - k * (BB_QT / 4);
+    st4(&sQ1[k][4 * c4], ldg4(P.q1 + (size_t)k * g.Npad + qbase + 4 * c4));
+    st4(&sQ2[k][4 * c4], ldg4(P.q2 + (size_t)k * g.Npad + qbase + 4 * c4));
+  }
+  if (tid < BB_QT) { sXn[tid] = __ldg(P.xn + qbase + tid); sGn[tid] = __ldg(P.gn + qbase + tid); }
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wq = warp >> 2, wc = warp & 3;  // 2 x 4 warps: 32 queries x 16 candidates each
+  const int lq = lane >> 2, lc = lane & 3;  // 8 x 4 lanes : 4 queries x 4 candidates each
+  const int q0 = wq * 32 + lq * 4;
+  const int c0 = wc * 16 + lc * 4;
+
+  float best[4];
+  int bidx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { best[i] = __int_as_float(0x7f800000); bidx[i] = 0x7fffffff; }
+
+  for (int chunk = 0; chunk < g.Mpad; chunk += BB_CT) {
+    __syncthreads();  // previous chunk fully consumed (also orders the query loads before first use)
+    for (int it = tid; it < BB_D * (BB_CT / 4); it += BB_NT) {
+      const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
+      st4(&sY[k][4 * c4], ldg4(P.y + (size_t)k * g.Mpad + chunk + 4 * c4));
+    }
+    if (tid < BB_CT) sYn[tid] = __ldg(P.yn + chunk + tid);
+    __syncthreads();
+
+    float a1[4][4], a2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a1[i][j] = 0.f; a2[i][j] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < BB_D; ++k) {
+      const float4 u = ld4(&sQ1[k][q0]);
+      const float4 v = ld4(&sQ2[k][q0]);
+      const float4 w = ld4(&sY[k][c0]);
+      const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {v.x, v.y, v.z, v.w}, ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          a1[i][j] = fmaf(uu[i], ww[j], a1[i][j]);
+          a2[i][j] = fmaf(vv[i], ww[j], a2[i][j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float yn = sYn[c0 + j];
+      const int cj = chunk + c0 + j;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float s = bb_score(sXn[q0 + i], sGn[q0 + i], yn, a1[i][j], a2[i][j], alpha, beta);
+        if (s < best[i]) { best[i] = s; bidx[i] = cj; }  // ascending cj per thread: first minimum kept
+      }
+    }
+  }
+
+  // argmin across the 4 candidate lanes (lc = lane bits 0-1), then across the 4 candidate warps
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      const float so = __shfl_xor_sync(0xffffffffu, best[i], o);
+      const int io = __shfl_xor_sync(0xffffffffu, bidx[i], o);
+      bb_argmin_merge(best[i], bidx[i], so, io);
+    }
+    if (lc == 0) { sBestS[wc][q0 + i] = best[i]; sBestI[wc][q0 + i] = bidx[i]; }
+  }
+  __syncthreads();
+  if (tid < BB_QT) {
+    float s = sBestS[0][tid];
+    int i = sBestI[0][tid];
+#pragma unroll
+    for (int w = 1; w < 4; ++w) bb_argmin_merge(s, i, sBestS[w][tid], sBestI[w][tid]);
+    if (qbase + tid < g.N) idx_out[(size_t)b * g.N + qbase + tid] = (int64_t)i;
+  }
+}
+
+// ---- loss ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BB_NT)
+bb_loss_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, const int64_t* __restrict__ idx,
+               int criterion, float* partials, unsigned int* ticket, float* loss_out) {
+  __shared__ float s_red[BB_NT / 32];
+  __shared__ unsigned int s_last;
+  const int tid = threadIdx.x;
+  const size_t t = (size_t)blockIdx.x * BB_NT + tid;
+  float acc = 0.f;
+  if (t < (size_t)g.B * g.N) {
+    const int b = (int)(t / g.N), i = (int)(t - (size_t)b * g.N);
+    const BbPtrs P = bb_image_ptrs(mats, per_image, b, g.Npad, g.Mpad);
+    const int j = (int)idx[t];
+#pragma unroll
+    for (int k = 0; k < BB_D; ++k) {
+      const float d = __ldg(P.q1 + (size_t)k * g.Npad + i) - __ldg(P.y + (size_t)k * g.Mpad + j);
+      acc += (criterion == 0) ? fabsf(d) : d * d;
+    }
+  }
+  acc = warp_sum(acc);
+  if ((tid & 31) == 0) s_red[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    float bs = 0.f;
+    for (int w = 0; w < BB_NT / 32; ++w) bs += s_red[w];
+    partials[blockIdx.x] = bs;
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && tid < 32) {
+    __threadfence();
+    double tot = 0.0;
+    for (unsigned int i = tid; i < gridDim.x; i += 32) { tot += (double)__ldcg(partials + i); partials[i] = 0.f; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (tid == 0) {
+      loss_out[0] = (float)(tot / ((double)g.B * g.N * BB_D));
+      *ticket = 0u;
+    }
+  }
+}
+
+// ---- backward -----------------------------------------------------------------------------------
+SRST_DEV float bb_candidate_value(const float* gt, const float* gt2, const float* gt4, const BbGeom& g, int b,
+                                  int j, int c, int ky, int kx) {
+  const float* img; int H, W, nx, p;
+  if (j < g.N0) { img = gt + (size_t)b * 3 * g.H * g.W; H = g.H; W = g.W; nx = g.n0x; p = j; }
+  else if (j < g.N0 + g.N2) { img = gt2 + (size_t)b * 3 * g.H2 * g.W2; H = g.H2; W = g.W2; nx = g.n2x; p = j - g.N0; }
+  else { img = gt4 + (size_t)b * 3 * g.H4 * g.W4; H = g.H4; W = g.W4; nx = g.n4x; p = j - g.N0 - g.N2; }
+  const int py = p / nx, px = p - py * nx;
+  return __ldg(img + ((size_t)c * H + 3 * py + ky) * W + 3 * px + kx);
+}
+
+__global__ void __launch_bounds__(256)
+bb_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const float* __restrict__ gt2,
+                   const float* __restrict__ gt4, const int64_t* __restrict__ idx, const float* __restrict__ grad_out,
+                   BbGeom g, int criterion, float* __restrict__ d_sr) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)g.B * 3 * g.H * g.W;
+  if (t >= total) return;
+  const int x = (int)(t % g.W);
+  const int y = (int)((t / g.W) % g.H);
+  const int c = (int)((t / ((size_t)g.W * g.H)) % 3);
+  const int b = (int)(t / ((size_t)3 * g.W * g.H));
+  const int py = y / 3, px = x / 3;
+  float out = 0.f;
+  if (py < g.H / 3 && px < g.n0x) {
+    const int i = py * g.n0x + px;
+    const int j = (int)idx[(size_t)b * g.N + i];
+    const float sel = bb_candidate_value(gt, gt2, gt4, g, b, j, c, y - 3 * py, x - 3 * px);
+    const float d = __ldg(sr + t) - sel;
+    const float scale = __ldg(grad_out) / ((float)g.B * (float)g.N * (float)BB_D);
+    out = (criterion == 0) ? ((d > 0.f) ? scale : ((d < 0.f) ? -scale : 0.f)) : 2.0f * d * scale;
+  }
+  d_sr[t] = out;
+}
+
+}  // namespace srst

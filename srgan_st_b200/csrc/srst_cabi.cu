@@ -34,7 +34,9 @@ using BwdC = StBwdCfg<44, 48, 12, 288, 2, 8, 2>;
 constexpr int kMinFwdTH = 32, kMinFwdTW = 48;  // finest compiled forward tiling (workspace sizing)
 
 // Opt in to > 48 KB of dynamic shared memory once per (kernel, device).
-template <class K>
+// `Tag` makes the once-flag unique per kernel instantiation (all kernels of one direction share a
+// function-pointer type).
+template <class Tag, class K>
 static int ensure_smem(K kernel, size_t bytes) {
 #ifdef SRST_EMULATE
   (void)kernel; (void)bytes;
@@ -65,7 +67,7 @@ static int launch_st_forward(StFwdParams<C::RG, C::RK> P, void* stream) {
   P.tiles_y = (P.H + C::TH - 1) / C::TH;
   const long long nblk = (long long)P.B * P.tiles_x * P.tiles_y;
   if (nblk <= 0 || nblk > 0x7fffffffLL) return SRST_E_SHAPE;
-  int e = ensure_smem(st_forward_kernel<C>, C::SMEM_BYTES);
+  int e = ensure_smem<C>(st_forward_kernel<C>, C::SMEM_BYTES);
   if (e) return e;
   SRST_LAUNCH(st_forward_kernel<C>, dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
   return (int)cudaGetLastError();
@@ -77,7 +79,7 @@ static int launch_st_backward(StBwdParams<C::RG, C::RK> P, void* stream) {
   P.tiles_y = (P.H + C::TH - 1) / C::TH;
   const long long nblk = (long long)P.B * P.tiles_x * P.tiles_y;
   if (nblk <= 0 || nblk > 0x7fffffffLL) return SRST_E_SHAPE;
-  int e = ensure_smem(st_backward_kernel<C>, C::SMEM_BYTES);
+  int e = ensure_smem<C>(st_backward_kernel<C>, C::SMEM_BYTES);
   if (e) return e;
   SRST_LAUNCH(st_backward_kernel<C>, dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
   return (int)cudaGetLastError();
@@ -174,12 +176,79 @@ int srst_st_backward(const float* img, const float* ds, const float* grad_out, i
 
 }  // extern "C"
 
-// ---- Best-Buddy entry points: kernels land in bb_kernels.cuh (placeholder until then) ---------
+// ---- Best-Buddy entry points ---------------------------------------------------------------
 extern "C" {
-size_t srst_bb_workspace_bytes(int, int, int) { return 0; }
-int srst_bb_forward(const float*, const float*, const float*, const float*, int, int, int, float, float, int,
-                    int64_t*, float*, void*, size_t, void*) { return SRST_E_UNSUPPORTED; }
-int srst_bb_backward(const float*, const float*, const float*, const float*, const int64_t*, const float*, int,
-                     int, int, int, float*, void*, size_t, void*) { return SRST_E_UNSUPPORTED; }
-int srst_bb_pyramid(const float*, int, int, int, float*, float*, void*) { return SRST_E_UNSUPPORTED; }
+
+size_t srst_bb_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H < 12 || W < 12) return 0;
+  return bb_carve(nullptr, bb_geom(B, H, W)).total_bytes;
 }
+
+static int bb_launch_pyramid(const float* gt, const BbGeom& g, float* o2, float* o4, void* stream) {
+  const size_t n = (size_t)g.B * 3 * ((size_t)g.H2 * g.W2 + (size_t)g.H4 * g.W4);
+  const unsigned nblk = (unsigned)((n + 255) / 256);
+  SRST_LAUNCH(bb_pyramid_kernel, dim3(nblk), dim3(256), 0, stream, gt, o2, o4, g.B * 3, g.H, g.W, g.H2, g.W2,
+              g.H4, g.W4);
+  return (int)cudaGetLastError();
+}
+
+int srst_bb_pyramid(const float* gt, int B, int H, int W, float* out2, float* out4, void* stream) {
+  if (!gt || !out2 || !out4 || B <= 0) return SRST_E_INVALID;
+  if (H < 12 || W < 12) return SRST_E_SHAPE;
+  return bb_launch_pyramid(gt, bb_geom(B, H, W), out2, out4, stream);
+}
+
+int srst_bb_forward(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
+                    float alpha, float beta, int criterion, int64_t* idx_out, float* loss_out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  if (!sr || !gt || !idx_out || !loss_out || B <= 0) return SRST_E_INVALID;
+  if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
+  if (H < 12 || W < 12 || B > 65535) return SRST_E_SHAPE;
+  if ((gt2 == nullptr) != (gt4 == nullptr)) return SRST_E_INVALID;
+  const BbGeom g = bb_geom(B, H, W);
+  if (!workspace || !aligned16(workspace)) return SRST_E_WORKSPACE;
+  const BbWorkspace w = bb_carve(workspace, g);
+  if (workspace_bytes < w.total_bytes) return SRST_E_WORKSPACE;
+  int e;
+  if (!gt2) {
+    if ((e = bb_launch_pyramid(gt, g, w.pyr2, w.pyr4, stream)) != 0) return e;
+    gt2 = w.pyr2;
+    gt4 = w.pyr4;
+  }
+  const int npack = g.Npad > g.Mpad ? g.Npad : g.Mpad;
+  SRST_LAUNCH(bb_pack_kernel, dim3((npack + 255) / 256, B), dim3(256), 0, stream, sr, gt, gt2, gt4, w.mats,
+              w.per_image, g);
+  if ((e = (int)cudaGetLastError()) != 0) return e;
+  SRST_LAUNCH(bb_search_kernel, dim3(g.Npad / BB_QT, B), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, alpha,
+              beta, idx_out);
+  if ((e = (int)cudaGetLastError()) != 0) return e;
+  const unsigned nl = (unsigned)(((size_t)B * g.N + BB_NT - 1) / BB_NT);
+  SRST_LAUNCH(bb_loss_kernel, dim3(nl), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, idx_out, criterion,
+              w.partials, w.ticket, loss_out);
+  return (int)cudaGetLastError();
+}
+
+int srst_bb_backward(const float* sr, const float* gt, const float* gt2, const float* gt4, const int64_t* idx,
+                     const float* grad_out, int B, int H, int W, int criterion, float* d_sr, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (!sr || !gt || !idx || !grad_out || !d_sr || B <= 0) return SRST_E_INVALID;
+  if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
+  if (H < 12 || W < 12 || B > 65535) return SRST_E_SHAPE;
+  if ((gt2 == nullptr) != (gt4 == nullptr)) return SRST_E_INVALID;
+  const BbGeom g = bb_geom(B, H, W);
+  int e;
+  if (!gt2) {
+    if (!workspace || !aligned16(workspace)) return SRST_E_WORKSPACE;
+    const BbWorkspace w = bb_carve(workspace, g);
+    if (workspace_bytes < w.total_bytes) return SRST_E_WORKSPACE;
+    if ((e = bb_launch_pyramid(gt, g, w.pyr2, w.pyr4, stream)) != 0) return e;
+    gt2 = w.pyr2;
+    gt4 = w.pyr4;
+  }
+  const size_t total = (size_t)B * 3 * H * W;
+  SRST_LAUNCH(bb_backward_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, sr, gt, gt2, gt4, idx,
+              grad_out, g, criterion, d_sr);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -42,7 +42,7 @@ static inline cudaError_t cudaPeekAtLastError() { return 0; }
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 namespace emu {
 struct BlockCtx {
@@ -154,6 +154,10 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcg(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
 static inline float __ldcg(const float* p) { return *reinterpret_cast<const volatile float*>(p); }
 
+using std::max;
+using std::min;
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline float __frsqrt_rn(float x) { return 1.0f / std::sqrt(x); }
 static inline float __frcp_rn(float x) { return 1.0f / x; }
