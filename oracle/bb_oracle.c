@@ -1,0 +1,123 @@
+/* CPU oracle for the Best-Buddy loss -- TEST INFRASTRUCTURE ONLY (see oracle/bb_oracle.py).
+ *
+ * Plain-C restatement of the reference's algorithm (SebastianBitsch/SRGAN-ST loss.py:115-141,
+ * utils.py:173-187), in fp32 with one fixed operation order, so that argmin indices can be
+ * compared bit-exactly with the CUDA path:
+ *   patches   : F.unfold(k=3, stride=3, pad=0): element c*9+ky*3+kx, patch py*(W/3)+px  (loss.py:116-121)
+ *   pyramid   : bicubic (A=-0.75), align_corners=False, scale 1/2 and 1/4 of gt itself  (loss.py:123,127)
+ *   distance  : (|x|^2 + |y|^2) - 2 x.y, clamped at 0                                   (utils.py:183-187)
+ *   score     : alpha*d(sr_i, y_j) + beta*d(gt_i, y_j)                                  (loss.py:132-133)
+ *   argmin    : first minimal index (torch.min)                                         (loss.py:135)
+ *   loss      : mean |sr_patch - y[argmin]| (L1) or mean square (L2)                    (loss.py:139)
+ * The 27-term dot products and norms are accumulated with fmaf in k = 0..26 order; torch's bmm uses
+ * an unspecified order, so against the reference itself indices are compared under the near-tie
+ * protocol of tests/test_bb_*.py.  Build: make -C oracle  (gcc -O2 -ffp-contract=off).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#define D 27
+
+static float cubic4(float a, float b, float c, float d) {
+  const float w0 = -0.09375f, w1 = 0.59375f; /* cubic convolution weights at t = 0.5, A = -0.75 */
+  return ((a * w0 + b * w1) + c * w1) + d * w0;
+}
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* gt [planes,H,W] -> o2 [planes,H/2,W/2], o4 [planes,H/4,W/4] */
+void bb_oracle_pyramid(const float* gt, int planes, int H, int W, float* o2, float* o4) {
+  for (int lvl = 0; lvl < 2; ++lvl) {
+    const int s = lvl ? 4 : 2, Ho = H / s, Wo = W / s;
+    float* o = lvl ? o4 : o2;
+    for (int p = 0; p < planes; ++p)
+      for (int y = 0; y < Ho; ++y)
+        for (int x = 0; x < Wo; ++x) {
+          const int sy = lvl ? 4 * y : 2 * y - 1, sx = lvl ? 4 * x : 2 * x - 1;
+          float r[4];
+          for (int i = 0; i < 4; ++i) {
+            const float* row = gt + ((size_t)p * H + clampi(sy + i, 0, H - 1)) * W;
+            r[i] = cubic4(row[clampi(sx, 0, W - 1)], row[clampi(sx + 1, 0, W - 1)], row[clampi(sx + 2, 0, W - 1)],
+                          row[clampi(sx + 3, 0, W - 1)]);
+          }
+          o[((size_t)p * Ho + y) * Wo + x] = cubic4(r[0], r[1], r[2], r[3]);
+        }
+  }
+}
+
+static void read_patch(const float* img, int H, int W, int nx, int p, float* v) {
+  const int py = p / nx, px = p % nx;
+  for (int c = 0; c < 3; ++c)
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) v[c * 9 + ky * 3 + kx] = img[((size_t)c * H + 3 * py + ky) * W + 3 * px + kx];
+}
+static float norm27(const float* v) {
+  float n = 0.f;
+  for (int k = 0; k < D; ++k) n = fmaf(v[k], v[k], n);
+  return n;
+}
+static float dot27(const float* a, const float* b) {
+  float s = 0.f;
+  for (int k = 0; k < D; ++k) s = fmaf(a[k], b[k], s);
+  return s;
+}
+
+/* Returns 0 on success.  idx [B,N] int64; loss_out 1 double; best/second [B,N] fp32 scores (may be NULL). */
+int bb_oracle_forward(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
+                      float alpha, float beta, int criterion, int64_t* idx, double* loss_out, float* best_out,
+                      float* second_out) {
+  const int n0x = W / 3, N0 = (H / 3) * n0x;
+  const int H2 = H / 2, W2 = W / 2, n2x = W2 / 3, N2 = (H2 / 3) * n2x;
+  const int H4 = H / 4, W4 = W / 4, n4x = W4 / 3, N4 = (H4 / 3) * n4x;
+  const int N = N0, M = N0 + N2 + N4;
+  float* q1 = malloc(sizeof(float) * (size_t)N * D);
+  float* q2 = malloc(sizeof(float) * (size_t)N * D);
+  float* y = malloc(sizeof(float) * (size_t)M * D);
+  float* xn = malloc(sizeof(float) * N);
+  float* gn = malloc(sizeof(float) * N);
+  float* yn = malloc(sizeof(float) * M);
+  if (!q1 || !q2 || !y || !xn || !gn || !yn) return 1;
+  double total = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const float* s0 = sr + (size_t)b * 3 * H * W;
+    const float* g0 = gt + (size_t)b * 3 * H * W;
+    const float* g2 = gt2 + (size_t)b * 3 * H2 * W2;
+    const float* g4 = gt4 + (size_t)b * 3 * H4 * W4;
+    for (int i = 0; i < N; ++i) {
+      read_patch(s0, H, W, n0x, i, q1 + (size_t)i * D);
+      xn[i] = norm27(q1 + (size_t)i * D);
+      read_patch(g0, H, W, n0x, i, q2 + (size_t)i * D);
+      gn[i] = norm27(q2 + (size_t)i * D);
+    }
+    for (int j = 0; j < M; ++j) {
+      if (j < N0) read_patch(g0, H, W, n0x, j, y + (size_t)j * D);
+      else if (j < N0 + N2) read_patch(g2, H2, W2, n2x, j - N0, y + (size_t)j * D);
+      else read_patch(g4, H4, W4, n4x, j - N0 - N2, y + (size_t)j * D);
+      yn[j] = norm27(y + (size_t)j * D);
+    }
+    for (int i = 0; i < N; ++i) {
+      float best = INFINITY, second = INFINITY;
+      int bi = 0;
+      for (int j = 0; j < M; ++j) {
+        float d1 = fmaf(-2.0f, dot27(q1 + (size_t)i * D, y + (size_t)j * D), xn[i] + yn[j]);
+        float d2 = fmaf(-2.0f, dot27(q2 + (size_t)i * D, y + (size_t)j * D), gn[i] + yn[j]);
+        d1 = d1 > 0.f ? d1 : 0.f;
+        d2 = d2 > 0.f ? d2 : 0.f;
+        const float a = alpha * d1, bb = beta * d2;
+        const float s = a + bb;
+        if (s < best) { second = best; best = s; bi = j; }
+        else if (s < second) second = s;
+      }
+      idx[(size_t)b * N + i] = bi;
+      if (best_out) best_out[(size_t)b * N + i] = best;
+      if (second_out) second_out[(size_t)b * N + i] = second;
+      for (int k = 0; k < D; ++k) {
+        const float d = q1[(size_t)i * D + k] - y[(size_t)bi * D + k];
+        total += criterion == 0 ? fabs((double)d) : (double)d * (double)d;
+      }
+    }
+  }
+  *loss_out = total / ((double)B * N * D);
+  free(q1); free(q2); free(y); free(xn); free(gn); free(yn);
+  return 0;
+}

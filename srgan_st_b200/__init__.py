@@ -4,7 +4,7 @@ Public surface (mirrors reference loss.py): ``StructureTensorLoss``, ``BestBuddy
 Importing this package needs ``libsrst.so`` (build: ``python -m srgan_st_b200.build``); there is
 no CPU or PyTorch fallback.
 """
-from .loss import StructureTensorLoss  # noqa: F401
+from .loss import BestBuddyLoss, StructureTensorLoss  # noqa: F401
 
-__all__ = ["StructureTensorLoss"]
+__all__ = ["StructureTensorLoss", "BestBuddyLoss"]
 __version__ = "0.1.0"

@@ -134,3 +134,109 @@ class StructureTensorLoss(nn.Module):
 
     def extra_repr(self) -> str:
         return f"sigma={self.sigma}, rho={self.rho}, normalize={self.normalize}"
+
+
+class _BestBuddyLossFn(torch.autograd.Function):
+    """autograd boundary of the Best-Buddy loss.  Only the final criterion is differentiable
+    (w.r.t. the SR patches): the argmin is not, and gt carries no gradient (reference loss.py:135-139)."""
+
+    @staticmethod
+    def forward(ctx, sr, gt, alpha, beta, criterion, pyramid):
+        lib = _cabi.lib()
+        sr = sr.contiguous()
+        gt = gt.contiguous()
+        B, _, H, W = sr.shape
+        if H < 12 or W < 12:
+            raise ValueError(f"BestBuddyLoss: images must be at least 12x12 (got {H}x{W})")
+        with torch.cuda.device(sr.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            if pyramid == "aten":
+                # the reference's own op for the HR pyramid (loss.py:123,127)
+                with torch.no_grad():
+                    gt2 = torch.nn.functional.interpolate(gt, scale_factor=0.5, mode="bicubic",
+                                                          align_corners=False).contiguous()
+                    gt4 = torch.nn.functional.interpolate(gt, scale_factor=0.25, mode="bicubic",
+                                                          align_corners=False).contiguous()
+            else:
+                gt2 = gt4 = None  # libsrst computes them (srst_bb_pyramid taps)
+            N = (H // 3) * (W // 3)
+            idx = torch.empty((B, N), dtype=torch.int64, device=sr.device)
+            loss = torch.empty((), dtype=torch.float32, device=sr.device)
+            nbytes = lib.srst_bb_workspace_bytes(B, H, W)
+            ws = _workspace(sr.device, stream, nbytes)
+            rc = lib.srst_bb_forward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), B, H, W, float(alpha), float(beta),
+                                     int(criterion), _ptr(idx), _ptr(loss), _ptr(ws), ws.numel(),
+                                     ctypes.c_void_p(stream))
+        _cabi.check(rc, "srst_bb_forward")
+        ctx.save_for_backward(sr, gt, gt2, gt4, idx)
+        ctx.criterion = int(criterion)
+        ctx.mark_non_differentiable(idx)
+        return loss, idx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out, _grad_idx):
+        lib = _cabi.lib()
+        sr, gt, gt2, gt4, idx = ctx.saved_tensors
+        B, _, H, W = sr.shape
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None, None
+        grad_out = grad_out.to(torch.float32).contiguous()
+        with torch.cuda.device(sr.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            d_sr = torch.empty_like(sr)
+            nbytes = lib.srst_bb_workspace_bytes(B, H, W)
+            ws = _workspace(sr.device, stream, nbytes)
+            rc = lib.srst_bb_backward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
+                                      ctx.criterion, _ptr(d_sr), _ptr(ws), ws.numel(), ctypes.c_void_p(stream))
+        _cabi.check(rc, "srst_bb_backward")
+        return d_sr, None, None, None, None, None
+
+
+class BestBuddyLoss(nn.Module):
+    """Best-Buddy loss; same signature and semantics as reference loss.py:78-141.
+
+    ``forward(x, gt)``: for every 3x3 SR patch pick the HR candidate patch (three pyramid levels)
+    minimising ``alpha*|sr-cand|^2 + beta*|gt-cand|^2`` and return the L1 (or MSE) distance to it.
+    Only the reference's default patch geometry (ksize=3, pad=0, stride=3) and ``dist_norm='l2'``
+    have kernels; other values raise ``NotImplementedError``.
+
+    ``pyramid``: "aten" (default) builds the two HR pyramid levels with the reference's own
+    ``F.interpolate`` call; "fused" lets libsrst build them with the same cubic taps.
+    ``last_indices`` holds the argmin indices ``[B,N]`` (int64) of the most recent call.
+    """
+
+    def __init__(self, alpha: float = 1.0, beta: float = 1.0, ksize: int = 3, pad: int = 0, stride: int = 3,
+                 dist_norm: str = "l2", criterion: str = "l1", pyramid: str = "aten"):
+        super().__init__()
+        self.alpha = alpha
+        self.beta = beta
+        self.ksize = ksize
+        self.pad = pad
+        self.stride = stride
+        self.dist_norm = dist_norm
+        if criterion == "l1":
+            self.criterion = torch.nn.L1Loss()   # kept for repr/config parity (config.py:133-139)
+            self._crit = 0
+        elif criterion == "l2" or criterion == "mse":
+            self.criterion = torch.nn.MSELoss()
+            self._crit = 1
+        else:
+            raise NotImplementedError("%s criterion has not been implmented." % criterion)  # loss.py:113
+        if dist_norm not in ("l1", "l2"):
+            raise NotImplementedError("%s norm has not been supported." % dist_norm)        # utils.py:189
+        if dist_norm != "l2" or (ksize, pad, stride) != (3, 0, 3):
+            raise NotImplementedError(
+                "BestBuddyLoss: libsrst.so implements the reference default geometry only "
+                "(ksize=3, pad=0, stride=3, dist_norm='l2')")
+        if pyramid not in ("aten", "fused"):
+            raise ValueError("pyramid must be 'aten' or 'fused'")
+        self.pyramid = pyramid
+        self.last_indices = None
+        _cabi.lib()
+
+    def forward(self, x, gt):
+        _check_pair(x, gt, "BestBuddyLoss")
+        loss, idx = _BestBuddyLossFn.apply(x, gt, self.alpha, self.beta, self._crit, self.pyramid)
+        self.last_indices = idx
+        return loss

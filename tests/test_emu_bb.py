@@ -1,0 +1,58 @@
+"""CPU: execute the real Best-Buddy kernel sources under the test-only host emulation and compare
+indices bit-exactly with the C oracle (same fp32 operation order) and with the reference's golden
+indices."""
+import numpy as np
+import pytest
+
+from oracle import bb_oracle as O
+from tests.helpers import emu_bb, emu_lib, golden, golden_names, maxnorm_err, rel_err
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return emu_lib()
+
+
+@pytest.mark.parametrize("name", golden_names("bb_"))
+@pytest.mark.parametrize("own_pyramid", [False, True])
+def test_emulated_bb_matches_oracle_and_reference(lib, name, own_pyramid):
+    z = golden(name)
+    a, b = float(z["alpha"]), float(z["beta"])
+    crit = 0 if str(z["criterion"]) == "l1" else 1
+    gt2, gt4 = (None, None) if own_pyramid else (z["hr2"], z["hr4"])
+    out = emu_bb(lib, z["sr"], z["hr"], gt2, gt4, a, b, crit)
+    orc = O.bb_forward_c(z["sr"], z["hr"], gt2, gt4, a, b, str(z["criterion"]))
+    assert np.array_equal(out["idx"], orc["idx"]), "indices must be bit-exact vs the C oracle"
+    assert np.array_equal(out["idx"], z["ind"]), "and equal the reference's torch.min indices"
+    assert rel_err(out["loss"], z["loss"]) < 1e-5 or abs(out["loss"] - float(z["loss"])) < 1e-9
+    if np.abs(z["d_sr"]).max() == 0:
+        assert np.abs(out["d_sr"]).max() == 0
+    else:
+        assert maxnorm_err(out["d_sr"], z["d_sr"]) < 1e-5
+
+
+def test_emulated_pyramid_kernel_matches_oracle(lib):
+    import ctypes
+    z = golden("bb_rand_1x48x36")
+    hr = np.ascontiguousarray(z["hr"], np.float32)
+    o2 = np.empty_like(z["hr2"]); o4 = np.empty_like(z["hr4"])
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    assert lib.srst_bb_pyramid(p(hr), 1, 48, 36, p(o2), p(o4), None) == 0
+    r2, r4 = O.pyramid_c(hr)
+    assert np.array_equal(o2, r2) and np.array_equal(o4, r4)
+    assert np.abs(o2 - z["hr2"]).max() < 5e-7
+
+
+def test_emulated_bb_ragged_shape_and_ties(lib):
+    """H, W not multiples of 3/12 (floor semantics of unfold/interpolate) and exact ties: a constant
+    image makes every candidate equal, so index 0 must win everywhere (torch.min rule)."""
+    rng = np.random.default_rng(3)
+    sr = rng.random((1, 3, 26, 31), dtype=np.float32)
+    gt = rng.random((1, 3, 26, 31), dtype=np.float32)
+    out = emu_bb(lib, sr, gt)
+    orc = O.bb_forward_c(sr, gt)
+    assert np.array_equal(out["idx"], orc["idx"]) and rel_err(out["loss"], orc["loss"]) < 1e-6
+    assert np.all(out["d_sr"][:, :, 24:, :] == 0) and np.all(out["d_sr"][:, :, :, 30:] == 0)
+    flat = np.full((1, 3, 24, 24), 0.25, np.float32)
+    out = emu_bb(lib, flat, flat)
+    assert np.all(out["idx"] == 0) and out["loss"] == 0.0

@@ -38,3 +38,13 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_cabi.SrstError, match="no CPU or PyTorch fallback"):
         _cabi.lib()
+
+
+def test_best_buddy_module_surface_matches_reference():
+    import srgan_st_b200 as pkg
+    m = pkg.BestBuddyLoss()
+    assert (m.alpha, m.beta, m.ksize, m.pad, m.stride, m.dist_norm) == (1.0, 1.0, 3, 0, 3, "l2")
+    assert isinstance(m.criterion, torch.nn.L1Loss)
+    assert isinstance(pkg.BestBuddyLoss(criterion="mse").criterion, torch.nn.MSELoss)
+    with pytest.raises(NotImplementedError):
+        pkg.BestBuddyLoss(criterion="huber")
