@@ -22,16 +22,34 @@ static int env_int(const char* name, int dflt) {
 }
 
 // ---- compiled structure-tensor tile configurations ------------------------------------------
-//                         TH  TW  RS  RG RK MINB
-using FwdA = StFwdCfg<40, 64, 10, 2, 8, 2>;  // large images (DIV2K-sized validation)
-using FwdB = StFwdCfg<32, 96, 8, 2, 8, 2>;   // 96-wide training crops: a tile spans the row
-using FwdC = StFwdCfg<48, 48, 12, 2, 8, 2>;  // square quarter of a 96x96 crop
+//                         TH  TW  RS CSB NP RG RK MINB
+using FwdA = StFwdCfg<40, 64, 10, 4, 0, 2, 8, 2>;   // large images (DIV2K-sized validation)
+using FwdB = StFwdCfg<32, 96, 8, 4, 0, 2, 8, 2>;    // 96-wide training crops: a tile spans the row
+using FwdC = StFwdCfg<48, 48, 12, 4, 0, 2, 8, 2>;   // square quarter of a 96x96 crop
+using FwdD = StFwdCfg<32, 64, 16, 4, 0, 2, 8, 3>;   // small footprint: three CTAs per SM
+using FwdE = StFwdCfg<40, 64, 10, 8, 0, 2, 8, 2, true>;  // experiment: cp.async RGB staging, 8-column gradient items
 //                         TH  TW  RS   NT  RG RK MINB
-using BwdA = StBwdCfg<32, 64, 12, 352, 2, 8, 2>;
-using BwdB = StBwdCfg<24, 96, 14, 288, 2, 8, 2>;
-using BwdC = StBwdCfg<44, 48, 12, 288, 2, 8, 2>;
+using BwdA = StBwdCfg<24, 64, 14, 256, 2, 8, 2>;  // large images
+using BwdB = StBwdCfg<16, 96, 10, 256, 2, 8, 2>;  // 96-wide training crops
+using BwdC = StBwdCfg<32, 64, 12, 352, 2, 8, 1>;  // one big CTA per SM
 
 constexpr int kMinFwdTH = 32, kMinFwdTW = 48;  // finest compiled forward tiling (workspace sizing)
+
+static int sm_count() {
+#ifdef SRST_EMULATE
+  return 2;  // small persistent grid so the emulation exercises the tile loop
+#else
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+#endif
+}
 
 // Opt in to > 48 KB of dynamic shared memory once per (kernel, device).
 // `Tag` makes the once-flag unique per kernel instantiation (all kernels of one direction share a
@@ -59,16 +77,25 @@ static void fill_taps(StTaps<RG, RK>& t, const float* g, const float* dg, const 
   std::memcpy(t.g, g, sizeof(t.g));
   std::memcpy(t.dg, dg, sizeof(t.dg));
   std::memcpy(t.k, k, sizeof(t.k));
+  // tap pairs (t[u], t[u-1]) for the row-pair (FFMA2) vertical passes
+  for (int u = 0; u <= 2 * RG + 1; ++u) {
+    t.gp[u] = make_float2(u <= 2 * RG ? g[u] : 0.f, u >= 1 ? g[u - 1] : 0.f);
+    t.dgp[u] = make_float2(u <= 2 * RG ? dg[u] : 0.f, u >= 1 ? dg[u - 1] : 0.f);
+  }
+  for (int u = 0; u <= 2 * RK + 1; ++u) t.kp[u] = make_float2(u <= 2 * RK ? k[u] : 0.f, u >= 1 ? k[u - 1] : 0.f);
 }
 
 template <class C>
 static int launch_st_forward(StFwdParams<C::RG, C::RK> P, void* stream) {
   P.tiles_x = (P.W + C::TW - 1) / C::TW;
   P.tiles_y = (P.H + C::TH - 1) / C::TH;
-  const long long nblk = (long long)P.B * P.tiles_x * P.tiles_y;
-  if (nblk <= 0 || nblk > 0x7fffffffLL) return SRST_E_SHAPE;
+  const long long ntiles = (long long)P.B * P.tiles_x * P.tiles_y;
+  if (ntiles <= 0 || ntiles > 0x7fffffffLL) return SRST_E_SHAPE;
   int e = ensure_smem<C>(st_forward_kernel<C>, C::SMEM_BYTES);
   if (e) return e;
+  // persistent grid: one wave of resident CTAs, each looping over tiles
+  const long long slots = (long long)sm_count() * C::MINB;
+  const long long nblk = (C::NP == 0 || ntiles < slots) ? ntiles : slots;
   SRST_LAUNCH(st_forward_kernel<C>, dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
   return (int)cudaGetLastError();
 }
@@ -87,7 +114,7 @@ static int launch_st_backward(StBwdParams<C::RG, C::RK> P, void* stream) {
 
 static int pick_fwd_cfg(int H, int W) {
   const int forced = env_int("SRST_ST_FWD_CFG", -1);
-  if (forced >= 0 && forced <= 2) return forced;
+  if (forced >= 0 && forced <= 4) return forced;
   if (W <= 96) return 1;
   return 0;
 }
@@ -152,6 +179,8 @@ int srst_st_forward(const float* sr, const float* hr, int B, int H, int W, const
   switch (pick_fwd_cfg(H, W)) {
     case 1: return launch_st_forward<FwdB>(P, stream);
     case 2: return launch_st_forward<FwdC>(P, stream);
+    case 3: return launch_st_forward<FwdD>(P, stream);
+    case 4: return launch_st_forward<FwdE>(P, stream);
     default: return launch_st_forward<FwdA>(P, stream);
   }
 }
@@ -164,7 +193,7 @@ int srst_st_backward(const float* img, const float* ds, const float* grad_out, i
   StBwdParams<2, 8> P;
   P.img = img; P.ds = ds; P.grad_out = grad_out; P.d_img = d_img;
   P.B = B; P.H = H; P.W = W; P.tiles_x = P.tiles_y = 0;
-  P.vec4 = (W % 4 == 0 && aligned16(img) && aligned16(d_img)) ? 1 : 0;
+  P.vec4 = (W % 4 == 0 && aligned16(img) && aligned16(d_img) && aligned16(ds)) ? 1 : 0;
   P.inv_count = (float)(1.0 / ((double)B * H * W));
   fill_taps(P.taps, g, dg, k);
   switch (pick_bwd_cfg(H, W)) {

@@ -47,6 +47,45 @@ SRST_DEV float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float
 constexpr float kGrayR = 0.2989f, kGrayG = 0.587f, kGrayB = 0.114f;
 SRST_DEV float gray_of(float r, float g, float b) { return (kGrayR * r + kGrayG * g) + kGrayB * b; }
 
+// Raw SFU approximations (MUFU.RSQ / MUFU.LG2 / MUFU.RCP, <= 2 ulp) without the denormal/special
+// fix-up code that rsqrtf()/__logf()/__fdividef() add; callers guarantee normal-range inputs.
+#ifdef SRST_EMULATE
+SRST_DEV float fast_rsqrt(float x) { return 1.0f / std::sqrt(x); }
+SRST_DEV float fast_lg2(float x) { return std::log2(x); }
+SRST_DEV float fast_rcp(float x) { return 1.0f / x; }
+#else
+SRST_DEV float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+SRST_DEV float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+SRST_DEV float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+
+// 16-byte asynchronous global->shared copy (LDGSTS); `valid == false` zero-fills the destination
+// without reading `gsrc` (src-size 0), which implements the reference's zero padding for free.
+#ifdef SRST_EMULATE
+SRST_DEV void cp_async16(float* sdst, const float* gsrc, bool valid) {
+  if (valid) std::memcpy(sdst, gsrc, 16); else std::memset(sdst, 0, 16);
+}
+SRST_DEV void cp_async_commit() {}
+SRST_DEV void cp_async_wait_all() {}
+#else
+SRST_DEV void cp_async16(float* sdst, const float* gsrc, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gsrc), "r"(sz) : "memory");
+}
+SRST_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+SRST_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
+
+// Named barriers for producer/consumer warp roles: `n` = number of participating threads.
+#ifdef SRST_EMULATE
+SRST_DEV void bar_sync(int id, int n) { emu_bar_sync(id, n); }
+SRST_DEV void bar_arrive(int id, int n) { emu_bar_arrive(id, n); }
+#else
+SRST_DEV void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+SRST_DEV void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+#endif
+
 SRST_DEV float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -10,13 +10,19 @@
 //   st_backward_kernel: ds planes -> adjoint rho-smoothing -> product rule with recomputed Ix, Iy
 //                       -> adjoint derivative filters -> grayscale weights -> d_img.
 //
-// Both are FP32 CUDA-core stencils (no tensor cores by design: see DESIGN.md), tiled in shared
-// memory with the halo recomputed per tile.  Thread mapping alternates between "a lane owns 8
-// consecutive columns of one row" (horizontal filters, LDS.128 on a pitch == 4 mod 8) and "a lane
-// owns one column of RS rows" (vertical filters, conflict-free LDS.32), so every filter pass is
-// register-blocked: each shared-memory value feeds >= 5 FMAs.  Filter taps live in kernel
-// parameters (constant bank) and every tap index is a compile-time constant after unrolling, so
-// the FMAs take the tap as a constant/uniform operand.
+// Both are FP32 CUDA-core stencils (no tensor cores by design: see DESIGN.md).  The measured
+// bound on B200 is the FP32 pipe (128 lane-FMA/clk/SM, tools/ubench_fma.cu), not HBM, so the
+// design minimises issue slots per FMA:
+//   * every shared-memory plane is stored ROW-PAIR INTERLEAVED: element (row r, col c) lives at
+//     (r/2)*pitch + 2*c + (r&1), so a float2 holds one column of two adjacent rows;
+//   * every filter pass works on such row pairs with packed fma.rn.f32x2 (SASS FFMA2): horizontal
+//     passes multiply a register pair by one tap broadcast from the constant bank, vertical passes
+//     multiply one value (broadcast) by the tap PAIR (k[t], k[t-1]) that maps it onto the two
+//     output rows.  Both operand forms are native (FFMA2 Rd, Ra.F32, URb.F32x2, Rc), so a 17-tap
+//     pass costs 17 issue slots per pixel pair and no register moves;
+//   * horizontal passes are register-blocked (4 columns x 2 rows per thread, LDS.128 on a pitch
+//     == 4 mod 8), vertical passes own one column and RS rows (conflict-free LDS.64/STS.64);
+//   * taps live in kernel parameters and every tap index is a compile-time constant.
 #pragma once
 #include "srst_device.cuh"
 
@@ -24,9 +30,14 @@ namespace srst {
 
 template <int RG, int RK>
 struct StTaps {
-  float g[2 * RG + 1];   // Gaussian(sigma), utils.py:194-205
-  float dg[2 * RG + 1];  // its derivative taps, utils.py:206
-  float k[2 * RK + 1];   // Gaussian(rho)
+  float g[2 * RG + 1];    // Gaussian(sigma), utils.py:194-205
+  float dg[2 * RG + 1];   // its derivative taps, utils.py:206
+  float k[2 * RK + 1];    // Gaussian(rho)
+  // tap pairs (t[u], t[u-1]) with zeros outside the support: input row u of a row pair's window
+  // contributes t[u] to the even output row and t[u-1] to the odd one.
+  float2 gp[2 * RG + 2];
+  float2 dgp[2 * RG + 2];
+  float2 kp[2 * RK + 2];
 };
 
 template <int RG, int RK>
@@ -58,81 +69,98 @@ struct StBwdParams {
   StTaps<RG, RK> taps;
 };
 
+SRST_DEV float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+SRST_DEV float2 bcast2(float v) { return make_float2(v, v); }
+SRST_DEV float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+SRST_DEV void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+
 // ------------------------------------------------------------------------------------------------
 // Per-pixel chain: utils.py:236-279 forward and its adjoint.
 //   S1 = (a,b,c) raw SR tensor (Jxx,Jyy,Jxy); S2 = (e,f,h) raw HR tensor.
 // The discriminant is evaluated as (A-B)^2 + 4CD, algebraically equal to the reference's
 // (A+B)^2 - 4(AB-CD) (utils.py:261) but without its catastrophic cancellation near A=B=1.
 // NaN/clamp behaviour follows torch: clamp(min) keeps NaN; clamp gradient passes where x >= min.
+// Transcendentals use the SFU (MUFU.RSQ/LG2/RCP): rsqrt of the two determinants gets one Newton
+// step (they scale everything downstream); the rest stay at SFU accuracy (<= 2 ulp), far inside
+// the 1e-5 / 1e-4 parity budget, at ~1/10 of the issue slots of sqrtf/logf/division.
 // ------------------------------------------------------------------------------------------------
 struct StPixelGrad {
   float da, db, dc;  // d dist / d (a,b,c)
   float de, df, dh;  // d dist / d (e,f,h)
 };
 
+SRST_DEV float rsqrt_nr(float x) {
+  const float y = fast_rsqrt(x);
+  return y * fmaf(-0.5f * x, y * y, 1.5f);  // one Newton step; NaN for x < 0 like 1/sqrt(x)
+}
+
 template <bool WANT_SR, bool WANT_HR>
 SRST_DEV float st_pixel(float a, float b, float c, float e, float f, float h, bool normalize, float eps,
                         StPixelGrad& G) {
+  constexpr float kLn2 = 0.6931471805599453f;
   float iq1 = 1.0f, iq2 = 1.0f;
   if (normalize) {
-    iq1 = 1.0f / sqrtf(a * b - c * c + eps);
-    iq2 = 1.0f / sqrtf(e * f - h * h + eps);
+    iq1 = rsqrt_nr(fmaf(a, b, -c * c) + eps);
+    iq2 = rsqrt_nr(fmaf(e, f, -h * h) + eps);
   }
   const float ah = a * iq1, bh = b * iq1, ch = c * iq1;
   const float eh = e * iq2, fh = f * iq2, hh = h * iq2;
   const float chh = ch * hh;
-  const float A = bh * eh - chh;
-  const float Bm = ah * fh - chh;
-  const float Cc = bh * hh - ch * fh;
-  const float Dd = ah * hh - ch * eh;
+  const float A = fmaf(bh, eh, -chh);
+  const float Bm = fmaf(ah, fh, -chh);
+  const float Cc = fmaf(bh, hh, -ch * fh);
+  const float Dd = fmaf(ah, hh, -ch * eh);
   const float T = A + Bm;
   const float amb = A - Bm;
-  const float disc_raw = amb * amb + 4.0f * (Cc * Dd);
+  const float disc_raw = fmaf(amb, amb, 4.0f * (Cc * Dd));
   const float disc = (disc_raw < eps) ? eps : disc_raw;
-  const float r = sqrtf(disc);
-  const float l1r = 0.5f * (T - r), l2r = 0.5f * (T + r);
+  const float ir = fast_rsqrt(disc);
+  const float r = disc * ir;
+  const float hT = 0.5f * T;
+  const float l1r = fmaf(-0.5f, r, hT), l2r = fmaf(0.5f, r, hT);
   const float l1 = (l1r < 1.0f) ? 1.0f : l1r;
   const float l2 = (l2r < 1.0f) ? 1.0f : l2r;
-  const float L1 = logf(l1), L2 = logf(l2);
-  const float d = sqrtf(L1 * L1 + L2 * L2 + eps);
+  // natural logs: det M == 1 makes l1 <= 1 <= l2, so L1 is 0 except for rounding stragglers
+  const float L1 = kLn2 * fast_lg2(l1), L2 = kLn2 * fast_lg2(l2);
+  const float arg = fmaf(L1, L1, fmaf(L2, L2, eps));
+  const float inv_d = fast_rsqrt(arg);
+  const float d = arg * inv_d;
   if (WANT_SR || WANT_HR) {
-    const float inv_d = 1.0f / d;
-    const float dl1 = (L1 * inv_d / l1) * ((l1r >= 1.0f) ? 1.0f : 0.0f);
-    const float dl2 = (L2 * inv_d / l2) * ((l2r >= 1.0f) ? 1.0f : 0.0f);
-    float dT = 0.5f * (dl1 + dl2);
+    const float dl1 = (l1r >= 1.0f) ? (L1 * inv_d) * fast_rcp(l1) : (l1r * 0.0f);  // x*0 keeps NaN
+    const float dl2 = (l2r >= 1.0f) ? (L2 * inv_d) * fast_rcp(l2) : (l2r * 0.0f);
     const float dr = 0.5f * (dl2 - dl1);
-    const float ddisc = (dr / (2.0f * r)) * ((disc_raw >= eps) ? 1.0f : 0.0f);
-    dT += 2.0f * T * ddisc;
+    const float ddisc = (disc_raw >= eps) ? (0.5f * dr * ir) : (disc_raw * 0.0f);
+    const float dT = fmaf(2.0f * T, ddisc, 0.5f * (dl1 + dl2));
     const float dd4 = 4.0f * ddisc;
-    const float dA = dT - dd4 * Bm;
-    const float dB = dT - dd4 * A;
+    const float dA = fmaf(-dd4, Bm, dT);
+    const float dB = fmaf(-dd4, A, dT);
     const float dC = dd4 * Dd;
     const float dD = dd4 * Cc;
     if (WANT_SR) {
-      const float dah = dB * fh + dD * hh;
-      const float dbh = dA * eh + dC * hh;
-      const float dch = -(dA + dB) * hh - dC * fh - dD * eh;
+      const float dah = fmaf(dB, fh, dD * hh);
+      const float dbh = fmaf(dA, eh, dC * hh);
+      const float dch = -fmaf(dA + dB, hh, fmaf(dC, fh, dD * eh));
       if (normalize) {
         // S^ = S/q, q = sqrt(det+eps): dS = dS^/q - S * <S,dS^>/(2 q^3) * d(det)/dS
-        const float s = a * dah + b * dbh + c * dch;
-        const float ddet = -0.5f * s * iq1 * iq1 * iq1;
-        G.da = dah * iq1 + ddet * b;
-        G.db = dbh * iq1 + ddet * a;
-        G.dc = dch * iq1 - 2.0f * ddet * c;
+        const float s = fmaf(a, dah, fmaf(b, dbh, c * dch));
+        const float ddet = (-0.5f * s) * (iq1 * iq1) * iq1;
+        G.da = fmaf(dah, iq1, ddet * b);
+        G.db = fmaf(dbh, iq1, ddet * a);
+        G.dc = fmaf(dch, iq1, -2.0f * ddet * c);
       } else {
         G.da = dah; G.db = dbh; G.dc = dch;
       }
     }
     if (WANT_HR) {
-      const float deh = dA * bh - dD * ch;
-      const float dfh = dB * ah - dC * ch;
-      const float dhh = -(dA + dB) * ch + dC * bh + dD * ah;
+      const float deh = fmaf(dA, bh, -dD * ch);
+      const float dfh = fmaf(dB, ah, -dC * ch);
+      const float dhh = fmaf(-(dA + dB), ch, fmaf(dC, bh, dD * ah));
       if (normalize) {
-        const float s = e * deh + f * dfh + h * dhh;
-        const float ddet = -0.5f * s * iq2 * iq2 * iq2;
-        G.de = deh * iq2 + ddet * f;
-        G.df = dfh * iq2 + ddet * e;
-        G.dh = dhh * iq2 - 2.0f * ddet * h;
+        const float s = fmaf(e, deh, fmaf(f, dfh, h * dhh));
+        const float ddet = (-0.5f * s) * (iq2 * iq2) * iq2;
+        G.de = fmaf(deh, iq2, ddet * f);
+        G.df = fmaf(dfh, iq2, ddet * e);
+        G.dh = fmaf(dhh, iq2, -2.0f * ddet * h);
       } else {
         G.de = deh; G.df = dfh; G.dh = dhh;
       }
@@ -142,203 +170,376 @@ SRST_DEV float st_pixel(float a, float b, float c, float e, float f, float h, bo
 }
 
 // ------------------------------------------------------------------------------------------------
-// Shared building blocks
+// Shared building blocks (row-pair interleaved planes: float2 at rp*PITCH + 2*col)
 // ------------------------------------------------------------------------------------------------
 
 // Load the RGB pixels of rows [gy0, gy0+ROWS) x cols [gx0, gx0+COLS) of image `base` ([3,H,W]),
-// convert to grayscale and store into sG (pitch PITCH); zero outside the image (the reference
-// zero-pads: padding='same', utils.py:219-222).  gx0 and COLS are multiples of 4.
-template <int ROWS, int COLS, int PITCH, int NT>
+// convert to grayscale, store row-pair interleaved into sG; zero outside the image (the reference
+// zero-pads: padding='same', utils.py:219-222).  ROWS even; gx0 and COLS multiples of 4.
+// DEPTH items (6 x LDG.128 each) are in flight per thread before the first conversion.
+template <int ROWS, int COLS, int PITCH, int NT, int DEPTH>
 SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, int W, int gy0, int gx0,
                              bool vec4, int tid) {
   constexpr int C4 = COLS / 4;
+  constexpr int NITEM = (ROWS / 2) * C4;
   const size_t plane = (size_t)H * W;
-  for (int it = tid; it < ROWS * C4; it += NT) {
-    const int r = it / C4, c4 = it - r * C4;
-    const int gy = gy0 + r, gx = gx0 + 4 * c4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gy >= 0 && gy < H) {
-      const float* p = base + (size_t)gy * W + gx;
-      if (vec4) {
-        if (gx >= 0 && gx < W) {  // W % 4 == 0: the group is all-in or all-out
-          const float4 R = ldg4(p), Gc = ldg4(p + plane), Bc = ldg4(p + 2 * plane);
-          v.x = gray_of(R.x, Gc.x, Bc.x);
-          v.y = gray_of(R.y, Gc.y, Bc.y);
-          v.z = gray_of(R.z, Gc.z, Bc.z);
-          v.w = gray_of(R.w, Gc.w, Bc.w);
+  if (vec4) {
+#pragma unroll 1
+    for (int it0 = tid; it0 < NITEM; it0 += DEPTH * NT) {
+      float4 R[DEPTH][2], Gc[DEPTH][2], Bc[DEPTH][2];
+      bool ok[DEPTH][2];
+#pragma unroll
+      for (int u = 0; u < DEPTH; ++u) {
+        const int it = it0 + u * NT;
+        const int q = it / C4, c4 = it - q * C4;
+        const int gx = gx0 + 4 * c4;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int gy = gy0 + 2 * q + hf;
+          ok[u][hf] = (it < NITEM) && gy >= 0 && gy < H && gx >= 0 && gx < W;  // W % 4 == 0: all-in or all-out
+          if (ok[u][hf]) {
+            const float* p = base + (size_t)gy * W + gx;
+            R[u][hf] = ldg4(p); Gc[u][hf] = ldg4(p + plane); Bc[u][hf] = ldg4(p + 2 * plane);
+          }
         }
-      } else {
-        float t[4];
+      }
+#pragma unroll
+      for (int u = 0; u < DEPTH; ++u) {
+        const int it = it0 + u * NT;
+        if (it >= NITEM) break;
+        const int q = it / C4, c4 = it - q * C4;
+        float v[2][4];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (ok[u][hf]) {
+            v[hf][0] = gray_of(R[u][hf].x, Gc[u][hf].x, Bc[u][hf].x);
+            v[hf][1] = gray_of(R[u][hf].y, Gc[u][hf].y, Bc[u][hf].y);
+            v[hf][2] = gray_of(R[u][hf].z, Gc[u][hf].z, Bc[u][hf].z);
+            v[hf][3] = gray_of(R[u][hf].w, Gc[u][hf].w, Bc[u][hf].w);
+          } else {
+            v[hf][0] = v[hf][1] = v[hf][2] = v[hf][3] = 0.f;
+          }
+        }
+        float* o = sG + q * PITCH + 8 * c4;
+        st4(o, make_float4(v[0][0], v[1][0], v[0][1], v[1][1]));
+        st4(o + 4, make_float4(v[0][2], v[1][2], v[0][3], v[1][3]));
+      }
+    }
+  } else {
+    for (int it = tid; it < NITEM; it += NT) {
+      const int q = it / C4, c4 = it - q * C4;
+      const int gx = gx0 + 4 * c4;
+      float v[2][4];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int gy = gy0 + 2 * q + hf;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int x = gx + j;
-          t[j] = (x >= 0 && x < W) ? gray_of(__ldg(p + j), __ldg(p + j + plane), __ldg(p + j + 2 * plane)) : 0.f;
+          v[hf][j] = 0.f;
+          if (gy >= 0 && gy < H && x >= 0 && x < W) {
+            const float* p = base + (size_t)gy * W + x;
+            v[hf][j] = gray_of(__ldg(p), __ldg(p + plane), __ldg(p + 2 * plane));
+          }
         }
-        v = make_float4(t[0], t[1], t[2], t[3]);
       }
+      float* o = sG + q * PITCH + 8 * c4;
+      st4(o, make_float4(v[0][0], v[1][0], v[0][1], v[1][1]));
+      st4(o + 4, make_float4(v[0][2], v[1][2], v[0][3], v[1][3]));
     }
-    st4(sG + r * PITCH + 4 * c4, v);
   }
 }
 
-// Gaussian-derivative gradients for 8 consecutive pixels of one row, from a gray tile in smem.
-//   Ix = (im * dg|) * g-   (derivative along H),  Iy = (im * g|) * dg-   (utils.py:219-222)
-// `row0` points at gray[(first needed row)][window start]; the window is WIN floats wide and the
-// 8 outputs are centred at window index CEN..CEN+7.
-template <int RG, int WIN, int CEN, int PITCH, class Taps>
-SRST_DEV void grad8(const float* row0, const Taps& tp, float (&Ix)[8], float (&Iy)[8]) {
-  float tA[WIN], tB[WIN];
+// Asynchronous staging of the raw RGB rows [gy0, gy0+ROWS) x cols [gx0, gx0+COLS) of one image
+// into shared memory ([3][ROWS][COLS] row-major) with 16-byte LDGSTS copies: no registers are
+// held while the data is in flight, every copy of the tile is outstanding at once (one exposed
+// round trip per tile), and pixels outside the image are zero-filled by the copy itself.
+template <int ROWS, int COLS, int NT>
+SRST_DEV void stage_rgb_async(float* sS, const float* __restrict__ base, int H, int W, int gy0, int gx0, int tid) {
+  constexpr int C4 = COLS / 4;
+  const size_t plane = (size_t)H * W;
+  for (int it = tid; it < 3 * ROWS * C4; it += NT) {
+    const int c4 = it % C4, rc = it / C4;
+    const int r = rc % ROWS, c = rc / ROWS;
+    const int gy = gy0 + r, gx = gx0 + 4 * c4;
+    const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;  // W % 4 == 0: all-in or all-out
+    cp_async16(sS + (c * ROWS + r) * COLS + 4 * c4, ok ? base + c * plane + (size_t)gy * W + gx : base, ok);
+  }
+  cp_async_commit();
+}
+
+// Staged RGB -> grayscale, row-pair interleaved (loss.py:400-401).
+template <int ROWS, int COLS, int PITCH, int NT>
+SRST_DEV void convert_staged_gray(float* sG, const float* sS, int tid) {
+  constexpr int C4 = COLS / 4;
+  for (int it = tid; it < (ROWS / 2) * C4; it += NT) {
+    const int q = it / C4, c4 = it - q * C4;
+    float v[2][4];
 #pragma unroll
-  for (int j = 0; j < WIN; ++j) { tA[j] = 0.f; tB[j] = 0.f; }
+    for (int hf = 0; hf < 2; ++hf) {
+      const float* p = sS + (2 * q + hf) * COLS + 4 * c4;
+      const float4 R = ld4(p), Gc = ld4(p + ROWS * COLS), Bc = ld4(p + 2 * ROWS * COLS);
+      v[hf][0] = gray_of(R.x, Gc.x, Bc.x);
+      v[hf][1] = gray_of(R.y, Gc.y, Bc.y);
+      v[hf][2] = gray_of(R.z, Gc.z, Bc.z);
+      v[hf][3] = gray_of(R.w, Gc.w, Bc.w);
+    }
+    float* o = sG + q * PITCH + 8 * c4;
+    st4(o, make_float4(v[0][0], v[1][0], v[0][1], v[1][1]));
+    st4(o + 4, make_float4(v[0][2], v[1][2], v[0][3], v[1][3]));
+  }
+}
+
+// L2 prefetch of the rows [gy0, gy0+ROWS) x cols [gx0, gx0+COLS) of the three planes of an image
+// (one prefetch per 128-byte line): issued for the HR tile before the SR tile is processed.
+template <int ROWS, int COLS, int NT>
+SRST_DEV void prefetch_tile_l2(const float* __restrict__ base, int H, int W, int gy0, int gx0, int tid) {
+#ifndef SRST_EMULATE
+  constexpr int L = (COLS + 31) / 32 + 1;
+  const size_t plane = (size_t)H * W;
+  for (int it = tid; it < ROWS * 3 * L; it += NT) {
+    const int l = it % L, rc = it / L;
+    const int c = rc % 3, r = rc / 3;
+    const int gy = gy0 + r, gx = gx0 + 32 * l;
+    if (gy >= 0 && gy < H && gx < W && gx + 31 >= 0) {
+      const float* p = base + c * plane + (size_t)gy * W + max(gx, 0);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
+#endif
+}
+
+// Gaussian-derivative filter pair on a row pair, CS output columns:
+//   ox = (A * dg|) * g-     oy = (B * g|) * dg-       (utils.py:219-222; A == B == gray forward)
+// pa / pb point at (first input row pair, window start column) of planes A / B; the window is WIN
+// columns wide and the CS outputs are centred at window columns CEN..CEN+CS-1.  RG+1 input row pairs
+// feed the two output rows through the tap pairs dgp / gp.
+template <int RG, int CS, int WIN, int CEN, int PITCH, bool SAME, class Taps>
+SRST_DEV void grad_rowpair(const float* pa, const float* pb, const Taps& tp, float2 (&ox)[CS], float2 (&oy)[CS]) {
+  static_assert(RG % 2 == 0 && WIN % 2 == 0, "row-pair gradient needs an even radius");
+  float2 tA[WIN], tB[WIN];
 #pragma unroll
-  for (int i = 0; i <= 2 * RG; ++i) {
-    float v[WIN];
+  for (int j = 0; j < WIN; ++j) { tA[j] = make_float2(0.f, 0.f); tB[j] = make_float2(0.f, 0.f); }
 #pragma unroll
-    for (int q = 0; q < WIN / 4; ++q) {
-      const float4 t = ld4(row0 + i * PITCH + 4 * q);
-      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  for (int q = 0; q <= RG; ++q) {
+    float2 va[WIN], vb[WIN];
+#pragma unroll
+    for (int m = 0; m < WIN / 2; ++m) {
+      const float4 t = ld4(pa + q * PITCH + 4 * m);
+      va[2 * m] = make_float2(t.x, t.y);
+      va[2 * m + 1] = make_float2(t.z, t.w);
+      if (!SAME) {
+        const float4 u = ld4(pb + q * PITCH + 4 * m);
+        vb[2 * m] = make_float2(u.x, u.y);
+        vb[2 * m + 1] = make_float2(u.z, u.w);
+      }
     }
 #pragma unroll
-    for (int j = CEN - RG; j < CEN + 8 + RG; ++j) {
-      if (i != RG) tA[j] = fmaf(tp.dg[i], v[j], tA[j]);  // dg[RG] = phi*(-0)/sigma^2 == 0
-      tB[j] = fmaf(tp.g[i], v[j], tB[j]);
+    for (int j = CEN - RG; j < CEN + CS + RG; ++j) {
+      const float2 a = va[j], b = SAME ? va[j] : vb[j];
+      // input rows 2q (.x) and 2q+1 (.y) of the window
+      tA[j] = ffma2(bcast2(a.x), tp.dgp[2 * q], tA[j]);
+      tA[j] = ffma2(bcast2(a.y), tp.dgp[2 * q + 1], tA[j]);
+      tB[j] = ffma2(bcast2(b.x), tp.gp[2 * q], tB[j]);
+      tB[j] = ffma2(bcast2(b.y), tp.gp[2 * q + 1], tB[j]);
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float sx = 0.f, sy = 0.f;
+  for (int j = 0; j < CS; ++j) {
+    float2 sx = make_float2(0.f, 0.f), sy = make_float2(0.f, 0.f);
 #pragma unroll
     for (int t = 0; t <= 2 * RG; ++t) {
-      sx = fmaf(tp.g[t], tA[CEN + j + t - RG], sx);
-      if (t != RG) sy = fmaf(tp.dg[t], tB[CEN + j + t - RG], sy);
+      sx = ffma2(tA[CEN + j + t - RG], bcast2(tp.g[t]), sx);
+      if (t != RG) sy = ffma2(tB[CEN + j + t - RG], bcast2(tp.dg[t]), sy);  // dg[RG] == 0
     }
-    Ix[j] = sx;
-    Iy[j] = sy;
+    ox[j] = sx;
+    oy[j] = sy;
+  }
+}
+
+// Horizontal rho-pass on a row pair, 4 output columns: out[j] = sum_t k[t] * v[CEN + j + t - RK].
+template <int RK, int WIN, int CEN, class Taps>
+SRST_DEV void smooth_h_rowpair(const float* row, const Taps& tp, float2 (&out)[4]) {
+  float2 v[WIN];
+#pragma unroll
+  for (int m = 0; m < WIN / 2; ++m) {
+    const float4 t = ld4(row + 4 * m);
+    v[2 * m] = make_float2(t.x, t.y);
+    v[2 * m + 1] = make_float2(t.z, t.w);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t <= 2 * RK; ++t) s = ffma2(v[CEN + j + t - RK], bcast2(tp.k[t]), s);
+    out[j] = s;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Forward
+//
+// Persistent, warp-specialised CTA.  NC compute threads run the filter phases; NP producer threads
+// (one or two warps) only move data: they read the RGB tile (+halo) of the NEXT unit -- a unit is
+// one image of one tile, SR then HR -- convert it to grayscale and park it in shared memory while
+// the compute warps are still smoothing the current unit, so no compute warp ever waits on HBM/L2.
+// Hand-off uses named barriers: FULL (producer arrives, consumers sync) and EMPTY (consumers
+// arrive once the gradient phase has consumed the gray tile, producer syncs).
 // ------------------------------------------------------------------------------------------------
-template <int TH_, int TW_, int RS_, int RG_, int RK_, int MINB_>
+constexpr int kBarFull = 1, kBarEmpty = 2, kBarCompute = 3;
+
+template <int TH_, int TW_, int RS_, int CSB_, int NP_, int RG_, int RK_, int MINB_, bool STAGE_ = false>
 struct StFwdCfg {
-  static constexpr int TH = TH_, TW = TW_, RS = RS_, RG = RG_, RK = RK_, MINB = MINB_;
-  static constexpr int CS = 8;
-  static constexpr int NT = TH * TW / CS;    // one horizontal-pass item per thread
+  static constexpr int TH = TH_, TW = TW_, RS = RS_, CSB = CSB_, NP = NP_, RG = RG_, RK = RK_, MINB = MINB_;
+  static constexpr bool STAGE = STAGE_;  // stage raw RGB with cp.async over D|V instead of LDG -> registers
+  static constexpr int NC = TH * TW / 8;     // one horizontal-pass item (2 rows x 4 cols) per compute thread
+  static constexpr int NT = NC + NP;
   static constexpr int HXD = round_up4(RK);  // x halo of the gradient (D) and V regions
   static constexpr int OFF = round_up4(RG);
   static constexpr int HXG = HXD + OFF;      // x halo of the gray (G) region
-  static constexpr int GH = TH + 2 * (RG + RK), GW = TW + 2 * HXG, PG = smem_pitch(GW);
-  static constexpr int DH = TH + 2 * RK, DW = TW + 2 * HXD, PD = smem_pitch(DW);
+  static constexpr int GH = TH + 2 * (RG + RK), GW = TW + 2 * HXG, PG = smem_pitch(2 * GW);
+  static constexpr int DH = TH + 2 * RK, DW = TW + 2 * HXD, PD = smem_pitch(2 * DW);
   static constexpr int PV = PD;
   static constexpr int NSEG = TH / RS;
-  static constexpr int BW_LO = round_dn4(OFF - RG), BW_HI = round_up4(OFF + CS + RG), BWIN = BW_HI - BW_LO;
-  static constexpr int DW_LO = round_dn4(HXD - RK), DW_HI = round_up4(HXD + CS + RK), DWIN = DW_HI - DW_LO;
-  static constexpr int SMEM_FLOATS = 2 * DH * PD + cmax(3 * TH * PV, GH * PG);
+  static constexpr int BW_LO = (OFF - RG) / 2 * 2, BW_HI = (OFF + CSB + RG + 1) / 2 * 2, BWIN = BW_HI - BW_LO;
+  static constexpr int DW_LO = (HXD - RK) / 2 * 2, DW_HI = (HXD + 4 + RK + 1) / 2 * 2, DWIN = DW_HI - DW_LO;
+  static constexpr int D_FLOATS = (DH / 2) * PD, V_FLOATS = (TH / 2) * PV, G_FLOATS = (GH / 2) * PG;
+  // smem: D (Ix, Iy) | V (3 planes) | G (gray).  With producer warps or RGB staging the gray tile
+  // needs its own buffer; otherwise it aliases V (it is dead once the gradient phase is done).
+  static constexpr bool G_ALIAS = (NP == 0) && !STAGE;
+  static constexpr int G_OFF = 2 * D_FLOATS + (G_ALIAS ? 0 : 3 * V_FLOATS);
+  static constexpr int SMEM_FLOATS = G_ALIAS ? 2 * D_FLOATS + cmax(3 * V_FLOATS, G_FLOATS) : G_OFF + G_FLOATS;
   static constexpr size_t SMEM_BYTES = sizeof(float) * SMEM_FLOATS;
-  static_assert(TH % RS == 0 && TW % CS == 0 && NT % 32 == 0 && NT <= 1024, "bad forward tile");
+  static_assert(!STAGE || 3 * GH * GW <= 2 * D_FLOATS + 3 * V_FLOATS, "RGB staging does not fit over the D|V region");
+  static_assert((CSB == 4 || CSB == 8) && DW % CSB == 0, "bad gradient segment width");
+  static_assert(TH % RS == 0 && RS % 2 == 0 && TH % 2 == 0 && TW % 4 == 0 && RG % 2 == 0 && RK % 2 == 0,
+                "bad forward tile");
+  static_assert(NC % 32 == 0 && NP % 32 == 0 && NT <= 1024, "bad forward block size");
 };
 
-// Phases A-D for one image of the pair: leaves the smoothed tensor (Jxx,Jyy,Jxy) of this thread's
-// 8 pixels (row oy, cols ox0..ox0+7 of the tile) in S[3][8].
+// Compute-warp phases B-D for one unit: consumes the gray tile the producer parked in sG and leaves
+// the smoothed tensor (Jxx,Jyy,Jxy) of this thread's 8 pixels (rows 2q, 2q+1; cols ox0..ox0+3 of the
+// tile) in S[3][4] (.x = even row, .y = odd row).
 template <class C, class Taps>
-SRST_DEV void st_tile_tensor(float* smem, const float* __restrict__ base, int H, int W, int y0, int x0,
-                             bool vec4, const Taps& tp, int tid, float (&S)[3][8]) {
+SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, bool vec4, int H, int W, int y0, int x0,
+                             const Taps& tp, int tid, bool last_unit, float2 (&S)[3][4]) {
   float* sD0 = smem;
-  float* sD1 = sD0 + C::DH * C::PD;
-  float* sV = sD1 + C::DH * C::PD;
-  float* sG = sV;  // gray tile aliases V: it is dead once phase B is done
+  float* sD1 = sD0 + C::D_FLOATS;
+  float* sV = sD1 + C::D_FLOATS;
+  float* sG = smem + C::G_OFF;
 
-  // Phase A: global -> gray tile (with halo RG+RK rows, HXG cols)
-  load_gray_tile<C::GH, C::GW, C::PG, C::NT>(sG, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, vec4, tid);
-  __syncthreads();
+  if (C::NP > 0) {
+    bar_sync(kBarFull, C::NT);  // gray tile of this unit is in sG (also: every compute thread is done with sV)
+  } else {
+    bar_sync(kBarCompute, C::NC);  // every thread is done with sD / sV of the previous unit
+    if (C::STAGE && vec4) {
+      stage_rgb_async<C::GH, C::GW, C::NC>(smem, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, tid);
+      cp_async_wait_all();
+      bar_sync(kBarCompute, C::NC);
+      convert_staged_gray<C::GH, C::GW, C::PG, C::NC>(sG, smem, tid);
+    } else {
+      load_gray_tile<C::GH, C::GW, C::PG, C::NC, 1>(sG, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, vec4, tid);
+    }
+    bar_sync(kBarCompute, C::NC);
+  }
 
   // Phase B: Ix, Iy on the D region; forced to zero outside the image because the reference
   // zero-pads the *products* for the rho-smoothing (utils.py:225-230).
-  for (int it = tid; it < C::DH * (C::DW / 8); it += C::NT) {
-    const int seg = it / C::DH, r = it - seg * C::DH;
-    const int dx0 = 8 * seg;
-    const int gy = y0 - C::RK + r, gx0 = x0 - C::HXD + dx0;
-    float Ix[8], Iy[8];
-    if (gy >= 0 && gy < H && gx0 + 7 >= 0 && gx0 < W) {
-      grad8<C::RG, C::BWIN, C::OFF - C::BW_LO, C::PG>(sG + r * C::PG + dx0 + C::BW_LO, tp, Ix, Iy);
+  for (int it = tid; it < (C::DH / 2) * (C::DW / C::CSB); it += C::NC) {
+    const int seg = it / (C::DH / 2), q = it - seg * (C::DH / 2);
+    const int dx0 = C::CSB * seg;
+    const int gy = y0 - C::RK + 2 * q, gx0 = x0 - C::HXD + dx0;
+    float2 Ix[C::CSB], Iy[C::CSB];
+    if (gy + 1 >= 0 && gy < H && gx0 + C::CSB - 1 >= 0 && gx0 < W) {
+      const float* p = sG + q * C::PG + 2 * (dx0 + C::BW_LO);
+      grad_rowpair<C::RG, C::CSB, C::BWIN, C::OFF - C::BW_LO, C::PG, true>(p, p, tp, Ix, Iy);
+      const bool r0 = gy >= 0, r1 = gy + 1 < H;  // gy < H and gy + 1 >= 0 hold here
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < C::CSB; ++j) {
         const bool ok = (gx0 + j >= 0) && (gx0 + j < W);
-        Ix[j] = ok ? Ix[j] : 0.f;
-        Iy[j] = ok ? Iy[j] : 0.f;
+        Ix[j].x = (ok && r0) ? Ix[j].x : 0.f;
+        Ix[j].y = (ok && r1) ? Ix[j].y : 0.f;
+        Iy[j].x = (ok && r0) ? Iy[j].x : 0.f;
+        Iy[j].y = (ok && r1) ? Iy[j].y : 0.f;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { Ix[j] = 0.f; Iy[j] = 0.f; }
+      for (int j = 0; j < C::CSB; ++j) { Ix[j] = make_float2(0.f, 0.f); Iy[j] = make_float2(0.f, 0.f); }
     }
-    float* o0 = sD0 + r * C::PD + dx0;
-    float* o1 = sD1 + r * C::PD + dx0;
-    st4(o0, make_float4(Ix[0], Ix[1], Ix[2], Ix[3]));
-    st4(o0 + 4, make_float4(Ix[4], Ix[5], Ix[6], Ix[7]));
-    st4(o1, make_float4(Iy[0], Iy[1], Iy[2], Iy[3]));
-    st4(o1 + 4, make_float4(Iy[4], Iy[5], Iy[6], Iy[7]));
+    float* o0 = sD0 + q * C::PD + 2 * dx0;
+    float* o1 = sD1 + q * C::PD + 2 * dx0;
+#pragma unroll
+    for (int j = 0; j < C::CSB; j += 2) {
+      st4(o0 + 2 * j, make_float4(Ix[j].x, Ix[j].y, Ix[j + 1].x, Ix[j + 1].y));
+      st4(o1 + 2 * j, make_float4(Iy[j].x, Iy[j].y, Iy[j + 1].x, Iy[j + 1].y));
+    }
   }
-  __syncthreads();
+  if (C::NP > 0 && !last_unit) bar_arrive(kBarEmpty, C::NT);  // sG may be refilled with the next unit's tile
+  bar_sync(kBarCompute, C::NC);
 
-  // Phase C: vertical rho-pass of the three products; a lane owns one column and RS output rows.
-  for (int it = tid; it < C::DW * C::NSEG; it += C::NT) {
-    const int seg = it / C::DW, dx = it - seg * C::DW;
-    const int gx = x0 - C::HXD + dx;
-    float acc[3][C::RS];
+  // Phase C: vertical rho-pass of the three products; a lane owns one column and RS output rows
+  // (RS/2 row pairs).  Columns outside the image hold zeros and are only cleared.
+  {
+    const int c_lo = max(0, C::HXD - x0), c_hi = min(C::DW, W + C::HXD - x0);  // valid D columns
+    const int ncol = c_hi - c_lo;
+    const int nclr = C::DW - ncol;
+    for (int it = tid; it < nclr * (C::TH / 2); it += C::NC) {
+      const int q = it / nclr, u = it - q * nclr;
+      const int dx = (u < c_lo) ? u : (c_hi + (u - c_lo));
 #pragma unroll
-    for (int j = 0; j < C::RS; ++j) { acc[0][j] = 0.f; acc[1][j] = 0.f; acc[2][j] = 0.f; }
-    if (gx >= 0 && gx < W) {
-      const float* p0 = sD0 + (seg * C::RS) * C::PD + dx;
-      const float* p1 = sD1 + (seg * C::RS) * C::PD + dx;
+      for (int c = 0; c < 3; ++c) st2(sV + c * C::V_FLOATS + q * C::PV + 2 * dx, make_float2(0.f, 0.f));
+    }
+    for (int it = tid; it < ncol * C::NSEG; it += C::NC) {
+      const int seg = it / ncol, dx = c_lo + (it - seg * ncol);
+      float2 acc[3][C::RS / 2];
 #pragma unroll
-      for (int r = 0; r < C::RS + 2 * C::RK; ++r) {
-        const float ix = p0[r * C::PD], iy = p1[r * C::PD];
-        const float pxx = ix * ix, pyy = iy * iy, pxy = ix * iy;
+      for (int j = 0; j < C::RS / 2; ++j) {
+        acc[0][j] = make_float2(0.f, 0.f); acc[1][j] = make_float2(0.f, 0.f); acc[2][j] = make_float2(0.f, 0.f);
+      }
+      const float* p0 = sD0 + (seg * (C::RS / 2)) * C::PD + 2 * dx;
+      const float* p1 = sD1 + (seg * (C::RS / 2)) * C::PD + 2 * dx;
 #pragma unroll
-        for (int j = 0; j < C::RS; ++j) {
-          const int t = r - j;
-          if (t >= 0 && t <= 2 * C::RK) {
-            acc[0][j] = fmaf(tp.k[t], pxx, acc[0][j]);
-            acc[1][j] = fmaf(tp.k[t], pyy, acc[1][j]);
-            acc[2][j] = fmaf(tp.k[t], pxy, acc[2][j]);
+      for (int rq = 0; rq < C::RS / 2 + C::RK; ++rq) {
+        const float2 ix = ld2(p0 + rq * C::PD), iy = ld2(p1 + rq * C::PD);
+        const float2 pxx = make_float2(ix.x * ix.x, ix.y * ix.y);
+        const float2 pyy = make_float2(iy.x * iy.x, iy.y * iy.y);
+        const float2 pxy = make_float2(ix.x * iy.x, ix.y * iy.y);
+#pragma unroll
+        for (int jp = 0; jp < C::RS / 2; ++jp) {
+          const int u0 = 2 * rq - 2 * jp;  // tap-pair index of input row 2rq for output pair jp
+          if (u0 >= 0 && u0 <= 2 * C::RK + 1) {
+            acc[0][jp] = ffma2(bcast2(pxx.x), tp.kp[u0], acc[0][jp]);
+            acc[1][jp] = ffma2(bcast2(pyy.x), tp.kp[u0], acc[1][jp]);
+            acc[2][jp] = ffma2(bcast2(pxy.x), tp.kp[u0], acc[2][jp]);
+          }
+          if (u0 + 1 >= 0 && u0 + 1 <= 2 * C::RK + 1) {
+            acc[0][jp] = ffma2(bcast2(pxx.y), tp.kp[u0 + 1], acc[0][jp]);
+            acc[1][jp] = ffma2(bcast2(pyy.y), tp.kp[u0 + 1], acc[1][jp]);
+            acc[2][jp] = ffma2(bcast2(pxy.y), tp.kp[u0 + 1], acc[2][jp]);
           }
         }
       }
-    }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float* o = sV + c * (C::TH * C::PV) + (seg * C::RS) * C::PV + dx;
+      for (int c = 0; c < 3; ++c) {
+        float* o = sV + c * C::V_FLOATS + (seg * (C::RS / 2)) * C::PV + 2 * dx;
 #pragma unroll
-      for (int j = 0; j < C::RS; ++j) o[j * C::PV] = acc[c][j];
+        for (int jp = 0; jp < C::RS / 2; ++jp) st2(o + jp * C::PV, acc[c][jp]);
+      }
     }
   }
-  __syncthreads();
+  bar_sync(kBarCompute, C::NC);
 
-  // Phase D: horizontal rho-pass; a lane owns 8 consecutive columns of one row.
+  // Phase D: horizontal rho-pass; a lane owns 4 consecutive columns of one row pair.
   {
-    const int seg = tid / C::TH, oy = tid - seg * C::TH;
-    const int ox0 = 8 * seg;
-    constexpr int CEN = C::HXD - C::DW_LO;
+    const int seg = tid / (C::TH / 2), q = tid - seg * (C::TH / 2);
+    const int ox0 = 4 * seg;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* row = sV + c * (C::TH * C::PV) + oy * C::PV + ox0 + C::DW_LO;
-      float v[C::DWIN];
-#pragma unroll
-      for (int q = 0; q < C::DWIN / 4; ++q) {
-        const float4 t = ld4(row + 4 * q);
-        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float s = 0.f;
-#pragma unroll
-        for (int t = 0; t <= 2 * C::RK; ++t) s = fmaf(tp.k[t], v[CEN + j + t - C::RK], s);
-        S[c][j] = s;
-      }
-    }
+    for (int c = 0; c < 3; ++c)
+      smooth_h_rowpair<C::RK, C::DWIN, C::HXD - C::DW_LO>(sV + c * C::V_FLOATS + q * C::PV + 2 * (ox0 + C::DW_LO), tp,
+                                                          S[c]);
   }
-  __syncthreads();  // the next image's phase A overwrites sG (== sV)
+  // no barrier here: the next unit starts with bar_sync(kBarFull) over all compute threads, which
+  // orders these sV reads before the next phase C and the sD reads of phase C before the next phase B
 }
 
 template <class C>
@@ -348,81 +549,112 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
   __shared__ float s_red[32];
   __shared__ unsigned int s_last;
   const int tid = threadIdx.x;
-  int tile = blockIdx.x;
-  const int tx = tile % P.tiles_x;
-  tile /= P.tiles_x;
-  const int ty = tile % P.tiles_y;
-  const int b = tile / P.tiles_y;
-  const int y0 = ty * C::TH, x0 = tx * C::TW;
-  const size_t img_off = (size_t)b * 3 * P.H * P.W;
+  const int ntiles = P.B * P.tiles_y * P.tiles_x;
 
-  float S1[3][8], S2[3][8];
-  st_tile_tensor<C>(smem, P.sr + img_off, P.H, P.W, y0, x0, P.vec4 != 0, P.taps, tid, S1);
-  st_tile_tensor<C>(smem, P.hr + img_off, P.H, P.W, y0, x0, P.vec4 != 0, P.taps, tid, S2);
+  if (C::NP > 0 && tid >= C::NC) {
+    // ---- producer warps: RGB tile (+halo) -> gray -> sG, one unit ahead of the compute warps ----
+    float* sG = smem + C::G_OFF;
+    const int ptid = tid - C::NC;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int t = tile;
+      const int tx = t % P.tiles_x;
+      t /= P.tiles_x;
+      const int ty = t % P.tiles_y;
+      const int b = t / P.tiles_y;
+      const size_t img_off = (size_t)b * 3 * P.H * P.W;
+#pragma unroll 1
+      for (int img = 0; img < 2; ++img) {
+        if (!first) bar_sync(kBarEmpty, C::NT);  // compute warps are done with the previous gray tile
+        first = false;
+        load_gray_tile<C::GH, C::GW, C::PG, (C::NP > 0 ? C::NP : 32), 3>(sG, (img ? P.hr : P.sr) + img_off, P.H, P.W,
+                                                   ty * C::TH - (C::RG + C::RK), tx * C::TW - C::HXG, P.vec4 != 0, ptid);
+        __threadfence_block();
+        bar_arrive(kBarFull, C::NT);
+      }
+    }
+    return;
+  }
 
-  // Per-pixel chain on this thread's 8 pixels.
-  const int seg = tid / C::TH, oy = tid - seg * C::TH;
-  const int gy = y0 + oy, gx0 = x0 + 8 * seg;
+  // ---- compute warps ----
   const bool want_sr = P.ds_sr != nullptr, want_hr = P.ds_hr != nullptr;
   const bool norm = P.normalize != 0;
+  const int seg = tid / (C::TH / 2), q = tid - seg * (C::TH / 2);
   float lsum = 0.f;
-  float g_sr[3][8], g_hr[3][8];
+  // NP > 0: persistent loop over tiles (the producer runs one unit ahead); NP == 0: one tile per CTA
+  int tile = blockIdx.x;
+  do {
+    int t = tile;
+    const int tx = t % P.tiles_x;
+    t /= P.tiles_x;
+    const int ty = t % P.tiles_y;
+    const int b = t / P.tiles_y;
+    const int y0 = ty * C::TH, x0 = tx * C::TW;
+    const size_t img_off = (size_t)b * 3 * P.H * P.W;
+    const bool last_tile = tile + (int)gridDim.x >= ntiles;
+
+    float2 S1[3][4], S2[3][4];
+    st_unit_tensor<C>(smem, P.sr + img_off, P.vec4 != 0, P.H, P.W, y0, x0, P.taps, tid, false, S1);
+    st_unit_tensor<C>(smem, P.hr + img_off, P.vec4 != 0, P.H, P.W, y0, x0, P.taps, tid, last_tile, S2);
+
+    // Per-pixel chain on this thread's 2 x 4 pixels.
+    const int gy0 = y0 + 2 * q, gx0 = x0 + 4 * seg;
+    float g_sr[2][3][4], g_hr[2][3][4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    StPixelGrad G;
-    G.da = G.db = G.dc = G.de = G.df = G.dh = 0.f;
-    float d;
-    if (want_hr)
-      d = st_pixel<true, true>(S1[0][j], S1[1][j], S1[2][j], S2[0][j], S2[1][j], S2[2][j], norm, P.eps, G);
-    else if (want_sr)
-      d = st_pixel<true, false>(S1[0][j], S1[1][j], S1[2][j], S2[0][j], S2[1][j], S2[2][j], norm, P.eps, G);
-    else
-      d = st_pixel<false, false>(S1[0][j], S1[1][j], S1[2][j], S2[0][j], S2[1][j], S2[2][j], norm, P.eps, G);
-    const bool ok = (gy < P.H) && (gx0 + j < P.W);
-    lsum += ok ? d : 0.f;
-    g_sr[0][j] = G.da; g_sr[1][j] = G.db; g_sr[2][j] = G.dc;
-    g_hr[0][j] = G.de; g_hr[1][j] = G.df; g_hr[2][j] = G.dh;
-  }
-  if (gy < P.H && gx0 < P.W) {
-    const size_t plane = (size_t)P.H * P.W;
-    const size_t o = img_off + (size_t)gy * P.W + gx0;
+    for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (P.vec4) {
-        if (want_sr) {
-          st4(P.ds_sr + o + c * plane, make_float4(g_sr[c][0], g_sr[c][1], g_sr[c][2], g_sr[c][3]));
-          if (gx0 + 4 < P.W) st4(P.ds_sr + o + c * plane + 4, make_float4(g_sr[c][4], g_sr[c][5], g_sr[c][6], g_sr[c][7]));
-        }
-        if (want_hr) {
-          st4(P.ds_hr + o + c * plane, make_float4(g_hr[c][0], g_hr[c][1], g_hr[c][2], g_hr[c][3]));
-          if (gx0 + 4 < P.W) st4(P.ds_hr + o + c * plane + 4, make_float4(g_hr[c][4], g_hr[c][5], g_hr[c][6], g_hr[c][7]));
-        }
-      } else {
+      for (int j = 0; j < 4; ++j) {
+        const float a = hf ? S1[0][j].y : S1[0][j].x, bq = hf ? S1[1][j].y : S1[1][j].x, c = hf ? S1[2][j].y : S1[2][j].x;
+        const float e = hf ? S2[0][j].y : S2[0][j].x, f = hf ? S2[1][j].y : S2[1][j].x, h = hf ? S2[2][j].y : S2[2][j].x;
+        StPixelGrad G;
+        G.da = G.db = G.dc = G.de = G.df = G.dh = 0.f;
+        const float d = want_hr ? st_pixel<true, true>(a, bq, c, e, f, h, norm, P.eps, G)
+                                : st_pixel<true, false>(a, bq, c, e, f, h, norm, P.eps, G);
+        const bool ok = (gy0 + hf < P.H) && (gx0 + j < P.W);
+        lsum += ok ? d : 0.f;
+        g_sr[hf][0][j] = G.da; g_sr[hf][1][j] = G.db; g_sr[hf][2][j] = G.dc;
+        g_hr[hf][0][j] = G.de; g_hr[hf][1][j] = G.df; g_hr[hf][2][j] = G.dh;
+      }
+    }
+    if (gx0 < P.W) {
+      const size_t plane = (size_t)P.H * P.W;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (gx0 + j < P.W) {
-            if (want_sr) P.ds_sr[o + c * plane + j] = g_sr[c][j];
-            if (want_hr) P.ds_hr[o + c * plane + j] = g_hr[c][j];
+      for (int hf = 0; hf < 2; ++hf) {
+        if (gy0 + hf >= P.H) continue;
+        const size_t o = img_off + (size_t)(gy0 + hf) * P.W + gx0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (P.vec4) {
+            if (want_sr) st4(P.ds_sr + o + c * plane, make_float4(g_sr[hf][c][0], g_sr[hf][c][1], g_sr[hf][c][2], g_sr[hf][c][3]));
+            if (want_hr) st4(P.ds_hr + o + c * plane, make_float4(g_hr[hf][c][0], g_hr[hf][c][1], g_hr[hf][c][2], g_hr[hf][c][3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (gx0 + j < P.W) {
+                if (want_sr) P.ds_sr[o + c * plane + j] = g_sr[hf][c][j];
+                if (want_hr) P.ds_hr[o + c * plane + j] = g_hr[hf][c][j];
+              }
+            }
           }
         }
       }
     }
-  }
+  } while (C::NP > 0 && (tile += (int)gridDim.x) < ntiles);
 
   // Deterministic loss reduction: block partial -> workspace; the last block to finish sums all
   // partials in a fixed order (double) and re-zeroes the workspace for the next call.
   lsum = warp_sum(lsum);
   if ((tid & 31) == 0) s_red[tid >> 5] = lsum;
-  __syncthreads();
+  bar_sync(kBarCompute, C::NC);
   if (tid == 0) {
     float bs = 0.f;
-    for (int w = 0; w < C::NT / 32; ++w) bs += s_red[w];
+    for (int w = 0; w < C::NC / 32; ++w) bs += s_red[w];
     P.partials[blockIdx.x] = bs;
     __threadfence();
     const unsigned int t = atomicAdd(P.ticket, 1u);
     s_last = (t == gridDim.x - 1) ? 1u : 0u;
   }
-  __syncthreads();
+  bar_sync(kBarCompute, C::NC);
   if (s_last) {
     __threadfence();
     if (tid < 32) {
@@ -449,33 +681,37 @@ struct StBwdCfg {
   static constexpr int TH = TH_, TW = TW_, RS = RS_, NT = NT_, RG = RG_, RK = RK_, MINB = MINB_;
   static constexpr int HXE = round_up4(RG);  // x halo of the E region (where dIx, dIy are needed)
   static constexpr int HXK = round_up4(RK);
-  static constexpr int EH = TH + 2 * RG, EW = TW + 2 * HXE, PE = smem_pitch(EW);
-  static constexpr int GH = EH + 2 * RG, GW = EW + 2 * HXE, PG = smem_pitch(GW);  // gray region
-  static constexpr int VW = EW + 2 * HXK, PV = smem_pitch(VW);                     // vertical-pass output
+  static constexpr int EH = TH + 2 * RG, EW = TW + 2 * HXE, PE = smem_pitch(2 * EW);
+  static constexpr int GH = EH + 2 * RG, GW = EW + 2 * HXE, PG = smem_pitch(2 * GW);  // gray region
+  static constexpr int VW = EW + 2 * HXK, PV = smem_pitch(2 * VW);                     // vertical-pass output
+  static constexpr int SH = EH + 2 * RK;                                              // staged ds rows
   static constexpr int NSEG = EH / RS;
-  // gradient window (same geometry as the forward phase B, output cols relative to the E region)
-  static constexpr int BW_LO = round_dn4(HXE - RG), BW_HI = round_up4(HXE + 8 + RG), BWIN = BW_HI - BW_LO;
-  // horizontal rho-pass window on the V region
-  static constexpr int DW_LO = round_dn4(HXK - RK), DW_HI = round_up4(HXK + 8 + RK), DWIN = DW_HI - DW_LO;
-  // smem: V (3 planes) | I (Ix, Iy) | dI (dIx, dIy);  gray aliases dI (dead before dI is written)
-  static constexpr int V_FLOATS = 3 * EH * PV, I_FLOATS = 2 * EH * PE;
-  static constexpr int X_FLOATS = cmax(2 * EH * PE, GH * PG);
-  static constexpr int SMEM_FLOATS = V_FLOATS + I_FLOATS + X_FLOATS;
+  static constexpr int BW_LO = (HXE - RG) / 2 * 2, BW_HI = (HXE + 4 + RG + 1) / 2 * 2, BWIN = BW_HI - BW_LO;
+  static constexpr int DW_LO = (HXK - RK) / 2 * 2, DW_HI = (HXK + 4 + RK + 1) / 2 * 2, DWIN = DW_HI - DW_LO;
+  // smem: V (3 planes) | I (Ix, Iy) | G (gray) | X: staged ds planes [3][SH][VW] row-major, later
+  // dIx|dIy (the staging is dead once the vertical pass has consumed it)
+  static constexpr int V_FLOATS = (EH / 2) * PV, I_FLOATS = (EH / 2) * PE, G_FLOATS = (GH / 2) * PG;
+  static constexpr int S_FLOATS = SH * VW;
+  static constexpr int X_FLOATS = cmax(2 * I_FLOATS, 3 * S_FLOATS);
+  static constexpr int SMEM_FLOATS = 3 * V_FLOATS + 2 * I_FLOATS + G_FLOATS + X_FLOATS;
   static constexpr size_t SMEM_BYTES = sizeof(float) * SMEM_FLOATS;
-  static_assert(EH % RS == 0 && TW % 8 == 0 && NT % 32 == 0 && NT <= 1024, "bad backward tile");
+  static_assert(EH % RS == 0 && RS % 2 == 0 && TH % 2 == 0 && TW % 4 == 0 && RG % 2 == 0 && RK % 2 == 0,
+                "bad backward tile");
+  static_assert(NT % 32 == 0 && NT <= 1024, "bad backward block size");
 };
 
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   SRST_DYN_SMEM(float, smem);
-  float* sV = smem;                  // [3][EH][PV]  vertical rho-pass of ds
-  float* sI0 = sV + C::V_FLOATS;     // Ix [EH][PE]
-  float* sI1 = sI0 + C::EH * C::PE;  // Iy
-  float* sX = sI1 + C::EH * C::PE;   // gray [GH][PG], later dIx|dIy [2][EH][PE]
-  float* sG = sX;
+  float* sV = smem;                    // [3][EH/2][PV]  vertical rho-pass of ds
+  float* sI0 = sV + 3 * C::V_FLOATS;   // Ix [EH/2][PE]
+  float* sI1 = sI0 + C::I_FLOATS;      // Iy
+  float* sG = sI1 + C::I_FLOATS;       // gray [GH/2][PG]
+  float* sX = sG + C::G_FLOATS;        // staged ds [3][SH][VW], later dIx|dIy
+  float* sS = sX;
   float* sdI0 = sX;
-  float* sdI1 = sX + C::EH * C::PE;
+  float* sdI1 = sX + C::I_FLOATS;
 
   const int tid = threadIdx.x;
   int tile = blockIdx.x;
@@ -488,118 +724,136 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   const size_t plane = (size_t)H * W;
   const size_t img_off = (size_t)b * 3 * plane;
   const auto& tp = P.taps;
+  const int xv0 = x0 - C::HXE - C::HXK;        // first staged / V column
+  const int yv0 = y0 - C::RG - C::RK;          // first staged row
 
-  // Phase A': gray tile of the image (halo 2*RG rows, 2*HXE cols)
-  load_gray_tile<C::GH, C::GW, C::PG, C::NT>(sG, P.img + img_off, H, W, y0 - 2 * C::RG, x0 - 2 * C::HXE,
-                                             P.vec4 != 0, tid);
-
-  // Phase C': vertical rho-pass of the three ds planes straight from global memory (coalesced:
-  // consecutive lanes read consecutive columns).  The adjoint of the zero-padded symmetric
-  // smoothing is the same zero-padded smoothing.
+  // Stage the three ds planes (+halo) with asynchronous 16-byte copies; rows/columns outside the
+  // image are zero-filled, which is exactly the zero padding of the adjoint smoothing.
   {
     const float* dsb = P.ds + img_off;
-    for (int it = tid; it < C::VW * C::NSEG; it += C::NT) {
-      const int seg = it / C::VW, vx = it - seg * C::VW;
-      const int gx = x0 - C::HXE - C::HXK + vx;
-      const int gyb = y0 - C::RG - C::RK + seg * C::RS;  // first input row
-      const bool colok = gx >= 0 && gx < W;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float acc[C::RS];
-#pragma unroll
-        for (int j = 0; j < C::RS; ++j) acc[j] = 0.f;
-        if (colok) {
-          const float* p = dsb + c * plane + gx;
-          float v[C::RS + 2 * C::RK];
-#pragma unroll
-          for (int r = 0; r < C::RS + 2 * C::RK; ++r) {
-            const int gy = gyb + r;
-            v[r] = (gy >= 0 && gy < H) ? __ldg(p + (size_t)gy * W) : 0.f;
-          }
-#pragma unroll
-          for (int r = 0; r < C::RS + 2 * C::RK; ++r) {
-#pragma unroll
-            for (int j = 0; j < C::RS; ++j) {
-              const int t = r - j;
-              if (t >= 0 && t <= 2 * C::RK) acc[j] = fmaf(tp.k[t], v[r], acc[j]);
-            }
-          }
-        }
-        float* o = sV + c * (C::EH * C::PV) + (seg * C::RS) * C::PV + vx;
-#pragma unroll
-        for (int j = 0; j < C::RS; ++j) o[j * C::PV] = acc[j];
+    constexpr int C4 = C::VW / 4;
+    if (P.vec4) {
+      for (int it = tid; it < 3 * C::SH * C4; it += C::NT) {
+        const int c4 = it % C4, rc = it / C4;
+        const int r = rc % C::SH, c = rc / C::SH;
+        const int gy = yv0 + r, gx = xv0 + 4 * c4;
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        cp_async16(sS + (c * C::SH + r) * C::VW + 4 * c4, ok ? dsb + c * plane + (size_t)gy * W + gx : dsb, ok);
+      }
+      cp_async_commit();
+    } else {
+      for (int it = tid; it < 3 * C::SH * C::VW; it += C::NT) {
+        const int vx = it % C::VW, rc = it / C::VW;
+        const int r = rc % C::SH, c = rc / C::SH;
+        const int gy = yv0 + r, gx = xv0 + vx;
+        sS[it] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(dsb + c * plane + (size_t)gy * W + gx) : 0.f;
       }
     }
   }
+
+  // Phase A': gray tile of the image (halo 2*RG rows, 2*HXE cols)
+  load_gray_tile<C::GH, C::GW, C::PG, C::NT, 1>(sG, P.img + img_off, H, W, y0 - 2 * C::RG, x0 - 2 * C::HXE,
+                                                P.vec4 != 0, tid);
   __syncthreads();
 
   // Phase B': recompute Ix, Iy on the E region (zero outside the image).
-  for (int it = tid; it < C::EH * (C::EW / 8); it += C::NT) {
-    const int seg = it / C::EH, r = it - seg * C::EH;
-    const int ex0 = 8 * seg;
-    const int gy = y0 - C::RG + r, gx0 = x0 - C::HXE + ex0;
-    float Ix[8], Iy[8];
-    if (gy >= 0 && gy < H && gx0 + 7 >= 0 && gx0 < W) {
-      grad8<C::RG, C::BWIN, C::HXE - C::BW_LO, C::PG>(sG + r * C::PG + ex0 + C::BW_LO, tp, Ix, Iy);
+  for (int it = tid; it < (C::EH / 2) * (C::EW / 4); it += C::NT) {
+    const int seg = it / (C::EH / 2), q = it - seg * (C::EH / 2);
+    const int ex0 = 4 * seg;
+    const int gy = y0 - C::RG + 2 * q, gx0 = x0 - C::HXE + ex0;
+    float2 Ix[4], Iy[4];
+    if (gy + 1 >= 0 && gy < H && gx0 + 3 >= 0 && gx0 < W) {
+      const float* p = sG + q * C::PG + 2 * (ex0 + C::BW_LO);
+      grad_rowpair<C::RG, 4, C::BWIN, C::HXE - C::BW_LO, C::PG, true>(p, p, tp, Ix, Iy);
+      const bool r0 = gy >= 0, r1 = gy + 1 < H;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         const bool ok = (gx0 + j >= 0) && (gx0 + j < W);
-        Ix[j] = ok ? Ix[j] : 0.f;
-        Iy[j] = ok ? Iy[j] : 0.f;
+        Ix[j].x = (ok && r0) ? Ix[j].x : 0.f;
+        Ix[j].y = (ok && r1) ? Ix[j].y : 0.f;
+        Iy[j].x = (ok && r0) ? Iy[j].x : 0.f;
+        Iy[j].y = (ok && r1) ? Iy[j].y : 0.f;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { Ix[j] = 0.f; Iy[j] = 0.f; }
+      for (int j = 0; j < 4; ++j) { Ix[j] = make_float2(0.f, 0.f); Iy[j] = make_float2(0.f, 0.f); }
     }
-    float* o0 = sI0 + r * C::PE + ex0;
-    float* o1 = sI1 + r * C::PE + ex0;
-    st4(o0, make_float4(Ix[0], Ix[1], Ix[2], Ix[3]));
-    st4(o0 + 4, make_float4(Ix[4], Ix[5], Ix[6], Ix[7]));
-    st4(o1, make_float4(Iy[0], Iy[1], Iy[2], Iy[3]));
-    st4(o1 + 4, make_float4(Iy[4], Iy[5], Iy[6], Iy[7]));
+    float* o0 = sI0 + q * C::PE + 2 * ex0;
+    float* o1 = sI1 + q * C::PE + 2 * ex0;
+    st4(o0, make_float4(Ix[0].x, Ix[0].y, Ix[1].x, Ix[1].y));
+    st4(o0 + 4, make_float4(Ix[2].x, Ix[2].y, Ix[3].x, Ix[3].y));
+    st4(o1, make_float4(Iy[0].x, Iy[0].y, Iy[1].x, Iy[1].y));
+    st4(o1 + 4, make_float4(Iy[2].x, Iy[2].y, Iy[3].x, Iy[3].y));
   }
-  __syncthreads();  // gray is dead from here on: sdI may overwrite it
+  cp_async_wait_all();
+  __syncthreads();  // Ix, Iy complete; staged ds planes have landed
+
+  // Phase C': vertical rho-pass of the three staged ds planes; a lane owns one column and RS rows.
+  // The adjoint of the zero-padded symmetric smoothing is the same zero-padded smoothing.
+  {
+    const int c_lo = max(0, -xv0), c_hi = min(C::VW, W - xv0);
+    const int ncol = c_hi - c_lo;
+    const int nclr = C::VW - ncol;
+    for (int it = tid; it < nclr * (C::EH / 2); it += C::NT) {
+      const int q = it / nclr, u = it - q * nclr;
+      const int vx = (u < c_lo) ? u : (c_hi + (u - c_lo));
+#pragma unroll
+      for (int c = 0; c < 3; ++c) st2(sV + c * C::V_FLOATS + q * C::PV + 2 * vx, make_float2(0.f, 0.f));
+    }
+    for (int it = tid; it < ncol * C::NSEG; it += C::NT) {
+      const int seg = it / ncol, vx = c_lo + (it - seg * ncol);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float2 acc[C::RS / 2];
+#pragma unroll
+        for (int j = 0; j < C::RS / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+        const float* p = sS + (c * C::SH + seg * C::RS) * C::VW + vx;
+#pragma unroll
+        for (int r = 0; r < C::RS + 2 * C::RK; ++r) {
+          const float v = p[r * C::VW];
+#pragma unroll
+          for (int jp = 0; jp < C::RS / 2; ++jp) {
+            const int u = r - 2 * jp;
+            if (u >= 0 && u <= 2 * C::RK + 1) acc[jp] = ffma2(bcast2(v), tp.kp[u], acc[jp]);
+          }
+        }
+        float* o = sV + c * C::V_FLOATS + (seg * (C::RS / 2)) * C::PV + 2 * vx;
+#pragma unroll
+        for (int jp = 0; jp < C::RS / 2; ++jp) st2(o + jp * C::PV, acc[jp]);
+      }
+    }
+  }
+  __syncthreads();  // the staging is dead from here on: sdI may overwrite it
 
   // Phase D': horizontal rho-pass -> E = K*ds at the E-region pixels, then the product rule
   //   dIx = 2 Ix Exx + Iy Exy ,  dIy = 2 Iy Eyy + Ix Exy      (adjoint of utils.py:225-229)
-  for (int it = tid; it < C::EH * (C::EW / 8); it += C::NT) {
-    const int seg = it / C::EH, r = it - seg * C::EH;
-    const int ex0 = 8 * seg;
-    constexpr int CEN = C::HXK - C::DW_LO;
-    float E[3][8];
+  for (int it = tid; it < (C::EH / 2) * (C::EW / 4); it += C::NT) {
+    const int seg = it / (C::EH / 2), q = it - seg * (C::EH / 2);
+    const int ex0 = 4 * seg;
+    float2 E[3][4];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float* row = sV + c * (C::EH * C::PV) + r * C::PV + ex0 + C::DW_LO;
-      float v[C::DWIN];
+    for (int c = 0; c < 3; ++c)
+      smooth_h_rowpair<C::RK, C::DWIN, C::HXK - C::DW_LO>(sV + c * C::V_FLOATS + q * C::PV + 2 * (ex0 + C::DW_LO), tp,
+                                                          E[c]);
+    const float4 ixa = ld4(sI0 + q * C::PE + 2 * ex0), ixb = ld4(sI0 + q * C::PE + 2 * ex0 + 4);
+    const float4 iya = ld4(sI1 + q * C::PE + 2 * ex0), iyb = ld4(sI1 + q * C::PE + 2 * ex0 + 4);
+    const float2 ix[4] = {make_float2(ixa.x, ixa.y), make_float2(ixa.z, ixa.w), make_float2(ixb.x, ixb.y),
+                          make_float2(ixb.z, ixb.w)};
+    const float2 iy[4] = {make_float2(iya.x, iya.y), make_float2(iya.z, iya.w), make_float2(iyb.x, iyb.y),
+                          make_float2(iyb.z, iyb.w)};
+    float2 dx[4], dy[4];
 #pragma unroll
-      for (int q = 0; q < C::DWIN / 4; ++q) {
-        const float4 t = ld4(row + 4 * q);
-        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float s = 0.f;
-#pragma unroll
-        for (int t = 0; t <= 2 * C::RK; ++t) s = fmaf(tp.k[t], v[CEN + j + t - C::RK], s);
-        E[c][j] = s;
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float2 ix2 = make_float2(2.0f * ix[j].x, 2.0f * ix[j].y), iy2 = make_float2(2.0f * iy[j].x, 2.0f * iy[j].y);
+      dx[j] = ffma2(ix2, E[0][j], make_float2(iy[j].x * E[2][j].x, iy[j].y * E[2][j].y));
+      dy[j] = ffma2(iy2, E[1][j], make_float2(ix[j].x * E[2][j].x, ix[j].y * E[2][j].y));
     }
-    const float4 ixa = ld4(sI0 + r * C::PE + ex0), ixb = ld4(sI0 + r * C::PE + ex0 + 4);
-    const float4 iya = ld4(sI1 + r * C::PE + ex0), iyb = ld4(sI1 + r * C::PE + ex0 + 4);
-    const float ix[8] = {ixa.x, ixa.y, ixa.z, ixa.w, ixb.x, ixb.y, ixb.z, ixb.w};
-    const float iy[8] = {iya.x, iya.y, iya.z, iya.w, iyb.x, iyb.y, iyb.z, iyb.w};
-    float dx[8], dy[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      dx[j] = 2.0f * ix[j] * E[0][j] + iy[j] * E[2][j];
-      dy[j] = 2.0f * iy[j] * E[1][j] + ix[j] * E[2][j];
-    }
-    float* o0 = sdI0 + r * C::PE + ex0;
-    float* o1 = sdI1 + r * C::PE + ex0;
-    st4(o0, make_float4(dx[0], dx[1], dx[2], dx[3]));
-    st4(o0 + 4, make_float4(dx[4], dx[5], dx[6], dx[7]));
-    st4(o1, make_float4(dy[0], dy[1], dy[2], dy[3]));
-    st4(o1 + 4, make_float4(dy[4], dy[5], dy[6], dy[7]));
+    float* o0 = sdI0 + q * C::PE + 2 * ex0;
+    float* o1 = sdI1 + q * C::PE + 2 * ex0;
+    st4(o0, make_float4(dx[0].x, dx[0].y, dx[1].x, dx[1].y));
+    st4(o0 + 4, make_float4(dx[2].x, dx[2].y, dx[3].x, dx[3].y));
+    st4(o1, make_float4(dy[0].x, dy[0].y, dy[1].x, dy[1].y));
+    st4(o1 + 4, make_float4(dy[2].x, dy[2].y, dy[3].x, dy[3].y));
   }
   __syncthreads();
 
@@ -607,57 +861,32 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   // correlation with flipped taps; g is symmetric and dg antisymmetric, so
   //   dgray = -[ (dIx * dg|) * g-  +  (dIy * g|) * dg- ]
   // i.e. the forward gradient operators applied to dIx and dIy, negated.
-  const float scale = __ldg(P.grad_out) * P.inv_count;
-  for (int it = tid; it < C::TH * (C::TW / 8); it += C::NT) {
-    const int seg = it / C::TH, oy = it - seg * C::TH;
-    const int ox0 = 8 * seg;
-    const int gy = y0 + oy, gx0 = x0 + ox0;
+  const float scale = -__ldg(P.grad_out) * P.inv_count;
+  for (int it = tid; it < (C::TH / 2) * (C::TW / 4); it += C::NT) {
+    const int seg = it / (C::TH / 2), q = it - seg * (C::TH / 2);
+    const int ox0 = 4 * seg;
+    const int gy = y0 + 2 * q, gx0 = x0 + ox0;
     if (gy >= H || gx0 >= W) continue;
-    constexpr int WIN = C::BWIN, CEN = C::HXE - C::BW_LO;
-    float tA[WIN], tB[WIN];
-#pragma unroll
-    for (int j = 0; j < WIN; ++j) { tA[j] = 0.f; tB[j] = 0.f; }
-#pragma unroll
-    for (int i = 0; i <= 2 * C::RG; ++i) {
-      const float* ra = sdI0 + (oy + i) * C::PE + ox0 + C::BW_LO;
-      const float* rb = sdI1 + (oy + i) * C::PE + ox0 + C::BW_LO;
-      float u[WIN], v[WIN];
-#pragma unroll
-      for (int q = 0; q < WIN / 4; ++q) {
-        const float4 t = ld4(ra + 4 * q);
-        u[4 * q] = t.x; u[4 * q + 1] = t.y; u[4 * q + 2] = t.z; u[4 * q + 3] = t.w;
-        const float4 s = ld4(rb + 4 * q);
-        v[4 * q] = s.x; v[4 * q + 1] = s.y; v[4 * q + 2] = s.z; v[4 * q + 3] = s.w;
-      }
-#pragma unroll
-      for (int j = CEN - C::RG; j < CEN + 8 + C::RG; ++j) {
-        if (i != C::RG) tA[j] = fmaf(tp.dg[i], u[j], tA[j]);
-        tB[j] = fmaf(tp.g[i], v[j], tB[j]);
-      }
-    }
-    float dgr[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int t = 0; t <= 2 * C::RG; ++t) {
-        s = fmaf(tp.g[t], tA[CEN + j + t - C::RG], s);
-        if (t != C::RG) s = fmaf(tp.dg[t], tB[CEN + j + t - C::RG], s);
-      }
-      dgr[j] = -s * scale;
-    }
-    float* o = P.d_img + img_off + (size_t)gy * W + gx0;
+    float2 ax[4], ay[4];
+    grad_rowpair<C::RG, 4, C::BWIN, C::HXE - C::BW_LO, C::PE, false>(sdI0 + q * C::PE + 2 * (ox0 + C::BW_LO),
+                                                                   sdI1 + q * C::PE + 2 * (ox0 + C::BW_LO), tp, ax, ay);
     const float coef[3] = {kGrayR, kGrayG, kGrayB};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (P.vec4) {
-        st4(o + c * plane, make_float4(coef[c] * dgr[0], coef[c] * dgr[1], coef[c] * dgr[2], coef[c] * dgr[3]));
-        if (gx0 + 4 < W)
-          st4(o + c * plane + 4, make_float4(coef[c] * dgr[4], coef[c] * dgr[5], coef[c] * dgr[6], coef[c] * dgr[7]));
-      } else {
+    for (int hf = 0; hf < 2; ++hf) {
+      if (gy + hf >= H) continue;
+      float dgr[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (gx0 + j < W) o[c * plane + j] = coef[c] * dgr[j];
+      for (int j = 0; j < 4; ++j) dgr[j] = ((hf ? ax[j].y : ax[j].x) + (hf ? ay[j].y : ay[j].x)) * scale;
+      float* o = P.d_img + img_off + (size_t)(gy + hf) * W + gx0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (P.vec4) {
+          st4(o + c * plane, make_float4(coef[c] * dgr[0], coef[c] * dgr[1], coef[c] * dgr[2], coef[c] * dgr[3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (gx0 + j < W) o[c * plane + j] = coef[c] * dgr[j];
+        }
       }
     }
   }

@@ -14,7 +14,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -51,6 +53,14 @@ struct BlockCtx {
   std::vector<uint64_t> warp_xchg;  // 32 slots per warp
   unsigned char* dyn_smem = nullptr;
   unsigned nthreads = 0;
+  std::mutex named_mu;
+  std::map<int, std::unique_ptr<std::barrier<>>> named;  // bar.sync/bar.arrive id -> barrier(count)
+  std::barrier<>* named_bar(int id, int count) {
+    std::lock_guard<std::mutex> lk(named_mu);
+    auto& b = named[id];
+    if (!b) b = std::make_unique<std::barrier<>>(count);
+    return b.get();
+  }
 };
 inline BlockCtx* g_block = nullptr;
 inline dim3 g_blockDim, g_gridDim;
@@ -124,6 +134,10 @@ static inline void __syncthreads() { emu::g_block->bar->arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {
   emu::g_block->warp_bar[emu::t_linear_tid / 32]->arrive_and_wait();
 }
+// named barriers (PTX bar.sync / bar.arrive with an id and a participating-thread count)
+static inline void emu_bar_sync(int id, int count) { emu::g_block->named_bar(id, count)->arrive_and_wait(); }
+static inline void emu_bar_arrive(int id, int count) { (void)emu::g_block->named_bar(id, count)->arrive(); }
+static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) {

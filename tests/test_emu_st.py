@@ -15,10 +15,10 @@ def lib():
     return emu_lib()
 
 
-@pytest.fixture(params=[0, 1, 2])
+@pytest.fixture(params=[0, 1, 2, 3, 4])
 def tile_cfg(request, monkeypatch):
     monkeypatch.setenv("SRST_ST_FWD_CFG", str(request.param))
-    monkeypatch.setenv("SRST_ST_BWD_CFG", str(request.param))
+    monkeypatch.setenv("SRST_ST_BWD_CFG", str(min(request.param, 2)))
     return request.param
 
 
