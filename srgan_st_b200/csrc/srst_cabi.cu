@@ -115,8 +115,10 @@ static int launch_st_backward(StBwdParams<C::RG, C::RK> P, void* stream) {
 static int pick_fwd_cfg(int H, int W) {
   const int forced = env_int("SRST_ST_FWD_CFG", -1);
   if (forced >= 0 && forced <= 4) return forced;
-  if (W <= 96) return 1;
-  return 0;
+  // measured on B200 (profiles/r01_v2_tile_sweep.log): square 48x48 tiles win on 96-wide crops,
+  // the 3-CTA/SM 32x64 tile wins on large images
+  if (W <= 96) return 2;
+  return 3;
 }
 static int pick_bwd_cfg(int H, int W) {
   const int forced = env_int("SRST_ST_BWD_CFG", -1);
