@@ -308,6 +308,13 @@ def run_gpu(args):
 
         if with_e2e:
             crit = StructureTensorLoss()
+            bucket = None
+            if world > 1:
+                # the step's only exchange: one all-reduce of a generator-sized flat
+                # gradient bucket (SRResNet: 1 547 350 fp32 params, model.py:193) with the loss in its tail
+                from srgan_st_b200.dist import FlatGradBucket
+                gen_like = torch.nn.Parameter(torch.zeros(1547350, device=dev))
+                bucket = FlatGradBucket([gen_like])
             n_host = 4
             host = [(sr.cpu().pin_memory(), hr.cpu().pin_memory()) for sr, hr in pool[:n_host]]
             sr_d = torch.empty(B, 3, H, W, device=dev)
@@ -320,6 +327,9 @@ def run_gpu(args):
                 x = sr_d.detach().requires_grad_(True)
                 l = crit(x, hr_d)
                 l.backward()
+                if bucket is not None:
+                    bucket.set_loss(l)
+                    l = bucket.all_reduce_mean()
                 return l.item()  # device->host read of the step's result, as train.py:141
 
             for i in range(max(Wm, 3)):
@@ -334,7 +344,9 @@ def run_gpu(args):
             ms = max_over_ranks(e0.elapsed_time(e1))
             res["e2e"] = {"value": world * B * K / (ms * 1e-3), "unit": UNIT,
                           "h2d_bytes_per_step": bytes_pair, "d2h_bytes_per_step": 4,
-                          "ms_per_step": ms / K}
+                          "ms_per_step": ms / K,
+                          "collective": (f"one NCCL all-reduce of {bucket.nbytes} B (generator-grad bucket + loss) per step"
+                                         if bucket is not None else "none (1 GPU)")}
         res["clocks"] = sampler.stop() if rank == 0 else None
         del pool
         torch.cuda.empty_cache()
