@@ -28,12 +28,15 @@ using FwdB = StFwdCfg<32, 96, 8, 4, 0, 2, 8, 2>;    // 96-wide training crops: a
 using FwdC = StFwdCfg<48, 48, 12, 4, 0, 2, 8, 2>;   // square quarter of a 96x96 crop
 using FwdD = StFwdCfg<32, 64, 16, 4, 0, 2, 8, 3>;   // small footprint: three CTAs per SM
 using FwdE = StFwdCfg<40, 64, 10, 8, 0, 2, 8, 2, true>;  // experiment: cp.async RGB staging, 8-column gradient items
+using FwdF = StFwdCfg<24, 64, 12, 4, 0, 2, 8, 4>;   // experiment: four small CTAs per SM
+using FwdG = StFwdCfg<32, 32, 16, 4, 0, 2, 8, 4>;   // experiment: four 128-thread CTAs per SM
+using FwdH = StFwdCfg<48, 64, 12, 4, 0, 2, 8, 2>;   // experiment: taller tile, two CTAs per SM
 //                         TH  TW  RS   NT  RG RK MINB
 using BwdA = StBwdCfg<24, 64, 14, 256, 2, 8, 2>;  // large images
 using BwdB = StBwdCfg<16, 96, 10, 256, 2, 8, 2>;  // 96-wide training crops
 using BwdC = StBwdCfg<32, 64, 12, 352, 2, 8, 1>;  // one big CTA per SM
 
-constexpr int kMinFwdTH = 32, kMinFwdTW = 48;  // finest compiled forward tiling (workspace sizing)
+constexpr int kMinFwdTH = 24, kMinFwdTW = 32;  // finest compiled forward tiling (workspace sizing)
 
 static int sm_count() {
 #ifdef SRST_EMULATE
@@ -114,7 +117,7 @@ static int launch_st_backward(StBwdParams<C::RG, C::RK> P, void* stream) {
 
 static int pick_fwd_cfg(int H, int W) {
   const int forced = env_int("SRST_ST_FWD_CFG", -1);
-  if (forced >= 0 && forced <= 4) return forced;
+  if (forced >= 0 && forced <= 7) return forced;
   // measured on B200 (profiles/r01_v2_tile_sweep.log): square 48x48 tiles win on 96-wide crops,
   // the 3-CTA/SM 32x64 tile wins on large images
   if (W <= 96) return 2;
@@ -183,6 +186,9 @@ int srst_st_forward(const float* sr, const float* hr, int B, int H, int W, const
     case 2: return launch_st_forward<FwdC>(P, stream);
     case 3: return launch_st_forward<FwdD>(P, stream);
     case 4: return launch_st_forward<FwdE>(P, stream);
+    case 5: return launch_st_forward<FwdF>(P, stream);
+    case 6: return launch_st_forward<FwdG>(P, stream);
+    case 7: return launch_st_forward<FwdH>(P, stream);
     default: return launch_st_forward<FwdA>(P, stream);
   }
 }

@@ -169,6 +169,152 @@ SRST_DEV float st_pixel(float a, float b, float c, float e, float f, float h, bo
   return d;
 }
 
+// Packed form of st_pixel: the same chain on TWO pixels at once (.x = even row, .y = odd row of a
+// row pair), every add/mul/fma issued as FADD2/FMUL2/FFMA2; SFU ops and selects stay per lane.
+struct StPixelGrad2 {
+  float2 da, db, dc, de, df, dh;
+};
+SRST_DEV float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+SRST_DEV float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+SRST_DEV float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+SRST_DEV float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, neg2(b)); }
+SRST_DEV float2 rsq2(float2 a) { return make_float2(fast_rsqrt(a.x), fast_rsqrt(a.y)); }
+SRST_DEV float2 rcp2(float2 a) { return make_float2(fast_rcp(a.x), fast_rcp(a.y)); }
+SRST_DEV float2 lg22(float2 a) { return make_float2(fast_lg2(a.x), fast_lg2(a.y)); }
+SRST_DEV float2 rsqrt_nr2(float2 x) {
+  const float2 y = rsq2(x);
+  return mul2(y, ffma2(mul2(bcast2(-0.5f), x), mul2(y, y), bcast2(1.5f)));
+}
+
+template <bool WANT_SR, bool WANT_HR>
+SRST_DEV float2 st_pixel2(float2 a, float2 b, float2 c, float2 e, float2 f, float2 h, bool normalize, float eps,
+                          StPixelGrad2& G) {
+  constexpr float kLn2 = 0.6931471805599453f;
+  const float2 eps2 = bcast2(eps);
+  float2 iq1 = bcast2(1.0f), iq2 = bcast2(1.0f);
+  if (normalize) {
+    iq1 = rsqrt_nr2(add2(ffma2(a, b, neg2(mul2(c, c))), eps2));
+    iq2 = rsqrt_nr2(add2(ffma2(e, f, neg2(mul2(h, h))), eps2));
+  }
+  const float2 ah = mul2(a, iq1), bh = mul2(b, iq1), ch = mul2(c, iq1);
+  const float2 eh = mul2(e, iq2), fh = mul2(f, iq2), hh = mul2(h, iq2);
+  const float2 nchh = neg2(mul2(ch, hh));
+  const float2 A = ffma2(bh, eh, nchh);
+  const float2 Bm = ffma2(ah, fh, nchh);
+  const float2 Cc = ffma2(bh, hh, neg2(mul2(ch, fh)));
+  const float2 Dd = ffma2(ah, hh, neg2(mul2(ch, eh)));
+  const float2 T = add2(A, Bm);
+  const float2 amb = sub2(A, Bm);
+  const float2 disc_raw = ffma2(amb, amb, mul2(bcast2(4.0f), mul2(Cc, Dd)));
+  const float2 disc = make_float2((disc_raw.x < eps) ? eps : disc_raw.x, (disc_raw.y < eps) ? eps : disc_raw.y);
+  const float2 ir = rsq2(disc);
+  const float2 r = mul2(disc, ir);
+  const float2 hT = mul2(bcast2(0.5f), T);
+  const float2 l1r = ffma2(bcast2(-0.5f), r, hT), l2r = ffma2(bcast2(0.5f), r, hT);
+  const float2 l1 = make_float2((l1r.x < 1.0f) ? 1.0f : l1r.x, (l1r.y < 1.0f) ? 1.0f : l1r.y);
+  const float2 l2 = make_float2((l2r.x < 1.0f) ? 1.0f : l2r.x, (l2r.y < 1.0f) ? 1.0f : l2r.y);
+  const float2 L1 = mul2(bcast2(kLn2), lg22(l1)), L2 = mul2(bcast2(kLn2), lg22(l2));
+  const float2 arg = ffma2(L1, L1, ffma2(L2, L2, eps2));
+  const float2 inv_d = rsq2(arg);
+  const float2 d = mul2(arg, inv_d);
+  if (WANT_SR || WANT_HR) {
+    const float2 q1 = mul2(mul2(L1, inv_d), rcp2(l1)), q2 = mul2(mul2(L2, inv_d), rcp2(l2));
+    // clamp sub-gradients (pass where raw >= 1); x*0 keeps NaN like torch
+    const float2 dl1 = make_float2((l1r.x >= 1.0f) ? q1.x : l1r.x * 0.0f, (l1r.y >= 1.0f) ? q1.y : l1r.y * 0.0f);
+    const float2 dl2 = make_float2((l2r.x >= 1.0f) ? q2.x : l2r.x * 0.0f, (l2r.y >= 1.0f) ? q2.y : l2r.y * 0.0f);
+    const float2 dr = mul2(bcast2(0.5f), sub2(dl2, dl1));
+    const float2 dq = mul2(mul2(bcast2(0.5f), dr), ir);
+    const float2 ddisc = make_float2((disc_raw.x >= eps) ? dq.x : disc_raw.x * 0.0f,
+                                     (disc_raw.y >= eps) ? dq.y : disc_raw.y * 0.0f);
+    const float2 dT = ffma2(mul2(bcast2(2.0f), T), ddisc, mul2(bcast2(0.5f), add2(dl1, dl2)));
+    const float2 dd4 = mul2(bcast2(4.0f), ddisc);
+    const float2 dA = ffma2(neg2(dd4), Bm, dT);
+    const float2 dB = ffma2(neg2(dd4), A, dT);
+    const float2 dC = mul2(dd4, Dd);
+    const float2 dD = mul2(dd4, Cc);
+    if (WANT_SR) {
+      const float2 dah = ffma2(dB, fh, mul2(dD, hh));
+      const float2 dbh = ffma2(dA, eh, mul2(dC, hh));
+      const float2 dch = neg2(ffma2(add2(dA, dB), hh, ffma2(dC, fh, mul2(dD, eh))));
+      if (normalize) {
+        const float2 s = ffma2(a, dah, ffma2(b, dbh, mul2(c, dch)));
+        const float2 ddet = mul2(mul2(mul2(bcast2(-0.5f), s), mul2(iq1, iq1)), iq1);
+        G.da = ffma2(dah, iq1, mul2(ddet, b));
+        G.db = ffma2(dbh, iq1, mul2(ddet, a));
+        G.dc = ffma2(dch, iq1, mul2(mul2(bcast2(-2.0f), ddet), c));
+      } else {
+        G.da = dah; G.db = dbh; G.dc = dch;
+      }
+    }
+    if (WANT_HR) {
+      const float2 deh = ffma2(dA, bh, neg2(mul2(dD, ch)));
+      const float2 dfh = ffma2(dB, ah, neg2(mul2(dC, ch)));
+      const float2 dhh = ffma2(neg2(add2(dA, dB)), ch, ffma2(dC, bh, mul2(dD, ah)));
+      if (normalize) {
+        const float2 s = ffma2(e, deh, ffma2(f, dfh, mul2(h, dhh)));
+        const float2 ddet = mul2(mul2(mul2(bcast2(-0.5f), s), mul2(iq2, iq2)), iq2);
+        G.de = ffma2(deh, iq2, mul2(ddet, f));
+        G.df = ffma2(dfh, iq2, mul2(ddet, e));
+        G.dh = ffma2(dhh, iq2, mul2(mul2(bcast2(-2.0f), ddet), h));
+      } else {
+        G.de = deh; G.df = dfh; G.dh = dhh;
+      }
+    }
+  }
+  return d;
+}
+
+// Chain + stores for one thread's 2 x 4 pixels; returns the sum of the valid distances.
+template <bool WANT_HR>
+SRST_DEV float st_chain_store(const float2 (&S1)[3][4], const float2 (&S2)[3][4], bool norm, float eps,
+                              float* __restrict__ ds_sr, float* __restrict__ ds_hr, size_t img_off, int H, int W,
+                              int gy0, int gx0, bool vec4) {
+  float lsum = 0.f;
+  float2 gs[3][4], gh[3][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    StPixelGrad2 G;
+    G.da = G.db = G.dc = G.de = G.df = G.dh = make_float2(0.f, 0.f);
+    const float2 d = st_pixel2<true, WANT_HR>(S1[0][j], S1[1][j], S1[2][j], S2[0][j], S2[1][j], S2[2][j], norm, eps, G);
+    const bool okx = gx0 + j < W;
+    lsum += (okx && gy0 < H) ? d.x : 0.f;
+    lsum += (okx && gy0 + 1 < H) ? d.y : 0.f;
+    gs[0][j] = G.da; gs[1][j] = G.db; gs[2][j] = G.dc;
+    if (WANT_HR) { gh[0][j] = G.de; gh[1][j] = G.df; gh[2][j] = G.dh; }
+  }
+  if (gx0 >= W) return lsum;
+  const size_t plane = (size_t)H * W;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    if (gy0 + hf >= H) continue;
+    const size_t o = img_off + (size_t)(gy0 + hf) * W + gx0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v0 = hf ? gs[c][0].y : gs[c][0].x, v1 = hf ? gs[c][1].y : gs[c][1].x;
+      const float v2 = hf ? gs[c][2].y : gs[c][2].x, v3 = hf ? gs[c][3].y : gs[c][3].x;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+      if (WANT_HR) {
+        w0 = hf ? gh[c][0].y : gh[c][0].x; w1 = hf ? gh[c][1].y : gh[c][1].x;
+        w2 = hf ? gh[c][2].y : gh[c][2].x; w3 = hf ? gh[c][3].y : gh[c][3].x;
+      }
+      if (vec4) {
+        if (ds_sr) st4(ds_sr + o + c * plane, make_float4(v0, v1, v2, v3));
+        if (WANT_HR) st4(ds_hr + o + c * plane, make_float4(w0, w1, w2, w3));
+      } else {
+        const float vv[4] = {v0, v1, v2, v3}, ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (gx0 + j < W) {
+            if (ds_sr) ds_sr[o + c * plane + j] = vv[j];
+            if (WANT_HR) ds_hr[o + c * plane + j] = ww[j];
+          }
+        }
+      }
+    }
+  }
+  return lsum;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Shared building blocks (row-pair interleaved planes: float2 at rp*PITCH + 2*col)
 // ------------------------------------------------------------------------------------------------
@@ -577,7 +723,7 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
   }
 
   // ---- compute warps ----
-  const bool want_sr = P.ds_sr != nullptr, want_hr = P.ds_hr != nullptr;
+  const bool want_hr = P.ds_hr != nullptr;
   const bool norm = P.normalize != 0;
   const int seg = tid / (C::TH / 2), q = tid - seg * (C::TH / 2);
   float lsum = 0.f;
@@ -597,48 +743,13 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
     st_unit_tensor<C>(smem, P.sr + img_off, P.vec4 != 0, P.H, P.W, y0, x0, P.taps, tid, false, S1);
     st_unit_tensor<C>(smem, P.hr + img_off, P.vec4 != 0, P.H, P.W, y0, x0, P.taps, tid, last_tile, S2);
 
-    // Per-pixel chain on this thread's 2 x 4 pixels.
-    const int gy0 = y0 + 2 * q, gx0 = x0 + 4 * seg;
-    float g_sr[2][3][4], g_hr[2][3][4];
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a = hf ? S1[0][j].y : S1[0][j].x, bq = hf ? S1[1][j].y : S1[1][j].x, c = hf ? S1[2][j].y : S1[2][j].x;
-        const float e = hf ? S2[0][j].y : S2[0][j].x, f = hf ? S2[1][j].y : S2[1][j].x, h = hf ? S2[2][j].y : S2[2][j].x;
-        StPixelGrad G;
-        G.da = G.db = G.dc = G.de = G.df = G.dh = 0.f;
-        const float d = want_hr ? st_pixel<true, true>(a, bq, c, e, f, h, norm, P.eps, G)
-                                : st_pixel<true, false>(a, bq, c, e, f, h, norm, P.eps, G);
-        const bool ok = (gy0 + hf < P.H) && (gx0 + j < P.W);
-        lsum += ok ? d : 0.f;
-        g_sr[hf][0][j] = G.da; g_sr[hf][1][j] = G.db; g_sr[hf][2][j] = G.dc;
-        g_hr[hf][0][j] = G.de; g_hr[hf][1][j] = G.df; g_hr[hf][2][j] = G.dh;
-      }
-    }
-    if (gx0 < P.W) {
-      const size_t plane = (size_t)P.H * P.W;
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        if (gy0 + hf >= P.H) continue;
-        const size_t o = img_off + (size_t)(gy0 + hf) * P.W + gx0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          if (P.vec4) {
-            if (want_sr) st4(P.ds_sr + o + c * plane, make_float4(g_sr[hf][c][0], g_sr[hf][c][1], g_sr[hf][c][2], g_sr[hf][c][3]));
-            if (want_hr) st4(P.ds_hr + o + c * plane, make_float4(g_hr[hf][c][0], g_hr[hf][c][1], g_hr[hf][c][2], g_hr[hf][c][3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (gx0 + j < P.W) {
-                if (want_sr) P.ds_sr[o + c * plane + j] = g_sr[hf][c][j];
-                if (want_hr) P.ds_hr[o + c * plane + j] = g_hr[hf][c][j];
-              }
-            }
-          }
-        }
-      }
-    }
+    // Per-pixel chain on this thread's 2 x 4 pixels, then the ds stores.
+    if (want_hr)
+      lsum += st_chain_store<true>(S1, S2, norm, P.eps, P.ds_sr, P.ds_hr, img_off, P.H, P.W, y0 + 2 * q, x0 + 4 * seg,
+                                   P.vec4 != 0);
+    else
+      lsum += st_chain_store<false>(S1, S2, norm, P.eps, P.ds_sr, P.ds_hr, img_off, P.H, P.W, y0 + 2 * q, x0 + 4 * seg,
+                                    P.vec4 != 0);
   } while (C::NP > 0 && (tile += (int)gridDim.x) < ntiles);
 
   // Deterministic loss reduction: block partial -> workspace; the last block to finish sums all
