@@ -31,6 +31,8 @@ using FwdE = StFwdCfg<40, 64, 10, 8, 0, 2, 8, 2, true>;  // experiment: cp.async
 using FwdF = StFwdCfg<24, 64, 12, 4, 0, 2, 8, 4>;   // experiment: four small CTAs per SM
 using FwdG = StFwdCfg<32, 32, 16, 4, 0, 2, 8, 4>;   // experiment: four 128-thread CTAs per SM
 using FwdH = StFwdCfg<48, 64, 12, 4, 0, 2, 8, 2>;   // experiment: taller tile, two CTAs per SM
+using FwdI = StFwdCfg<48, 96, 12, 4, 0, 2, 8, 1>;   // experiment: half a 96x96 crop per CTA, one 576-thread CTA per SM
+using FwdJ = StFwdCfg<64, 64, 16, 4, 0, 2, 8, 1>;   // experiment: 512-thread CTA, one per SM
 //                         TH  TW  RS   NT  RG RK MINB
 using BwdA = StBwdCfg<24, 64, 14, 256, 2, 8, 2>;  // large images
 using BwdB = StBwdCfg<16, 96, 10, 256, 2, 8, 2>;  // 96-wide training crops
@@ -75,17 +77,25 @@ static int ensure_smem(K kernel, size_t bytes) {
 #endif
 }
 
+// Copies the (2*rs+1)- and (2*rk+1)-tap filters into the compiled radii (RG >= rs, RK >= rk),
+// centred and zero-padded: a filter with extra zero taps at both ends is the same filter.
 template <int RG, int RK>
-static void fill_taps(StTaps<RG, RK>& t, const float* g, const float* dg, const float* k) {
-  std::memcpy(t.g, g, sizeof(t.g));
-  std::memcpy(t.dg, dg, sizeof(t.dg));
-  std::memcpy(t.k, k, sizeof(t.k));
+static void fill_taps(StTaps<RG, RK>& t, const float* g, const float* dg, int rs, const float* k, int rk) {
+  for (int i = 0; i <= 2 * RG; ++i) {
+    const int j = i - (RG - rs);
+    t.g[i] = (j >= 0 && j <= 2 * rs) ? g[j] : 0.f;
+    t.dg[i] = (j >= 0 && j <= 2 * rs) ? dg[j] : 0.f;
+  }
+  for (int i = 0; i <= 2 * RK; ++i) {
+    const int j = i - (RK - rk);
+    t.k[i] = (j >= 0 && j <= 2 * rk) ? k[j] : 0.f;
+  }
   // tap pairs (t[u], t[u-1]) for the row-pair (FFMA2) vertical passes
   for (int u = 0; u <= 2 * RG + 1; ++u) {
-    t.gp[u] = make_float2(u <= 2 * RG ? g[u] : 0.f, u >= 1 ? g[u - 1] : 0.f);
-    t.dgp[u] = make_float2(u <= 2 * RG ? dg[u] : 0.f, u >= 1 ? dg[u - 1] : 0.f);
+    t.gp[u] = make_float2(u <= 2 * RG ? t.g[u] : 0.f, u >= 1 ? t.g[u - 1] : 0.f);
+    t.dgp[u] = make_float2(u <= 2 * RG ? t.dg[u] : 0.f, u >= 1 ? t.dg[u - 1] : 0.f);
   }
-  for (int u = 0; u <= 2 * RK + 1; ++u) t.kp[u] = make_float2(u <= 2 * RK ? k[u] : 0.f, u >= 1 ? k[u - 1] : 0.f);
+  for (int u = 0; u <= 2 * RK + 1; ++u) t.kp[u] = make_float2(u <= 2 * RK ? t.k[u] : 0.f, u >= 1 ? t.k[u - 1] : 0.f);
 }
 
 template <class C>
@@ -117,7 +127,7 @@ static int launch_st_backward(StBwdParams<C::RG, C::RK> P, void* stream) {
 
 static int pick_fwd_cfg(int H, int W) {
   const int forced = env_int("SRST_ST_FWD_CFG", -1);
-  if (forced >= 0 && forced <= 7) return forced;
+  if (forced >= 0 && forced <= 9) return forced;
   // measured on B200 (profiles/r01_v2_tile_sweep.log): square 48x48 tiles win on 96-wide crops,
   // the 3-CTA/SM 32x64 tile wins on large images
   if (W <= 96) return 2;
@@ -153,7 +163,10 @@ const char* srst_error_string(int code) {
   return "srst: unknown error";
 }
 
-int srst_st_supported(int r_sigma, int r_rho) { return (r_sigma == 2 && r_rho == 8) ? 1 : 0; }
+// Compiled radius classes: r_sigma is padded up to 2 or 4, r_rho up to 4, 8 or 12 (zero taps).
+// (2, 8) -- the reference default sigma=0.5, rho=2.0 -- has the tuned tile shapes; the other
+// classes use one generic shape each.
+int srst_st_supported(int r_sigma, int r_rho) { return (r_sigma >= 1 && r_sigma <= 4 && r_rho >= 1 && r_rho <= 12) ? 1 : 0; }
 
 size_t srst_st_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
@@ -162,6 +175,83 @@ size_t srst_st_workspace_bytes(int B, int H, int W) {
   return ((tiles + 4) * sizeof(float) + 255) / 256 * 256;
 }
 
+}  // extern "C"
+
+namespace srst {
+
+struct StCall {
+  const float *a, *b, *grad_out;  // forward: sr, hr ; backward: img, ds, grad_out
+  float *o0, *o1, *loss_out;      // forward: ds_sr, ds_hr ; backward: d_img
+  int B, H, W, normalize, vec4;
+  float eps;
+  void* workspace;
+  const float *g, *dg, *k;
+  int rs, rk;
+  void* stream;
+};
+
+template <int RG, int RK>
+static int st_forward_rr(const StCall& c) {
+  StFwdParams<RG, RK> P;
+  P.sr = c.a; P.hr = c.b; P.ds_sr = c.o0; P.ds_hr = c.o1;
+  P.ticket = reinterpret_cast<unsigned int*>(c.workspace);
+  P.partials = reinterpret_cast<float*>(c.workspace) + 4;
+  P.loss_out = c.loss_out;
+  P.B = c.B; P.H = c.H; P.W = c.W; P.tiles_x = P.tiles_y = 0;
+  P.normalize = c.normalize; P.vec4 = c.vec4; P.eps = c.eps;
+  P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
+  fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
+  if constexpr (RG == 2 && RK == 8) {
+    switch (pick_fwd_cfg(c.H, c.W)) {
+      case 0: return launch_st_forward<FwdA>(P, c.stream);
+      case 1: return launch_st_forward<FwdB>(P, c.stream);
+      case 2: return launch_st_forward<FwdC>(P, c.stream);
+      case 4: return launch_st_forward<FwdE>(P, c.stream);
+      case 5: return launch_st_forward<FwdF>(P, c.stream);
+      case 6: return launch_st_forward<FwdG>(P, c.stream);
+      case 7: return launch_st_forward<FwdH>(P, c.stream);
+      case 8: return launch_st_forward<FwdI>(P, c.stream);
+      case 9: return launch_st_forward<FwdJ>(P, c.stream);
+      default: return launch_st_forward<FwdD>(P, c.stream);
+    }
+  } else {
+    return launch_st_forward<StFwdCfg<32, 64, 16, 4, 0, RG, RK, (RK <= 8 ? 2 : 1)>>(P, c.stream);
+  }
+}
+
+template <int RG, int RK>
+static int st_backward_rr(const StCall& c) {
+  StBwdParams<RG, RK> P;
+  P.img = c.a; P.ds = c.b; P.grad_out = c.grad_out; P.d_img = c.o0;
+  P.B = c.B; P.H = c.H; P.W = c.W; P.tiles_x = P.tiles_y = 0;
+  P.vec4 = c.vec4;
+  P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
+  fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
+  if constexpr (RG == 2 && RK == 8) {
+    switch (pick_bwd_cfg(c.H, c.W)) {
+      case 1: return launch_st_backward<BwdB>(P, c.stream);
+      case 2: return launch_st_backward<BwdC>(P, c.stream);
+      default: return launch_st_backward<BwdA>(P, c.stream);
+    }
+  } else {
+    return launch_st_backward<StBwdCfg<24, 64, (24 + 2 * RG) / 2, 256, RG, RK, (RK <= 8 ? 2 : 1)>>(P, c.stream);
+  }
+}
+
+static int st_dispatch(const StCall& c, bool forward) {
+  const int rg = c.rs <= 2 ? 2 : 4;
+  const int rk = c.rk <= 4 ? 4 : (c.rk <= 8 ? 8 : 12);
+#define SRST_RR(RG_, RK_) \
+  if (rg == RG_ && rk == RK_) return forward ? st_forward_rr<RG_, RK_>(c) : st_backward_rr<RG_, RK_>(c);
+  SRST_RR(2, 8) SRST_RR(2, 4) SRST_RR(2, 12) SRST_RR(4, 4) SRST_RR(4, 8) SRST_RR(4, 12)
+#undef SRST_RR
+  return SRST_E_UNSUPPORTED;
+}
+
+}  // namespace srst
+
+extern "C" {
+
 int srst_st_forward(const float* sr, const float* hr, int B, int H, int W, const float* g, const float* dg,
                     int r_sigma, const float* k, int r_rho, int normalize, float eps, float* loss_out,
                     float* ds_sr, float* ds_hr, void* workspace, size_t workspace_bytes, void* stream) {
@@ -169,28 +259,13 @@ int srst_st_forward(const float* sr, const float* hr, int B, int H, int W, const
   if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
   if (!workspace || !aligned16(workspace) || workspace_bytes < srst_st_workspace_bytes(B, H, W))
     return SRST_E_WORKSPACE;
-  StFwdParams<2, 8> P;
-  P.sr = sr; P.hr = hr; P.ds_sr = ds_sr; P.ds_hr = ds_hr;
-  P.ticket = reinterpret_cast<unsigned int*>(workspace);
-  P.partials = reinterpret_cast<float*>(workspace) + 4;
-  P.loss_out = loss_out;
-  P.B = B; P.H = H; P.W = W; P.tiles_x = P.tiles_y = 0;
-  P.normalize = normalize ? 1 : 0;
-  P.vec4 = (W % 4 == 0 && aligned16(sr) && aligned16(hr) && (!ds_sr || aligned16(ds_sr)) &&
+  StCall c{};
+  c.a = sr; c.b = hr; c.o0 = ds_sr; c.o1 = ds_hr; c.loss_out = loss_out;
+  c.B = B; c.H = H; c.W = W; c.normalize = normalize ? 1 : 0; c.eps = eps;
+  c.vec4 = (W % 4 == 0 && aligned16(sr) && aligned16(hr) && (!ds_sr || aligned16(ds_sr)) &&
             (!ds_hr || aligned16(ds_hr))) ? 1 : 0;
-  P.eps = eps;
-  P.inv_count = (float)(1.0 / ((double)B * H * W));
-  fill_taps(P.taps, g, dg, k);
-  switch (pick_fwd_cfg(H, W)) {
-    case 1: return launch_st_forward<FwdB>(P, stream);
-    case 2: return launch_st_forward<FwdC>(P, stream);
-    case 3: return launch_st_forward<FwdD>(P, stream);
-    case 4: return launch_st_forward<FwdE>(P, stream);
-    case 5: return launch_st_forward<FwdF>(P, stream);
-    case 6: return launch_st_forward<FwdG>(P, stream);
-    case 7: return launch_st_forward<FwdH>(P, stream);
-    default: return launch_st_forward<FwdA>(P, stream);
-  }
+  c.workspace = workspace; c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;
+  return st_dispatch(c, true);
 }
 
 int srst_st_backward(const float* img, const float* ds, const float* grad_out, int B, int H, int W,
@@ -198,17 +273,12 @@ int srst_st_backward(const float* img, const float* ds, const float* grad_out, i
                      void* stream) {
   if (!img || !ds || !grad_out || !g || !dg || !k || !d_img || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
   if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
-  StBwdParams<2, 8> P;
-  P.img = img; P.ds = ds; P.grad_out = grad_out; P.d_img = d_img;
-  P.B = B; P.H = H; P.W = W; P.tiles_x = P.tiles_y = 0;
-  P.vec4 = (W % 4 == 0 && aligned16(img) && aligned16(d_img) && aligned16(ds)) ? 1 : 0;
-  P.inv_count = (float)(1.0 / ((double)B * H * W));
-  fill_taps(P.taps, g, dg, k);
-  switch (pick_bwd_cfg(H, W)) {
-    case 1: return launch_st_backward<BwdB>(P, stream);
-    case 2: return launch_st_backward<BwdC>(P, stream);
-    default: return launch_st_backward<BwdA>(P, stream);
-  }
+  StCall c{};
+  c.a = img; c.b = ds; c.grad_out = grad_out; c.o0 = d_img;
+  c.B = B; c.H = H; c.W = W;
+  c.vec4 = (W % 4 == 0 && aligned16(img) && aligned16(d_img) && aligned16(ds)) ? 1 : 0;
+  c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;
+  return st_dispatch(c, false);
 }
 
 }  // extern "C"

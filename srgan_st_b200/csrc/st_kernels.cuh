@@ -844,12 +844,18 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
     const float* dsb = P.ds + img_off;
     constexpr int C4 = C::VW / 4;
     if (P.vec4) {
-      for (int it = tid; it < 3 * C::SH * C4; it += C::NT) {
-        const int c4 = it % C4, rc = it / C4;
-        const int r = rc % C::SH, c = rc / C::SH;
+      // (plane c, row r, 16-byte column group c4) walked incrementally: no div/mod in the loop
+      constexpr int DC4 = C::NT % C4, DR = C::NT / C4;
+      static_assert(DR + 1 < C::SH, "staging walk assumes at most one row wrap per step");
+      int c4 = tid % C4, r = tid / C4, c = 0;
+      while (r >= C::SH) { r -= C::SH; ++c; }
+      while (c < 3) {
         const int gy = yv0 + r, gx = xv0 + 4 * c4;
         const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
         cp_async16(sS + (c * C::SH + r) * C::VW + 4 * c4, ok ? dsb + c * plane + (size_t)gy * W + gx : dsb, ok);
+        c4 += DC4; r += DR;
+        if (c4 >= C4) { c4 -= C4; ++r; }
+        if (r >= C::SH) { r -= C::SH; ++c; }
       }
       cp_async_commit();
     } else {

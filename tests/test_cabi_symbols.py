@@ -37,7 +37,8 @@ def test_no_compute_entry_points_that_need_no_gpu():
     lib = _cabi.lib()
     assert lib.srst_version() == 100
     assert lib.srst_st_supported(2, 8) == 1
-    assert lib.srst_st_supported(3, 3) == 0
+    assert lib.srst_st_supported(4, 12) == 1 and lib.srst_st_supported(1, 3) == 1   # padded radius classes
+    assert lib.srst_st_supported(5, 8) == 0 and lib.srst_st_supported(2, 13) == 0
     assert lib.srst_st_workspace_bytes(16, 96, 96) >= 16 * 3 * 2 * 4
     assert lib.srst_st_workspace_bytes(0, 96, 96) == 0
     assert b"workspace" in lib.srst_error_string(-3)

@@ -57,3 +57,25 @@ def test_emulated_grad_out_scaling_and_nonorm(lib):
     zn = golden("st_rand_nonorm_1x24x36")
     c = emu_st(lib, zn["sr"], zn["hr"], taps, normalize=False)
     assert rel_err(c["loss"], zn["loss"]) < 1e-5 and np.abs(c["d_sr"]).max() == 0.0
+
+
+@pytest.mark.parametrize("sigma,rho", [(1.0, 2.5), (0.3, 1.0), (0.75, 1.5), (0.5, 3.0)])
+def test_emulated_other_filter_radii(lib, sigma, rho):
+    """Non-default sigma/rho run through the padded radius classes (odd radii get zero taps)."""
+    rng = np.random.default_rng(int(10 * sigma + rho))
+    sr = rng.random((1, 3, 40, 72), dtype=np.float32)
+    hr = rng.random((1, 3, 40, 72), dtype=np.float32)
+    taps = (*O.gaussian_taps(sigma, True), O.gaussian_taps(rho))
+    out = emu_st(lib, sr, hr, taps)
+    ref = O.st_loss(sr, hr, taps=taps)
+    assert rel_err(out["loss"], ref["loss"]) < 1e-5
+    assert maxnorm_err(out["d_sr"], ref["d_sr"]) < 1e-4
+
+
+def test_emulated_golden_sigma1_rho25(lib):
+    z = golden("st_rand_s1_r25_1x32x40")
+    taps = (z["g"], z["dg"], z["k"])
+    out = emu_st(lib, z["sr"], z["hr"], taps, want_hr=True)
+    assert rel_err(out["loss"], z["loss"]) < 1e-5
+    ref = O.st_loss(z["sr"], z["hr"], taps=taps, want_hr_grad=True)
+    assert maxnorm_err(out["d_sr"], ref["d_sr"]) < 1e-4 and maxnorm_err(out["d_hr"], ref["d_hr"]) < 1e-4

@@ -144,3 +144,32 @@ def test_rejects_what_the_kernels_cannot_do():
         m(a.cuda().half(), a.cuda().half())
     with pytest.raises(ValueError):
         m(a.cuda()[:, :2], a.cuda()[:, :2])
+
+
+@pytest.mark.parametrize("sigma,rho", [(1.0, 2.5), (0.3, 1.0), (0.75, 1.5), (0.5, 3.0), (1.0, 1.0)])
+def test_other_filter_radii_match_oracle(sigma, rho):
+    rng = np.random.default_rng(int(10 * sigma + rho))
+    sr = rng.random((2, 3, 100, 152), dtype=np.float32)
+    hr = rng.random((2, 3, 100, 152), dtype=np.float32)
+    loss, d_sr, d_hr = _run(sr, hr, sigma=sigma, rho=rho)
+    ref = O.st_loss(sr, hr, sigma=sigma, rho=rho, want_hr_grad=True)
+    assert rel_err(loss, ref["loss"]) < 1e-5
+    assert maxnorm_err(d_sr, ref["d_sr"]) < 1e-4 and maxnorm_err(d_hr, ref["d_hr"]) < 1e-4
+
+
+def test_golden_sigma1_rho25_matches_reference():
+    z = golden("st_rand_s1_r25_1x32x40")
+    loss, d_sr, d_hr = _run(z["sr"], z["hr"], sigma=1.0, rho=2.5)
+    ref = O.st_loss(z["sr"], z["hr"], taps=(z["g"], z["dg"], z["k"]), want_hr_grad=True)
+    assert rel_err(loss, z["loss"]) < 1e-5
+    assert maxnorm_err(d_sr, ref["d_sr"]) < 1e-4
+    assert maxnorm_err(d_sr, z["d_sr"]) < 1e-4 + maxnorm_err(z["d_sr"], ref["d_sr"])
+
+
+def test_unsupported_radius_raises():
+    from srgan_st_b200 import StructureTensorLoss
+    a = torch.rand(1, 3, 32, 32, device="cuda")
+    with pytest.raises(NotImplementedError):
+        StructureTensorLoss(sigma=2.0)(a, a)      # radius 8 > 4
+    with pytest.raises(NotImplementedError):
+        StructureTensorLoss(rho=4.0)(a, a)        # radius 16 > 12

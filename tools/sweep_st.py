@@ -72,7 +72,7 @@ def run(B, H, W, iters=40):
     px = B * H * W
     for cfg in FWD_CFGS:
         os.environ["SRST_ST_FWD_CFG"] = str(cfg)
-        os.environ["SRST_ST_BWD_CFG"] = str(min(cfg, BWD_MAX))
+        os.environ["SRST_ST_BWD_CFG"] = str(cfg % (BWD_MAX + 1))
         tf, tb = timeit(fwd), timeit(bwd)
         print(f"B={B:3d} {H}x{W} cfg={cfg}: fwd {tf*1e3:8.1f} us ({24*px/tf/1e6/HBM*100:5.1f}% HBM)  "
               f"bwd {tb*1e3:8.1f} us ({36*px/tb/1e6/HBM*100:5.1f}% HBM)  pair {60*px/(tf+tb)/1e6/HBM*100:5.1f}%  "
