@@ -538,6 +538,7 @@ template <int TH_, int TW_, int RS_, int CSB_, int NP_, int RG_, int RK_, int MI
 struct StFwdCfg {
   static constexpr int TH = TH_, TW = TW_, RS = RS_, CSB = CSB_, NP = NP_, RG = RG_, RK = RK_, MINB = MINB_;
   static constexpr bool STAGE = STAGE_;  // stage raw RGB with cp.async over D|V instead of LDG -> registers
+  static constexpr int LDEPTH = 2;       // gray-tile items (6 x LDG.128 each) in flight per thread
   static constexpr int NC = TH * TW / 8;     // one horizontal-pass item (2 rows x 4 cols) per compute thread
   static constexpr int NT = NC + NP;
   static constexpr int HXD = round_up4(RK);  // x halo of the gradient (D) and V regions
@@ -584,7 +585,7 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, bool v
       bar_sync(kBarCompute, C::NC);
       convert_staged_gray<C::GH, C::GW, C::PG, C::NC>(sG, smem, tid);
     } else {
-      load_gray_tile<C::GH, C::GW, C::PG, C::NC, 1>(sG, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, vec4, tid);
+      load_gray_tile<C::GH, C::GW, C::PG, C::NC, C::LDEPTH>(sG, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, vec4, tid);
     }
     bar_sync(kBarCompute, C::NC);
   }
