@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "st_kernels.cuh"
+#include "st_stream.cuh"
 #include "bb_kernels.cuh"
 
 namespace srst {
@@ -27,7 +28,7 @@ using FwdA = StFwdCfg<40, 64, 10, 4, 0, 2, 8, 2>;   // large images (DIV2K-sized
 using FwdB = StFwdCfg<32, 96, 8, 4, 0, 2, 8, 2>;    // 96-wide training crops: a tile spans the row
 using FwdC = StFwdCfg<48, 48, 12, 4, 0, 2, 8, 2>;   // square quarter of a 96x96 crop
 using FwdD = StFwdCfg<32, 64, 16, 4, 0, 2, 8, 3>;   // small footprint: three CTAs per SM
-using FwdE = StFwdCfg<40, 64, 10, 8, 0, 2, 8, 2, true>;  // experiment: cp.async RGB staging, 8-column gradient items
+using FwdE = StFwdCfg<32, 64, 16, 4, 64, 2, 8, 2>;  // FwdD + two producer warps, double-buffered gray tile (persistent)
 using FwdF = StFwdCfg<24, 64, 12, 4, 0, 2, 8, 4>;   // experiment: four small CTAs per SM
 using FwdG = StFwdCfg<32, 32, 16, 4, 0, 2, 8, 4>;   // experiment: four 128-thread CTAs per SM
 using FwdH = StFwdCfg<48, 64, 12, 4, 0, 2, 8, 2>;   // experiment: taller tile, two CTAs per SM
@@ -172,7 +173,7 @@ size_t srst_st_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
   // one float per CTA of the finest compiled tiling + the ticket counter, rounded to 256 bytes
   const size_t tiles = (size_t)B * ((H + kMinFwdTH - 1) / kMinFwdTH) * ((W + kMinFwdTW - 1) / kMinFwdTW);
-  return ((tiles + 4) * sizeof(float) + 255) / 256 * 256;
+  return ((tiles + 4 + 1024) * sizeof(float) + 255) / 256 * 256;  // + room for one partial per persistent CTA
 }
 
 }  // extern "C"
@@ -190,6 +191,43 @@ struct StCall {
   void* stream;
 };
 
+//                            TW  LG GR VS HC (warps per role)
+using StreamA = StStreamCfg<64, 4, 4, 5, 8>;
+
+// Streaming forward: auto-selected for (2, 8) filters on 16-byte aligned tensors when the problem
+// has enough rows per SM to keep the pipeline full; SRST_ST_STREAM=0/1 forces it off/on.
+template <class C>
+static int launch_st_stream(const StCall& c) {
+  StStreamParams P;
+  P.sr = c.a; P.hr = c.b; P.ds_sr = c.o0; P.ds_hr = c.o1;
+  P.ticket = reinterpret_cast<unsigned int*>(c.workspace);
+  P.partials = reinterpret_cast<float*>(c.workspace) + 4;
+  P.loss_out = c.loss_out;
+  P.B = c.B; P.H = c.H; P.W = c.W;
+  P.normalize = c.normalize; P.eps = c.eps;
+  P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
+  // SRST_ST_STREAM_DEBUG=1: CTA 0 dumps per-warp (work, wait) cycles at byte 2048 of the workspace
+  P.debug = env_int("SRST_ST_STREAM_DEBUG", 0) ? reinterpret_cast<long long*>(reinterpret_cast<char*>(c.workspace) + 2048) : nullptr;
+  fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
+  const int nsm = sm_count();
+  P.nstrips = (c.W + C::TW - 1) / C::TW;
+  const long long cols = (long long)c.B * P.nstrips;
+  long long want = (2LL * nsm + cols - 1) / cols;           // row segments per strip for ~2 units per SM
+  const long long max_segs = c.H / 32 > 0 ? c.H / 32 : 1;
+  if (want > max_segs) want = max_segs;
+  if (want < 1) want = 1;
+  P.segh = (int)(((c.H + want - 1) / want + 15) / 16 * 16);
+  P.nsegs = (c.H + P.segh - 1) / P.segh;
+  const long long nunits = cols * P.nsegs;
+  if (nunits > 0x7fffffffLL) return SRST_E_SHAPE;
+  P.nunits = (int)nunits;
+  int e = ensure_smem<C>(st_stream_forward_kernel<C>, C::SMEM_BYTES);
+  if (e) return e;
+  const int grid = nunits < nsm ? (int)nunits : nsm;
+  SRST_LAUNCH(st_stream_forward_kernel<C>, dim3(grid), dim3(C::NT), C::SMEM_BYTES, c.stream, P);
+  return (int)cudaGetLastError();
+}
+
 template <int RG, int RK>
 static int st_forward_rr(const StCall& c) {
   StFwdParams<RG, RK> P;
@@ -202,6 +240,7 @@ static int st_forward_rr(const StCall& c) {
   P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
   fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
+    if (c.vec4 && env_int("SRST_ST_STREAM", 0) == 1) return launch_st_stream<StreamA>(c);
     switch (pick_fwd_cfg(c.H, c.W)) {
       case 0: return launch_st_forward<FwdA>(P, c.stream);
       case 1: return launch_st_forward<FwdB>(P, c.stream);

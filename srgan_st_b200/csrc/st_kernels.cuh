@@ -460,8 +460,9 @@ SRST_DEV void prefetch_tile_l2(const float* __restrict__ base, int H, int W, int
 // pa / pb point at (first input row pair, window start column) of planes A / B; the window is WIN
 // columns wide and the CS outputs are centred at window columns CEN..CEN+CS-1.  RG+1 input row pairs
 // feed the two output rows through the tap pairs dgp / gp.
-template <int RG, int CS, int WIN, int CEN, int PITCH, bool SAME, class Taps>
-SRST_DEV void grad_rowpair(const float* pa, const float* pb, const Taps& tp, float2 (&ox)[CS], float2 (&oy)[CS]) {
+template <int RG, int CS, int WIN, int CEN, bool SAME, class Taps>
+SRST_DEV void grad_rowpair_rows(const float* const (&pa)[RG + 1], const float* const (&pb)[RG + 1], const Taps& tp,
+                                float2 (&ox)[CS], float2 (&oy)[CS]) {
   static_assert(RG % 2 == 0 && WIN % 2 == 0, "row-pair gradient needs an even radius");
   float2 tA[WIN], tB[WIN];
 #pragma unroll
@@ -471,11 +472,11 @@ SRST_DEV void grad_rowpair(const float* pa, const float* pb, const Taps& tp, flo
     float2 va[WIN], vb[WIN];
 #pragma unroll
     for (int m = 0; m < WIN / 2; ++m) {
-      const float4 t = ld4(pa + q * PITCH + 4 * m);
+      const float4 t = ld4(pa[q] + 4 * m);
       va[2 * m] = make_float2(t.x, t.y);
       va[2 * m + 1] = make_float2(t.z, t.w);
       if (!SAME) {
-        const float4 u = ld4(pb + q * PITCH + 4 * m);
+        const float4 u = ld4(pb[q] + 4 * m);
         vb[2 * m] = make_float2(u.x, u.y);
         vb[2 * m + 1] = make_float2(u.z, u.w);
       }
@@ -503,7 +504,35 @@ SRST_DEV void grad_rowpair(const float* pa, const float* pb, const Taps& tp, flo
   }
 }
 
+// Same, for planes whose RG+1 input row pairs are PITCH floats apart.
+template <int RG, int CS, int WIN, int CEN, int PITCH, bool SAME, class Taps>
+SRST_DEV void grad_rowpair(const float* pa, const float* pb, const Taps& tp, float2 (&ox)[CS], float2 (&oy)[CS]) {
+  const float* ra[RG + 1];
+  const float* rb[RG + 1];
+#pragma unroll
+  for (int q = 0; q <= RG; ++q) { ra[q] = pa + q * PITCH; rb[q] = pb + q * PITCH; }
+  grad_rowpair_rows<RG, CS, WIN, CEN, SAME>(ra, rb, tp, ox, oy);
+}
+
 // Horizontal rho-pass on a row pair, 4 output columns: out[j] = sum_t k[t] * v[CEN + j + t - RK].
+template <int RK, int CS, int WIN, int CEN, class Taps>
+SRST_DEV void smooth_h_rowpair_n(const float* row, const Taps& tp, float2 (&out)[CS]) {
+  float2 v[WIN];
+#pragma unroll
+  for (int m = 0; m < WIN / 2; ++m) {
+    const float4 t = ld4(row + 4 * m);
+    v[2 * m] = make_float2(t.x, t.y);
+    v[2 * m + 1] = make_float2(t.z, t.w);
+  }
+#pragma unroll
+  for (int j = 0; j < CS; ++j) {
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t <= 2 * RK; ++t) s = ffma2(v[CEN + j + t - RK], bcast2(tp.k[t]), s);
+    out[j] = s;
+  }
+}
+
 template <int RK, int WIN, int CEN, class Taps>
 SRST_DEV void smooth_h_rowpair(const float* row, const Taps& tp, float2 (&out)[4]) {
   float2 v[WIN];
@@ -532,7 +561,7 @@ SRST_DEV void smooth_h_rowpair(const float* row, const Taps& tp, float2 (&out)[4
 // Hand-off uses named barriers: FULL (producer arrives, consumers sync) and EMPTY (consumers
 // arrive once the gradient phase has consumed the gray tile, producer syncs).
 // ------------------------------------------------------------------------------------------------
-constexpr int kBarFull = 1, kBarEmpty = 2, kBarCompute = 3;
+constexpr int kBarFull = 1 /* +buffer (1,2) */, kBarCompute = 3, kBarEmpty = 4 /* +buffer (4,5) */;
 
 template <int TH_, int TW_, int RS_, int CSB_, int NP_, int RG_, int RK_, int MINB_, bool STAGE_ = false>
 struct StFwdCfg {
@@ -555,7 +584,8 @@ struct StFwdCfg {
   // needs its own buffer; otherwise it aliases V (it is dead once the gradient phase is done).
   static constexpr bool G_ALIAS = (NP == 0) && !STAGE;
   static constexpr int G_OFF = 2 * D_FLOATS + (G_ALIAS ? 0 : 3 * V_FLOATS);
-  static constexpr int SMEM_FLOATS = G_ALIAS ? 2 * D_FLOATS + cmax(3 * V_FLOATS, G_FLOATS) : G_OFF + G_FLOATS;
+  static constexpr int NGBUF = NP > 0 ? 2 : 1;  // the producer runs a whole unit ahead: two gray buffers
+  static constexpr int SMEM_FLOATS = G_ALIAS ? 2 * D_FLOATS + cmax(3 * V_FLOATS, G_FLOATS) : G_OFF + NGBUF * G_FLOATS;
   static constexpr size_t SMEM_BYTES = sizeof(float) * SMEM_FLOATS;
   static_assert(!STAGE || 3 * GH * GW <= 2 * D_FLOATS + 3 * V_FLOATS, "RGB staging does not fit over the D|V region");
   static_assert((CSB == 4 || CSB == 8) && DW % CSB == 0, "bad gradient segment width");
@@ -569,14 +599,14 @@ struct StFwdCfg {
 // tile) in S[3][4] (.x = even row, .y = odd row).
 template <class C, class Taps>
 SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, bool vec4, int H, int W, int y0, int x0,
-                             const Taps& tp, int tid, bool last_unit, float2 (&S)[3][4]) {
+                             const Taps& tp, int tid, int gbuf, bool release_gray, float2 (&S)[3][4]) {
   float* sD0 = smem;
   float* sD1 = sD0 + C::D_FLOATS;
   float* sV = sD1 + C::D_FLOATS;
-  float* sG = smem + C::G_OFF;
+  float* sG = smem + C::G_OFF + gbuf * C::G_FLOATS;
 
   if (C::NP > 0) {
-    bar_sync(kBarFull, C::NT);  // gray tile of this unit is in sG (also: every compute thread is done with sV)
+    bar_sync(kBarFull + gbuf, C::NT);  // gray tile of this unit is in sG (also: every compute thread is done with sV)
   } else {
     bar_sync(kBarCompute, C::NC);  // every thread is done with sD / sV of the previous unit
     if (C::STAGE && vec4) {
@@ -621,7 +651,7 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, bool v
       st4(o1 + 2 * j, make_float4(Iy[j].x, Iy[j].y, Iy[j + 1].x, Iy[j + 1].y));
     }
   }
-  if (C::NP > 0 && !last_unit) bar_arrive(kBarEmpty, C::NT);  // sG may be refilled with the next unit's tile
+  if (C::NP > 0 && release_gray) bar_arrive(kBarEmpty + gbuf, C::NT);  // this gray buffer may be refilled (unit + 2)
   bar_sync(kBarCompute, C::NC);
 
   // Phase C: vertical rho-pass of the three products; a lane owns one column and RS output rows
@@ -700,9 +730,8 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
 
   if (C::NP > 0 && tid >= C::NC) {
     // ---- producer warps: RGB tile (+halo) -> gray -> sG, one unit ahead of the compute warps ----
-    float* sG = smem + C::G_OFF;
     const int ptid = tid - C::NC;
-    bool first = true;
+    int u = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int t = tile;
       const int tx = t % P.tiles_x;
@@ -711,13 +740,14 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
       const int b = t / P.tiles_y;
       const size_t img_off = (size_t)b * 3 * P.H * P.W;
 #pragma unroll 1
-      for (int img = 0; img < 2; ++img) {
-        if (!first) bar_sync(kBarEmpty, C::NT);  // compute warps are done with the previous gray tile
-        first = false;
-        load_gray_tile<C::GH, C::GW, C::PG, (C::NP > 0 ? C::NP : 32), 3>(sG, (img ? P.hr : P.sr) + img_off, P.H, P.W,
-                                                   ty * C::TH - (C::RG + C::RK), tx * C::TW - C::HXG, P.vec4 != 0, ptid);
+      for (int img = 0; img < 2; ++img, ++u) {
+        const int gb = u & 1;
+        if (u >= 2) bar_sync(kBarEmpty + gb, C::NT);  // compute warps consumed the tile of unit u-2
+        load_gray_tile<C::GH, C::GW, C::PG, (C::NP > 0 ? C::NP : 32), 3>(
+            smem + C::G_OFF + gb * C::G_FLOATS, (img ? P.hr : P.sr) + img_off, P.H, P.W,
+            ty * C::TH - (C::RG + C::RK), tx * C::TW - C::HXG, P.vec4 != 0, ptid);
         __threadfence_block();
-        bar_arrive(kBarFull, C::NT);
+        bar_arrive(kBarFull + gb, C::NT);
       }
     }
     return;
@@ -738,11 +768,11 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
     const int b = t / P.tiles_y;
     const int y0 = ty * C::TH, x0 = tx * C::TW;
     const size_t img_off = (size_t)b * 3 * P.H * P.W;
-    const bool last_tile = tile + (int)gridDim.x >= ntiles;
+    const bool last_tile = tile + (int)gridDim.x >= ntiles;  // units of the last tile have no unit + 2
 
     float2 S1[3][4], S2[3][4];
-    st_unit_tensor<C>(smem, P.sr + img_off, P.vec4 != 0, P.H, P.W, y0, x0, P.taps, tid, false, S1);
-    st_unit_tensor<C>(smem, P.hr + img_off, P.vec4 != 0, P.H, P.W, y0, x0, P.taps, tid, last_tile, S2);
+    st_unit_tensor<C>(smem, P.sr + img_off, P.vec4 != 0, P.H, P.W, y0, x0, P.taps, tid, 0, !last_tile, S1);
+    st_unit_tensor<C>(smem, P.hr + img_off, P.vec4 != 0, P.H, P.W, y0, x0, P.taps, tid, (C::NP > 0 ? 1 : 0), !last_tile, S2);
 
     // Per-pixel chain on this thread's 2 x 4 pixels, then the ds stores.
     if (want_hr)

@@ -78,6 +78,11 @@ def run(B, H, W, iters=40):
               f"bwd {tb*1e3:8.1f} us ({36*px/tb/1e6/HBM*100:5.1f}% HBM)  pair {60*px/(tf+tb)/1e6/HBM*100:5.1f}%  "
               f"{B/((tf+tb)*1e-3):.0f} img/s", flush=True)
     os.environ.pop("SRST_ST_FWD_CFG"); os.environ.pop("SRST_ST_BWD_CFG")
+    if os.environ.get("SWEEP_STREAM", "1") == "1":
+        os.environ["SRST_ST_STREAM"] = "1"
+        tf = timeit(fwd)
+        os.environ["SRST_ST_STREAM"] = "0"
+        print(f"B={B:3d} {H}x{W} STREAM: fwd {tf*1e3:8.1f} us ({24*px/tf/1e6/HBM*100:5.1f}% HBM)", flush=True)
 
 
 if __name__ == "__main__":
