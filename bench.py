@@ -50,6 +50,15 @@ WORKLOADS = {
 BYTES_FWD, BYTES_BWD = 24, 36  # algorithmic bytes per pixel
 
 
+def _traffic(workload, kernel):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/r01_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return int(json.load(open(p))[workload][kernel])
+    except Exception:
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -387,7 +396,9 @@ def run_gpu(args):
             "e2e": main.get("e2e"),
             "gpu_launches": 2 * K,
             "roofline": {"bound": "hbm", "kernel": "st_forward_kernel", "achieved": main["roofline_fwd"], "peak": hbm_peak,
-                         "unit": "GB/s", "frac": main["roofline_fwd"] / hbm_peak, "traffic": None,
+                         "unit": "GB/s", "frac": main["roofline_fwd"] / hbm_peak,
+                         "traffic": _traffic(args.workload, "st_forward_kernel"),
+                         "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read+write per launch)",
                          "peak_source": peak_src, "bytes_per_pixel": BYTES_FWD,
                          "backward": {"kernel": "st_backward_kernel", "achieved": main["roofline_bwd"],
                                       "frac": main["roofline_bwd"] / hbm_peak, "bytes_per_pixel": BYTES_BWD},
