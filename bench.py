@@ -326,28 +326,50 @@ def run_gpu(args):
                 bucket = FlatGradBucket([gen_like])
             n_host = 4
             host = [(sr.cpu().pin_memory(), hr.cpu().pin_memory()) for sr, hr in pool[:n_host]]
-            sr_d = torch.empty(B, 3, H, W, device=dev)
-            hr_d = torch.empty(B, 3, H, W, device=dev)
+            # two device slots: the copy stream fills slot (i+1)%2 while step i computes on slot i%2
+            # (the DataLoader pin_memory + non_blocking pattern of train.py:47,119-120); every step's
+            # copy is issued and completed inside the timed region
+            slots = [(torch.empty(B, 3, H, W, device=dev), torch.empty(B, 3, H, W, device=dev)) for _ in range(2)]
+            copy_stream = torch.cuda.Stream(device=dev)
+            copied = [torch.cuda.Event(), torch.cuda.Event()]
+            consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-            def step(i):
+            def issue_copy(i):
                 sr_h, hr_h = host[i % n_host]
-                sr_d.copy_(sr_h, non_blocking=True)
-                hr_d.copy_(hr_h, non_blocking=True)
+                sr_d, hr_d = slots[i % 2]
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[i % 2])     # slot free (previous user finished)
+                    sr_d.copy_(sr_h, non_blocking=True)
+                    hr_d.copy_(hr_h, non_blocking=True)
+                    copied[i % 2].record(copy_stream)
+
+            def step(i, last):
+                sr_d, hr_d = slots[i % 2]
+                cur = torch.cuda.current_stream()
+                cur.wait_event(copied[i % 2])
+                if not last:
+                    issue_copy(i + 1)
                 x = sr_d.detach().requires_grad_(True)
                 l = crit(x, hr_d)
                 l.backward()
+                consumed[i % 2].record(cur)
                 if bucket is not None:
                     bucket.set_loss(l)
                     l = bucket.all_reduce_mean()
                 return l.item()  # device->host read of the step's result, as train.py:141
 
-            for i in range(max(Wm, 3)):
-                step(i)
+            for ev in consumed:
+                ev.record()
+            nw = max(Wm, 3)
+            issue_copy(0)
+            for i in range(nw):
+                step(i, i == nw - 1)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            issue_copy(0)
             for i in range(K):
-                step(i)
+                step(i, i == K - 1)
             e1.record()
             barrier()
             ms = max_over_ranks(e0.elapsed_time(e1))
