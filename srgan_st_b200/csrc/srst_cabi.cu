@@ -114,8 +114,43 @@ static int launch_st_forward(StFwdParams<C::RG, C::RK> P, void* stream) {
   return (int)cudaGetLastError();
 }
 
+// Tensor map of a [planes][H][W] fp32 tensor with a [3][box_h][box_w] box (no swizzle, zero OOB fill).
+// Returns false when TMA cannot be used (unaligned tensor, driver entry point missing): the kernel
+// then stages with cp.async instead.
+static bool make_plane_map(SrstTmap* map, const float* base, long long planes, int H, int W, int box_w, int box_h) {
+#ifdef SRST_EMULATE
+  (void)box_w; (void)box_h;
+  map->base = base; map->W = W; map->H = H; map->P = (int)planes;
+  return true;
+#else
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  static bool looked_up = false;
+  if (!looked_up) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeFn>(fn);
+    looked_up = true;
+  }
+  if (!encode || !aligned16(base) || (W % 4) != 0 || box_w > 256 || box_h > 256) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 3};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+#endif
+}
+
 template <class C>
 static int launch_st_backward(StBwdParams<C::RG, C::RK> P, void* stream) {
+  P.use_tma = (P.vec4 && env_int("SRST_ST_BWD_TMA", 1) != 0 &&
+               make_plane_map(&P.ds_map, P.ds, (long long)P.B * 3, P.H, P.W, C::VW, C::SH)) ? 1 : 0;
   P.tiles_x = (P.W + C::TW - 1) / C::TW;
   P.tiles_y = (P.H + C::TH - 1) / C::TH;
   const long long nblk = (long long)P.B * P.tiles_x * P.tiles_y;
@@ -261,6 +296,8 @@ static int st_forward_rr(const StCall& c) {
 template <int RG, int RK>
 static int st_backward_rr(const StCall& c) {
   StBwdParams<RG, RK> P;
+  std::memset(&P.ds_map, 0, sizeof(P.ds_map));
+  P.use_tma = 0;
   P.img = c.a; P.ds = c.b; P.grad_out = c.grad_out; P.d_img = c.o0;
   P.B = c.B; P.H = c.H; P.W = c.W; P.tiles_x = P.tiles_y = 0;
   P.vec4 = c.vec4;

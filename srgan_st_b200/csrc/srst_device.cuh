@@ -15,7 +15,7 @@
 #define SRST_SET_SMEM(kernel, bytes) (0)
 #else
 #include <cuda_runtime.h>
-#define SRST_DYN_SMEM(T, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; \
+#define SRST_DYN_SMEM(T, name) extern __shared__ __align__(128) unsigned char name##_raw_[]; \
   T* name = reinterpret_cast<T*>(name##_raw_)
 #define SRST_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
@@ -75,6 +75,57 @@ SRST_DEV void cp_async16(float* sdst, const float* gsrc, bool valid) {
 }
 SRST_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 SRST_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
+
+// TMA (cp.async.bulk.tensor) staging of a 3-D box [bp planes][bh rows][bw cols] of an fp32 tensor
+// viewed as [P planes][H][W] into shared memory.  One thread issues ONE instruction for the whole
+// box; coordinates may start outside the tensor (negative or past the end) and the hardware fills
+// those elements with zeros -- the reference's zero padding.  Completion is signalled on an
+// mbarrier that every consumer thread polls.
+#ifdef SRST_EMULATE
+struct SrstTmap { const float* base; int W, H, P; };
+SRST_DEV void tma_stage_begin(unsigned long long* mbar, float* dst, const SrstTmap* m, int x, int y, int z, int bw,
+                              int bh, int bp) {
+  (void)mbar;
+  for (int p = 0; p < bp; ++p)
+    for (int r = 0; r < bh; ++r)
+      for (int c = 0; c < bw; ++c) {
+        const int gx = x + c, gy = y + r, gp = z + p;
+        const bool ok = gx >= 0 && gx < m->W && gy >= 0 && gy < m->H && gp >= 0 && gp < m->P;
+        dst[(p * bh + r) * bw + c] = ok ? m->base[((size_t)gp * m->H + gy) * m->W + gx] : 0.f;
+      }
+}
+SRST_DEV void tma_stage_wait(unsigned long long* mbar) { (void)mbar; }
+#else
+}  // namespace srst
+#include <cuda.h>
+namespace srst {
+typedef CUtensorMap SrstTmap;
+SRST_DEV void tma_stage_begin(unsigned long long* mbar, float* dst, const SrstTmap* m, int x, int y, int z, int bw,
+                              int bh, int bp) {
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
+  const unsigned sdst = (unsigned)__cvta_generic_to_shared(dst);
+  const unsigned bytes = (unsigned)(bw * bh * bp * 4);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(sdst), "l"(reinterpret_cast<unsigned long long>(m)), "r"(x), "r"(y), "r"(z), "r"(bar)
+      : "memory");
+}
+SRST_DEV void tma_stage_wait(unsigned long long* mbar) {
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar)
+        : "memory");
+  }
+}
 #endif
 
 // Named barriers for producer/consumer warp roles: `n` = number of participating threads.

@@ -59,12 +59,14 @@ struct StFwdParams {
 
 template <int RG, int RK>
 struct StBwdParams {
+  SrstTmap ds_map;  // tensor map of ds viewed as [B*3][H][W] (valid when use_tma)
   const float* img;
   const float* ds;
   const float* grad_out;
   float* d_img;
   int B, H, W, tiles_x, tiles_y;
   int vec4;
+  int use_tma;
   float inv_count;
   StTaps<RG, RK> taps;
 };
@@ -835,7 +837,8 @@ struct StBwdCfg {
   static constexpr int V_FLOATS = (EH / 2) * PV, I_FLOATS = (EH / 2) * PE, G_FLOATS = (GH / 2) * PG;
   static constexpr int S_FLOATS = SH * VW;
   static constexpr int X_FLOATS = cmax(2 * I_FLOATS, 3 * S_FLOATS);
-  static constexpr int SMEM_FLOATS = 3 * V_FLOATS + 2 * I_FLOATS + G_FLOATS + X_FLOATS;
+  static constexpr int X_OFF = (3 * V_FLOATS + 2 * I_FLOATS + G_FLOATS + 31) / 32 * 32;  // 128-byte aligned (TMA destination)
+  static constexpr int SMEM_FLOATS = X_OFF + X_FLOATS;
   static constexpr size_t SMEM_BYTES = sizeof(float) * SMEM_FLOATS;
   static_assert(EH % RS == 0 && RS % 2 == 0 && TH % 2 == 0 && TW % 4 == 0 && RG % 2 == 0 && RK % 2 == 0,
                 "bad backward tile");
@@ -850,7 +853,7 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   float* sI0 = sV + 3 * C::V_FLOATS;   // Ix [EH/2][PE]
   float* sI1 = sI0 + C::I_FLOATS;      // Iy
   float* sG = sI1 + C::I_FLOATS;       // gray [GH/2][PG]
-  float* sX = sG + C::G_FLOATS;        // staged ds [3][SH][VW], later dIx|dIy
+  float* sX = smem + C::X_OFF;         // staged ds [3][SH][VW], later dIx|dIy
   float* sS = sX;
   float* sdI0 = sX;
   float* sdI1 = sX + C::I_FLOATS;
@@ -869,9 +872,13 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   const int xv0 = x0 - C::HXE - C::HXK;        // first staged / V column
   const int yv0 = y0 - C::RG - C::RK;          // first staged row
 
-  // Stage the three ds planes (+halo) with asynchronous 16-byte copies; rows/columns outside the
-  // image are zero-filled, which is exactly the zero padding of the adjoint smoothing.
-  {
+  // Stage the three ds planes (+halo).  Preferred path: ONE TMA box copy issued by one thread
+  // (rows/columns outside the image are zero-filled by the hardware = the zero padding of the
+  // adjoint smoothing); otherwise 16-byte cp.async copies, or scalar loads for unaligned tensors.
+  __shared__ __align__(8) unsigned long long s_mbar;
+  if (P.use_tma) {
+    if (tid == 0) tma_stage_begin(&s_mbar, sS, &P.ds_map, xv0, yv0, b * 3, C::VW, C::SH, 3);
+  } else {
     const float* dsb = P.ds + img_off;
     constexpr int C4 = C::VW / 4;
     if (P.vec4) {
@@ -933,7 +940,7 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
     st4(o1, make_float4(Iy[0].x, Iy[0].y, Iy[1].x, Iy[1].y));
     st4(o1 + 4, make_float4(Iy[2].x, Iy[2].y, Iy[3].x, Iy[3].y));
   }
-  cp_async_wait_all();
+  if (P.use_tma) tma_stage_wait(&s_mbar); else cp_async_wait_all();
   __syncthreads();  // Ix, Iy complete; staged ds planes have landed
 
   // Phase C': vertical rho-pass of the three staged ds planes; a lane owns one column and RS rows.
