@@ -46,11 +46,11 @@ const char* srst_error_string(int code);
  *
  * g, dg: 2*r_sigma+1 host floats (utils.get_gaussian_kernel(sigma, also_dg=True), utils.py:194-208)
  * k    : 2*r_rho+1   host floats (utils.get_gaussian_kernel(rho))
- * Compiled radius pairs are listed by srst_st_supported(); the reference default
- * (sigma=0.5, rho=2.0) is (2, 8).
+ * Radii are padded with zero taps to the compiled classes r_sigma in {2,4}, r_rho in {4,8,12};
+ * srst_st_supported() tells whether a pair fits.  The reference default (sigma=0.5, rho=2.0) is (2, 8).
  * ------------------------------------------------------------------------------------------- */
 
-/* 1 if the (r_sigma, r_rho) pair has a compiled kernel, else 0. */
+/* 1 if the (r_sigma, r_rho) pair fits a compiled radius class, else 0. */
 int srst_st_supported(int r_sigma, int r_rho);
 
 /* Scratch bytes srst_st_forward needs for a [B,3,H,W] problem (per-CTA partial sums + ticket).
@@ -62,20 +62,23 @@ size_t srst_st_workspace_bytes(int B, int H, int W);
  *   loss_out[0]  = mean over B*H*W pixels of the Riemannian distance   (device, 1 float)
  *   ds_sr        = d(sum of distances)/d(Jxx,Jyy,Jxy of SR), device [B,3,H,W], or NULL to skip
  *   ds_hr        = same w.r.t. the HR tensor, or NULL (only needed when hr requires grad)
+ *   gray_sr/_hr  = grayscale planes, device [B,H,W], or NULL; when given, srst_st_backward can
+ *                  fetch its gray tile with one TMA copy instead of re-reading and converting RGB
  * The ds_* planes are the "saved intermediates" the backward pass consumes; they are unscaled
  * (neither 1/(B*H*W) nor the upstream gradient is applied yet). */
 int srst_st_forward(const float* sr, const float* hr, int B, int H, int W,
                     const float* g, const float* dg, int r_sigma,
                     const float* k, int r_rho,
                     int normalize, float eps,
-                    float* loss_out, float* ds_sr, float* ds_hr,
+                    float* loss_out, float* ds_sr, float* ds_hr, float* gray_sr, float* gray_hr,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward for one image tensor.  img: the same [B,3,H,W] tensor the forward saw (sr or hr);
+ * gray: the matching gray_* planes the forward saved, or NULL (then img is re-read and converted);
  * ds: the matching ds_* planes; grad_out: device pointer to the upstream scalar gradient.
  * Writes d_img[B,3,H,W] = grad_out/(B*H*W) * dLoss_sum/dimg (adjoint smoothing, product rule,
  * adjoint Gaussian-derivative filters, grayscale weights). */
-int srst_st_backward(const float* img, const float* ds, const float* grad_out,
+int srst_st_backward(const float* img, const float* gray, const float* ds, const float* grad_out,
                      int B, int H, int W,
                      const float* g, const float* dg, int r_sigma,
                      const float* k, int r_rho,
@@ -91,7 +94,8 @@ int srst_st_backward(const float* img, const float* ds, const float* grad_out,
  * levels of gt ([B,3,H/2,W/2], [B,3,H/4,W/4]); pass NULL to have the library compute them with
  * the same taps F.interpolate(mode='bicubic', align_corners=False) uses (loss.py:123,127),
  * in which case `workspace` must also hold them (see srst_bb_workspace_bytes).
- * H and W must be multiples of 12.
+ * H, W >= 12; sizes that are not multiples of 3 / 12 follow the floor semantics of F.unfold and
+ * F.interpolate(scale_factor=...).
  * ------------------------------------------------------------------------------------------- */
 #define SRST_BB_L1 0
 #define SRST_BB_L2 1

@@ -23,9 +23,9 @@ SIGNATURES = {
     "srst_st_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
     "srst_st_forward": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
-                                       ctypes.c_int, ctypes.c_float, vp, vp, vp,
+                                       ctypes.c_int, ctypes.c_float, vp, vp, vp, vp, vp,
                                        vp, ctypes.c_size_t, vp]),
-    "srst_st_backward": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+    "srst_st_backward": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
                                         vp, vp]),
     "srst_bb_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),

@@ -117,9 +117,10 @@ static int launch_st_forward(StFwdParams<C::RG, C::RK> P, void* stream) {
 // Tensor map of a [planes][H][W] fp32 tensor with a [3][box_h][box_w] box (no swizzle, zero OOB fill).
 // Returns false when TMA cannot be used (unaligned tensor, driver entry point missing): the kernel
 // then stages with cp.async instead.
-static bool make_plane_map(SrstTmap* map, const float* base, long long planes, int H, int W, int box_w, int box_h) {
+static bool make_plane_map(SrstTmap* map, const float* base, long long planes, int H, int W, int box_w, int box_h,
+                           int box_p) {
 #ifdef SRST_EMULATE
-  (void)box_w; (void)box_h;
+  (void)box_w; (void)box_h; (void)box_p;
   map->base = base; map->W = W; map->H = H; map->P = (int)planes;
   return true;
 #else
@@ -139,7 +140,7 @@ static bool make_plane_map(SrstTmap* map, const float* base, long long planes, i
   if (!encode || !aligned16(base) || (W % 4) != 0 || box_w > 256 || box_h > 256) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
   const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 3};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_p};
   const cuuint32_t estr[3] = {1, 1, 1};
   return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -148,9 +149,10 @@ static bool make_plane_map(SrstTmap* map, const float* base, long long planes, i
 }
 
 template <class C>
-static int launch_st_backward(StBwdParams<C::RG, C::RK> P, void* stream) {
-  P.use_tma = (P.vec4 && env_int("SRST_ST_BWD_TMA", 1) != 0 &&
-               make_plane_map(&P.ds_map, P.ds, (long long)P.B * 3, P.H, P.W, C::VW, C::SH)) ? 1 : 0;
+static int launch_st_backward(StBwdParams<C::RG, C::RK> P, const float* gray, void* stream) {
+  const bool tma_ok = P.vec4 && env_int("SRST_ST_BWD_TMA", 1) != 0;
+  P.use_tma = (tma_ok && make_plane_map(&P.ds_map, P.ds, (long long)P.B * 3, P.H, P.W, C::VW, C::SH, 3)) ? 1 : 0;
+  P.use_gray = (tma_ok && gray && make_plane_map(&P.gray_map, gray, (long long)P.B, P.H, P.W, C::GW, C::GH, 1)) ? 1 : 0;
   P.tiles_x = (P.W + C::TW - 1) / C::TW;
   P.tiles_y = (P.H + C::TH - 1) / C::TH;
   const long long nblk = (long long)P.B * P.tiles_x * P.tiles_y;
@@ -218,6 +220,8 @@ namespace srst {
 struct StCall {
   const float *a, *b, *grad_out;  // forward: sr, hr ; backward: img, ds, grad_out
   float *o0, *o1, *loss_out;      // forward: ds_sr, ds_hr ; backward: d_img
+  float *gray0, *gray1;           // forward: gray_sr, gray_hr outputs
+  const float* gray;              // backward: saved gray planes or null
   int B, H, W, normalize, vec4;
   float eps;
   void* workspace;
@@ -266,7 +270,7 @@ static int launch_st_stream(const StCall& c) {
 template <int RG, int RK>
 static int st_forward_rr(const StCall& c) {
   StFwdParams<RG, RK> P;
-  P.sr = c.a; P.hr = c.b; P.ds_sr = c.o0; P.ds_hr = c.o1;
+  P.sr = c.a; P.hr = c.b; P.ds_sr = c.o0; P.ds_hr = c.o1; P.gray_sr = c.gray0; P.gray_hr = c.gray1;
   P.ticket = reinterpret_cast<unsigned int*>(c.workspace);
   P.partials = reinterpret_cast<float*>(c.workspace) + 4;
   P.loss_out = c.loss_out;
@@ -275,7 +279,7 @@ static int st_forward_rr(const StCall& c) {
   P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
   fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
-    if (c.vec4 && env_int("SRST_ST_STREAM", 0) == 1) return launch_st_stream<StreamA>(c);
+    if (c.vec4 && !c.gray0 && !c.gray1 && env_int("SRST_ST_STREAM", 0) == 1) return launch_st_stream<StreamA>(c);
     switch (pick_fwd_cfg(c.H, c.W)) {
       case 0: return launch_st_forward<FwdA>(P, c.stream);
       case 1: return launch_st_forward<FwdB>(P, c.stream);
@@ -297,7 +301,8 @@ template <int RG, int RK>
 static int st_backward_rr(const StCall& c) {
   StBwdParams<RG, RK> P;
   std::memset(&P.ds_map, 0, sizeof(P.ds_map));
-  P.use_tma = 0;
+  std::memset(&P.gray_map, 0, sizeof(P.gray_map));
+  P.use_tma = 0; P.use_gray = 0;
   P.img = c.a; P.ds = c.b; P.grad_out = c.grad_out; P.d_img = c.o0;
   P.B = c.B; P.H = c.H; P.W = c.W; P.tiles_x = P.tiles_y = 0;
   P.vec4 = c.vec4;
@@ -305,12 +310,12 @@ static int st_backward_rr(const StCall& c) {
   fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
     switch (pick_bwd_cfg(c.H, c.W)) {
-      case 1: return launch_st_backward<BwdB>(P, c.stream);
-      case 2: return launch_st_backward<BwdC>(P, c.stream);
-      default: return launch_st_backward<BwdA>(P, c.stream);
+      case 1: return launch_st_backward<BwdB>(P, c.gray, c.stream);
+      case 2: return launch_st_backward<BwdC>(P, c.gray, c.stream);
+      default: return launch_st_backward<BwdA>(P, c.gray, c.stream);
     }
   } else {
-    return launch_st_backward<StBwdCfg<24, 64, (24 + 2 * RG) / 2, 256, RG, RK, (RK <= 8 ? 2 : 1)>>(P, c.stream);
+    return launch_st_backward<StBwdCfg<24, 64, (24 + 2 * RG) / 2, 256, RG, RK, (RK <= 8 ? 2 : 1)>>(P, c.gray, c.stream);
   }
 }
 
@@ -330,27 +335,28 @@ extern "C" {
 
 int srst_st_forward(const float* sr, const float* hr, int B, int H, int W, const float* g, const float* dg,
                     int r_sigma, const float* k, int r_rho, int normalize, float eps, float* loss_out,
-                    float* ds_sr, float* ds_hr, void* workspace, size_t workspace_bytes, void* stream) {
+                    float* ds_sr, float* ds_hr, float* gray_sr, float* gray_hr, void* workspace,
+                    size_t workspace_bytes, void* stream) {
   if (!sr || !hr || !g || !dg || !k || !loss_out || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
   if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
   if (!workspace || !aligned16(workspace) || workspace_bytes < srst_st_workspace_bytes(B, H, W))
     return SRST_E_WORKSPACE;
   StCall c{};
-  c.a = sr; c.b = hr; c.o0 = ds_sr; c.o1 = ds_hr; c.loss_out = loss_out;
+  c.a = sr; c.b = hr; c.o0 = ds_sr; c.o1 = ds_hr; c.loss_out = loss_out; c.gray0 = gray_sr; c.gray1 = gray_hr;
   c.B = B; c.H = H; c.W = W; c.normalize = normalize ? 1 : 0; c.eps = eps;
   c.vec4 = (W % 4 == 0 && aligned16(sr) && aligned16(hr) && (!ds_sr || aligned16(ds_sr)) &&
-            (!ds_hr || aligned16(ds_hr))) ? 1 : 0;
+            (!ds_hr || aligned16(ds_hr)) && (!gray_sr || aligned16(gray_sr)) && (!gray_hr || aligned16(gray_hr))) ? 1 : 0;
   c.workspace = workspace; c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;
   return st_dispatch(c, true);
 }
 
-int srst_st_backward(const float* img, const float* ds, const float* grad_out, int B, int H, int W,
+int srst_st_backward(const float* img, const float* gray, const float* ds, const float* grad_out, int B, int H, int W,
                      const float* g, const float* dg, int r_sigma, const float* k, int r_rho, float* d_img,
                      void* stream) {
   if (!img || !ds || !grad_out || !g || !dg || !k || !d_img || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
   if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
   StCall c{};
-  c.a = img; c.b = ds; c.grad_out = grad_out; c.o0 = d_img;
+  c.a = img; c.b = ds; c.grad_out = grad_out; c.o0 = d_img; c.gray = gray;
   c.B = B; c.H = H; c.W = W;
   c.vec4 = (W % 4 == 0 && aligned16(img) && aligned16(d_img) && aligned16(ds)) ? 1 : 0;
   c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;

@@ -46,6 +46,8 @@ struct StFwdParams {
   const float* hr;
   float* ds_sr;  // [B,3,H,W] or null
   float* ds_hr;  // [B,3,H,W] or null
+  float* gray_sr;  // [B,H,W] or null: grayscale planes saved for the backward pass
+  float* gray_hr;
   float* partials;
   unsigned int* ticket;
   float* loss_out;
@@ -59,7 +61,8 @@ struct StFwdParams {
 
 template <int RG, int RK>
 struct StBwdParams {
-  SrstTmap ds_map;  // tensor map of ds viewed as [B*3][H][W] (valid when use_tma)
+  SrstTmap ds_map;    // tensor map of ds viewed as [B*3][H][W] (valid when use_tma)
+  SrstTmap gray_map;  // tensor map of the saved gray planes [B][H][W] (valid when use_gray)
   const float* img;
   const float* ds;
   const float* grad_out;
@@ -67,6 +70,7 @@ struct StBwdParams {
   int B, H, W, tiles_x, tiles_y;
   int vec4;
   int use_tma;
+  int use_gray;  // 1: the gray tile comes from gray_map by TMA instead of RGB loads + conversion
   float inv_count;
   StTaps<RG, RK> taps;
 };
@@ -325,9 +329,12 @@ SRST_DEV float st_chain_store(const float2 (&S1)[3][4], const float2 (&S2)[3][4]
 // convert to grayscale, store row-pair interleaved into sG; zero outside the image (the reference
 // zero-pads: padding='same', utils.py:219-222).  ROWS even; gx0 and COLS multiples of 4.
 // DEPTH items (6 x LDG.128 each) are in flight per thread before the first conversion.
+// If `gray_out` ([H][W] plane of this image) is given, the pixels of the tile interior
+// rows [iy0, iy1) x cols [ix0, ix1) are also written there (once per pixel across tiles).
 template <int ROWS, int COLS, int PITCH, int NT, int DEPTH>
 SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, int W, int gy0, int gx0,
-                             bool vec4, int tid) {
+                             bool vec4, int tid, float* __restrict__ gray_out = nullptr, int iy0 = 0, int iy1 = 0,
+                             int ix0 = 0, int ix1 = 0) {
   constexpr int C4 = COLS / 4;
   constexpr int NITEM = (ROWS / 2) * C4;
   const size_t plane = (size_t)H * W;
@@ -371,6 +378,15 @@ SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, i
         float* o = sG + q * PITCH + 8 * c4;
         st4(o, make_float4(v[0][0], v[1][0], v[0][1], v[1][1]));
         st4(o + 4, make_float4(v[0][2], v[1][2], v[0][3], v[1][3]));
+        if (gray_out) {
+          const int gx = gx0 + 4 * c4;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int gy = gy0 + 2 * q + hf;
+            if (ok[u][hf] && gy >= iy0 && gy < iy1 && gx >= ix0 && gx < ix1)
+              st4(gray_out + (size_t)gy * W + gx, make_float4(v[hf][0], v[hf][1], v[hf][2], v[hf][3]));
+          }
+        }
       }
     }
   } else {
@@ -388,6 +404,7 @@ SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, i
           if (gy >= 0 && gy < H && x >= 0 && x < W) {
             const float* p = base + (size_t)gy * W + x;
             v[hf][j] = gray_of(__ldg(p), __ldg(p + plane), __ldg(p + 2 * plane));
+            if (gray_out && gy >= iy0 && gy < iy1 && x >= ix0 && x < ix1) gray_out[(size_t)gy * W + x] = v[hf][j];
           }
         }
       }
@@ -506,6 +523,44 @@ SRST_DEV void grad_rowpair_rows(const float* const (&pa)[RG + 1], const float* c
   }
 }
 
+// Same filter pair from a ROW-MAJOR plane (row pitch PITCH floats): `p` points at (first input row,
+// window start column); rows 2q and 2q+1 are loaded separately and used as broadcast scalars.
+template <int RG, int CS, int WIN, int CEN, int PITCH, class Taps>
+SRST_DEV void grad_rowpair_rm(const float* p, const Taps& tp, float2 (&ox)[CS], float2 (&oy)[CS]) {
+  static_assert(RG % 2 == 0 && WIN % 4 == 0, "row-major gradient window must be a multiple of 4 columns");
+  float2 tA[WIN], tB[WIN];
+#pragma unroll
+  for (int j = 0; j < WIN; ++j) { tA[j] = make_float2(0.f, 0.f); tB[j] = make_float2(0.f, 0.f); }
+#pragma unroll
+  for (int q = 0; q <= RG; ++q) {
+    float r0[WIN], r1[WIN];
+#pragma unroll
+    for (int m = 0; m < WIN / 4; ++m) {
+      const float4 a = ld4(p + (2 * q) * PITCH + 4 * m), b = ld4(p + (2 * q + 1) * PITCH + 4 * m);
+      r0[4 * m] = a.x; r0[4 * m + 1] = a.y; r0[4 * m + 2] = a.z; r0[4 * m + 3] = a.w;
+      r1[4 * m] = b.x; r1[4 * m + 1] = b.y; r1[4 * m + 2] = b.z; r1[4 * m + 3] = b.w;
+    }
+#pragma unroll
+    for (int j = CEN - RG; j < CEN + CS + RG; ++j) {
+      tA[j] = ffma2(bcast2(r0[j]), tp.dgp[2 * q], tA[j]);
+      tA[j] = ffma2(bcast2(r1[j]), tp.dgp[2 * q + 1], tA[j]);
+      tB[j] = ffma2(bcast2(r0[j]), tp.gp[2 * q], tB[j]);
+      tB[j] = ffma2(bcast2(r1[j]), tp.gp[2 * q + 1], tB[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < CS; ++j) {
+    float2 sx = make_float2(0.f, 0.f), sy = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t <= 2 * RG; ++t) {
+      sx = ffma2(tA[CEN + j + t - RG], bcast2(tp.g[t]), sx);
+      if (t != RG) sy = ffma2(tB[CEN + j + t - RG], bcast2(tp.dg[t]), sy);
+    }
+    ox[j] = sx;
+    oy[j] = sy;
+  }
+}
+
 // Same, for planes whose RG+1 input row pairs are PITCH floats apart.
 template <int RG, int CS, int WIN, int CEN, int PITCH, bool SAME, class Taps>
 SRST_DEV void grad_rowpair(const float* pa, const float* pb, const Taps& tp, float2 (&ox)[CS], float2 (&oy)[CS]) {
@@ -600,8 +655,9 @@ struct StFwdCfg {
 // the smoothed tensor (Jxx,Jyy,Jxy) of this thread's 8 pixels (rows 2q, 2q+1; cols ox0..ox0+3 of the
 // tile) in S[3][4] (.x = even row, .y = odd row).
 template <class C, class Taps>
-SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, bool vec4, int H, int W, int y0, int x0,
-                             const Taps& tp, int tid, int gbuf, bool release_gray, float2 (&S)[3][4]) {
+SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float* __restrict__ gray_out, bool vec4, int H,
+                             int W, int y0, int x0, const Taps& tp, int tid, int gbuf, bool release_gray,
+                             float2 (&S)[3][4]) {
   float* sD0 = smem;
   float* sD1 = sD0 + C::D_FLOATS;
   float* sV = sD1 + C::D_FLOATS;
@@ -617,7 +673,8 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, bool v
       bar_sync(kBarCompute, C::NC);
       convert_staged_gray<C::GH, C::GW, C::PG, C::NC>(sG, smem, tid);
     } else {
-      load_gray_tile<C::GH, C::GW, C::PG, C::NC, C::LDEPTH>(sG, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, vec4, tid);
+      load_gray_tile<C::GH, C::GW, C::PG, C::NC, C::LDEPTH>(sG, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, vec4, tid,
+                                                            gray_out, y0, y0 + C::TH, x0, x0 + C::TW);
     }
     bar_sync(kBarCompute, C::NC);
   }
@@ -747,7 +804,9 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
         if (u >= 2) bar_sync(kBarEmpty + gb, C::NT);  // compute warps consumed the tile of unit u-2
         load_gray_tile<C::GH, C::GW, C::PG, (C::NP > 0 ? C::NP : 32), 3>(
             smem + C::G_OFF + gb * C::G_FLOATS, (img ? P.hr : P.sr) + img_off, P.H, P.W,
-            ty * C::TH - (C::RG + C::RK), tx * C::TW - C::HXG, P.vec4 != 0, ptid);
+            ty * C::TH - (C::RG + C::RK), tx * C::TW - C::HXG, P.vec4 != 0, ptid,
+            (img ? P.gray_hr : P.gray_sr) ? (img ? P.gray_hr : P.gray_sr) + (size_t)b * P.H * P.W : nullptr, ty * C::TH,
+            ty * C::TH + C::TH, tx * C::TW, tx * C::TW + C::TW);
         __threadfence_block();
         bar_arrive(kBarFull + gb, C::NT);
       }
@@ -773,8 +832,11 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
     const bool last_tile = tile + (int)gridDim.x >= ntiles;  // units of the last tile have no unit + 2
 
     float2 S1[3][4], S2[3][4];
-    st_unit_tensor<C>(smem, P.sr + img_off, P.vec4 != 0, P.H, P.W, y0, x0, P.taps, tid, 0, !last_tile, S1);
-    st_unit_tensor<C>(smem, P.hr + img_off, P.vec4 != 0, P.H, P.W, y0, x0, P.taps, tid, (C::NP > 0 ? 1 : 0), !last_tile, S2);
+    const size_t gray_off = (size_t)b * P.H * P.W;
+    st_unit_tensor<C>(smem, P.sr + img_off, P.gray_sr ? P.gray_sr + gray_off : nullptr, P.vec4 != 0, P.H, P.W, y0, x0,
+                      P.taps, tid, 0, !last_tile, S1);
+    st_unit_tensor<C>(smem, P.hr + img_off, P.gray_hr ? P.gray_hr + gray_off : nullptr, P.vec4 != 0, P.H, P.W, y0, x0,
+                      P.taps, tid, (C::NP > 0 ? 1 : 0), !last_tile, S2);
 
     // Per-pixel chain on this thread's 2 x 4 pixels, then the ds stores.
     if (want_hr)
@@ -837,7 +899,10 @@ struct StBwdCfg {
   static constexpr int V_FLOATS = (EH / 2) * PV, I_FLOATS = (EH / 2) * PE, G_FLOATS = (GH / 2) * PG;
   static constexpr int S_FLOATS = SH * VW;
   static constexpr int X_FLOATS = cmax(2 * I_FLOATS, 3 * S_FLOATS);
-  static constexpr int X_OFF = (3 * V_FLOATS + 2 * I_FLOATS + G_FLOATS + 31) / 32 * 32;  // 128-byte aligned (TMA destination)
+  static constexpr int G_OFF = (3 * V_FLOATS + 2 * I_FLOATS + 31) / 32 * 32;             // 128-byte aligned (TMA destination)
+  static constexpr int X_OFF = (G_OFF + G_FLOATS + 31) / 32 * 32;
+  static constexpr int RMW_LO = (HXE - RG) / 4 * 4, RMWIN = (HXE + 4 + RG + 3) / 4 * 4 - RMW_LO;  // row-major gradient window
+  static_assert(GH * GW <= G_FLOATS, "row-major gray tile must fit the gray region");
   static constexpr int SMEM_FLOATS = X_OFF + X_FLOATS;
   static constexpr size_t SMEM_BYTES = sizeof(float) * SMEM_FLOATS;
   static_assert(EH % RS == 0 && RS % 2 == 0 && TH % 2 == 0 && TW % 4 == 0 && RG % 2 == 0 && RK % 2 == 0,
@@ -852,7 +917,7 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   float* sV = smem;                    // [3][EH/2][PV]  vertical rho-pass of ds
   float* sI0 = sV + 3 * C::V_FLOATS;   // Ix [EH/2][PE]
   float* sI1 = sI0 + C::I_FLOATS;      // Iy
-  float* sG = sI1 + C::I_FLOATS;       // gray [GH/2][PG]
+  float* sG = smem + C::G_OFF;         // gray [GH/2][PG] (row pairs), or [GH][GW] row-major when it comes by TMA
   float* sX = smem + C::X_OFF;         // staged ds [3][SH][VW], later dIx|dIy
   float* sS = sX;
   float* sdI0 = sX;
@@ -876,6 +941,10 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   // (rows/columns outside the image are zero-filled by the hardware = the zero padding of the
   // adjoint smoothing); otherwise 16-byte cp.async copies, or scalar loads for unaligned tensors.
   __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ __align__(8) unsigned long long s_mbar_g;
+  // the gray box is needed first (phase B'): queue it ahead of the much larger ds box
+  if (P.use_gray && tid == 0)
+    tma_stage_begin(&s_mbar_g, sG, &P.gray_map, x0 - 2 * C::HXE, y0 - 2 * C::RG, b, C::GW, C::GH, 1);
   if (P.use_tma) {
     if (tid == 0) tma_stage_begin(&s_mbar, sS, &P.ds_map, xv0, yv0, b * 3, C::VW, C::SH, 3);
   } else {
@@ -906,10 +975,16 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
     }
   }
 
-  // Phase A': gray tile of the image (halo 2*RG rows, 2*HXE cols)
-  load_gray_tile<C::GH, C::GW, C::PG, C::NT, 1>(sG, P.img + img_off, H, W, y0 - 2 * C::RG, x0 - 2 * C::HXE,
-                                                P.vec4 != 0, tid);
-  __syncthreads();
+  // Phase A': gray tile of the image (halo 2*RG rows, 2*HXE cols): one TMA box of the gray plane
+  // the forward saved, or RGB loads + conversion.
+  if (P.use_gray) {
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    tma_stage_wait(&s_mbar_g);
+  } else {
+    load_gray_tile<C::GH, C::GW, C::PG, C::NT, 1>(sG, P.img + img_off, H, W, y0 - 2 * C::RG, x0 - 2 * C::HXE,
+                                                  P.vec4 != 0, tid);
+    __syncthreads();
+  }
 
   // Phase B': recompute Ix, Iy on the E region (zero outside the image).
   for (int it = tid; it < (C::EH / 2) * (C::EW / 4); it += C::NT) {
@@ -918,8 +993,12 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
     const int gy = y0 - C::RG + 2 * q, gx0 = x0 - C::HXE + ex0;
     float2 Ix[4], Iy[4];
     if (gy + 1 >= 0 && gy < H && gx0 + 3 >= 0 && gx0 < W) {
-      const float* p = sG + q * C::PG + 2 * (ex0 + C::BW_LO);
-      grad_rowpair<C::RG, 4, C::BWIN, C::HXE - C::BW_LO, C::PG, true>(p, p, tp, Ix, Iy);
+      if (P.use_gray) {
+        grad_rowpair_rm<C::RG, 4, C::RMWIN, C::HXE - C::RMW_LO, C::GW>(sG + (2 * q) * C::GW + ex0 + C::RMW_LO, tp, Ix, Iy);
+      } else {
+        const float* p = sG + q * C::PG + 2 * (ex0 + C::BW_LO);
+        grad_rowpair<C::RG, 4, C::BWIN, C::HXE - C::BW_LO, C::PG, true>(p, p, tp, Ix, Iy);
+      }
       const bool r0 = gy >= 0, r1 = gy + 1 < H;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

@@ -12,6 +12,7 @@ No CPU path, no PyTorch fallback: CPU tensors, non-fp32 dtypes and unsupported f
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Tuple
 
 import torch
@@ -76,13 +77,20 @@ class _StructureTensorLossFn(torch.autograd.Function):
             loss = torch.empty((), dtype=torch.float32, device=sr.device)
             ds_sr = torch.empty_like(sr) if need_sr else None
             ds_hr = torch.empty_like(hr) if need_hr else None
+            # The C ABI can also save gray planes for a TMA-fed backward gray tile; measured on B200 it
+            # is slower than re-reading RGB (extra forward stores, bank-conflicted row-major tile), so
+            # the module does not use it (SRST_ST_SAVE_GRAY=1 turns it on for experiments).
+            save_gray = os.environ.get("SRST_ST_SAVE_GRAY", "0") == "1"
+            gray_sr = torch.empty((B, H, W), dtype=torch.float32, device=sr.device) if (need_sr and save_gray) else None
+            gray_hr = torch.empty((B, H, W), dtype=torch.float32, device=sr.device) if (need_hr and save_gray) else None
             nbytes = lib.srst_st_workspace_bytes(B, H, W)
             ws = _workspace(sr.device, stream, nbytes)
             rc = lib.srst_st_forward(_ptr(sr), _ptr(hr), B, H, W, _taps.as_c(g), _taps.as_c(dg), rs,
                                      _taps.as_c(k), rk, int(bool(normalize)), 1e-12, _ptr(loss),
-                                     _ptr(ds_sr), _ptr(ds_hr), _ptr(ws), ws.numel(), ctypes.c_void_p(stream))
+                                     _ptr(ds_sr), _ptr(ds_hr), _ptr(gray_sr), _ptr(gray_hr), _ptr(ws), ws.numel(),
+                                     ctypes.c_void_p(stream))
         _cabi.check(rc, "srst_st_forward")
-        ctx.save_for_backward(sr, hr, ds_sr, ds_hr)
+        ctx.save_for_backward(sr, hr, ds_sr, ds_hr, gray_sr, gray_hr)
         ctx.taps = (g, dg, k)
         return loss
 
@@ -90,7 +98,7 @@ class _StructureTensorLossFn(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, grad_out):
         lib = _cabi.lib()
-        sr, hr, ds_sr, ds_hr = ctx.saved_tensors
+        sr, hr, ds_sr, ds_hr, gray_sr, gray_hr = ctx.saved_tensors
         g, dg, k = ctx.taps
         rs, rk = len(g) // 2, len(k) // 2
         B, _, H, W = sr.shape
@@ -98,11 +106,11 @@ class _StructureTensorLossFn(torch.autograd.Function):
         outs = [None, None]
         with torch.cuda.device(sr.device):
             stream = torch.cuda.current_stream().cuda_stream
-            for i, (img, ds) in enumerate(((sr, ds_sr), (hr, ds_hr))):
+            for i, (img, ds, gray) in enumerate(((sr, ds_sr, gray_sr), (hr, ds_hr, gray_hr))):
                 if ds is None or not ctx.needs_input_grad[i]:
                     continue
                 d_img = torch.empty_like(img)
-                rc = lib.srst_st_backward(_ptr(img), _ptr(ds), _ptr(grad_out), B, H, W, _taps.as_c(g),
+                rc = lib.srst_st_backward(_ptr(img), _ptr(gray), _ptr(ds), _ptr(grad_out), B, H, W, _taps.as_c(g),
                                           _taps.as_c(dg), rs, _taps.as_c(k), rk, _ptr(d_img),
                                           ctypes.c_void_p(stream))
                 _cabi.check(rc, "srst_st_backward")

@@ -57,7 +57,7 @@ def _fp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
 
 
-def emu_st(lib, sr, hr, taps, normalize=True, want_hr=False, grad_out=1.0):
+def emu_st(lib, sr, hr, taps, normalize=True, want_hr=False, grad_out=1.0, save_gray=True):
     """Run srst_st_forward + srst_st_backward of `lib` on host arrays (emulation library only)."""
     sr = np.ascontiguousarray(sr, np.float32)
     hr = np.ascontiguousarray(hr, np.float32)
@@ -68,19 +68,22 @@ def emu_st(lib, sr, hr, taps, normalize=True, want_hr=False, grad_out=1.0):
     loss = np.zeros(1, np.float32)
     ds_sr = np.full_like(sr, np.nan)
     ds_hr = np.full_like(sr, np.nan) if want_hr else None
+    gray_sr = np.full((B, H, W), np.nan, np.float32) if save_gray else None
+    gray_hr = np.full((B, H, W), np.nan, np.float32) if (save_gray and want_hr) else None
     rc = lib.srst_st_forward(_p(sr), _p(hr), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k), len(k) // 2,
-                             int(normalize), 1e-12, _p(loss), _p(ds_sr), _p(ds_hr), _p(ws), nb, None)
+                             int(normalize), 1e-12, _p(loss), _p(ds_sr), _p(ds_hr), _p(gray_sr), _p(gray_hr), _p(ws), nb,
+                             None)
     assert rc == 0, rc
     go = np.full(1, grad_out, np.float32)
-    out = dict(loss=float(loss[0]), ds_sr=ds_sr, ws=ws)
+    out = dict(loss=float(loss[0]), ds_sr=ds_sr, ws=ws, gray_sr=gray_sr)
     d_sr = np.full_like(sr, np.nan)
-    rc = lib.srst_st_backward(_p(sr), _p(ds_sr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
+    rc = lib.srst_st_backward(_p(sr), _p(gray_sr), _p(ds_sr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
                               len(k) // 2, _p(d_sr), None)
     assert rc == 0, rc
     out["d_sr"] = d_sr
     if want_hr:
         d_hr = np.full_like(sr, np.nan)
-        rc = lib.srst_st_backward(_p(hr), _p(ds_hr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
+        rc = lib.srst_st_backward(_p(hr), _p(gray_hr), _p(ds_hr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
                                   len(k) // 2, _p(d_hr), None)
         assert rc == 0, rc
         out["d_hr"] = d_hr

@@ -44,4 +44,4 @@ def test_no_compute_entry_points_that_need_no_gpu():
     assert b"workspace" in lib.srst_error_string(-3)
     # argument validation happens before any CUDA call
     assert lib.srst_st_forward(None, None, 1, 8, 8, None, None, 2, None, 8, 1, 1e-12, None, None, None,
-                               None, 0, None) == -1
+                               None, None, None, 0, None) == -1

@@ -79,3 +79,14 @@ def test_emulated_golden_sigma1_rho25(lib):
     assert rel_err(out["loss"], z["loss"]) < 1e-5
     ref = O.st_loss(z["sr"], z["hr"], taps=taps, want_hr_grad=True)
     assert maxnorm_err(out["d_sr"], ref["d_sr"]) < 1e-4 and maxnorm_err(out["d_hr"], ref["d_hr"]) < 1e-4
+
+
+def test_emulated_backward_without_saved_gray(lib):
+    """gray = NULL: the backward re-reads RGB and converts (same result as the TMA gray-tile path)."""
+    z = golden("st_srlike_2x40x52")
+    taps = (z["g"], z["dg"], z["k"])
+    a = emu_st(lib, z["sr"], z["hr"], taps, save_gray=True)
+    b = emu_st(lib, z["sr"], z["hr"], taps, save_gray=False)
+    assert np.allclose(a["d_sr"], b["d_sr"], rtol=1e-5, atol=1e-9)
+    gray = 0.2989 * z["sr"][:, 0] + 0.587 * z["sr"][:, 1] + 0.114 * z["sr"][:, 2]
+    assert np.allclose(a["gray_sr"], gray, rtol=1e-6, atol=1e-7)

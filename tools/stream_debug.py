@@ -11,7 +11,7 @@ for (B, H, W) in [(1, 1356, 2040), (64, 96, 96)]:
     ds = torch.empty_like(sr); loss = torch.zeros((), device="cuda")
     ws = torch.zeros(max(lib.srst_st_workspace_bytes(B, H, W), 8192), dtype=torch.uint8, device="cuda")
     for _ in range(3):
-        _cabi.check(lib.srst_st_forward(vp(sr), vp(hr), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8, 1, 1e-12, vp(loss), vp(ds), None, vp(ws), ws.numel(), None), "fwd")
+        _cabi.check(lib.srst_st_forward(vp(sr), vp(hr), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8, 1, 1e-12, vp(loss), vp(ds), None, None, None, vp(ws), ws.numel(), None), "fwd")
     torch.cuda.synchronize()
     d = ws[2048:2048 + 8 * 64].view(torch.int64).cpu().tolist()
     roles = ["HC"] * 8 + ["VS"] * 5 + ["GR"] * 4 + ["LG"] * 4

@@ -15,6 +15,7 @@ g, dg = T.gaussian_taps(0.5)
 k, _ = T.gaussian_taps(2.0)
 dev = torch.device("cuda:0")
 vp = lambda t: ctypes.c_void_p(t.data_ptr())
+GRAY = (lambda t: vp(t)) if os.environ.get("SRST_ST_SAVE_GRAY", "0") == "1" else (lambda t: None)
 HBM = 6539.9
 FWD_CFGS = [int(x) for x in os.environ.get('SWEEP_FWD', '0,1,2,3,4').split(',')]
 BWD_MAX = int(os.environ.get('SWEEP_BWD_MAX', '2'))
@@ -26,6 +27,7 @@ def run(B, H, W, iters=40):
     pool = [(torch.rand(B, 3, H, W, device=dev), torch.rand(B, 3, H, W, device=dev)) for _ in range(pool_n)]
     ds = torch.empty(B, 3, H, W, device=dev)
     d_sr = torch.empty(B, 3, H, W, device=dev)
+    gray = torch.empty(B, H, W, device=dev)
     loss = torch.zeros((), device=dev)
     go = torch.ones((), device=dev)
     ws = torch.zeros(max(lib.srst_st_workspace_bytes(B, H, W), 4096), dtype=torch.uint8, device=dev)
@@ -35,11 +37,11 @@ def run(B, H, W, iters=40):
     def fwd(i):
         sr, hr = pool[i % pool_n]
         _cabi.check(lib.srst_st_forward(vp(sr), vp(hr), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8, 1, 1e-12,
-                                        vp(loss), vp(ds), None, vp(ws), ws.numel(), sp), "fwd")
+                                        vp(loss), vp(ds), None, GRAY(gray), None, vp(ws), ws.numel(), sp), "fwd")
 
     def bwd(i):
         sr, _ = pool[i % pool_n]
-        _cabi.check(lib.srst_st_backward(vp(sr), vp(ds), vp(go), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8,
+        _cabi.check(lib.srst_st_backward(vp(sr), GRAY(gray), vp(ds), vp(go), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8,
                                          vp(d_sr), sp), "bwd")
 
     def timeit(fn):
