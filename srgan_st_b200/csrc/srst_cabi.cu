@@ -38,6 +38,8 @@ using FwdJ = StFwdCfg<64, 64, 16, 4, 0, 2, 8, 1>;   // experiment: 512-thread CT
 using BwdA = StBwdCfg<24, 64, 14, 256, 2, 8, 2>;  // large images
 using BwdB = StBwdCfg<16, 96, 10, 256, 2, 8, 2>;  // 96-wide training crops
 using BwdC = StBwdCfg<32, 64, 12, 352, 2, 8, 1>;  // one big CTA per SM
+using BwdD = StBwdCfg<28, 56, 16, 256, 2, 8, 2>;  // 16 row pairs per phase item column: no LDS bank conflicts
+using BwdE = StBwdCfg<28, 88, 16, 384, 2, 8, 1>;  // experiment
 
 constexpr int kMinFwdTH = 24, kMinFwdTW = 32;  // finest compiled forward tiling (workspace sizing)
 
@@ -173,9 +175,9 @@ static int pick_fwd_cfg(int H, int W) {
 }
 static int pick_bwd_cfg(int H, int W) {
   const int forced = env_int("SRST_ST_BWD_CFG", -1);
-  if (forced >= 0 && forced <= 2) return forced;
+  if (forced >= 0 && forced <= 4) return forced;
   if (W <= 96) return 1;
-  return 0;
+  return 3;
 }
 
 }  // namespace srst
@@ -312,6 +314,8 @@ static int st_backward_rr(const StCall& c) {
     switch (pick_bwd_cfg(c.H, c.W)) {
       case 1: return launch_st_backward<BwdB>(P, c.gray, c.stream);
       case 2: return launch_st_backward<BwdC>(P, c.gray, c.stream);
+      case 3: return launch_st_backward<BwdD>(P, c.gray, c.stream);
+      case 4: return launch_st_backward<BwdE>(P, c.gray, c.stream);
       default: return launch_st_backward<BwdA>(P, c.gray, c.stream);
     }
   } else {
