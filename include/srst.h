@@ -118,6 +118,21 @@ int srst_bb_backward(const float* sr, const float* gt, const float* gt2, const f
                      int B, int H, int W, int criterion,
                      float* d_sr, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Gram loss (reference loss.py:146-225): the same three-level best-buddy search, but every 3x3x3
+ * patch is replaced by its 3x3 Gram matrix (features [3][9], G = F F^T / 27; 9-dim descriptor) for
+ * both the search and the final L1/MSE criterion.  Workspace: srst_bb_workspace_bytes.
+ *   d_sr = through the criterion and the Gram descriptor of the SR patch (argmin is not differentiated).
+ * ------------------------------------------------------------------------------------------- */
+int srst_gram_forward(const float* sr, const float* gt, const float* gt2, const float* gt4,
+                      int B, int H, int W, float alpha, float beta, int criterion,
+                      int64_t* idx_out, float* loss_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int srst_gram_backward(const float* sr, const float* gt, const float* gt2, const float* gt4,
+                       const int64_t* idx, const float* grad_out,
+                       int B, int H, int W, int criterion,
+                       float* d_sr, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The HR pyramid on its own (exposed for tests): out2 [B,3,H/2,W/2], out4 [B,3,H/4,W/4]. */
 int srst_bb_pyramid(const float* gt, int B, int H, int W, float* out2, float* out4, void* stream);
 

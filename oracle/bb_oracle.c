@@ -51,28 +51,46 @@ static void read_patch(const float* img, int H, int W, int nx, int p, float* v) 
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) v[c * 9 + ky * 3 + kx] = img[((size_t)c * H + 3 * py + ky) * W + 3 * px + kx];
 }
-static float norm27(const float* v) {
+static float normd(const float* v, int d) {
   float n = 0.f;
-  for (int k = 0; k < D; ++k) n = fmaf(v[k], v[k], n);
+  for (int k = 0; k < d; ++k) n = fmaf(v[k], v[k], n);
   return n;
 }
-static float dot27(const float* a, const float* b) {
+static float dotd(const float* a, const float* b, int d) {
   float s = 0.f;
-  for (int k = 0; k < D; ++k) s = fmaf(a[k], b[k], s);
+  for (int k = 0; k < d; ++k) s = fmaf(a[k], b[k], s);
   return s;
+}
+/* GramLoss descriptor (reference loss.py:180-184 gram_matrix): patch viewed as features [3][9],
+ * G = F F^T / 27, flattened row-major.  Same fixed order as the CUDA kernel. */
+static void gram9(const float* v, float* g) {
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      float s = 0.f;
+      for (int t = 0; t < 9; ++t) s = fmaf(v[a * 9 + t], v[b * 9 + t], s);
+      g[a * 3 + b] = s / 27.0f;
+    }
+}
+/* descriptor of a patch: mode 0 = raw 27 values (BestBuddyLoss), mode 1 = Gram matrix (GramLoss) */
+static void describe(const float* img, int H, int W, int nx, int p, int mode, float* out) {
+  float v[D];
+  read_patch(img, H, W, nx, p, v);
+  if (mode == 0) for (int k = 0; k < D; ++k) out[k] = v[k];
+  else gram9(v, out);
 }
 
 /* Returns 0 on success.  idx [B,N] int64; loss_out 1 double; best/second [B,N] fp32 scores (may be NULL). */
-int bb_oracle_forward(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
-                      float alpha, float beta, int criterion, int64_t* idx, double* loss_out, float* best_out,
-                      float* second_out) {
+int bb_oracle_forward_mode(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
+                           float alpha, float beta, int criterion, int mode, int64_t* idx, double* loss_out,
+                           float* best_out, float* second_out) {
+  const int Dd = mode == 0 ? D : 9;
   const int n0x = W / 3, N0 = (H / 3) * n0x;
   const int H2 = H / 2, W2 = W / 2, n2x = W2 / 3, N2 = (H2 / 3) * n2x;
   const int H4 = H / 4, W4 = W / 4, n4x = W4 / 3, N4 = (H4 / 3) * n4x;
   const int N = N0, M = N0 + N2 + N4;
-  float* q1 = malloc(sizeof(float) * (size_t)N * D);
-  float* q2 = malloc(sizeof(float) * (size_t)N * D);
-  float* y = malloc(sizeof(float) * (size_t)M * D);
+  float* q1 = malloc(sizeof(float) * (size_t)N * Dd);
+  float* q2 = malloc(sizeof(float) * (size_t)N * Dd);
+  float* y = malloc(sizeof(float) * (size_t)M * Dd);
   float* xn = malloc(sizeof(float) * N);
   float* gn = malloc(sizeof(float) * N);
   float* yn = malloc(sizeof(float) * M);
@@ -84,23 +102,23 @@ int bb_oracle_forward(const float* sr, const float* gt, const float* gt2, const 
     const float* g2 = gt2 + (size_t)b * 3 * H2 * W2;
     const float* g4 = gt4 + (size_t)b * 3 * H4 * W4;
     for (int i = 0; i < N; ++i) {
-      read_patch(s0, H, W, n0x, i, q1 + (size_t)i * D);
-      xn[i] = norm27(q1 + (size_t)i * D);
-      read_patch(g0, H, W, n0x, i, q2 + (size_t)i * D);
-      gn[i] = norm27(q2 + (size_t)i * D);
+      describe(s0, H, W, n0x, i, mode, q1 + (size_t)i * Dd);
+      xn[i] = normd(q1 + (size_t)i * Dd, Dd);
+      describe(g0, H, W, n0x, i, mode, q2 + (size_t)i * Dd);
+      gn[i] = normd(q2 + (size_t)i * Dd, Dd);
     }
     for (int j = 0; j < M; ++j) {
-      if (j < N0) read_patch(g0, H, W, n0x, j, y + (size_t)j * D);
-      else if (j < N0 + N2) read_patch(g2, H2, W2, n2x, j - N0, y + (size_t)j * D);
-      else read_patch(g4, H4, W4, n4x, j - N0 - N2, y + (size_t)j * D);
-      yn[j] = norm27(y + (size_t)j * D);
+      if (j < N0) describe(g0, H, W, n0x, j, mode, y + (size_t)j * Dd);
+      else if (j < N0 + N2) describe(g2, H2, W2, n2x, j - N0, mode, y + (size_t)j * Dd);
+      else describe(g4, H4, W4, n4x, j - N0 - N2, mode, y + (size_t)j * Dd);
+      yn[j] = normd(y + (size_t)j * Dd, Dd);
     }
     for (int i = 0; i < N; ++i) {
       float best = INFINITY, second = INFINITY;
       int bi = 0;
       for (int j = 0; j < M; ++j) {
-        float d1 = fmaf(-2.0f, dot27(q1 + (size_t)i * D, y + (size_t)j * D), xn[i] + yn[j]);
-        float d2 = fmaf(-2.0f, dot27(q2 + (size_t)i * D, y + (size_t)j * D), gn[i] + yn[j]);
+        float d1 = fmaf(-2.0f, dotd(q1 + (size_t)i * Dd, y + (size_t)j * Dd, Dd), xn[i] + yn[j]);
+        float d2 = fmaf(-2.0f, dotd(q2 + (size_t)i * Dd, y + (size_t)j * Dd, Dd), gn[i] + yn[j]);
         d1 = d1 > 0.f ? d1 : 0.f;
         d2 = d2 > 0.f ? d2 : 0.f;
         const float a = alpha * d1, bb = beta * d2;
@@ -111,13 +129,20 @@ int bb_oracle_forward(const float* sr, const float* gt, const float* gt2, const 
       idx[(size_t)b * N + i] = bi;
       if (best_out) best_out[(size_t)b * N + i] = best;
       if (second_out) second_out[(size_t)b * N + i] = second;
-      for (int k = 0; k < D; ++k) {
-        const float d = q1[(size_t)i * D + k] - y[(size_t)bi * D + k];
+      for (int k = 0; k < Dd; ++k) {
+        const float d = q1[(size_t)i * Dd + k] - y[(size_t)bi * Dd + k];
         total += criterion == 0 ? fabs((double)d) : (double)d * (double)d;
       }
     }
   }
-  *loss_out = total / ((double)B * N * D);
+  *loss_out = total / ((double)B * N * Dd);
   free(q1); free(q2); free(y); free(xn); free(gn); free(yn);
   return 0;
+}
+
+int bb_oracle_forward(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
+                      float alpha, float beta, int criterion, int64_t* idx, double* loss_out, float* best_out,
+                      float* second_out) {
+  return bb_oracle_forward_mode(sr, gt, gt2, gt4, B, H, W, alpha, beta, criterion, 0, idx, loss_out, best_out,
+                                second_out);
 }

@@ -30,6 +30,7 @@ def _load():
             subprocess.run(["make", "-C", HERE], check=True, capture_output=True)
         _lib = ctypes.CDLL(LIB)
         _lib.bb_oracle_forward.restype = ctypes.c_int
+        _lib.bb_oracle_forward_mode.restype = ctypes.c_int
     return _lib
 
 
@@ -54,7 +55,8 @@ def geometry(H, W):
     return N0, N0 + N2 + N4
 
 
-def bb_forward_c(sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion="l1"):
+def bb_forward_c(sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion="l1", mode="patch"):
+    """mode="patch": BestBuddyLoss (27 raw values); mode="gram": GramLoss (3x3 Gram matrix, loss.py:146-225)."""
     sr = np.ascontiguousarray(sr, np.float32)
     gt = np.ascontiguousarray(gt, np.float32)
     if gt2 is None:
@@ -67,8 +69,8 @@ def bb_forward_c(sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion="l1"
     best = np.empty((B, N), np.float32)
     second = np.empty((B, N), np.float32)
     loss = ctypes.c_double(0.0)
-    rc = _load().bb_oracle_forward(_fp(sr), _fp(gt), _fp(gt2), _fp(gt4), B, H, W, ctypes.c_float(alpha),
-                                   ctypes.c_float(beta), 0 if criterion == "l1" else 1,
+    rc = _load().bb_oracle_forward_mode(_fp(sr), _fp(gt), _fp(gt2), _fp(gt4), B, H, W, ctypes.c_float(alpha),
+                                   ctypes.c_float(beta), 0 if criterion == "l1" else 1, 0 if mode == "patch" else 1,
                                    idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.byref(loss),
                                    _fp(best), _fp(second))
     assert rc == 0
@@ -106,4 +108,26 @@ def bb_backward(sr, cat_sel, criterion="l1"):
     g = (np.sign(diff) if criterion == "l1" else 2.0 * diff) / diff.size
     out = np.zeros_like(sr)
     out[:, :, :ny * 3, :nx * 3] = g.reshape(B, ny, nx, C, 3, 3).transpose(0, 3, 1, 4, 2, 5).reshape(B, C, ny * 3, nx * 3)
+    return out
+
+
+def gram_descriptors(img):
+    """[B,3,H,W] -> [B,N,9] Gram matrices of the 3x3x3 patches, float64 (loss.py:180-197)."""
+    p = unfold3(np.asarray(img, np.float64))          # [B,N,27] as (c, ky, kx)
+    f = p.reshape(p.shape[0], p.shape[1], 3, 9)
+    return (np.einsum("bnas,bncs->bnac", f, f) / 27.0).reshape(p.shape[0], p.shape[1], 9)
+
+
+def gram_backward(sr, sel_desc, criterion="l1"):
+    """d GramLoss / d sr given the selected candidate descriptors [B,N,9] (float64)."""
+    sr = np.asarray(sr, np.float64)
+    B, C, H, W = sr.shape
+    ny, nx = H // 3, W // 3
+    p = unfold3(sr).reshape(B, ny * nx, 3, 9)
+    G1 = np.einsum("bnas,bncs->bnac", p, p) / 27.0
+    diff = G1 - sel_desc.reshape(B, ny * nx, 3, 3)
+    dG = (np.sign(diff) if criterion == "l1" else 2.0 * diff) / diff.size
+    dF = np.einsum("bnac,bncs->bnas", dG + dG.transpose(0, 1, 3, 2), p) / 27.0
+    out = np.zeros_like(sr)
+    out[:, :, :ny * 3, :nx * 3] = dF.reshape(B, ny, nx, C, 3, 3).transpose(0, 3, 1, 4, 2, 5).reshape(B, C, ny * 3, nx * 3)
     return out

@@ -34,6 +34,11 @@ SIGNATURES = {
                                        vp, ctypes.c_size_t, vp]),
     "srst_bb_backward": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
+    "srst_gram_forward": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_float, ctypes.c_float, ctypes.c_int, vp, vp,
+                                         vp, ctypes.c_size_t, vp]),
+    "srst_gram_backward": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
     "srst_bb_pyramid": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
 }
 

@@ -61,7 +61,7 @@ struct BbWorkspace {
   size_t total_bytes;
 };
 
-inline BbWorkspace bb_carve(void* base, const BbGeom& g) {
+inline BbWorkspace bb_carve(void* base, const BbGeom& g, int D = BB_D) {
   BbWorkspace w;
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
@@ -70,7 +70,7 @@ inline BbWorkspace bb_carve(void* base, const BbGeom& g) {
   const size_t nblk_loss = ((size_t)g.B * g.N + BB_NT - 1) / BB_NT;
   w.partials = reinterpret_cast<float*>(p + off);
   off += (nblk_loss * sizeof(float) + 255) / 256 * 256;
-  w.per_image = (size_t)(BB_D + 1) * (2 * (size_t)g.Npad + g.Mpad);
+  w.per_image = (size_t)(D + 1) * (2 * (size_t)g.Npad + g.Mpad);
   w.mats = reinterpret_cast<float*>(p + off);
   off += (w.per_image * g.B * sizeof(float) + 255) / 256 * 256;
   w.pyr2 = reinterpret_cast<float*>(p + off);
@@ -84,13 +84,13 @@ inline BbWorkspace bb_carve(void* base, const BbGeom& g) {
 struct BbPtrs {
   const float* q1; const float* q2; const float* y; const float* xn; const float* gn; const float* yn;
 };
-SRST_DEV BbPtrs bb_image_ptrs(const float* mats, size_t per_image, int b, int Npad, int Mpad) {
+SRST_DEV BbPtrs bb_image_ptrs(const float* mats, size_t per_image, int b, int Npad, int Mpad, int D = BB_D) {
   const float* m = mats + per_image * b;
   BbPtrs p;
   p.q1 = m;
-  p.q2 = p.q1 + (size_t)BB_D * Npad;
-  p.y = p.q2 + (size_t)BB_D * Npad;
-  p.xn = p.y + (size_t)BB_D * Mpad;
+  p.q2 = p.q1 + (size_t)D * Npad;
+  p.y = p.q2 + (size_t)D * Npad;
+  p.xn = p.y + (size_t)D * Mpad;
   p.gn = p.xn + Npad;
   p.yn = p.gn + Npad;
   return p;
@@ -147,39 +147,73 @@ SRST_DEV void bb_read_patch(const float* __restrict__ img, int H, int W, int nx,
       for (int kx = 0; kx < 3; ++kx)
         v[c * 9 + ky * 3 + kx] = __ldg(img + ((size_t)c * H + 3 * py + ky) * W + 3 * px + kx);
 }
-SRST_DEV float bb_norm(const float (&v)[BB_D]) {
+template <int D>
+SRST_DEV float bb_norm(const float (&v)[D]) {
   float n = 0.f;
 #pragma unroll
-  for (int k = 0; k < BB_D; ++k) n = fmaf(v[k], v[k], n);
+  for (int k = 0; k < D; ++k) n = fmaf(v[k], v[k], n);
   return n;
 }
 
+// Gram descriptor of a 3x3x3 patch (reference loss.py:180-184 gram_matrix): features = patch viewed
+// as [3 channels][9], G = F F^T / 27, flattened row-major to 9 values.  Fixed order: sequential fma
+// over the 9 positions, then a division by 27 (oracle/bb_oracle.c restates the same order).
+SRST_DEV void bb_gram(const float (&v)[BB_D], float (&gm)[9]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) s = fmaf(v[a * 9 + t], v[b * 9 + t], s);
+      gm[a * 3 + b] = s / 27.0f;
+    }
+}
+
+// Descriptor of a patch: MODE 0 = the 27 raw values (BestBuddyLoss), MODE 1 = Gram matrix (GramLoss).
+template <int MODE>
+struct BbDesc {
+  static constexpr int D = MODE == 0 ? BB_D : 9;
+  SRST_DEV static void make(const float (&v)[BB_D], float (&d)[D]) {
+    if constexpr (MODE == 0) {
+#pragma unroll
+      for (int k = 0; k < BB_D; ++k) d[k] = v[k];
+    } else {
+      bb_gram(v, d);
+    }
+  }
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(256)
 bb_pack_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const float* __restrict__ gt2,
                const float* __restrict__ gt4, float* __restrict__ mats, size_t per_image, BbGeom g) {
+  constexpr int D = BbDesc<MODE>::D;
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   float* m = mats + per_image * b;
   float* q1 = m;
-  float* q2 = q1 + (size_t)BB_D * g.Npad;
-  float* y = q2 + (size_t)BB_D * g.Npad;
-  float* xn = y + (size_t)BB_D * g.Mpad;
+  float* q2 = q1 + (size_t)D * g.Npad;
+  float* y = q2 + (size_t)D * g.Npad;
+  float* xn = y + (size_t)D * g.Mpad;
   float* gn = xn + g.Npad;
   float* yn = gn + g.Npad;
-  float v[BB_D];
+  float v[BB_D], d[D];
   if (t < g.Npad) {  // query t
     if (t < g.N) {
       bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, t, v);
+      BbDesc<MODE>::make(v, d);
 #pragma unroll
-      for (int k = 0; k < BB_D; ++k) q1[(size_t)k * g.Npad + t] = v[k];
-      xn[t] = bb_norm(v);
+      for (int k = 0; k < D; ++k) q1[(size_t)k * g.Npad + t] = d[k];
+      xn[t] = bb_norm<D>(d);
       bb_read_patch(gt + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, t, v);
+      BbDesc<MODE>::make(v, d);
 #pragma unroll
-      for (int k = 0; k < BB_D; ++k) q2[(size_t)k * g.Npad + t] = v[k];
-      gn[t] = bb_norm(v);
+      for (int k = 0; k < D; ++k) q2[(size_t)k * g.Npad + t] = d[k];
+      gn[t] = bb_norm<D>(d);
     } else {
 #pragma unroll
-      for (int k = 0; k < BB_D; ++k) { q1[(size_t)k * g.Npad + t] = 0.f; q2[(size_t)k * g.Npad + t] = 0.f; }
+      for (int k = 0; k < D; ++k) { q1[(size_t)k * g.Npad + t] = 0.f; q2[(size_t)k * g.Npad + t] = 0.f; }
       xn[t] = 0.f;
       gn[t] = 0.f;
     }
@@ -189,12 +223,13 @@ bb_pack_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const
       if (t < g.N0) bb_read_patch(gt + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, t, v);
       else if (t < g.N0 + g.N2) bb_read_patch(gt2 + (size_t)b * 3 * g.H2 * g.W2, g.H2, g.W2, g.n2x, t - g.N0, v);
       else bb_read_patch(gt4 + (size_t)b * 3 * g.H4 * g.W4, g.H4, g.W4, g.n4x, t - g.N0 - g.N2, v);
+      BbDesc<MODE>::make(v, d);
 #pragma unroll
-      for (int k = 0; k < BB_D; ++k) y[(size_t)k * g.Mpad + t] = v[k];
-      yn[t] = bb_norm(v);
+      for (int k = 0; k < D; ++k) y[(size_t)k * g.Mpad + t] = d[k];
+      yn[t] = bb_norm<D>(d);
     } else {
 #pragma unroll
-      for (int k = 0; k < BB_D; ++k) y[(size_t)k * g.Mpad + t] = 0.f;
+      for (int k = 0; k < D; ++k) y[(size_t)k * g.Mpad + t] = 0.f;
       yn[t] = __int_as_float(0x7f800000);  // +inf: a padded candidate never wins
     }
   }
@@ -215,22 +250,23 @@ SRST_DEV void bb_argmin_merge(float& s, int& i, float so, int io) {
   if (so < s || (so == s && io < i)) { s = so; i = io; }
 }
 
+template <int D>
 __global__ void __launch_bounds__(BB_NT, 2)
 bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, float alpha, float beta,
                  int64_t* __restrict__ idx_out) {
-  __shared__ __align__(16) float sQ1[BB_D][BB_QT];
-  __shared__ __align__(16) float sQ2[BB_D][BB_QT];
-  __shared__ __align__(16) float sY[BB_D][BB_CT];
+  __shared__ __align__(16) float sQ1[D][BB_QT];
+  __shared__ __align__(16) float sQ2[D][BB_QT];
+  __shared__ __align__(16) float sY[D][BB_CT];
   __shared__ float sXn[BB_QT], sGn[BB_QT], sYn[BB_CT];
   __shared__ float sBestS[4][BB_QT];
   __shared__ int sBestI[4][BB_QT];
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y, qt = blockIdx.x;
-  const BbPtrs P = bb_image_ptrs(mats, per_image, b, g.Npad, g.Mpad);
+  const BbPtrs P = bb_image_ptrs(mats, per_image, b, g.Npad, g.Mpad, D);
   const int qbase = qt * BB_QT;
 
-  for (int it = tid; it < BB_D * (BB_QT / 4); it += BB_NT) {
+  for (int it = tid; it < D * (BB_QT / 4); it += BB_NT) {
     const int k = it / (BB_QT / 4), c4 = it - k * (BB_QT / 4);
     st4(&sQ1[k][4 * c4], ldg4(P.q1 + (size_t)k * g.Npad + qbase + 4 * c4));
     st4(&sQ2[k][4 * c4], ldg4(P.q2 + (size_t)k * g.Npad + qbase + 4 * c4));
@@ -250,7 +286,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
 
   for (int chunk = 0; chunk < g.Mpad; chunk += BB_CT) {
     __syncthreads();  // previous chunk fully consumed (also orders the query loads before first use)
-    for (int it = tid; it < BB_D * (BB_CT / 4); it += BB_NT) {
+    for (int it = tid; it < D * (BB_CT / 4); it += BB_NT) {
       const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
       st4(&sY[k][4 * c4], ldg4(P.y + (size_t)k * g.Mpad + chunk + 4 * c4));
     }
@@ -263,7 +299,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
 #pragma unroll
       for (int j = 0; j < 4; ++j) { a1[i][j] = 0.f; a2[i][j] = 0.f; }
 #pragma unroll
-    for (int k = 0; k < BB_D; ++k) {
+    for (int k = 0; k < D; ++k) {
       const float4 u = ld4(&sQ1[k][q0]);
       const float4 v = ld4(&sQ2[k][q0]);
       const float4 w = ld4(&sY[k][c0]);
@@ -310,6 +346,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
 }
 
 // ---- loss ---------------------------------------------------------------------------------------
+template <int D>
 __global__ void __launch_bounds__(BB_NT)
 bb_loss_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, const int64_t* __restrict__ idx,
                int criterion, float* partials, unsigned int* ticket, float* loss_out) {
@@ -320,10 +357,10 @@ bb_loss_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, const
   float acc = 0.f;
   if (t < (size_t)g.B * g.N) {
     const int b = (int)(t / g.N), i = (int)(t - (size_t)b * g.N);
-    const BbPtrs P = bb_image_ptrs(mats, per_image, b, g.Npad, g.Mpad);
+    const BbPtrs P = bb_image_ptrs(mats, per_image, b, g.Npad, g.Mpad, D);
     const int j = (int)idx[t];
 #pragma unroll
-    for (int k = 0; k < BB_D; ++k) {
+    for (int k = 0; k < D; ++k) {
       const float d = __ldg(P.q1 + (size_t)k * g.Npad + i) - __ldg(P.y + (size_t)k * g.Mpad + j);
       acc += (criterion == 0) ? fabsf(d) : d * d;
     }
@@ -346,7 +383,7 @@ bb_loss_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, const
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     if (tid == 0) {
-      loss_out[0] = (float)(tot / ((double)g.B * g.N * BB_D));
+      loss_out[0] = (float)(tot / ((double)g.B * g.N * D));
       *ticket = 0u;
     }
   }
@@ -385,6 +422,46 @@ bb_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt, c
     out = (criterion == 0) ? ((d > 0.f) ? scale : ((d < 0.f) ? -scale : 0.f)) : 2.0f * d * scale;
   }
   d_sr[t] = out;
+}
+
+// ---- GramLoss backward --------------------------------------------------------------------------
+// loss = mean over B*N*9 of |G1 - Gsel| (or squared); G1 = F F^T / 27 of the SR patch.
+//   dL/dG1[a][b] = scale * sign(G1 - Gsel)[a][b]                 (or 2*diff)
+//   dL/dF[a][s]  = sum_b (dG[a][b] + dG[b][a]) F[b][s] / 27
+// One thread per patch; every pixel covered by a patch belongs to exactly one, the rest stay 0.
+__global__ void __launch_bounds__(256)
+gram_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const float* __restrict__ gt2,
+                     const float* __restrict__ gt4, const int64_t* __restrict__ idx, const float* __restrict__ grad_out,
+                     BbGeom g, int criterion, float* __restrict__ d_sr) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)g.B * g.N) return;
+  const int b = (int)(t / g.N), i = (int)(t - (size_t)b * g.N);
+  float v[BB_D], w[BB_D], g1[9], gs[9];
+  bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, i, v);
+  bb_gram(v, g1);
+  const int j = (int)idx[t];
+  if (j < g.N0) bb_read_patch(gt + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, j, w);
+  else if (j < g.N0 + g.N2) bb_read_patch(gt2 + (size_t)b * 3 * g.H2 * g.W2, g.H2, g.W2, g.n2x, j - g.N0, w);
+  else bb_read_patch(gt4 + (size_t)b * 3 * g.H4 * g.W4, g.H4, g.W4, g.n4x, j - g.N0 - g.N2, w);
+  bb_gram(w, gs);
+  const float scale = __ldg(grad_out) / ((float)g.B * (float)g.N * 9.0f);
+  float dG[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float d = g1[k] - gs[k];
+    dG[k] = (criterion == 0) ? ((d > 0.f) ? scale : ((d < 0.f) ? -scale : 0.f)) : 2.0f * d * scale;
+  }
+  const int py = i / g.n0x, px = i - py * g.n0x;
+  float* o = d_sr + (size_t)b * 3 * g.H * g.W;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int s9 = 0; s9 < 9; ++s9) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc = fmaf(dG[a * 3 + c] + dG[c * 3 + a], v[c * 9 + s9], acc);
+      o[((size_t)a * g.H + 3 * py + s9 / 3) * g.W + 3 * px + s9 % 3] = acc / 27.0f;
+    }
 }
 
 }  // namespace srst

@@ -391,16 +391,20 @@ int srst_bb_pyramid(const float* gt, int B, int H, int W, float* out2, float* ou
   return bb_launch_pyramid(gt, bb_geom(B, H, W), out2, out4, stream);
 }
 
-int srst_bb_forward(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
-                    float alpha, float beta, int criterion, int64_t* idx_out, float* loss_out, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+template <int MODE>
+static int bb_forward_impl(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
+                           float alpha, float beta, int criterion, int64_t* idx_out, float* loss_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  constexpr int D = BbDesc<MODE>::D;
   if (!sr || !gt || !idx_out || !loss_out || B <= 0) return SRST_E_INVALID;
   if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
   if (H < 12 || W < 12 || B > 65535) return SRST_E_SHAPE;
   if ((gt2 == nullptr) != (gt4 == nullptr)) return SRST_E_INVALID;
   const BbGeom g = bb_geom(B, H, W);
   if (!workspace || !aligned16(workspace)) return SRST_E_WORKSPACE;
-  const BbWorkspace w = bb_carve(workspace, g);
+  const BbWorkspace w = bb_carve(workspace, g, D);
   if (workspace_bytes < w.total_bytes) return SRST_E_WORKSPACE;
   int e;
   if (!gt2) {
@@ -409,15 +413,61 @@ int srst_bb_forward(const float* sr, const float* gt, const float* gt2, const fl
     gt4 = w.pyr4;
   }
   const int npack = g.Npad > g.Mpad ? g.Npad : g.Mpad;
-  SRST_LAUNCH(bb_pack_kernel, dim3((npack + 255) / 256, B), dim3(256), 0, stream, sr, gt, gt2, gt4, w.mats,
+  SRST_LAUNCH(bb_pack_kernel<MODE>, dim3((npack + 255) / 256, B), dim3(256), 0, stream, sr, gt, gt2, gt4, w.mats,
               w.per_image, g);
   if ((e = (int)cudaGetLastError()) != 0) return e;
-  SRST_LAUNCH(bb_search_kernel, dim3(g.Npad / BB_QT, B), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, alpha,
+  SRST_LAUNCH(bb_search_kernel<D>, dim3(g.Npad / BB_QT, B), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, alpha,
               beta, idx_out);
   if ((e = (int)cudaGetLastError()) != 0) return e;
   const unsigned nl = (unsigned)(((size_t)B * g.N + BB_NT - 1) / BB_NT);
-  SRST_LAUNCH(bb_loss_kernel, dim3(nl), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, idx_out, criterion,
+  SRST_LAUNCH(bb_loss_kernel<D>, dim3(nl), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, idx_out, criterion,
               w.partials, w.ticket, loss_out);
+  return (int)cudaGetLastError();
+}
+
+extern "C" {
+
+int srst_bb_forward(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
+                    float alpha, float beta, int criterion, int64_t* idx_out, float* loss_out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  return bb_forward_impl<0>(sr, gt, gt2, gt4, B, H, W, alpha, beta, criterion, idx_out, loss_out, workspace,
+                            workspace_bytes, stream);
+}
+
+int srst_gram_forward(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
+                      float alpha, float beta, int criterion, int64_t* idx_out, float* loss_out, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return bb_forward_impl<1>(sr, gt, gt2, gt4, B, H, W, alpha, beta, criterion, idx_out, loss_out, workspace,
+                            workspace_bytes, stream);
+}
+
+int srst_gram_backward(const float* sr, const float* gt, const float* gt2, const float* gt4, const int64_t* idx,
+                       const float* grad_out, int B, int H, int W, int criterion, float* d_sr, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (!sr || !gt || !idx || !grad_out || !d_sr || B <= 0) return SRST_E_INVALID;
+  if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
+  if (H < 12 || W < 12 || B > 65535) return SRST_E_SHAPE;
+  if ((gt2 == nullptr) != (gt4 == nullptr)) return SRST_E_INVALID;
+  const BbGeom g = bb_geom(B, H, W);
+  int e;
+  if (!gt2) {
+    if (!workspace || !aligned16(workspace)) return SRST_E_WORKSPACE;
+    const BbWorkspace w = bb_carve(workspace, g);
+    if (workspace_bytes < w.total_bytes) return SRST_E_WORKSPACE;
+    if ((e = bb_launch_pyramid(gt, g, w.pyr2, w.pyr4, stream)) != 0) return e;
+    gt2 = w.pyr2;
+    gt4 = w.pyr4;
+  }
+  if (H % 3 != 0 || W % 3 != 0) {  // pixels outside every patch keep a zero gradient
+#ifdef SRST_EMULATE
+    std::memset(d_sr, 0, sizeof(float) * (size_t)B * 3 * H * W);
+#else
+    if ((e = (int)cudaMemsetAsync(d_sr, 0, sizeof(float) * (size_t)B * 3 * H * W, (cudaStream_t)stream)) != 0) return e;
+#endif
+  }
+  const size_t total = (size_t)B * g.N;
+  SRST_LAUNCH(gram_backward_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, sr, gt, gt2, gt4, idx,
+              grad_out, g, criterion, d_sr);
   return (int)cudaGetLastError();
 }
 

@@ -149,8 +149,9 @@ class _BestBuddyLossFn(torch.autograd.Function):
     (w.r.t. the SR patches): the argmin is not, and gt carries no gradient (reference loss.py:135-139)."""
 
     @staticmethod
-    def forward(ctx, sr, gt, alpha, beta, criterion, pyramid):
+    def forward(ctx, sr, gt, alpha, beta, criterion, pyramid, mode="patch"):
         lib = _cabi.lib()
+        fwd = lib.srst_bb_forward if mode == "patch" else lib.srst_gram_forward
         sr = sr.contiguous()
         gt = gt.contiguous()
         B, _, H, W = sr.shape
@@ -172,12 +173,13 @@ class _BestBuddyLossFn(torch.autograd.Function):
             loss = torch.empty((), dtype=torch.float32, device=sr.device)
             nbytes = lib.srst_bb_workspace_bytes(B, H, W)
             ws = _workspace(sr.device, stream, nbytes)
-            rc = lib.srst_bb_forward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), B, H, W, float(alpha), float(beta),
+            rc = fwd(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), B, H, W, float(alpha), float(beta),
                                      int(criterion), _ptr(idx), _ptr(loss), _ptr(ws), ws.numel(),
                                      ctypes.c_void_p(stream))
-        _cabi.check(rc, "srst_bb_forward")
+        _cabi.check(rc, "srst_bb_forward" if mode == "patch" else "srst_gram_forward")
         ctx.save_for_backward(sr, gt, gt2, gt4, idx)
         ctx.criterion = int(criterion)
+        ctx.mode = mode
         ctx.mark_non_differentiable(idx)
         return loss, idx
 
@@ -187,18 +189,19 @@ class _BestBuddyLossFn(torch.autograd.Function):
         lib = _cabi.lib()
         sr, gt, gt2, gt4, idx = ctx.saved_tensors
         B, _, H, W = sr.shape
+        bwd = lib.srst_bb_backward if ctx.mode == "patch" else lib.srst_gram_backward
         if not ctx.needs_input_grad[0]:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         grad_out = grad_out.to(torch.float32).contiguous()
         with torch.cuda.device(sr.device):
             stream = torch.cuda.current_stream().cuda_stream
             d_sr = torch.empty_like(sr)
             nbytes = lib.srst_bb_workspace_bytes(B, H, W)
             ws = _workspace(sr.device, stream, nbytes)
-            rc = lib.srst_bb_backward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
+            rc = bwd(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
                                       ctx.criterion, _ptr(d_sr), _ptr(ws), ws.numel(), ctypes.c_void_p(stream))
-        _cabi.check(rc, "srst_bb_backward")
-        return d_sr, None, None, None, None, None
+        _cabi.check(rc, "srst_bb_backward" if ctx.mode == "patch" else "srst_gram_backward")
+        return d_sr, None, None, None, None, None, None
 
 
 class BestBuddyLoss(nn.Module):
@@ -246,5 +249,42 @@ class BestBuddyLoss(nn.Module):
     def forward(self, x, gt):
         _check_pair(x, gt, "BestBuddyLoss")
         loss, idx = _BestBuddyLossFn.apply(x, gt, self.alpha, self.beta, self._crit, self.pyramid)
+        self.last_indices = idx
+        return loss
+
+
+class GramLoss(nn.Module):
+    """Gram loss; same signature and semantics as reference loss.py:146-225: the best-buddy search
+    and the final criterion run on the 3x3 Gram matrix of every 3x3x3 patch instead of its pixels.
+    Only ``ksize=3`` and ``dist_norm='l2'`` have kernels (the reference's defaults)."""
+
+    def __init__(self, alpha: float = 1.0, beta: float = 1.0, ksize: int = 3, dist_norm: str = "l2",
+                 criterion: str = "l1", pyramid: str = "aten"):
+        super().__init__()
+        self.alpha = alpha
+        self.beta = beta
+        self.ksize = ksize
+        self.dist_norm = dist_norm
+        if criterion == "l1":
+            self.criterion = torch.nn.L1Loss()
+            self._crit = 0
+        elif criterion == "l2" or criterion == "mse":
+            self.criterion = torch.nn.MSELoss()
+            self._crit = 1
+        else:
+            raise NotImplementedError("%s criterion has not been implmented." % criterion)  # loss.py:178
+        if dist_norm not in ("l1", "l2"):
+            raise NotImplementedError("%s norm has not been supported." % dist_norm)        # utils.py:189
+        if dist_norm != "l2" or ksize != 3:
+            raise NotImplementedError("GramLoss: libsrst.so implements ksize=3, dist_norm='l2' only")
+        if pyramid not in ("aten", "fused"):
+            raise ValueError("pyramid must be 'aten' or 'fused'")
+        self.pyramid = pyramid
+        self.last_indices = None
+        _cabi.lib()
+
+    def forward(self, x, gt):
+        _check_pair(x, gt, "GramLoss")
+        loss, idx = _BestBuddyLossFn.apply(x, gt, self.alpha, self.beta, self._crit, self.pyramid, "gram")
         self.last_indices = idx
         return loss

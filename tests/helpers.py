@@ -90,7 +90,7 @@ def emu_st(lib, sr, hr, taps, normalize=True, want_hr=False, grad_out=1.0, save_
     return out
 
 
-def emu_bb(lib, sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion=0, grad_out=1.0):
+def emu_bb(lib, sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion=0, grad_out=1.0, mode="patch"):
     """Run srst_bb_forward + srst_bb_backward of `lib` on host arrays (emulation library only)."""
     sr = np.ascontiguousarray(sr, np.float32)
     gt = np.ascontiguousarray(gt, np.float32)
@@ -102,12 +102,12 @@ def emu_bb(lib, sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion=0, gr
     ws = np.zeros(nb // 4 + 4, np.float32)
     idx = np.full((B, N), -1, np.int64)
     loss = np.zeros(1, np.float32)
-    rc = lib.srst_bb_forward(_p(sr), _p(gt), _p(gt2), _p(gt4), B, H, W, alpha, beta, criterion, _p(idx), _p(loss),
-                             _p(ws), nb, None)
+    fwd = lib.srst_bb_forward if mode == "patch" else lib.srst_gram_forward
+    bwd = lib.srst_bb_backward if mode == "patch" else lib.srst_gram_backward
+    rc = fwd(_p(sr), _p(gt), _p(gt2), _p(gt4), B, H, W, alpha, beta, criterion, _p(idx), _p(loss), _p(ws), nb, None)
     assert rc == 0, rc
     go = np.full(1, grad_out, np.float32)
     d_sr = np.full_like(sr, np.nan)
-    rc = lib.srst_bb_backward(_p(sr), _p(gt), _p(gt2), _p(gt4), _p(idx), _p(go), B, H, W, criterion, _p(d_sr),
-                              _p(ws), nb, None)
+    rc = bwd(_p(sr), _p(gt), _p(gt2), _p(gt4), _p(idx), _p(go), B, H, W, criterion, _p(d_sr), _p(ws), nb, None)
     assert rc == 0, rc
     return dict(loss=float(loss[0]), idx=idx, d_sr=d_sr)
