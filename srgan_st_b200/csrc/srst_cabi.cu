@@ -11,6 +11,7 @@
 
 #include "st_kernels.cuh"
 #include "st_stream.cuh"
+#include "st_wide.cuh"
 #include "bb_kernels.cuh"
 
 namespace srst {
@@ -40,6 +41,9 @@ using BwdB = StBwdCfg<16, 96, 10, 256, 2, 8, 2>;  // 96-wide training crops
 using BwdC = StBwdCfg<32, 64, 12, 352, 2, 8, 1>;  // one big CTA per SM
 using BwdD = StBwdCfg<28, 56, 16, 256, 2, 8, 2>;  // 16 row pairs per phase item column: no LDS bank conflicts
 using BwdE = StBwdCfg<28, 88, 16, 384, 2, 8, 1>;  // experiment
+
+//                             TH  TW  RS   NT
+using WideA = StWideFwdCfg<48, 96, 12, 384>;  // half a 96x96 training crop per CTA, one CTA per SM
 
 constexpr int kMinFwdTH = 24, kMinFwdTW = 32;  // finest compiled forward tiling (workspace sizing)
 
@@ -112,7 +116,19 @@ static int launch_st_forward(StFwdParams<C::RG, C::RK> P, void* stream) {
   // persistent grid: one wave of resident CTAs, each looping over tiles
   const long long slots = (long long)sm_count() * C::MINB;
   const long long nblk = (C::NP == 0 || ntiles < slots) ? ntiles : slots;
-  SRST_LAUNCH(st_forward_kernel<C>, dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  SRST_LAUNCH_PDL(st_forward_kernel<C>, dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  return (int)cudaGetLastError();
+}
+
+template <class C>
+static int launch_st_wide_forward(StFwdParams<C::RG, C::RK> P, void* stream) {
+  P.tiles_x = (P.W + C::TW - 1) / C::TW;
+  P.tiles_y = (P.H + C::TH - 1) / C::TH;
+  const long long ntiles = (long long)P.B * P.tiles_x * P.tiles_y;
+  if (ntiles <= 0 || ntiles > 0x7fffffffLL) return SRST_E_SHAPE;
+  int e = ensure_smem<C>(st_wide_forward_kernel<C>, C::SMEM_BYTES);
+  if (e) return e;
+  SRST_LAUNCH_PDL(st_wide_forward_kernel<C>, dim3((unsigned)ntiles), dim3(C::NT), C::SMEM_BYTES, stream, P);
   return (int)cudaGetLastError();
 }
 
@@ -161,13 +177,13 @@ static int launch_st_backward(StBwdParams<C::RG, C::RK> P, const float* gray, vo
   if (nblk <= 0 || nblk > 0x7fffffffLL) return SRST_E_SHAPE;
   int e = ensure_smem<C>(st_backward_kernel<C>, C::SMEM_BYTES);
   if (e) return e;
-  SRST_LAUNCH(st_backward_kernel<C>, dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  SRST_LAUNCH_PDL(st_backward_kernel<C>, dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
   return (int)cudaGetLastError();
 }
 
 static int pick_fwd_cfg(int H, int W) {
   const int forced = env_int("SRST_ST_FWD_CFG", -1);
-  if (forced >= 0 && forced <= 9) return forced;
+  if (forced >= 0 && forced <= 10) return forced;
   // measured on B200 (profiles/r01_v2_tile_sweep.log): square 48x48 tiles win on 96-wide crops,
   // the 3-CTA/SM 32x64 tile wins on large images
   if (W <= 96) return 2;
@@ -279,10 +295,14 @@ static int st_forward_rr(const StCall& c) {
   P.B = c.B; P.H = c.H; P.W = c.W; P.tiles_x = P.tiles_y = 0;
   P.normalize = c.normalize; P.vec4 = c.vec4; P.eps = c.eps;
   P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
+  // SRST_ST_DEBUG=1: CTA 0 writes per-warp phase time stamps at byte 4096 of the workspace (tools/wide_debug.py)
+  P.debug = env_int("SRST_ST_DEBUG", 0) ? reinterpret_cast<long long*>(reinterpret_cast<char*>(c.workspace) + 4096) : nullptr;
   fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
     if (c.vec4 && !c.gray0 && !c.gray1 && env_int("SRST_ST_STREAM", 0) == 1) return launch_st_stream<StreamA>(c);
-    switch (pick_fwd_cfg(c.H, c.W)) {
+    const int cfg = pick_fwd_cfg(c.H, c.W);
+    if (cfg == 10 && c.vec4 && !c.gray0 && !c.gray1) return launch_st_wide_forward<WideA>(P, c.stream);
+    switch (cfg) {
       case 0: return launch_st_forward<FwdA>(P, c.stream);
       case 1: return launch_st_forward<FwdB>(P, c.stream);
       case 2: return launch_st_forward<FwdC>(P, c.stream);
@@ -304,7 +324,7 @@ static int st_backward_rr(const StCall& c) {
   StBwdParams<RG, RK> P;
   std::memset(&P.ds_map, 0, sizeof(P.ds_map));
   std::memset(&P.gray_map, 0, sizeof(P.gray_map));
-  P.use_tma = 0; P.use_gray = 0;
+  P.use_tma = 0; P.use_gray = 0; P.debug = nullptr;
   P.img = c.a; P.ds = c.b; P.grad_out = c.grad_out; P.d_img = c.o0;
   P.B = c.B; P.H = c.H; P.W = c.W; P.tiles_x = P.tiles_y = 0;
   P.vec4 = c.vec4;

@@ -13,19 +13,52 @@
 #define SRST_LAUNCH(kernel, grid, block, smem, stream, ...) \
   emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
 #define SRST_SET_SMEM(kernel, bytes) (0)
+#define SRST_LAUNCH_PDL(kernel, grid, block, smem, stream, P) SRST_LAUNCH(kernel, grid, block, smem, stream, P)
 #else
 #include <cuda_runtime.h>
+#include <cstdlib>
 #define SRST_DYN_SMEM(T, name) extern __shared__ __align__(128) unsigned char name##_raw_[]; \
   T* name = reinterpret_cast<T*>(name##_raw_)
 #define SRST_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #define SRST_SET_SMEM(kernel, bytes) \
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+// Launch with programmatic stream serialization (PDL): the grid may be scheduled while the previous
+// kernel of the stream is still draining; the kernel itself calls pdl_wait() before it touches
+// global memory, so only launch latency and CTA set-up overlap.  SRST_PDL=0 turns it off.
+#define SRST_LAUNCH_PDL(kernel, grid, block, smem, stream, P)                                   \
+  do {                                                                                           \
+    cudaLaunchConfig_t cfg_ = {};                                                                \
+    cfg_.gridDim = (grid); cfg_.blockDim = (block); cfg_.dynamicSmemBytes = (smem);              \
+    cfg_.stream = (cudaStream_t)(stream);                                                        \
+    cudaLaunchAttribute at_[1];                                                                  \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                              \
+    at_[0].val.programmaticStreamSerializationAllowed = 1;                                       \
+    cfg_.attrs = at_; cfg_.numAttrs = srst::pdl_enabled() ? 1 : 0;                               \
+    cudaLaunchKernelEx(&cfg_, kernel, P);                                                        \
+  } while (0)
 #endif
 
 #define SRST_DEV __device__ __forceinline__
 
 namespace srst {
+
+#ifndef SRST_EMULATE
+inline bool pdl_enabled() {
+  const char* e = std::getenv("SRST_PDL");
+  return !(e && e[0] == '0');
+}
+#endif
+// Programmatic dependent launch hooks (no-ops for kernels launched without the PDL attribute):
+// pdl_wait() blocks until the previous kernel of the stream has completed and its writes are
+// visible; pdl_trigger() lets the next PDL-launched kernel of the stream start its own launch.
+#ifdef SRST_EMULATE
+SRST_DEV void pdl_wait() {}
+SRST_DEV void pdl_trigger() {}
+#else
+SRST_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+SRST_DEV void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 constexpr int round_up4(int x) { return (x + 3) / 4 * 4; }
 constexpr int round_dn4(int x) { return x / 4 * 4; }

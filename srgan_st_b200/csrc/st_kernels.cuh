@@ -56,6 +56,7 @@ struct StFwdParams {
   int vec4;  // 1: W % 4 == 0 and all base pointers 16-byte aligned
   float eps;
   float inv_count;
+  long long* debug;  // optional (SRST_ST_DEBUG=1): per-warp phase time stamps of CTA 0
   StTaps<RG, RK> taps;
 };
 
@@ -72,6 +73,7 @@ struct StBwdParams {
   int use_tma;
   int use_gray;  // 1: the gray tile comes from gray_map by TMA instead of RGB loads + conversion
   float inv_count;
+  long long* debug;
   StTaps<RG, RK> taps;
 };
 
@@ -786,6 +788,8 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
   __shared__ unsigned int s_last;
   const int tid = threadIdx.x;
   const int ntiles = P.B * P.tiles_y * P.tiles_x;
+  pdl_wait();     // previous kernel of the stream is complete (it may have produced sr or used the workspace)
+  pdl_trigger();  // the next PDL-launched kernel may start launching; it waits for this grid itself
 
   if (C::NP > 0 && tid >= C::NC) {
     // ---- producer warps: RGB tile (+halo) -> gray -> sG, one unit ahead of the compute warps ----
@@ -924,6 +928,8 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   float* sdI1 = sX + C::I_FLOATS;
 
   const int tid = threadIdx.x;
+  pdl_wait();     // the forward kernel that wrote ds is complete
+  pdl_trigger();
   int tile = blockIdx.x;
   const int tx = tile % P.tiles_x;
   tile /= P.tiles_x;

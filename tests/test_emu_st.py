@@ -15,7 +15,7 @@ def lib():
     return emu_lib()
 
 
-@pytest.fixture(params=[0, 1, 2, 3, 4])
+@pytest.fixture(params=[0, 1, 2, 3, 4, 10])
 def tile_cfg(request, monkeypatch):
     monkeypatch.setenv("SRST_ST_FWD_CFG", str(request.param))
     monkeypatch.setenv("SRST_ST_BWD_CFG", str(min(request.param, 2)))

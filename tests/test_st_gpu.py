@@ -31,9 +31,9 @@ def _run(sr, hr, normalize=True, want_hr=True, sigma=0.5, rho=2.0):
     return loss.item(), x.grad.cpu().numpy(), (y.grad.cpu().numpy() if want_hr else None)
 
 
-@pytest.fixture(params=[-1, 0, 1, 2, 3, 4, "stream"])
+@pytest.fixture(params=[-1, 0, 1, 2, 3, 4, 10, "stream"])
 def tile_cfg(request, monkeypatch):
-    """-1 = the library's own choice; 0..4 force a compiled tile shape; "stream" forces the
+    """-1 = the library's own choice; 0..4 force a compiled tile shape, 10 the wide-strip kernels; "stream" forces the
     row-marching forward kernel."""
     if request.param == "stream":
         monkeypatch.setenv("SRST_ST_STREAM", "1")
