@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRST_VERSION 100 /* major*10000 + minor*100 + patch */
+#define SRST_VERSION 101 /* major*10000 + minor*100 + patch */
 
 #define SRST_E_INVALID (-1)     /* null pointer / non-positive size / bad enum */
 #define SRST_E_UNSUPPORTED (-2) /* filter radius or patch geometry not compiled in */
@@ -132,6 +132,32 @@ int srst_gram_backward(const float* sr, const float* gt, const float* gt2, const
                        const int64_t* idx, const float* grad_out,
                        int B, int H, int W, int criterion,
                        float* d_sr, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Patchwise structure-tensor loss (reference loss.py:292-375): the same three-level best-buddy
+ * search, but every 3x3x3 patch is replaced by the det-normalised structure tensor of the patch
+ * seen as a 3x3 image (Grayscale -> utils.structure_tensor(sigma, rho) with zero 'same' padding
+ * -> utils.normalize; 27-dim descriptor c*9 + y*3 + x, c in Jxx,Jyy,Jxy), replacing
+ *   vmap(vmap(s_norm)) over [B,N,3,3,3]            (loss.py:325-345)
+ *   batch_pairwise_distance x2, torch.min, gather  (loss.py:361-369)
+ *   L1Loss / MSELoss on the descriptors            (loss.py:371)
+ * g, dg, k: host taps as for srst_st_forward; any radius >= 1 is accepted (a 3x3 image only sees
+ * the five central taps).  Workspace: srst_bb_workspace_bytes.
+ *   d_sr = through the criterion, utils.normalize and the structure tensor of the SR patch
+ *          (argmin is not differentiated).
+ * ------------------------------------------------------------------------------------------- */
+int srst_pst_forward(const float* sr, const float* gt, const float* gt2, const float* gt4,
+                     int B, int H, int W,
+                     const float* g, const float* dg, int r_sigma, const float* k, int r_rho,
+                     float alpha, float beta, int criterion,
+                     int64_t* idx_out, float* loss_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int srst_pst_backward(const float* sr, const float* gt, const float* gt2, const float* gt4,
+                      const int64_t* idx, const float* grad_out,
+                      int B, int H, int W,
+                      const float* g, const float* dg, int r_sigma, const float* k, int r_rho,
+                      int criterion,
+                      float* d_sr, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The HR pyramid on its own (exposed for tests): out2 [B,3,H/2,W/2], out4 [B,3,H/4,W/4]. */
 int srst_bb_pyramid(const float* gt, int B, int H, int W, float* out2, float* out4, void* stream);

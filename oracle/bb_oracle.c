@@ -71,19 +71,72 @@ static void gram9(const float* v, float* g) {
       g[a * 3 + b] = s / 27.0f;
     }
 }
-/* descriptor of a patch: mode 0 = raw 27 values (BestBuddyLoss), mode 1 = Gram matrix (GramLoss) */
+/* PatchwiseStructureTensorLoss descriptor (reference loss.py:325-345): the patch as a 3x3 image ->
+ * Grayscale (loss.py:327) -> utils.structure_tensor with zero 'same' padding (utils.py:212-233; on a
+ * 3x3 image only the five central taps of each filter matter) -> utils.normalize (utils.py:236-239).
+ * taps = g5[5] | dg5[5] | k5[5] (offsets -2..2).  Explicitly rounded fp32, fixed order, same as the
+ * CUDA kernel (bb_kernels.cuh pst_state). */
+static const float* g_pst_taps = 0;
+void bb_oracle_set_pst_taps(const float* taps15) { g_pst_taps = taps15; }
+static void vert3(const float* w, const float* X, float* o) {
+  for (int i = 0; i < 3; ++i)
+    for (int x = 0; x < 3; ++x) {
+      float s = 0.f;
+      for (int j = 0; j < 3; ++j) s = fmaf(w[j - i + 2], X[j * 3 + x], s);
+      o[i * 3 + x] = s;
+    }
+}
+static void horz3(const float* w, const float* X, float* o) {
+  for (int i = 0; i < 3; ++i)
+    for (int x = 0; x < 3; ++x) {
+      float s = 0.f;
+      for (int j = 0; j < 3; ++j) s = fmaf(w[j - x + 2], X[i * 3 + j], s);
+      o[i * 3 + x] = s;
+    }
+}
+static void pst27(const float* v, float* out) {
+  const float *g5 = g_pst_taps, *dg5 = g_pst_taps + 5, *k5 = g_pst_taps + 10;
+  float gray[9], t[9], Ix[9], Iy[9], p[9], J[3][9];
+  for (int i = 0; i < 9; ++i) {
+    const float a = 0.2989f * v[i], b = 0.587f * v[9 + i], c = 0.114f * v[18 + i];
+    const float ab = a + b;
+    gray[i] = ab + c;
+  }
+  vert3(dg5, gray, t); horz3(g5, t, Ix);
+  vert3(g5, gray, t);  horz3(dg5, t, Iy);
+  for (int c = 0; c < 3; ++c) {
+    for (int i = 0; i < 9; ++i) p[i] = (c == 1 ? Iy[i] : Ix[i]) * (c == 0 ? Ix[i] : Iy[i]);
+    vert3(k5, p, t);
+    horz3(k5, t, J[c]);
+  }
+  for (int i = 0; i < 9; ++i) {
+    const float ab = J[0][i] * J[1][i], cc = J[2][i] * J[2][i];
+    const float det = ab - cc;
+    const float q = sqrtf(det + 1e-12f);
+    for (int c = 0; c < 3; ++c) out[c * 9 + i] = J[c][i] / q;
+  }
+}
+/* descriptor of a patch: mode 0 = raw 27 values (BestBuddyLoss), mode 1 = Gram matrix (GramLoss),
+ * mode 2 = normalised structure tensor of the patch (PatchwiseStructureTensorLoss) */
 static void describe(const float* img, int H, int W, int nx, int p, int mode, float* out) {
   float v[D];
   read_patch(img, H, W, nx, p, v);
   if (mode == 0) for (int k = 0; k < D; ++k) out[k] = v[k];
-  else gram9(v, out);
+  else if (mode == 1) gram9(v, out);
+  else pst27(v, out);
+}
+/* descriptors of all level-0 patches of img [B,3,H,W] -> out [B,N,Dd] (tests) */
+void bb_oracle_describe(const float* img, int B, int H, int W, int mode, float* out) {
+  const int Dd = mode == 1 ? 9 : D, nx = W / 3, N = (H / 3) * nx;
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < N; ++i) describe(img + (size_t)b * 3 * H * W, H, W, nx, i, mode, out + ((size_t)b * N + i) * Dd);
 }
 
 /* Returns 0 on success.  idx [B,N] int64; loss_out 1 double; best/second [B,N] fp32 scores (may be NULL). */
 int bb_oracle_forward_mode(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
                            float alpha, float beta, int criterion, int mode, int64_t* idx, double* loss_out,
                            float* best_out, float* second_out) {
-  const int Dd = mode == 0 ? D : 9;
+  const int Dd = mode == 1 ? 9 : D;
   const int n0x = W / 3, N0 = (H / 3) * n0x;
   const int H2 = H / 2, W2 = W / 2, n2x = W2 / 3, N2 = (H2 / 3) * n2x;
   const int H4 = H / 4, W4 = W / 4, n4x = W4 / 3, N4 = (H4 / 3) * n4x;

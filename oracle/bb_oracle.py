@@ -55,8 +55,41 @@ def geometry(H, W):
     return N0, N0 + N2 + N4
 
 
-def bb_forward_c(sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion="l1", mode="patch"):
-    """mode="patch": BestBuddyLoss (27 raw values); mode="gram": GramLoss (3x3 Gram matrix, loss.py:146-225)."""
+_MODES = {"patch": 0, "gram": 1, "pst": 2}
+_taps_keepalive = None
+
+
+def pst_taps5(g, dg, k):
+    """Central five taps (offsets -2..2) of g, dg, k: all a 3x3 patch image can see."""
+    def c5(t):
+        t = np.asarray(t, np.float32)
+        r = len(t) // 2
+        return [t[r + i] if -r <= i <= r else np.float32(0) for i in range(-2, 3)]
+    return np.asarray(c5(g) + c5(dg) + c5(k), np.float32)
+
+
+def _set_pst_taps(taps):
+    global _taps_keepalive
+    _taps_keepalive = np.ascontiguousarray(pst_taps5(*taps), np.float32)
+    _load().bb_oracle_set_pst_taps(_fp(_taps_keepalive))
+
+
+def describe_c(img, mode="pst", taps=None):
+    """fp32 descriptors [B,N,D] of the level-0 patches, same operation order as the CUDA pack kernel."""
+    img = np.ascontiguousarray(img, np.float32)
+    B, _, H, W = img.shape
+    if mode == "pst":
+        _set_pst_taps(taps)
+    out = np.empty((B, (H // 3) * (W // 3), 9 if mode == "gram" else 27), np.float32)
+    _load().bb_oracle_describe(_fp(img), B, H, W, _MODES[mode], _fp(out))
+    return out
+
+
+def bb_forward_c(sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion="l1", mode="patch", taps=None):
+    """mode="patch": BestBuddyLoss (27 raw values); mode="gram": GramLoss (3x3 Gram matrix, loss.py:146-225);
+    mode="pst": PatchwiseStructureTensorLoss (loss.py:292-375), taps = (g, dg, k) of utils.get_gaussian_kernel."""
+    if mode == "pst":
+        _set_pst_taps(taps)
     sr = np.ascontiguousarray(sr, np.float32)
     gt = np.ascontiguousarray(gt, np.float32)
     if gt2 is None:
@@ -70,7 +103,7 @@ def bb_forward_c(sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion="l1"
     second = np.empty((B, N), np.float32)
     loss = ctypes.c_double(0.0)
     rc = _load().bb_oracle_forward_mode(_fp(sr), _fp(gt), _fp(gt2), _fp(gt4), B, H, W, ctypes.c_float(alpha),
-                                   ctypes.c_float(beta), 0 if criterion == "l1" else 1, 0 if mode == "patch" else 1,
+                                   ctypes.c_float(beta), 0 if criterion == "l1" else 1, _MODES[mode],
                                    idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.byref(loss),
                                    _fp(best), _fp(second))
     assert rc == 0
@@ -128,6 +161,68 @@ def gram_backward(sr, sel_desc, criterion="l1"):
     diff = G1 - sel_desc.reshape(B, ny * nx, 3, 3)
     dG = (np.sign(diff) if criterion == "l1" else 2.0 * diff) / diff.size
     dF = np.einsum("bnac,bncs->bnas", dG + dG.transpose(0, 1, 3, 2), p) / 27.0
+    out = np.zeros_like(sr)
+    out[:, :, :ny * 3, :nx * 3] = dF.reshape(B, ny, nx, C, 3, 3).transpose(0, 3, 1, 4, 2, 5).reshape(B, C, ny * 3, nx * 3)
+    return out
+
+
+# ---- PatchwiseStructureTensorLoss (loss.py:292-375), float64 -------------------------------------
+_GRAY = np.array([0.2989, 0.587, 0.114])
+
+
+def _band3(w):
+    """3x3 matrix M[i][j] = w[j - i + r] of a zero-padded cross-correlation on a length-3 signal."""
+    w = np.asarray(w, np.float64)
+    r = len(w) // 2
+    M = np.zeros((3, 3))
+    for i in range(3):
+        for j in range(3):
+            if 0 <= j - i + r < len(w):
+                M[i, j] = w[j - i + r]
+    return M
+
+
+def _pst_parts(img, taps):
+    g, dg, k = taps
+    G, DG, K = _band3(g), _band3(dg), _band3(k)
+    p = unfold3(np.asarray(img, np.float64))
+    p = p.reshape(p.shape[0], p.shape[1], 3, 3, 3)
+    gray = np.einsum("c,bncyx->bnyx", _GRAY, p)
+    Ix = np.einsum("ij,bnjk,xk->bnix", DG, gray, G)      # (im * dg|) * g-   utils.py:219-220
+    Iy = np.einsum("ij,bnjk,xk->bnix", G, gray, DG)      # (im * g|) * dg-   utils.py:221-222
+    sm = lambda a: np.einsum("ij,bnjk,xk->bnix", K, a, K)
+    J = np.stack([sm(Ix * Ix), sm(Iy * Iy), sm(Ix * Iy)], 2)   # [B,N,3,3,3]
+    q = np.sqrt(J[:, :, 0] * J[:, :, 1] - J[:, :, 2] ** 2 + 1e-12)
+    return Ix, Iy, J, q, (G, DG, K)
+
+
+def pst_descriptors(img, taps):
+    """[B,3,H,W] -> [B,N,27] float64: normalised structure tensor of every 3x3 patch (loss.py:325-345)."""
+    _, _, J, q, _ = _pst_parts(img, taps)
+    return (J / q[:, :, None]).reshape(J.shape[0], J.shape[1], 27)
+
+
+def pst_backward(sr, sel_desc, taps, criterion="l1"):
+    """d PatchwiseStructureTensorLoss / d sr given the selected candidate descriptors [B,N,27] (float64)."""
+    sr = np.asarray(sr, np.float64)
+    B, C, H, W = sr.shape
+    ny, nx = H // 3, W // 3
+    Ix, Iy, J, q, (G, DG, K) = _pst_parts(sr, taps)
+    Dn = J / q[:, :, None]
+    diff = Dn - sel_desc.reshape(Dn.shape)
+    dD = (np.sign(diff) if criterion == "l1" else 2.0 * diff) / diff.size
+    s = (J * dD).sum(2)
+    ddet = -s / (2.0 * q ** 3)
+    dJ = dD / q[:, :, None]
+    dJ[:, :, 0] += ddet * J[:, :, 1]
+    dJ[:, :, 1] += ddet * J[:, :, 0]
+    dJ[:, :, 2] -= 2.0 * ddet * J[:, :, 2]
+    smT = lambda a: np.einsum("ij,bnix,xk->bnjk", K, a, K)
+    dP = [smT(dJ[:, :, c]) for c in range(3)]
+    dIx = 2 * Ix * dP[0] + Iy * dP[2]
+    dIy = 2 * Iy * dP[1] + Ix * dP[2]
+    dgray = np.einsum("ij,bnix,xk->bnjk", DG, dIx, G) + np.einsum("ij,bnix,xk->bnjk", G, dIy, DG)
+    dF = _GRAY[None, None, :, None, None] * dgray[:, :, None]          # [B,N,3,3,3]
     out = np.zeros_like(sr)
     out[:, :, :ny * 3, :nx * 3] = dF.reshape(B, ny, nx, C, 3, 3).transpose(0, 3, 1, 4, 2, 5).reshape(B, C, ny * 3, nx * 3)
     return out

@@ -39,6 +39,13 @@ SIGNATURES = {
                                          vp, ctypes.c_size_t, vp]),
     "srst_gram_backward": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
+    "srst_pst_forward": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
+                                        ctypes.c_float, ctypes.c_float, ctypes.c_int, vp, vp,
+                                        vp, ctypes.c_size_t, vp]),
+    "srst_pst_backward": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
+                                         ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
     "srst_bb_pyramid": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
 }
 

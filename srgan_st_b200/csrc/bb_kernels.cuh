@@ -17,6 +17,10 @@
 //   alpha * max((xn + yn) - 2*dot1, 0) + beta * max((gn + yn) - 2*dot2, 0),
 // with a fixed fp32 order for the 27-term dot products and norms (sequential FMA, k = 0..26;
 // oracle/bb_oracle.c restates the same order so indices can be compared bit-exactly).
+//
+// The same pack / search / loss kernels serve three descriptor MODEs: 0 = raw 27 patch values
+// (BestBuddyLoss), 1 = 3x3 Gram matrix (GramLoss, loss.py:146-225), 2 = det-normalised structure
+// tensor of the 3x3 grayscale patch (PatchwiseStructureTensorLoss, loss.py:292-375).
 #pragma once
 #include <cstdint>
 
@@ -170,16 +174,112 @@ SRST_DEV void bb_gram(const float (&v)[BB_D], float (&gm)[9]) {
     }
 }
 
-// Descriptor of a patch: MODE 0 = the 27 raw values (BestBuddyLoss), MODE 1 = Gram matrix (GramLoss).
+
+// ---- PatchwiseStructureTensorLoss descriptor (reference loss.py:325-345 s_norm / compute_patches) ----
+// Every 3x3x3 patch is treated as a 3x3 IMAGE: Grayscale -> utils.structure_tensor(sigma, rho) with
+// zero 'same' padding -> utils.normalize.  On a 3x3 image only the five central taps of each filter
+// can touch a pixel, so a separable pass is a 3x3 banded matrix product:
+//   vert(w, X)[i][x] = sum_j w[j-i+2] X[j][x]      horz(w, X)[i][x] = sum_j w[j-x+2] X[i][j]
+// (cross-correlation like conv2d, utils.py:219-230).  Descriptor element c*9 + i*3 + x with c in
+// (Jxx, Jyy, Jxy) / sqrt(det + 1e-12).  Every operation is an explicitly rounded fp32 op in a fixed
+// order (oracle/bb_oracle.c restates it), so the search indices are bit-comparable.
+struct PstTaps {
+  float g[5], dg[5], k[5];  // central taps (offset -2..2) of Gaussian(sigma), its derivative, Gaussian(rho)
+};
+constexpr float kPstEps = 1e-12f;  // utils.normalize default (utils.py:236)
+
+SRST_DEV void pst_vert(const float (&w)[5], const float (&X)[9], float (&o)[9]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) s = fmaf(w[j - i + 2], X[j * 3 + x], s);
+      o[i * 3 + x] = s;
+    }
+}
+SRST_DEV void pst_horz(const float (&w)[5], const float (&X)[9], float (&o)[9]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) s = fmaf(w[j - x + 2], X[i * 3 + j], s);
+      o[i * 3 + x] = s;
+    }
+}
+// adjoints: vertT(w, dO)[j][x] = sum_i w[j-i+2] dO[i][x] ; horzT(w, dO)[i][j] = sum_x w[j-x+2] dO[i][x]
+SRST_DEV void pst_vert_t(const float (&w)[5], const float (&dO)[9], float (&o)[9]) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s = fmaf(w[j - i + 2], dO[i * 3 + x], s);
+      o[j * 3 + x] = s;
+    }
+}
+SRST_DEV void pst_horz_t(const float (&w)[5], const float (&dO)[9], float (&o)[9]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) s = fmaf(w[j - x + 2], dO[i * 3 + x], s);
+      o[i * 3 + j] = s;
+    }
+}
+
+// Gradients and raw structure tensor of one patch (v = 27 patch values, element c*9 + y*3 + x).
+struct PstState {
+  float Ix[9], Iy[9], J[3][9], q[9];  // q = sqrt(det + eps)
+};
+SRST_DEV void pst_state(const float (&v)[BB_D], const PstTaps& tp, PstState& S) {
+  float gray[9], t[9], p[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+    gray[i] = __fadd_rn(__fadd_rn(__fmul_rn(kGrayR, v[i]), __fmul_rn(kGrayG, v[9 + i])), __fmul_rn(kGrayB, v[18 + i]));
+  pst_vert(tp.dg, gray, t); pst_horz(tp.g, t, S.Ix);   // utils.py:219-220
+  pst_vert(tp.g, gray, t);  pst_horz(tp.dg, t, S.Iy);  // utils.py:221-222
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) p[i] = __fmul_rn(c == 1 ? S.Iy[i] : S.Ix[i], c == 0 ? S.Ix[i] : S.Iy[i]);
+    pst_vert(tp.k, p, t);
+    pst_horz(tp.k, t, S.J[c]);                         // utils.py:225-230
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const float det = __fsub_rn(__fmul_rn(S.J[0][i], S.J[1][i]), __fmul_rn(S.J[2][i], S.J[2][i]));
+    S.q[i] = __fsqrt_rn(__fadd_rn(det, kPstEps));      // utils.py:238-239
+  }
+}
+SRST_DEV void pst_descriptor(const float (&v)[BB_D], const PstTaps& tp, float (&d)[BB_D]) {
+  PstState S;
+  pst_state(v, tp, S);
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) d[c * 9 + i] = __fdiv_rn(S.J[c][i], S.q[i]);
+}
+
+// Descriptor of a patch: MODE 0 = the 27 raw values (BestBuddyLoss), MODE 1 = Gram matrix (GramLoss),
+// MODE 2 = normalised structure tensor of the patch (PatchwiseStructureTensorLoss).
 template <int MODE>
 struct BbDesc {
-  static constexpr int D = MODE == 0 ? BB_D : 9;
-  SRST_DEV static void make(const float (&v)[BB_D], float (&d)[D]) {
+  static constexpr int D = MODE == 1 ? 9 : BB_D;
+  SRST_DEV static void make(const float (&v)[BB_D], const PstTaps& tp, float (&d)[D]) {
     if constexpr (MODE == 0) {
 #pragma unroll
       for (int k = 0; k < BB_D; ++k) d[k] = v[k];
-    } else {
+    } else if constexpr (MODE == 1) {
       bb_gram(v, d);
+    } else {
+      pst_descriptor(v, tp, d);
     }
   }
 };
@@ -187,7 +287,7 @@ struct BbDesc {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 bb_pack_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const float* __restrict__ gt2,
-               const float* __restrict__ gt4, float* __restrict__ mats, size_t per_image, BbGeom g) {
+               const float* __restrict__ gt4, float* __restrict__ mats, size_t per_image, BbGeom g, PstTaps tp) {
   constexpr int D = BbDesc<MODE>::D;
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,12 +302,12 @@ bb_pack_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const
   if (t < g.Npad) {  // query t
     if (t < g.N) {
       bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, t, v);
-      BbDesc<MODE>::make(v, d);
+      BbDesc<MODE>::make(v, tp, d);
 #pragma unroll
       for (int k = 0; k < D; ++k) q1[(size_t)k * g.Npad + t] = d[k];
       xn[t] = bb_norm<D>(d);
       bb_read_patch(gt + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, t, v);
-      BbDesc<MODE>::make(v, d);
+      BbDesc<MODE>::make(v, tp, d);
 #pragma unroll
       for (int k = 0; k < D; ++k) q2[(size_t)k * g.Npad + t] = d[k];
       gn[t] = bb_norm<D>(d);
@@ -223,7 +323,7 @@ bb_pack_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const
       if (t < g.N0) bb_read_patch(gt + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, t, v);
       else if (t < g.N0 + g.N2) bb_read_patch(gt2 + (size_t)b * 3 * g.H2 * g.W2, g.H2, g.W2, g.n2x, t - g.N0, v);
       else bb_read_patch(gt4 + (size_t)b * 3 * g.H4 * g.W4, g.H4, g.W4, g.n4x, t - g.N0 - g.N2, v);
-      BbDesc<MODE>::make(v, d);
+      BbDesc<MODE>::make(v, tp, d);
 #pragma unroll
       for (int k = 0; k < D; ++k) y[(size_t)k * g.Mpad + t] = d[k];
       yn[t] = bb_norm<D>(d);
@@ -462,6 +562,69 @@ gram_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt,
       for (int c = 0; c < 3; ++c) acc = fmaf(dG[a * 3 + c] + dG[c * 3 + a], v[c * 9 + s9], acc);
       o[((size_t)a * g.H + 3 * py + s9 / 3) * g.W + 3 * px + s9 % 3] = acc / 27.0f;
     }
+}
+
+// ---- PatchwiseStructureTensorLoss backward ------------------------------------------------------
+// loss = mean over B*N*27 of |D1 - Dsel| (or squared), D1 = descriptor of the SR patch.  Per pixel of
+// the patch, through utils.normalize (q = sqrt(det+eps), s = <J, dD>, ddet = -s/(2 q^3)):
+//   dJxx = dDxx/q + ddet*Jyy , dJyy = dDyy/q + ddet*Jxx , dJxy = dDxy/q - 2 ddet*Jxy
+// then the adjoint 3x3 smoothing, the product rule dIx = 2 Ix dPxx + Iy dPxy, dIy = 2 Iy dPyy + Ix dPxy,
+// the adjoint derivative filters and the grayscale weights.  One thread per patch.
+__global__ void __launch_bounds__(128)
+pst_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const float* __restrict__ gt2,
+                    const float* __restrict__ gt4, const int64_t* __restrict__ idx, const float* __restrict__ grad_out,
+                    BbGeom g, PstTaps tp, int criterion, float* __restrict__ d_sr) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)g.B * g.N) return;
+  const int b = (int)(t / g.N), i = (int)(t - (size_t)b * g.N);
+  float v[BB_D], w[BB_D], dsel[BB_D];
+  const int j = (int)idx[t];
+  if (j < g.N0) bb_read_patch(gt + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, j, w);
+  else if (j < g.N0 + g.N2) bb_read_patch(gt2 + (size_t)b * 3 * g.H2 * g.W2, g.H2, g.W2, g.n2x, j - g.N0, w);
+  else bb_read_patch(gt4 + (size_t)b * 3 * g.H4 * g.W4, g.H4, g.W4, g.n4x, j - g.N0 - g.N2, w);
+  pst_descriptor(w, tp, dsel);
+  bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, i, v);
+  PstState S;
+  pst_state(v, tp, S);
+  const float scale = __ldg(grad_out) / ((float)g.B * (float)g.N * (float)BB_D);
+  float dJ[3][9];
+#pragma unroll
+  for (int p = 0; p < 9; ++p) {
+    float dd[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d = __fdiv_rn(S.J[c][p], S.q[p]) - dsel[c * 9 + p];
+      dd[c] = (criterion == 0) ? ((d > 0.f) ? scale : ((d < 0.f) ? -scale : 0.f)) : 2.0f * d * scale;
+    }
+    const float iq = 1.0f / S.q[p];
+    const float s = fmaf(S.J[0][p], dd[0], fmaf(S.J[1][p], dd[1], S.J[2][p] * dd[2]));
+    const float ddet = (-0.5f * s) * (iq * iq) * iq;
+    dJ[0][p] = fmaf(dd[0], iq, ddet * S.J[1][p]);
+    dJ[1][p] = fmaf(dd[1], iq, ddet * S.J[0][p]);
+    dJ[2][p] = fmaf(dd[2], iq, -2.0f * ddet * S.J[2][p]);
+  }
+  float dP[3][9], tmp[9];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    pst_horz_t(tp.k, dJ[c], tmp);
+    pst_vert_t(tp.k, tmp, dP[c]);
+  }
+  float dIx[9], dIy[9], ga[9], gb[9];
+#pragma unroll
+  for (int p = 0; p < 9; ++p) {
+    dIx[p] = fmaf(2.0f * S.Ix[p], dP[0][p], S.Iy[p] * dP[2][p]);
+    dIy[p] = fmaf(2.0f * S.Iy[p], dP[1][p], S.Ix[p] * dP[2][p]);
+  }
+  pst_horz_t(tp.g, dIx, tmp);  pst_vert_t(tp.dg, tmp, ga);
+  pst_horz_t(tp.dg, dIy, tmp); pst_vert_t(tp.g, tmp, gb);
+  const int py = i / g.n0x, px = i - py * g.n0x;
+  float* o = d_sr + (size_t)b * 3 * g.H * g.W;
+  const float coef[3] = {kGrayR, kGrayG, kGrayB};
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int p = 0; p < 9; ++p)
+      o[((size_t)c * g.H + 3 * py + p / 3) * g.W + 3 * px + p % 3] = coef[c] * (ga[p] + gb[p]);
 }
 
 }  // namespace srst

@@ -416,7 +416,7 @@ int srst_bb_pyramid(const float* gt, int B, int H, int W, float* out2, float* ou
 template <int MODE>
 static int bb_forward_impl(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
                            float alpha, float beta, int criterion, int64_t* idx_out, float* loss_out, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+                           size_t workspace_bytes, void* stream, const PstTaps& tp = PstTaps{}) {
   constexpr int D = BbDesc<MODE>::D;
   if (!sr || !gt || !idx_out || !loss_out || B <= 0) return SRST_E_INVALID;
   if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
@@ -434,7 +434,7 @@ static int bb_forward_impl(const float* sr, const float* gt, const float* gt2, c
   }
   const int npack = g.Npad > g.Mpad ? g.Npad : g.Mpad;
   SRST_LAUNCH(bb_pack_kernel<MODE>, dim3((npack + 255) / 256, B), dim3(256), 0, stream, sr, gt, gt2, gt4, w.mats,
-              w.per_image, g);
+              w.per_image, g, tp);
   if ((e = (int)cudaGetLastError()) != 0) return e;
   SRST_LAUNCH(bb_search_kernel<D>, dim3(g.Npad / BB_QT, B), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, alpha,
               beta, idx_out);
@@ -459,6 +459,69 @@ int srst_gram_forward(const float* sr, const float* gt, const float* gt2, const 
                       size_t workspace_bytes, void* stream) {
   return bb_forward_impl<1>(sr, gt, gt2, gt4, B, H, W, alpha, beta, criterion, idx_out, loss_out, workspace,
                             workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+// Central five taps (offsets -2..2) of a (2r+1)-tap filter: all a 3x3 patch image can see.
+static void central5(const float* t, int r, float (&o)[5]) {
+  for (int i = 0; i < 5; ++i) {
+    const int j = r + i - 2;
+    o[i] = (j >= 0 && j <= 2 * r) ? t[j] : 0.f;
+  }
+}
+static int pst_taps(const float* g, const float* dg, int r_sigma, const float* k, int r_rho, PstTaps& tp) {
+  if (!g || !dg || !k || r_sigma < 1 || r_rho < 1 || r_sigma > 4096 || r_rho > 4096) return SRST_E_INVALID;
+  central5(g, r_sigma, tp.g);
+  central5(dg, r_sigma, tp.dg);
+  central5(k, r_rho, tp.k);
+  return 0;
+}
+
+extern "C" {
+
+int srst_pst_forward(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W,
+                     const float* g, const float* dg, int r_sigma, const float* k, int r_rho, float alpha, float beta,
+                     int criterion, int64_t* idx_out, float* loss_out, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  PstTaps tp;
+  const int e = pst_taps(g, dg, r_sigma, k, r_rho, tp);
+  if (e) return e;
+  return bb_forward_impl<2>(sr, gt, gt2, gt4, B, H, W, alpha, beta, criterion, idx_out, loss_out, workspace,
+                            workspace_bytes, stream, tp);
+}
+
+int srst_pst_backward(const float* sr, const float* gt, const float* gt2, const float* gt4, const int64_t* idx,
+                      const float* grad_out, int B, int H, int W, const float* g, const float* dg, int r_sigma,
+                      const float* k, int r_rho, int criterion, float* d_sr, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  if (!sr || !gt || !idx || !grad_out || !d_sr || B <= 0) return SRST_E_INVALID;
+  if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
+  if (H < 12 || W < 12 || B > 65535) return SRST_E_SHAPE;
+  if ((gt2 == nullptr) != (gt4 == nullptr)) return SRST_E_INVALID;
+  PstTaps tp;
+  int e = pst_taps(g, dg, r_sigma, k, r_rho, tp);
+  if (e) return e;
+  const BbGeom gm = bb_geom(B, H, W);
+  if (!gt2) {
+    if (!workspace || !aligned16(workspace)) return SRST_E_WORKSPACE;
+    const BbWorkspace w = bb_carve(workspace, gm);
+    if (workspace_bytes < w.total_bytes) return SRST_E_WORKSPACE;
+    if ((e = bb_launch_pyramid(gt, gm, w.pyr2, w.pyr4, stream)) != 0) return e;
+    gt2 = w.pyr2;
+    gt4 = w.pyr4;
+  }
+  if (H % 3 != 0 || W % 3 != 0) {  // pixels outside every patch keep a zero gradient
+#ifdef SRST_EMULATE
+    std::memset(d_sr, 0, sizeof(float) * (size_t)B * 3 * H * W);
+#else
+    if ((e = (int)cudaMemsetAsync(d_sr, 0, sizeof(float) * (size_t)B * 3 * H * W, (cudaStream_t)stream)) != 0) return e;
+#endif
+  }
+  const size_t total = (size_t)B * gm.N;
+  SRST_LAUNCH(pst_backward_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, stream, sr, gt, gt2, gt4, idx,
+              grad_out, gm, tp, criterion, d_sr);
+  return (int)cudaGetLastError();
 }
 
 int srst_gram_backward(const float* sr, const float* gt, const float* gt2, const float* gt4, const int64_t* idx,

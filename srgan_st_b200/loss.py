@@ -1,6 +1,6 @@
 """Drop-in loss modules backed by the sm_100a kernels in libsrst.so.
 
-``StructureTensorLoss`` and ``BestBuddyLoss`` keep the reference's constructor signatures,
+``StructureTensorLoss``, ``BestBuddyLoss``, ``GramLoss`` and ``PatchwiseStructureTensorLoss`` keep the reference's constructor signatures,
 attributes and ``criterion(sr, gt) -> 0-dim fp32 tensor`` contract (reference loss.py:380-413 and
 loss.py:78-141; called from train.py:138 and warmup.py:91), so they register through
 ``config.add_g_criterion(name, module, weight)`` (config.py:122-125) unchanged.  Underneath, each is
@@ -286,5 +286,106 @@ class GramLoss(nn.Module):
     def forward(self, x, gt):
         _check_pair(x, gt, "GramLoss")
         loss, idx = _BestBuddyLossFn.apply(x, gt, self.alpha, self.beta, self._crit, self.pyramid, "gram")
+        self.last_indices = idx
+        return loss
+
+
+class _PatchwiseStLossFn(torch.autograd.Function):
+    """autograd boundary of the patchwise structure-tensor loss: differentiable through the final
+    criterion and the SR patch descriptors only (argmin is not; gt carries no gradient, loss.py:366-371)."""
+
+    @staticmethod
+    def forward(ctx, sr, gt, sigma, rho, alpha, beta, criterion, pyramid):
+        lib = _cabi.lib()
+        sr = sr.contiguous()
+        gt = gt.contiguous()
+        B, _, H, W = sr.shape
+        if H < 12 or W < 12:
+            raise ValueError(f"PatchwiseStructureTensorLoss: images must be at least 12x12 (got {H}x{W})")
+        g, dg = _taps.gaussian_taps(float(sigma))
+        k, _ = _taps.gaussian_taps(float(rho))
+        with torch.cuda.device(sr.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            if pyramid == "aten":
+                with torch.no_grad():  # the reference's own op for the HR pyramid (loss.py:353,356)
+                    gt2 = torch.nn.functional.interpolate(gt, scale_factor=0.5, mode="bicubic",
+                                                          align_corners=False).contiguous()
+                    gt4 = torch.nn.functional.interpolate(gt, scale_factor=0.25, mode="bicubic",
+                                                          align_corners=False).contiguous()
+            else:
+                gt2 = gt4 = None
+            N = (H // 3) * (W // 3)
+            idx = torch.empty((B, N), dtype=torch.int64, device=sr.device)
+            loss = torch.empty((), dtype=torch.float32, device=sr.device)
+            ws = _workspace(sr.device, stream, lib.srst_bb_workspace_bytes(B, H, W))
+            rc = lib.srst_pst_forward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), B, H, W, _taps.as_c(g), _taps.as_c(dg),
+                                      len(g) // 2, _taps.as_c(k), len(k) // 2, float(alpha), float(beta),
+                                      int(criterion), _ptr(idx), _ptr(loss), _ptr(ws), ws.numel(),
+                                      ctypes.c_void_p(stream))
+        _cabi.check(rc, "srst_pst_forward")
+        ctx.save_for_backward(sr, gt, gt2, gt4, idx)
+        ctx.taps = (g, dg, k)
+        ctx.criterion = int(criterion)
+        ctx.mark_non_differentiable(idx)
+        return loss, idx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out, _grad_idx):
+        lib = _cabi.lib()
+        sr, gt, gt2, gt4, idx = ctx.saved_tensors
+        g, dg, k = ctx.taps
+        B, _, H, W = sr.shape
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 8
+        grad_out = grad_out.to(torch.float32).contiguous()
+        with torch.cuda.device(sr.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            d_sr = torch.empty_like(sr)
+            ws = _workspace(sr.device, stream, lib.srst_bb_workspace_bytes(B, H, W))
+            rc = lib.srst_pst_backward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
+                                       _taps.as_c(g), _taps.as_c(dg), len(g) // 2, _taps.as_c(k), len(k) // 2,
+                                       ctx.criterion, _ptr(d_sr), _ptr(ws), ws.numel(), ctypes.c_void_p(stream))
+        _cabi.check(rc, "srst_pst_backward")
+        return (d_sr,) + (None,) * 7
+
+
+class PatchwiseStructureTensorLoss(nn.Module):
+    """Patchwise structure-tensor loss; same signature and semantics as reference loss.py:292-375:
+    the best-buddy search and the final criterion run on the det-normalised structure tensor of
+    every 3x3 patch (seen as a 3x3 image, zero 'same' padding) instead of its pixels.
+    Only ``ksize=3`` and ``dist_norm='l2'`` have kernels (the reference's defaults)."""
+
+    def __init__(self, sigma: float = 0.5, rho: float = 2, alpha: float = 1.0, beta: float = 1.0, ksize: int = 3,
+                 dist_norm: str = "l2", criterion: str = "l1", pyramid: str = "aten"):
+        super().__init__()
+        self.alpha = alpha
+        self.beta = beta
+        self.ksize = ksize
+        self.dist_norm = dist_norm
+        self.sigma = sigma
+        self.rho = rho
+        if criterion == "l1":
+            self.criterion = torch.nn.L1Loss(reduction="mean")
+            self._crit = 0
+        elif criterion == "l2" or criterion == "mse":
+            self.criterion = torch.nn.MSELoss(reduction="mean")
+            self._crit = 1
+        else:
+            raise NotImplementedError("%s criterion has not been supported." % criterion)  # loss.py:323
+        if dist_norm not in ("l1", "l2"):
+            raise NotImplementedError("%s norm has not been supported." % dist_norm)       # utils.py:189
+        if dist_norm != "l2" or ksize != 3:
+            raise NotImplementedError("PatchwiseStructureTensorLoss: libsrst.so implements ksize=3, dist_norm='l2' only")
+        if pyramid not in ("aten", "fused"):
+            raise ValueError("pyramid must be 'aten' or 'fused'")
+        self.pyramid = pyramid
+        self.last_indices = None
+        _cabi.lib()
+
+    def forward(self, x, gt):
+        _check_pair(x, gt, "PatchwiseStructureTensorLoss")
+        loss, idx = _PatchwiseStLossFn.apply(x, gt, self.sigma, self.rho, self.alpha, self.beta, self._crit,
+                                             self.pyramid)
         self.last_indices = idx
         return loss

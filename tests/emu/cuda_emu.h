@@ -180,6 +180,8 @@ static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline float __fsqrt_rn(float a) { volatile float r = std::sqrt(a); return r; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
 static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) {
   return float2{std::fma(a.x, b.x, c.x), std::fma(a.y, b.y, c.y)};

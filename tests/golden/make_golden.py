@@ -147,13 +147,51 @@ def make_gram(ref_loss, ref_utils):
         print(f"{name}: loss={loss.item():.8g} N={p1.shape[1]} M={cat.shape[1]}")
 
 
+PST_CASES = [
+    # name, kind, B, H, W, seed, sigma, rho, alpha, beta, criterion
+    ("pst_rand_2x24x24", "rand", 2, 24, 24, 31, 0.5, 2.0, 1.0, 1.0, "l1"),
+    ("pst_srlike_2x48x36", "srlike", 2, 48, 36, 32, 0.5, 2.0, 1.0, 1.0, "l1"),
+    ("pst_rand_ab_s1_1x36x36", "rand", 1, 36, 36, 33, 1.0, 2.5, 0.5, 2.0, "l2"),
+]
+
+
+def make_pst(ref_loss, ref_utils):
+    import torch.nn.functional as F
+    for name, kind, B, H, W, seed, sigma, rho, alpha, beta, crit in PST_CASES:
+        sr, hr = _inputs(kind, B, H, W, seed)
+        sr.requires_grad_(True)
+        m = ref_loss.PatchwiseStructureTensorLoss(sigma=sigma, rho=rho, alpha=alpha, beta=beta, criterion=crit)
+        loss = m(sr, hr)
+        loss.backward()
+        with torch.no_grad():  # indices / top-2 gaps with the reference's own helpers (loss.py:347-369)
+            p1, p2 = m.compute_patches(sr), m.compute_patches(hr)
+            hr2 = F.interpolate(hr, scale_factor=0.5, mode="bicubic", align_corners=False)
+            hr4 = F.interpolate(hr, scale_factor=0.25, mode="bicubic", align_corners=False)
+            cat = torch.cat([p2, m.compute_patches(hr2), m.compute_patches(hr4)], 1)
+            score = alpha * ref_utils.batch_pairwise_distance(p1, cat, "l2") \
+                + beta * ref_utils.batch_pairwise_distance(p2, cat, "l2")
+            _, ind = torch.min(score, dim=2)
+            top2 = torch.topk(score, 2, dim=2, largest=False).values
+        g, dg = ref_utils.get_gaussian_kernel(sigma, also_dg=True)
+        k = ref_utils.get_gaussian_kernel(rho)
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            sr=sr.detach().numpy(), hr=hr.detach().numpy(), loss=np.float32(loss.item()),
+            d_sr=sr.grad.numpy(), ind=ind.numpy(), top2=top2.numpy(), hr2=hr2.numpy(), hr4=hr4.numpy(),
+            p1=p1.numpy(), g=g.numpy(), dg=dg.numpy(), k=k.numpy(), sigma=np.float64(sigma), rho=np.float64(rho),
+            alpha=np.float64(alpha), beta=np.float64(beta), criterion=np.str_(crit))
+        print(f"{name}: loss={loss.item():.8g} N={p1.shape[1]} M={cat.shape[1]}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # fixed summation order inside MKL for reproducible fixtures
     rl, ru = _import_reference()
-    which = sys.argv[1:] or ["st", "bb", "gram"]
+    which = sys.argv[1:] or ["st", "bb", "gram", "pst"]
     if "st" in which:
         make_st(rl, ru)
     if "bb" in which:
         make_bb(rl, ru)
     if "gram" in which:
         make_gram(rl, ru)
+    if "pst" in which:
+        make_pst(rl, ru)

@@ -90,8 +90,9 @@ def emu_st(lib, sr, hr, taps, normalize=True, want_hr=False, grad_out=1.0, save_
     return out
 
 
-def emu_bb(lib, sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion=0, grad_out=1.0, mode="patch"):
-    """Run srst_bb_forward + srst_bb_backward of `lib` on host arrays (emulation library only)."""
+def emu_bb(lib, sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion=0, grad_out=1.0, mode="patch", taps=None):
+    """Run srst_bb_forward + srst_bb_backward of `lib` on host arrays (emulation library only).
+    mode: "patch" (BestBuddyLoss), "gram" (GramLoss) or "pst" (PatchwiseStructureTensorLoss, taps = (g, dg, k))."""
     sr = np.ascontiguousarray(sr, np.float32)
     gt = np.ascontiguousarray(gt, np.float32)
     gt2 = np.ascontiguousarray(gt2, np.float32) if gt2 is not None else None
@@ -102,12 +103,22 @@ def emu_bb(lib, sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion=0, gr
     ws = np.zeros(nb // 4 + 4, np.float32)
     idx = np.full((B, N), -1, np.int64)
     loss = np.zeros(1, np.float32)
+    go = np.full(1, grad_out, np.float32)
+    d_sr = np.full_like(sr, np.nan)
+    if mode == "pst":
+        g, dg, k = [np.ascontiguousarray(t, np.float32) for t in taps]
+        tp = (_fp(g), _fp(dg), len(g) // 2, _fp(k), len(k) // 2)
+        rc = lib.srst_pst_forward(_p(sr), _p(gt), _p(gt2), _p(gt4), B, H, W, *tp, alpha, beta, criterion, _p(idx),
+                                  _p(loss), _p(ws), nb, None)
+        assert rc == 0, rc
+        rc = lib.srst_pst_backward(_p(sr), _p(gt), _p(gt2), _p(gt4), _p(idx), _p(go), B, H, W, *tp, criterion, _p(d_sr),
+                                   _p(ws), nb, None)
+        assert rc == 0, rc
+        return dict(loss=float(loss[0]), idx=idx, d_sr=d_sr)
     fwd = lib.srst_bb_forward if mode == "patch" else lib.srst_gram_forward
     bwd = lib.srst_bb_backward if mode == "patch" else lib.srst_gram_backward
     rc = fwd(_p(sr), _p(gt), _p(gt2), _p(gt4), B, H, W, alpha, beta, criterion, _p(idx), _p(loss), _p(ws), nb, None)
     assert rc == 0, rc
-    go = np.full(1, grad_out, np.float32)
-    d_sr = np.full_like(sr, np.nan)
     rc = bwd(_p(sr), _p(gt), _p(gt2), _p(gt4), _p(idx), _p(go), B, H, W, criterion, _p(d_sr), _p(ws), nb, None)
     assert rc == 0, rc
     return dict(loss=float(loss[0]), idx=idx, d_sr=d_sr)
