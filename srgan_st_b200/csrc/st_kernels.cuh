@@ -341,66 +341,52 @@ SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, i
   constexpr int NITEM = (ROWS / 2) * C4;
   const size_t plane = (size_t)H * W;
   if (vec4) {
-    // A thread owns ONE 4-column group and walks down the tile RPI row pairs at a time: column
-    // validity, the three plane pointers and the shared-memory slot are computed once, and a step
-    // only adds a compile-time multiple of W (no div/mod, one 32-bit offset per row).
-    constexpr int RPI = NT / C4;               // row pairs covered per step
-    constexpr int NQ = ROWS / 2;
-    constexpr int STEPS = (NQ + RPI - 1) / RPI;
-    static_assert(RPI >= 1, "gray tile wider than the thread block");
-    const int q0 = tid / C4, c4 = tid - q0 * C4;
-    if (q0 < RPI) {
-      const int gx = gx0 + 4 * c4;
-      const bool okx = gx >= 0 && gx < W;      // W % 4 == 0: a group is all-in or all-out
-      const int gyb = gy0 + 2 * q0;
-      const float* pr = base + ((long long)gyb * W + gx);  // only dereferenced where the pixel exists
-      const float* pg = pr + plane;
-      const float* pb = pg + plane;
-      float* ob = sG + q0 * PITCH + 8 * c4;
+#pragma unroll 1
+    for (int it0 = tid; it0 < NITEM; it0 += DEPTH * NT) {
+      float4 R[DEPTH][2], Gc[DEPTH][2], Bc[DEPTH][2];
+      bool ok[DEPTH][2];
 #pragma unroll
-      for (int s0 = 0; s0 < STEPS; s0 += DEPTH) {
-        float4 R[DEPTH][2], Gc[DEPTH][2], Bc[DEPTH][2];
-        bool ok[DEPTH][2];
+      for (int u = 0; u < DEPTH; ++u) {
+        const int it = it0 + u * NT;
+        const int q = it / C4, c4 = it - q * C4;
+        const int gx = gx0 + 4 * c4;
 #pragma unroll
-        for (int u = 0; u < DEPTH; ++u) {
-          const int s = s0 + u;
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int dr = 2 * s * RPI + hf;   // row offset from gyb (compile-time)
-            const int gy = gyb + dr;
-            ok[u][hf] = (s < STEPS) && (q0 + s * RPI < NQ) && okx && gy >= 0 && gy < H;
-            if (ok[u][hf]) {
-              const int off = dr * W;
-              R[u][hf] = ldg4(pr + off); Gc[u][hf] = ldg4(pg + off); Bc[u][hf] = ldg4(pb + off);
-            }
+        for (int hf = 0; hf < 2; ++hf) {
+          const int gy = gy0 + 2 * q + hf;
+          ok[u][hf] = (it < NITEM) && gy >= 0 && gy < H && gx >= 0 && gx < W;  // W % 4 == 0: all-in or all-out
+          if (ok[u][hf]) {
+            const float* p = base + (size_t)gy * W + gx;
+            R[u][hf] = ldg4(p); Gc[u][hf] = ldg4(p + plane); Bc[u][hf] = ldg4(p + 2 * plane);
           }
         }
+      }
 #pragma unroll
-        for (int u = 0; u < DEPTH; ++u) {
-          const int s = s0 + u;
-          if (s >= STEPS || q0 + s * RPI >= NQ) break;
-          float v[2][4];
+      for (int u = 0; u < DEPTH; ++u) {
+        const int it = it0 + u * NT;
+        if (it >= NITEM) break;
+        const int q = it / C4, c4 = it - q * C4;
+        float v[2][4];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (ok[u][hf]) {
+            v[hf][0] = gray_of(R[u][hf].x, Gc[u][hf].x, Bc[u][hf].x);
+            v[hf][1] = gray_of(R[u][hf].y, Gc[u][hf].y, Bc[u][hf].y);
+            v[hf][2] = gray_of(R[u][hf].z, Gc[u][hf].z, Bc[u][hf].z);
+            v[hf][3] = gray_of(R[u][hf].w, Gc[u][hf].w, Bc[u][hf].w);
+          } else {
+            v[hf][0] = v[hf][1] = v[hf][2] = v[hf][3] = 0.f;
+          }
+        }
+        float* o = sG + q * PITCH + 8 * c4;
+        st4(o, make_float4(v[0][0], v[1][0], v[0][1], v[1][1]));
+        st4(o + 4, make_float4(v[0][2], v[1][2], v[0][3], v[1][3]));
+        if (gray_out) {
+          const int gx = gx0 + 4 * c4;
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
-            if (ok[u][hf]) {
-              v[hf][0] = gray_of(R[u][hf].x, Gc[u][hf].x, Bc[u][hf].x);
-              v[hf][1] = gray_of(R[u][hf].y, Gc[u][hf].y, Bc[u][hf].y);
-              v[hf][2] = gray_of(R[u][hf].z, Gc[u][hf].z, Bc[u][hf].z);
-              v[hf][3] = gray_of(R[u][hf].w, Gc[u][hf].w, Bc[u][hf].w);
-            } else {
-              v[hf][0] = v[hf][1] = v[hf][2] = v[hf][3] = 0.f;
-            }
-          }
-          float* o = ob + s * RPI * PITCH;
-          st4(o, make_float4(v[0][0], v[1][0], v[0][1], v[1][1]));
-          st4(o + 4, make_float4(v[0][2], v[1][2], v[0][3], v[1][3]));
-          if (gray_out) {
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const int gy = gyb + 2 * s * RPI + hf;
-              if (ok[u][hf] && gy >= iy0 && gy < iy1 && gx >= ix0 && gx < ix1)
-                st4(gray_out + (size_t)gy * W + gx, make_float4(v[hf][0], v[hf][1], v[hf][2], v[hf][3]));
-            }
+            const int gy = gy0 + 2 * q + hf;
+            if (ok[u][hf] && gy >= iy0 && gy < iy1 && gx >= ix0 && gx < ix1)
+              st4(gray_out + (size_t)gy * W + gx, make_float4(v[hf][0], v[hf][1], v[hf][2], v[hf][3]));
           }
         }
       }

@@ -10,7 +10,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from srgan_st_b200 import _cabi, taps as T  # noqa: E402
 
-lib = _cabi.lib()
+lib = _cabi.bind(os.environ['SRST_LIB']) if os.environ.get('SRST_LIB') else _cabi.lib()  # A/B builds
 g, dg = T.gaussian_taps(0.5)
 k, _ = T.gaussian_taps(2.0)
 dev = torch.device("cuda:0")
