@@ -41,6 +41,7 @@ using BwdB = StBwdCfg<16, 96, 10, 256, 2, 8, 2>;  // 96-wide training crops
 using BwdC = StBwdCfg<32, 64, 12, 352, 2, 8, 1>;  // one big CTA per SM
 using BwdD = StBwdCfg<28, 56, 16, 256, 2, 8, 2>;  // 16 row pairs per phase item column: no LDS bank conflicts
 using BwdE = StBwdCfg<28, 88, 16, 384, 2, 8, 1>;  // experiment
+using BwdF = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8>;  // BwdD with 8-column horizontal-pass items (less shared-memory traffic)
 
 //                             TH  TW  RS   NT
 using WideA = StWideFwdCfg<48, 96, 12, 384>;  // half a 96x96 training crop per CTA, one CTA per SM
@@ -191,9 +192,10 @@ static int pick_fwd_cfg(int H, int W) {
 }
 static int pick_bwd_cfg(int H, int W) {
   const int forced = env_int("SRST_ST_BWD_CFG", -1);
-  if (forced >= 0 && forced <= 4) return forced;
-  // measured on B200 (gpurun sweep, round 1): the conflict-free 28x56 tile wins at every size
-  return 3;
+  if (forced >= 0 && forced <= 5) return forced;
+  // measured on B200 (gpurun sweep, round 1): the conflict-free 28x56 tile wins at every size,
+  // its 8-column horizontal-pass variant by another 1 %
+  return 5;
 }
 
 }  // namespace srst
@@ -336,6 +338,7 @@ static int st_backward_rr(const StCall& c) {
       case 2: return launch_st_backward<BwdC>(P, c.gray, c.stream);
       case 3: return launch_st_backward<BwdD>(P, c.gray, c.stream);
       case 4: return launch_st_backward<BwdE>(P, c.gray, c.stream);
+      case 5: return launch_st_backward<BwdF>(P, c.gray, c.stream);
       default: return launch_st_backward<BwdA>(P, c.gray, c.stream);
     }
   } else {

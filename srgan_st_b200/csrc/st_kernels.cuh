@@ -886,9 +886,11 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
 // ------------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------------
-template <int TH_, int TW_, int RS_, int NT_, int RG_, int RK_, int MINB_>
+template <int TH_, int TW_, int RS_, int NT_, int RG_, int RK_, int MINB_, int CSD_ = 4>
 struct StBwdCfg {
   static constexpr int TH = TH_, TW = TW_, RS = RS_, NT = NT_, RG = RG_, RK = RK_, MINB = MINB_;
+  static constexpr int CSD = CSD_;  // output columns per phase-D' item: 8 reads a 24-column window per 8 outputs
+                                    // (3x shared-memory amplification) instead of 20 per 4 (5x)
   static constexpr int HXE = round_up4(RG);  // x halo of the E region (where dIx, dIy are needed)
   static constexpr int HXK = round_up4(RK);
   static constexpr int EH = TH + 2 * RG, EW = TW + 2 * HXE, PE = smem_pitch(2 * EW);
@@ -897,7 +899,7 @@ struct StBwdCfg {
   static constexpr int SH = EH + 2 * RK;                                              // staged ds rows
   static constexpr int NSEG = EH / RS;
   static constexpr int BW_LO = (HXE - RG) / 2 * 2, BW_HI = (HXE + 4 + RG + 1) / 2 * 2, BWIN = BW_HI - BW_LO;
-  static constexpr int DW_LO = (HXK - RK) / 2 * 2, DW_HI = (HXK + 4 + RK + 1) / 2 * 2, DWIN = DW_HI - DW_LO;
+  static constexpr int DW_LO = (HXK - RK) / 2 * 2, DW_HI = (HXK + CSD + RK + 1) / 2 * 2, DWIN = DW_HI - DW_LO;
   // smem: V (3 planes) | I (Ix, Iy) | G (gray) | X: staged ds planes [3][SH][VW] row-major, later
   // dIx|dIy (the staging is dead once the vertical pass has consumed it)
   static constexpr int V_FLOATS = (EH / 2) * PV, I_FLOATS = (EH / 2) * PE, G_FLOATS = (GH / 2) * PG;
@@ -912,6 +914,7 @@ struct StBwdCfg {
   static_assert(EH % RS == 0 && RS % 2 == 0 && TH % 2 == 0 && TW % 4 == 0 && RG % 2 == 0 && RK % 2 == 0,
                 "bad backward tile");
   static_assert(NT % 32 == 0 && NT <= 1024, "bad backward block size");
+  static_assert((CSD == 4 || CSD == 8) && EW % CSD == 0, "bad phase-D' item width");
 };
 
 template <class C>
@@ -1040,60 +1043,59 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) st2(sV + c * C::V_FLOATS + q * C::PV + 2 * vx, make_float2(0.f, 0.f));
     }
-    for (int it = tid; it < ncol * C::NSEG; it += C::NT) {
-      const int seg = it / ncol, vx = c_lo + (it - seg * ncol);
+    // one item = (plane, row segment, column): the three ds planes are independent, so splitting them
+    // over threads costs nothing and keeps every lane busy (ncol * NSEG alone is < NT for most tiles)
+    for (int it = tid; it < 3 * ncol * C::NSEG; it += C::NT) {
+      const int cs = it / ncol, vx = c_lo + (it - cs * ncol);
+      const int c = cs / C::NSEG, seg = cs - c * C::NSEG;
+      float2 acc[C::RS / 2];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float2 acc[C::RS / 2];
+      for (int j = 0; j < C::RS / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+      const float* p = sS + (c * C::SH + seg * C::RS) * C::VW + vx;
 #pragma unroll
-        for (int j = 0; j < C::RS / 2; ++j) acc[j] = make_float2(0.f, 0.f);
-        const float* p = sS + (c * C::SH + seg * C::RS) * C::VW + vx;
+      for (int r = 0; r < C::RS + 2 * C::RK; ++r) {
+        const float v = p[r * C::VW];
 #pragma unroll
-        for (int r = 0; r < C::RS + 2 * C::RK; ++r) {
-          const float v = p[r * C::VW];
-#pragma unroll
-          for (int jp = 0; jp < C::RS / 2; ++jp) {
-            const int u = r - 2 * jp;
-            if (u >= 0 && u <= 2 * C::RK + 1) acc[jp] = ffma2(bcast2(v), tp.kp[u], acc[jp]);
-          }
+        for (int jp = 0; jp < C::RS / 2; ++jp) {
+          const int u = r - 2 * jp;
+          if (u >= 0 && u <= 2 * C::RK + 1) acc[jp] = ffma2(bcast2(v), tp.kp[u], acc[jp]);
         }
-        float* o = sV + c * C::V_FLOATS + (seg * (C::RS / 2)) * C::PV + 2 * vx;
-#pragma unroll
-        for (int jp = 0; jp < C::RS / 2; ++jp) st2(o + jp * C::PV, acc[jp]);
       }
+      float* o = sV + c * C::V_FLOATS + (seg * (C::RS / 2)) * C::PV + 2 * vx;
+#pragma unroll
+      for (int jp = 0; jp < C::RS / 2; ++jp) st2(o + jp * C::PV, acc[jp]);
     }
   }
   __syncthreads();  // the staging is dead from here on: sdI may overwrite it
 
   // Phase D': horizontal rho-pass -> E = K*ds at the E-region pixels, then the product rule
   //   dIx = 2 Ix Exx + Iy Exy ,  dIy = 2 Iy Eyy + Ix Exy      (adjoint of utils.py:225-229)
-  for (int it = tid; it < (C::EH / 2) * (C::EW / 4); it += C::NT) {
+  for (int it = tid; it < (C::EH / 2) * (C::EW / C::CSD); it += C::NT) {
     const int seg = it / (C::EH / 2), q = it - seg * (C::EH / 2);
-    const int ex0 = 4 * seg;
-    float2 E[3][4];
+    const int ex0 = C::CSD * seg;
+    float2 E[3][C::CSD];
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-      smooth_h_rowpair<C::RK, C::DWIN, C::HXK - C::DW_LO>(sV + c * C::V_FLOATS + q * C::PV + 2 * (ex0 + C::DW_LO), tp,
-                                                          E[c]);
-    const float4 ixa = ld4(sI0 + q * C::PE + 2 * ex0), ixb = ld4(sI0 + q * C::PE + 2 * ex0 + 4);
-    const float4 iya = ld4(sI1 + q * C::PE + 2 * ex0), iyb = ld4(sI1 + q * C::PE + 2 * ex0 + 4);
-    const float2 ix[4] = {make_float2(ixa.x, ixa.y), make_float2(ixa.z, ixa.w), make_float2(ixb.x, ixb.y),
-                          make_float2(ixb.z, ixb.w)};
-    const float2 iy[4] = {make_float2(iya.x, iya.y), make_float2(iya.z, iya.w), make_float2(iyb.x, iyb.y),
-                          make_float2(iyb.z, iyb.w)};
-    float2 dx[4], dy[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 ix2 = make_float2(2.0f * ix[j].x, 2.0f * ix[j].y), iy2 = make_float2(2.0f * iy[j].x, 2.0f * iy[j].y);
-      dx[j] = ffma2(ix2, E[0][j], make_float2(iy[j].x * E[2][j].x, iy[j].y * E[2][j].y));
-      dy[j] = ffma2(iy2, E[1][j], make_float2(ix[j].x * E[2][j].x, ix[j].y * E[2][j].y));
-    }
+      smooth_h_rowpair_n<C::RK, C::CSD, C::DWIN, C::HXK - C::DW_LO>(
+          sV + c * C::V_FLOATS + q * C::PV + 2 * (ex0 + C::DW_LO), tp, E[c]);
     float* o0 = sdI0 + q * C::PE + 2 * ex0;
     float* o1 = sdI1 + q * C::PE + 2 * ex0;
-    st4(o0, make_float4(dx[0].x, dx[0].y, dx[1].x, dx[1].y));
-    st4(o0 + 4, make_float4(dx[2].x, dx[2].y, dx[3].x, dx[3].y));
-    st4(o1, make_float4(dy[0].x, dy[0].y, dy[1].x, dy[1].y));
-    st4(o1 + 4, make_float4(dy[2].x, dy[2].y, dy[3].x, dy[3].y));
+#pragma unroll
+    for (int m = 0; m < C::CSD / 2; ++m) {  // two columns per LDS.128 / STS.128
+      const float4 ixv = ld4(sI0 + q * C::PE + 2 * ex0 + 4 * m), iyv = ld4(sI1 + q * C::PE + 2 * ex0 + 4 * m);
+      const float2 ix[2] = {make_float2(ixv.x, ixv.y), make_float2(ixv.z, ixv.w)};
+      const float2 iy[2] = {make_float2(iyv.x, iyv.y), make_float2(iyv.z, iyv.w)};
+      float2 dx[2], dy[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 2 * m + h;
+        const float2 ix2 = make_float2(2.0f * ix[h].x, 2.0f * ix[h].y), iy2 = make_float2(2.0f * iy[h].x, 2.0f * iy[h].y);
+        dx[h] = ffma2(ix2, E[0][j], make_float2(iy[h].x * E[2][j].x, iy[h].y * E[2][j].y));
+        dy[h] = ffma2(iy2, E[1][j], make_float2(ix[h].x * E[2][j].x, ix[h].y * E[2][j].y));
+      }
+      st4(o0 + 4 * m, make_float4(dx[0].x, dx[0].y, dx[1].x, dx[1].y));
+      st4(o1 + 4 * m, make_float4(dy[0].x, dy[0].y, dy[1].x, dy[1].y));
+    }
   }
   __syncthreads();
 

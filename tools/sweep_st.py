@@ -19,6 +19,7 @@ GRAY = (lambda t: vp(t)) if os.environ.get("SRST_ST_SAVE_GRAY", "0") == "1" else
 HBM = 6539.9
 FWD_CFGS = [int(x) for x in os.environ.get('SWEEP_FWD', '0,1,2,3,4').split(',')]
 BWD_MAX = int(os.environ.get('SWEEP_BWD_MAX', '2'))
+BWD_CFGS = [int(x) for x in os.environ['SWEEP_BWD'].split(',')] if os.environ.get('SWEEP_BWD') else None
 
 
 def run(B, H, W, iters=40):
@@ -79,7 +80,12 @@ def run(B, H, W, iters=40):
         print(f"B={B:3d} {H}x{W} cfg={cfg}: fwd {tf*1e3:8.1f} us ({24*px/tf/1e6/HBM*100:5.1f}% HBM)  "
               f"bwd {tb*1e3:8.1f} us ({36*px/tb/1e6/HBM*100:5.1f}% HBM)  pair {60*px/(tf+tb)/1e6/HBM*100:5.1f}%  "
               f"{B/((tf+tb)*1e-3):.0f} img/s", flush=True)
-    os.environ.pop("SRST_ST_FWD_CFG"); os.environ.pop("SRST_ST_BWD_CFG")
+    if BWD_CFGS:
+        for cfg in BWD_CFGS:
+            os.environ["SRST_ST_BWD_CFG"] = str(cfg)
+            tb = timeit(bwd)
+            print(f"B={B:3d} {H}x{W} bwd cfg={cfg}: {tb*1e3:8.1f} us ({36*px/tb/1e6/HBM*100:5.1f}% HBM)", flush=True)
+    os.environ.pop("SRST_ST_FWD_CFG", None); os.environ.pop("SRST_ST_BWD_CFG", None)
     if os.environ.get("SWEEP_STREAM", "1") == "1":
         os.environ["SRST_ST_STREAM"] = "1"
         tf = timeit(fwd)
