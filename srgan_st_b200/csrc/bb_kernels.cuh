@@ -350,14 +350,24 @@ SRST_DEV void bb_argmin_merge(float& s, int& i, float so, int io) {
   if (so < s || (so == s && io < i)) { s = so; i = io; }
 }
 
+// Search kernel.  256 threads = 2 x 4 warps (32 queries x 16 candidates each), 8 x 4 lanes (4 queries x 4
+// candidates each): a 4 x 4 register tile with TWO dot products per pair, issued as packed
+// fma.rn.f32x2 (SASS FFMA2) on query PAIRS: the candidate chunk sits in shared memory with every
+// value duplicated, (w, w), so one LDS.128 yields two ready-made f32x2 operands and the query
+// pair (u_i, u_i+1) comes straight out of the k-major query tile.  An FFMA2 is two IEEE fmas, so
+// every dot product keeps the fixed k = 0..D-1 order of oracle/bb_oracle.c.  The candidate chunks are
+// double-buffered: chunk c+1 travels global -> registers while chunk c is being evaluated, and
+// is committed to the other buffer before the one barrier per chunk.
 template <int D>
 __global__ void __launch_bounds__(BB_NT, 2)
 bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, float alpha, float beta,
                  int64_t* __restrict__ idx_out) {
   __shared__ __align__(16) float sQ1[D][BB_QT];
   __shared__ __align__(16) float sQ2[D][BB_QT];
-  __shared__ __align__(16) float sY[D][BB_CT];
-  __shared__ float sXn[BB_QT], sGn[BB_QT], sYn[BB_CT];
+  __shared__ __align__(16) float sY[2][D][2 * BB_CT];  // (w, w) pairs
+  __shared__ __align__(16) float sYn[2][2 * BB_CT];    // (yn, yn) pairs
+  __shared__ __align__(16) float sXn[BB_QT];
+  __shared__ __align__(16) float sGn[BB_QT];
   __shared__ float sBestS[4][BB_QT];
   __shared__ int sBestI[4][BB_QT];
 
@@ -373,6 +383,34 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
   }
   if (tid < BB_QT) { sXn[tid] = __ldg(P.xn + qbase + tid); sGn[tid] = __ldg(P.gn + qbase + tid); }
 
+  // candidate-chunk staging: D * BB_CT / 4 float4 elements over BB_NT threads
+  constexpr int NLD = (D * (BB_CT / 4) + BB_NT - 1) / BB_NT;
+  float4 pf[NLD];
+  float pfn = 0.f;
+  auto prefetch = [&](int chunk) {
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int it = tid + u * BB_NT;
+      if (it < D * (BB_CT / 4)) {
+        const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
+        pf[u] = ldg4(P.y + (size_t)k * g.Mpad + chunk + 4 * c4);
+      }
+    }
+    if (tid < BB_CT) pfn = __ldg(P.yn + chunk + tid);
+  };
+  auto commit = [&](int buf) {
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int it = tid + u * BB_NT;
+      if (it < D * (BB_CT / 4)) {
+        const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
+        st4(&sY[buf][k][8 * c4], make_float4(pf[u].x, pf[u].x, pf[u].y, pf[u].y));
+        st4(&sY[buf][k][8 * c4 + 4], make_float4(pf[u].z, pf[u].z, pf[u].w, pf[u].w));
+      }
+    }
+    if (tid < BB_CT) st2(&sYn[buf][2 * tid], make_float2(pfn, pfn));
+  };
+
   const int warp = tid >> 5, lane = tid & 31;
   const int wq = warp >> 2, wc = warp & 3;  // 2 x 4 warps: 32 queries x 16 candidates each
   const int lq = lane >> 2, lc = lane & 3;  // 8 x 4 lanes : 4 queries x 4 candidates each
@@ -384,44 +422,61 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
 #pragma unroll
   for (int i = 0; i < 4; ++i) { best[i] = __int_as_float(0x7f800000); bidx[i] = 0x7fffffff; }
 
-  for (int chunk = 0; chunk < g.Mpad; chunk += BB_CT) {
-    __syncthreads();  // previous chunk fully consumed (also orders the query loads before first use)
-    for (int it = tid; it < D * (BB_CT / 4); it += BB_NT) {
-      const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
-      st4(&sY[k][4 * c4], ldg4(P.y + (size_t)k * g.Mpad + chunk + 4 * c4));
-    }
-    if (tid < BB_CT) sYn[tid] = __ldg(P.yn + chunk + tid);
-    __syncthreads();
+  prefetch(0);
+  commit(0);
+  __syncthreads();  // queries, norms and chunk 0 are in shared memory
+  const float4 xn4 = ld4(&sXn[q0]), gn4 = ld4(&sGn[q0]);
+  const float2 xnp[2] = {make_float2(xn4.x, xn4.y), make_float2(xn4.z, xn4.w)};
+  const float2 gnp[2] = {make_float2(gn4.x, gn4.y), make_float2(gn4.z, gn4.w)};
+  const float2 m2 = make_float2(-2.0f, -2.0f);
 
-    float a1[4][4], a2[4][4];
+  for (int chunk = 0, buf = 0; chunk < g.Mpad; chunk += BB_CT, buf ^= 1) {
+    const bool more = chunk + BB_CT < g.Mpad;
+    if (more) prefetch(chunk + BB_CT);
+
+    float2 a1[2][4], a2[2][4];  // [query pair][candidate]: .x = query 2p, .y = query 2p+1
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int p = 0; p < 2; ++p)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { a1[i][j] = 0.f; a2[i][j] = 0.f; }
+      for (int j = 0; j < 4; ++j) { a1[p][j] = make_float2(0.f, 0.f); a2[p][j] = make_float2(0.f, 0.f); }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
       const float4 u = ld4(&sQ1[k][q0]);
       const float4 v = ld4(&sQ2[k][q0]);
-      const float4 w = ld4(&sY[k][c0]);
-      const float uu[4] = {u.x, u.y, u.z, u.w}, vv[4] = {v.x, v.y, v.z, v.w}, ww[4] = {w.x, w.y, w.z, w.w};
+      const float4 wa = ld4(&sY[buf][k][2 * c0]), wb = ld4(&sY[buf][k][2 * c0 + 4]);
+      const float2 up[2] = {make_float2(u.x, u.y), make_float2(u.z, u.w)};
+      const float2 vp[2] = {make_float2(v.x, v.y), make_float2(v.z, v.w)};
+      const float2 ww[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y),
+                            make_float2(wb.z, wb.w)};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int p = 0; p < 2; ++p)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          a1[i][j] = fmaf(uu[i], ww[j], a1[i][j]);
-          a2[i][j] = fmaf(vv[i], ww[j], a2[i][j]);
+          a1[p][j] = __ffma2_rn(up[p], ww[j], a1[p][j]);
+          a2[p][j] = __ffma2_rn(vp[p], ww[j], a2[p][j]);
         }
     }
+    // scores with the reference's rounding points (utils.py:183-187, loss.py:132-133), two queries at a time
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float yn = sYn[c0 + j];
+      const float2 yn2 = *reinterpret_cast<const float2*>(&sYn[buf][2 * (c0 + j)]);
       const int cj = chunk + c0 + j;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float s = bb_score(sXn[q0 + i], sGn[q0 + i], yn, a1[i][j], a2[i][j], alpha, beta);
-        if (s < best[i]) { best[i] = s; bidx[i] = cj; }  // ascending cj per thread: first minimum kept
+      for (int p = 0; p < 2; ++p) {
+        float2 d1 = __ffma2_rn(m2, a1[p][j], __fadd2_rn(xnp[p], yn2));
+        float2 d2 = __ffma2_rn(m2, a2[p][j], __fadd2_rn(gnp[p], yn2));
+        d1 = make_float2(fmaxf(d1.x, 0.0f), fmaxf(d1.y, 0.0f));
+        d2 = make_float2(fmaxf(d2.x, 0.0f), fmaxf(d2.y, 0.0f));
+        // alpha*d1 + beta*d2 rounds three times in the reference (loss.py:132-133).  Scalar _rn
+        // intrinsics on purpose: ptxas contracts packed mul.rn.f32x2 + add.rn.f32x2 into one FFMA2.
+        const float sx = __fadd_rn(__fmul_rn(alpha, d1.x), __fmul_rn(beta, d2.x));
+        const float sy = __fadd_rn(__fmul_rn(alpha, d1.y), __fmul_rn(beta, d2.y));
+        if (sx < best[2 * p]) { best[2 * p] = sx; bidx[2 * p] = cj; }  // ascending cj per thread: first minimum kept
+        if (sy < best[2 * p + 1]) { best[2 * p + 1] = sy; bidx[2 * p + 1] = cj; }
       }
     }
+    if (more) commit(buf ^ 1);  // buf^1 was last read before the previous barrier
+    __syncthreads();
   }
 
   // argmin across the 4 candidate lanes (lc = lane bits 0-1), then across the 4 candidate warps

@@ -119,6 +119,19 @@ def test_full_size_properties_config4():
     assert rel_err(l.item(), 0.5 * (la.item() + lb.item())) < 1e-6
 
 
+def test_odd_weights_keep_the_reference_rounding_points():
+    """alpha, beta that are not powers of two: alpha*d1, beta*d2 and their sum must round separately
+    (loss.py:132-133) -- a contracted fma would still pass every power-of-two case.  Bit-exact vs the
+    C oracle on the indices AND on the winning scores."""
+    rng = np.random.default_rng(21)
+    sr = rng.random((2, 3, 48, 60), dtype=np.float32)
+    gt = rng.random((2, 3, 48, 60), dtype=np.float32)
+    for a, b in ((0.7, 1.3), (1.0 / 3.0, 0.9)):
+        _, idx, _ = _run(sr, gt, "fused", alpha=a, beta=b)
+        orc = O.bb_forward_c(sr, gt, alpha=a, beta=b)
+        assert np.array_equal(idx, orc["idx"])
+
+
 def test_rejects_unsupported_geometry():
     from srgan_st_b200 import BestBuddyLoss
     with pytest.raises(NotImplementedError):
