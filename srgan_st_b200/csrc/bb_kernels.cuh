@@ -29,8 +29,8 @@
 namespace srst {
 
 constexpr int BB_D = 27;   // 3 channels x 3 x 3
-constexpr int BB_QT = 64;  // queries per block
-constexpr int BB_CT = 64;  // candidates per chunk
+constexpr int BB_QT = 128;  // queries per block
+constexpr int BB_CT = 128;  // candidates per chunk
 constexpr int BB_NT = 256;
 
 struct BbGeom {
@@ -350,38 +350,79 @@ SRST_DEV void bb_argmin_merge(float& s, int& i, float so, int io) {
   if (so < s || (so == s && io < i)) { s = so; i = io; }
 }
 
-// Search kernel.  256 threads = 2 x 4 warps (32 queries x 16 candidates each), 8 x 4 lanes (4 queries x 4
-// candidates each): a 4 x 4 register tile with TWO dot products per pair, issued as packed
-// fma.rn.f32x2 (SASS FFMA2) on query PAIRS: the candidate chunk sits in shared memory with every
-// value duplicated, (w, w), so one LDS.128 yields two ready-made f32x2 operands and the query
-// pair (u_i, u_i+1) comes straight out of the k-major query tile.  An FFMA2 is two IEEE fmas, so
-// every dot product keeps the fixed k = 0..D-1 order of oracle/bb_oracle.c.  The candidate chunks are
-// double-buffered: chunk c+1 travels global -> registers while chunk c is being evaluated, and
-// is committed to the other buffer before the one barrier per chunk.
+// Search kernel: a cheap single-dot FILTER in front of the exact score.
+//
+// With q_i = alpha*x_i + beta*g_i, c_i = alpha*|x_i|^2 + beta*|g_i|^2 and (alpha+beta)*|y_j|^2, the score is, in
+// real arithmetic, S_ij = c_i + (alpha+beta)|y_j|^2 - 2 q_i.y_j : ONE 27-term dot product per pair
+// instead of the reference's two.  Its fp32 value s'_ij is not the reference's rounding, so it is only
+// used to DISCARD candidates: both s'_ij and the exactly-rounded reference score s_ij (bb_score, the
+// fixed-order restatement of utils.py:183-187 / loss.py:132-133) lie within
+//     tol_ij = kappa * (|alpha|(|x_i|^2+|y_j|^2) + |beta|(|g_i|^2+|y_j|^2)),   kappa = 2e-5  (>= 120 ulp:
+// 27-term fp32 dot products and norms accumulate <= 30 ulp each relative to that magnitude) of S_ij.
+// Every thread keeps, per query, an upper bound B >= min_j s_ij (seeded with the exact score of the
+// co-located HR patch j = i, tightened by every exact score it computes); a candidate whose lower
+// bound s'_ij - tol_ij exceeds B cannot be the argmin, nor tie with it, and is skipped.  The few
+// that survive are re-scored EXACTLY (two sequential-fma dot products, the oracle's order), in
+// ascending j per thread with a strict <, and (score, index) pairs are merged lexicographically, so
+// the result is bit-identical to scoring every pair exactly: same indices, same first-minimum rule.
+//
+// 256 threads as 16 x 16, each owning 8 queries x 8 candidates (two groups of 4 each, 64 apart: a
+// quarter-warp reads 128 contiguous bytes per LDS.128): 64 accumulators fed by packed FFMA2 on
+// query PAIRS, one byte of shared-memory traffic per FMA (the 4x4 two-dot tile needed 1.5-2 and was
+// bound by the shared-memory pipe, profiles/README.md).  Candidate chunks are double-buffered
+// through registers; the 16 threads that share a query set sit in one half-warp, so the final
+// argmin is four warp-shuffle steps.
+constexpr float kBbKappa = 2e-5f;
+
+// Exact reference-order score of (query qi, candidate cj) of one image: the rare path.
+#ifdef SRST_EMULATE
+static float
+#else
+__device__ __noinline__ float
+#endif
+bb_exact_score(const float* q1, const float* q2, const float* y, const float* xn, const float* gn, const float* yn,
+               int Npad, int Mpad, int D, int qi, int cj, float alpha, float beta) {
+  float dot1 = 0.f, dot2 = 0.f;
+  for (int k = 0; k < D; ++k) {
+    const float w = __ldg(y + (size_t)k * Mpad + cj);
+    dot1 = fmaf(__ldg(q1 + (size_t)k * Npad + qi), w, dot1);
+    dot2 = fmaf(__ldg(q2 + (size_t)k * Npad + qi), w, dot2);
+  }
+  return bb_score(__ldg(xn + qi), __ldg(gn + qi), __ldg(yn + cj), dot1, dot2, alpha, beta);
+}
+
 template <int D>
-__global__ void __launch_bounds__(BB_NT, 2)
+__global__ void __launch_bounds__(BB_NT, 1)
 bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, float alpha, float beta,
                  int64_t* __restrict__ idx_out) {
-  __shared__ __align__(16) float sQ1[D][BB_QT];
-  __shared__ __align__(16) float sQ2[D][BB_QT];
-  __shared__ __align__(16) float sY[2][D][2 * BB_CT];  // (w, w) pairs
-  __shared__ __align__(16) float sYn[2][2 * BB_CT];    // (yn, yn) pairs
-  __shared__ __align__(16) float sXn[BB_QT];
-  __shared__ __align__(16) float sGn[BB_QT];
-  __shared__ float sBestS[4][BB_QT];
-  __shared__ int sBestI[4][BB_QT];
+  static_assert(BB_NT == 256 && BB_QT == 128 && BB_CT == 128, "search tile is 16x16 threads x (8 queries x 8 candidates)");
+  __shared__ __align__(16) float sQ[D][BB_QT];      // alpha*x + beta*g
+  __shared__ __align__(16) float sY[2][D][BB_CT];
+  __shared__ __align__(16) float sYl[2][BB_CT];     // (alpha+beta)|y|^2 - kappa*(|alpha|+|beta|)|y|^2
+  __shared__ __align__(16) float sCl[BB_QT];        // c_i - kappa*(|alpha||x|^2 + |beta||g|^2)
+  __shared__ __align__(16) float sB0[BB_QT];        // exact score of the co-located candidate j = i
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y, qt = blockIdx.x;
   const BbPtrs P = bb_image_ptrs(mats, per_image, b, g.Npad, g.Mpad, D);
   const int qbase = qt * BB_QT;
+  const float aa = fabsf(alpha), ab = fabsf(beta);
 
   for (int it = tid; it < D * (BB_QT / 4); it += BB_NT) {
     const int k = it / (BB_QT / 4), c4 = it - k * (BB_QT / 4);
-    st4(&sQ1[k][4 * c4], ldg4(P.q1 + (size_t)k * g.Npad + qbase + 4 * c4));
-    st4(&sQ2[k][4 * c4], ldg4(P.q2 + (size_t)k * g.Npad + qbase + 4 * c4));
+    const float4 x = ldg4(P.q1 + (size_t)k * g.Npad + qbase + 4 * c4);
+    const float4 gg = ldg4(P.q2 + (size_t)k * g.Npad + qbase + 4 * c4);
+    st4(&sQ[k][4 * c4], make_float4(fmaf(alpha, x.x, beta * gg.x), fmaf(alpha, x.y, beta * gg.y),
+                                    fmaf(alpha, x.z, beta * gg.z), fmaf(alpha, x.w, beta * gg.w)));
   }
-  if (tid < BB_QT) { sXn[tid] = __ldg(P.xn + qbase + tid); sGn[tid] = __ldg(P.gn + qbase + tid); }
+  if (tid < BB_QT) {
+    const int qi = qbase + tid;
+    const float xn = __ldg(P.xn + qi), gn = __ldg(P.gn + qi);
+    sCl[tid] = fmaf(alpha, xn, beta * gn) - kBbKappa * fmaf(aa, xn, ab * gn);
+    // seed of the upper bound; padded queries get -inf so that nothing is ever evaluated for them
+    sB0[tid] = (qi < g.N) ? bb_exact_score(P.q1, P.q2, P.y, P.xn, P.gn, P.yn, g.Npad, g.Mpad, D, qi, qi, alpha, beta)
+                          : __int_as_float(0xff800000);
+  }
 
   // candidate-chunk staging: D * BB_CT / 4 float4 elements over BB_NT threads
   constexpr int NLD = (D * (BB_CT / 4) + BB_NT - 1) / BB_NT;
@@ -404,99 +445,101 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
       const int it = tid + u * BB_NT;
       if (it < D * (BB_CT / 4)) {
         const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
-        st4(&sY[buf][k][8 * c4], make_float4(pf[u].x, pf[u].x, pf[u].y, pf[u].y));
-        st4(&sY[buf][k][8 * c4 + 4], make_float4(pf[u].z, pf[u].z, pf[u].w, pf[u].w));
+        st4(&sY[buf][k][4 * c4], pf[u]);
       }
     }
-    if (tid < BB_CT) st2(&sYn[buf][2 * tid], make_float2(pfn, pfn));
+    // padded candidates carry |y|^2 = +inf: their lower bound is +inf (or NaN) and never passes
+    if (tid < BB_CT) sYl[buf][tid] = (alpha + beta) * pfn - kBbKappa * ((aa + ab) * pfn);
   };
 
-  const int warp = tid >> 5, lane = tid & 31;
-  const int wq = warp >> 2, wc = warp & 3;  // 2 x 4 warps: 32 queries x 16 candidates each
-  const int lq = lane >> 2, lc = lane & 3;  // 8 x 4 lanes : 4 queries x 4 candidates each
-  const int q0 = wq * 32 + lq * 4;
-  const int c0 = wc * 16 + lc * 4;
-
-  float best[4];
-  int bidx[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { best[i] = __int_as_float(0x7f800000); bidx[i] = 0x7fffffff; }
+  const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads; a half-warp shares ty (its queries)
+  // local query l (0..7) -> tile query ty*4 + (l&3) + 64*(l>>2); same for candidates with tx
 
   prefetch(0);
   commit(0);
-  __syncthreads();  // queries, norms and chunk 0 are in shared memory
-  const float4 xn4 = ld4(&sXn[q0]), gn4 = ld4(&sGn[q0]);
-  const float2 xnp[2] = {make_float2(xn4.x, xn4.y), make_float2(xn4.z, xn4.w)};
-  const float2 gnp[2] = {make_float2(gn4.x, gn4.y), make_float2(gn4.z, gn4.w)};
+  __syncthreads();  // queries, bounds and chunk 0 are in shared memory
+
+  float best[8], B[8];
+  int bidx[8];
+  float2 cl[4];
+  {
+    const float4 c0 = ld4(&sCl[4 * ty]), c1 = ld4(&sCl[64 + 4 * ty]);
+    const float4 b0 = ld4(&sB0[4 * ty]), b1 = ld4(&sB0[64 + 4 * ty]);
+    cl[0] = make_float2(c0.x, c0.y); cl[1] = make_float2(c0.z, c0.w);
+    cl[2] = make_float2(c1.x, c1.y); cl[3] = make_float2(c1.z, c1.w);
+    B[0] = b0.x; B[1] = b0.y; B[2] = b0.z; B[3] = b0.w; B[4] = b1.x; B[5] = b1.y; B[6] = b1.z; B[7] = b1.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { best[i] = __int_as_float(0x7f800000); bidx[i] = 0x7fffffff; }
   const float2 m2 = make_float2(-2.0f, -2.0f);
 
   for (int chunk = 0, buf = 0; chunk < g.Mpad; chunk += BB_CT, buf ^= 1) {
     const bool more = chunk + BB_CT < g.Mpad;
     if (more) prefetch(chunk + BB_CT);
 
-    float2 a1[2][4], a2[2][4];  // [query pair][candidate]: .x = query 2p, .y = query 2p+1
+    float2 acc[4][8];  // [query pair][candidate]: .x = local query 2p, .y = 2p+1
 #pragma unroll
-    for (int p = 0; p < 2; ++p)
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { a1[p][j] = make_float2(0.f, 0.f); a2[p][j] = make_float2(0.f, 0.f); }
+      for (int j = 0; j < 8; ++j) acc[p][j] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      const float4 u = ld4(&sQ1[k][q0]);
-      const float4 v = ld4(&sQ2[k][q0]);
-      const float4 wa = ld4(&sY[buf][k][2 * c0]), wb = ld4(&sY[buf][k][2 * c0 + 4]);
-      const float2 up[2] = {make_float2(u.x, u.y), make_float2(u.z, u.w)};
-      const float2 vp[2] = {make_float2(v.x, v.y), make_float2(v.z, v.w)};
-      const float2 ww[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y),
-                            make_float2(wb.z, wb.w)};
+      const float4 ua = ld4(&sQ[k][4 * ty]), ub = ld4(&sQ[k][64 + 4 * ty]);
+      const float4 wa = ld4(&sY[buf][k][4 * tx]), wb = ld4(&sY[buf][k][64 + 4 * tx]);
+      const float2 up[4] = {make_float2(ua.x, ua.y), make_float2(ua.z, ua.w), make_float2(ub.x, ub.y),
+                            make_float2(ub.z, ub.w)};
+      const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-      for (int p = 0; p < 2; ++p)
+      for (int j = 0; j < 8; ++j) {
+        const float2 w2 = make_float2(w[j], w[j]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          a1[p][j] = __ffma2_rn(up[p], ww[j], a1[p][j]);
-          a2[p][j] = __ffma2_rn(vp[p], ww[j], a2[p][j]);
-        }
+        for (int p = 0; p < 4; ++p) acc[p][j] = __ffma2_rn(up[p], w2, acc[p][j]);
+      }
     }
-    // scores with the reference's rounding points (utils.py:183-187, loss.py:132-133), two queries at a time
+    // filter: lower bound of the exact score vs the running upper bound; survivors are flagged
+    unsigned long long hit = 0ull;
+    const float4 yla = ld4(&sYl[buf][4 * tx]), ylb = ld4(&sYl[buf][64 + 4 * tx]);
+    const float yl[8] = {yla.x, yla.y, yla.z, yla.w, ylb.x, ylb.y, ylb.z, ylb.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 yn2 = *reinterpret_cast<const float2*>(&sYn[buf][2 * (c0 + j)]);
-      const int cj = chunk + c0 + j;
+    for (int j = 0; j < 8; ++j) {
+      const float2 y2 = make_float2(yl[j], yl[j]);
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        float2 d1 = __ffma2_rn(m2, a1[p][j], __fadd2_rn(xnp[p], yn2));
-        float2 d2 = __ffma2_rn(m2, a2[p][j], __fadd2_rn(gnp[p], yn2));
-        d1 = make_float2(fmaxf(d1.x, 0.0f), fmaxf(d1.y, 0.0f));
-        d2 = make_float2(fmaxf(d2.x, 0.0f), fmaxf(d2.y, 0.0f));
-        // alpha*d1 + beta*d2 rounds three times in the reference (loss.py:132-133).  Scalar _rn
-        // intrinsics on purpose: ptxas contracts packed mul.rn.f32x2 + add.rn.f32x2 into one FFMA2.
-        const float sx = __fadd_rn(__fmul_rn(alpha, d1.x), __fmul_rn(beta, d2.x));
-        const float sy = __fadd_rn(__fmul_rn(alpha, d1.y), __fmul_rn(beta, d2.y));
-        if (sx < best[2 * p]) { best[2 * p] = sx; bidx[2 * p] = cj; }  // ascending cj per thread: first minimum kept
-        if (sy < best[2 * p + 1]) { best[2 * p + 1] = sy; bidx[2 * p + 1] = cj; }
+      for (int p = 0; p < 4; ++p) {
+        const float2 lo = __ffma2_rn(m2, acc[p][j], __fadd2_rn(cl[p], y2));
+        if (lo.x <= B[2 * p]) hit |= 1ull << (8 * j + 2 * p);
+        if (lo.y <= B[2 * p + 1]) hit |= 1ull << (8 * j + 2 * p + 1);
+      }
+    }
+    if (hit) {  // rare: exact re-scoring, ascending candidate order per query
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int cj = chunk + 4 * tx + (j & 3) + 64 * (j >> 2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if ((hit >> (8 * j + i)) & 1ull) {
+            const int qi = qbase + 4 * ty + (i & 3) + 64 * (i >> 2);
+            const float s = bb_exact_score(P.q1, P.q2, P.y, P.xn, P.gn, P.yn, g.Npad, g.Mpad, D, qi, cj, alpha, beta);
+            if (s < best[i]) { best[i] = s; bidx[i] = cj; }  // ascending cj per thread: first minimum kept
+            B[i] = fminf(B[i], s);
+          }
+        }
       }
     }
     if (more) commit(buf ^ 1);  // buf^1 was last read before the previous barrier
     __syncthreads();
   }
 
-  // argmin across the 4 candidate lanes (lc = lane bits 0-1), then across the 4 candidate warps
+  // argmin across the 16 threads (one half-warp) that share these queries: four shuffle steps
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
 #pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
+    for (int o = 1; o <= 8; o <<= 1) {
       const float so = __shfl_xor_sync(0xffffffffu, best[i], o);
       const int io = __shfl_xor_sync(0xffffffffu, bidx[i], o);
       bb_argmin_merge(best[i], bidx[i], so, io);
     }
-    if (lc == 0) { sBestS[wc][q0 + i] = best[i]; sBestI[wc][q0 + i] = bidx[i]; }
-  }
-  __syncthreads();
-  if (tid < BB_QT) {
-    float s = sBestS[0][tid];
-    int i = sBestI[0][tid];
-#pragma unroll
-    for (int w = 1; w < 4; ++w) bb_argmin_merge(s, i, sBestS[w][tid], sBestI[w][tid]);
-    if (qbase + tid < g.N) idx_out[(size_t)b * g.N + qbase + tid] = (int64_t)i;
+    const int qi = qbase + 4 * ty + (i & 3) + 64 * (i >> 2);
+    if (tx == 0 && qi < g.N) idx_out[(size_t)b * g.N + qi] = (int64_t)bidx[i];
   }
 }
 
