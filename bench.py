@@ -399,6 +399,36 @@ def run_gpu(args):
                                 "hbm_frac_fwd": r["roofline_fwd"] / hbm_peak, "hbm_frac_bwd": r["roofline_bwd"] / hbm_peak,
                                 "hbm_frac_pair": r["roofline_pair"] / hbm_peak}
 
+    if not args.no_extra:
+        # BASELINE.json configs[3]: Best-Buddy patch search, batch 64 of 192x192 crops (per GPU), through the
+        # public module (pyramid built by libsrst).  FP32-FMA bound, no HBM claim.
+        from srgan_st_b200 import BestBuddyLoss
+        Bb, Hb, Wb = 64, 192, 192
+        gen = torch.Generator(device=dev).manual_seed(99 + rank)
+        gtb = torch.rand(Bb, 3, Hb, Wb, device=dev, generator=gen)
+        xb = (gtb + 0.1 * torch.randn(Bb, 3, Hb, Wb, device=dev, generator=gen)).clamp(0, 1).requires_grad_(True)
+        mb = BestBuddyLoss(pyramid="fused")
+        for _ in range(3):
+            mb(xb, gtb).backward()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tf = tb = 0.0
+        nb = 10
+        for _ in range(nb):
+            ev[0].record(); lb = mb(xb, gtb); ev[1].record(); lb.backward(); ev[2].record()
+            torch.cuda.synchronize()
+            tf += ev[0].elapsed_time(ev[1]) / nb; tb += ev[1].elapsed_time(ev[2]) / nb
+        Nq = (Hb // 3) * (Wb // 3)
+        Mc = Nq + ((Hb // 2) // 3) * ((Wb // 2) // 3) + ((Hb // 4) // 3) * ((Wb // 4) // 3)
+        others["bb_c4"] = {"workload": "Best-Buddy loss fwd+bwd, batch 64 x 3x192x192 per GPU (configs[3]), "
+                                       "pyramid+pack+search+loss kernels through the nn.Module",
+                           "images_per_s_per_gpu": Bb / ((tf + tb) * 1e-3), "ms_fwd": tf, "ms_bwd": tb,
+                           "reference_flop_per_step": 4.0 * Nq * Mc * 27 * Bb,
+                           "reference_tflops_equiv": 4.0 * Nq * Mc * 27 * Bb / (tf * 1e-3) / 1e12,
+                           "note": "reference work = two [N,M,27] SGEMMs (utils.py:183); the search kernel does ONE "
+                                   "filtered dot product per pair and re-scores survivors exactly (bit-identical indices)"}
+        del gtb, xb
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         wl = main["wl"]
