@@ -41,6 +41,7 @@ using BwdB = StBwdCfg<16, 96, 10, 256, 2, 8, 2>;  // 96-wide training crops
 using BwdC = StBwdCfg<32, 64, 12, 352, 2, 8, 1>;  // one big CTA per SM
 using BwdD = StBwdCfg<28, 56, 16, 256, 2, 8, 2>;  // 16 row pairs per phase item column: no LDS bank conflicts
 using BwdE = StBwdCfg<28, 88, 16, 384, 2, 8, 1>;  // experiment
+using BwdG = StBwdCfg<16, 96, 10, 256, 2, 8, 2, 8>;  // BwdB with 8-column horizontal-pass items
 using BwdF = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8>;  // BwdD with 8-column horizontal-pass items (less shared-memory traffic)
 
 //                             TH  TW  RS   NT
@@ -190,11 +191,12 @@ static int pick_fwd_cfg(int H, int W) {
   if (W <= 96) return 2;
   return 3;
 }
-static int pick_bwd_cfg(int H, int W) {
+static int pick_bwd_cfg(int B, int H, int W) {
   const int forced = env_int("SRST_ST_BWD_CFG", -1);
-  if (forced >= 0 && forced <= 5) return forced;
-  // measured on B200 (gpurun sweep, round 1): the conflict-free 28x56 tile wins at every size,
-  // its 8-column horizontal-pass variant by another 1 %
+  if (forced >= 0 && forced <= 6) return forced;
+  // measured on B200 (gpurun sweeps, round 1b): full-width 16x96 strips win on 96-wide crops once
+  // they fill the machine (two CTAs per SM); the conflict-free 28x56 tile wins everywhere else
+  if (W <= 96 && (long long)B * ((H + 15) / 16) >= 2LL * sm_count()) return 6;
   return 5;
 }
 
@@ -333,12 +335,13 @@ static int st_backward_rr(const StCall& c) {
   P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
   fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
-    switch (pick_bwd_cfg(c.H, c.W)) {
+    switch (pick_bwd_cfg(c.B, c.H, c.W)) {
       case 1: return launch_st_backward<BwdB>(P, c.gray, c.stream);
       case 2: return launch_st_backward<BwdC>(P, c.gray, c.stream);
       case 3: return launch_st_backward<BwdD>(P, c.gray, c.stream);
       case 4: return launch_st_backward<BwdE>(P, c.gray, c.stream);
       case 5: return launch_st_backward<BwdF>(P, c.gray, c.stream);
+      case 6: return launch_st_backward<BwdG>(P, c.gray, c.stream);
       default: return launch_st_backward<BwdA>(P, c.gray, c.stream);
     }
   } else {
