@@ -132,6 +132,21 @@ def test_odd_weights_keep_the_reference_rounding_points():
         assert np.array_equal(idx, orc["idx"])
 
 
+def test_search_filter_exact_on_ties_and_odd_weights_full_size():
+    """Search kernel = single-dot lower-bound filter + exact re-scoring.  Binary images (thousands of
+    exact ties), zero / negative weights, at the 96x96 training size: indices equal the C oracle."""
+    rng = np.random.default_rng(31)
+    gt = (rng.random((2, 3, 96, 96)) > 0.5).astype(np.float32)
+    sr = (rng.random((2, 3, 96, 96)) > 0.5).astype(np.float32)
+    _, idx, _ = _run(sr, gt, "fused")
+    assert np.array_equal(idx, O.bb_forward_c(sr, gt)["idx"])
+    gt = rng.random((2, 3, 96, 96), dtype=np.float32)
+    sr = np.clip(gt + 0.05 * rng.standard_normal(gt.shape).astype(np.float32), 0, 1)
+    for a, b in ((0.0, 1.0), (1.0, 0.0), (-0.25, 1.0)):
+        _, idx, _ = _run(sr, gt, "fused", alpha=a, beta=b)
+        assert np.array_equal(idx, O.bb_forward_c(sr, gt, alpha=a, beta=b)["idx"])
+
+
 def test_rejects_unsupported_geometry():
     from srgan_st_b200 import BestBuddyLoss
     with pytest.raises(NotImplementedError):

@@ -56,3 +56,29 @@ def test_emulated_bb_ragged_shape_and_ties(lib):
     flat = np.full((1, 3, 24, 24), 0.25, np.float32)
     out = emu_bb(lib, flat, flat)
     assert np.all(out["idx"] == 0) and out["loss"] == 0.0
+
+
+@pytest.mark.parametrize("alpha,beta", [(0.0, 1.0), (1.0, 0.0), (0.7, 1.3), (-0.25, 1.0)])
+def test_emulated_search_filter_is_exact_for_any_weights(lib, alpha, beta):
+    """The search kernel discards candidates with a single-dot lower bound and re-scores survivors
+    exactly: for zero, unequal and even negative weights the indices must still equal exhaustive
+    exact scoring (the C oracle), on smooth SR-like data (co-located patch usually wins) and on noise."""
+    rng = np.random.default_rng(17)
+    gt = rng.random((1, 3, 36, 48), dtype=np.float32)
+    for sr in (np.clip(gt + 0.05 * rng.standard_normal(gt.shape).astype(np.float32), 0, 1),
+               rng.random(gt.shape, dtype=np.float32)):
+        out = emu_bb(lib, sr, gt, alpha=alpha, beta=beta)
+        orc = O.bb_forward_c(sr, gt, alpha=alpha, beta=beta)
+        assert np.array_equal(out["idx"], orc["idx"])
+        assert rel_err(out["loss"], orc["loss"]) < 1e-6
+
+
+def test_emulated_search_many_near_ties(lib):
+    """Quantised 2-level images make thousands of exactly tied and nearly tied scores: the filter must
+    keep every co-minimal candidate so that the lowest index wins (torch.min rule)."""
+    rng = np.random.default_rng(23)
+    gt = (rng.random((1, 3, 48, 48)) > 0.5).astype(np.float32)
+    sr = (rng.random((1, 3, 48, 48)) > 0.5).astype(np.float32)
+    out = emu_bb(lib, sr, gt)
+    orc = O.bb_forward_c(sr, gt)
+    assert np.array_equal(out["idx"], orc["idx"])
