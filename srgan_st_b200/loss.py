@@ -50,6 +50,13 @@ def _check_pair(x: torch.Tensor, gt: torch.Tensor, who: str) -> None:
         raise ValueError(f"{who}: shape mismatch {tuple(x.shape)} vs {tuple(gt.shape)}")
 
 
+def _no_gt_grad(gt: torch.Tensor, who: str) -> None:
+    """The reference would send a gradient into gt through the gathered candidates (loss.py:137-139);
+    the training loops never ask for it (gt comes from the data loader) and libsrst has no kernel for it."""
+    if gt.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError(f"{who}: gradient w.r.t. gt is not implemented (pass gt.detach())")
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -248,6 +255,7 @@ class BestBuddyLoss(nn.Module):
 
     def forward(self, x, gt):
         _check_pair(x, gt, "BestBuddyLoss")
+        _no_gt_grad(gt, "BestBuddyLoss")
         loss, idx = _BestBuddyLossFn.apply(x, gt, self.alpha, self.beta, self._crit, self.pyramid)
         self.last_indices = idx
         return loss
@@ -285,6 +293,7 @@ class GramLoss(nn.Module):
 
     def forward(self, x, gt):
         _check_pair(x, gt, "GramLoss")
+        _no_gt_grad(gt, "GramLoss")
         loss, idx = _BestBuddyLossFn.apply(x, gt, self.alpha, self.beta, self._crit, self.pyramid, "gram")
         self.last_indices = idx
         return loss
@@ -385,6 +394,7 @@ class PatchwiseStructureTensorLoss(nn.Module):
 
     def forward(self, x, gt):
         _check_pair(x, gt, "PatchwiseStructureTensorLoss")
+        _no_gt_grad(gt, "PatchwiseStructureTensorLoss")
         loss, idx = _PatchwiseStLossFn.apply(x, gt, self.sigma, self.rho, self.alpha, self.beta, self._crit,
                                              self.pyramid)
         self.last_indices = idx

@@ -157,3 +157,5 @@ def test_rejects_unsupported_geometry():
         BestBuddyLoss(dist_norm="l1")
     with pytest.raises(RuntimeError):
         BestBuddyLoss()(torch.rand(1, 3, 24, 24), torch.rand(1, 3, 24, 24))
+    with pytest.raises(NotImplementedError):  # the reference would differentiate the gathered candidates
+        BestBuddyLoss()(torch.rand(1, 3, 24, 24, device="cuda"), torch.rand(1, 3, 24, 24, device="cuda").requires_grad_())
