@@ -138,7 +138,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 
@@ -465,7 +465,7 @@ def run_gpu(args):
             "loss_check": main["loss"],
             "other_workloads": others,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -481,14 +481,31 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    if args.gpus > 1 and "RANK" not in os.environ:
+    if args.gpus > 1 and "RANK" not in os.environ and args.impl != "reference":
         # convenience: re-launch under torchrun on one node
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner,
+    # library chatter) is sent to stderr, and the line itself goes to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+    if args.impl == "reference":
+        return run_reference(args)
     return run_gpu(args)
+
+
+_RESULT_FD = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
 
 
 if __name__ == "__main__":
