@@ -739,9 +739,7 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float*
 #pragma unroll
       for (int rq = 0; rq < C::RS / 2 + C::RK; ++rq) {
         const float2 ix = ld2(p0 + rq * C::PD), iy = ld2(p1 + rq * C::PD);
-        const float2 pxx = make_float2(ix.x * ix.x, ix.y * ix.y);
-        const float2 pyy = make_float2(iy.x * iy.x, iy.y * iy.y);
-        const float2 pxy = make_float2(ix.x * iy.x, ix.y * iy.y);
+        const float2 pxx = mul2(ix, ix), pyy = mul2(iy, iy), pxy = mul2(ix, iy);  // packed FMUL2
 #pragma unroll
         for (int jp = 0; jp < C::RS / 2; ++jp) {
           const int u0 = 2 * rq - 2 * jp;  // tap-pair index of input row 2rq for output pair jp
