@@ -90,3 +90,17 @@ def test_emulated_backward_without_saved_gray(lib):
     assert np.allclose(a["d_sr"], b["d_sr"], rtol=1e-5, atol=1e-9)
     gray = 0.2989 * z["sr"][:, 0] + 0.587 * z["sr"][:, 1] + 0.114 * z["sr"][:, 2]
     assert np.allclose(a["gray_sr"], gray, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 1, 1), (1, 3, 5, 7), (2, 3, 17, 4), (1, 3, 2, 130), (1, 3, 9, 9)])
+def test_emulated_tiny_and_degenerate_shapes(lib, shape):
+    """Images smaller than a tile, a single pixel, one-row strips: everything is halo."""
+    rng = np.random.default_rng(sum(shape))
+    sr = rng.random(shape, dtype=np.float32)
+    hr = rng.random(shape, dtype=np.float32)
+    z = golden("st_rand_2x24x36")
+    taps = (z["g"], z["dg"], z["k"])
+    out = emu_st(lib, sr, hr, taps, want_hr=True)
+    ref = O.st_loss(sr, hr, taps=taps, want_hr_grad=True)
+    assert rel_err(out["loss"], ref["loss"]) < 1e-5
+    assert maxnorm_err(out["d_sr"], ref["d_sr"]) < 1e-4 and maxnorm_err(out["d_hr"], ref["d_hr"]) < 1e-4

@@ -106,6 +106,18 @@ def test_matches_oracle_on_larger_shapes(shape):
     assert maxnorm_err(d_hr, ref["d_hr"]) < 1e-4
 
 
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 5, 7), (2, 17, 4), (1, 2, 130), (3, 9, 9)])
+def test_tiny_and_degenerate_shapes(shape):
+    """Images smaller than a tile, a single pixel, one-row strips: everything is halo."""
+    rng = np.random.default_rng(sum(shape))
+    sr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+    hr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+    loss, d_sr, d_hr = _run(sr, hr)
+    ref = O.st_loss(sr, hr, want_hr_grad=True)
+    assert rel_err(loss, ref["loss"]) < 1e-5
+    assert maxnorm_err(d_sr, ref["d_sr"]) < 1e-4 and maxnorm_err(d_hr, ref["d_hr"]) < 1e-4
+
+
 def test_full_size_properties_div2k():
     """Config 5 size (1356x2040): batch additivity (mean of means), translation of the tiling
     (crop consistency far from borders is NOT expected -- zero padding -- so use batch splits),
