@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRST_VERSION 101 /* major*10000 + minor*100 + patch */
+#define SRST_VERSION 102 /* major*10000 + minor*100 + patch */
 
 #define SRST_E_INVALID (-1)     /* null pointer / non-positive size / bad enum */
 #define SRST_E_UNSUPPORTED (-2) /* filter radius or patch geometry not compiled in */
@@ -53,7 +53,7 @@ const char* srst_error_string(int code);
 /* 1 if the (r_sigma, r_rho) pair fits a compiled radius class, else 0. */
 int srst_st_supported(int r_sigma, int r_rho);
 
-/* Scratch bytes srst_st_forward needs for a [B,3,H,W] problem (per-CTA partial sums + ticket).
+/* Scratch bytes srst_st_forward / srst_stpx_forward need for a [B,3,H,W] problem (per-CTA partial sums + ticket).
  * The workspace must be 16-byte aligned and ZERO-FILLED ONCE before its first use; the kernels
  * leave it zeroed again, so it can be reused by later calls on the same stream. */
 size_t srst_st_workspace_bytes(int B, int H, int W);
@@ -83,6 +83,30 @@ int srst_st_backward(const float* img, const float* gray, const float* ds, const
                      const float* g, const float* dg, int r_sigma,
                      const float* k, int r_rho,
                      float* d_img, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Structure-tensor loss with the "Pixel" MSE criterion fused in.  The warm-up
+ * and training loops evaluate MSELoss(sr, gt) and StructureTensorLoss(sr, gt) on the same two
+ * tensors one after the other (warmup.py:88-96, train.py:131-144, criteria registered in
+ * config.py:71-93); here the squared RGB difference is accumulated while the forward kernel has
+ * the HR tile in registers, and the backward kernel adds 2 (sr - hr) / (3 B H W) * grad_px to d_sr
+ * in its final store -- no extra pass over either tensor.
+ *   loss2_out[0] = structure-tensor loss (as srst_st_forward), loss2_out[1] = mean((sr - hr)^2)
+ *   grad_st, grad_px: device scalars, the upstream gradients of the two terms.
+ * Workspace: srst_st_workspace_bytes.
+ * ------------------------------------------------------------------------------------------- */
+int srst_stpx_forward(const float* sr, const float* hr, int B, int H, int W,
+                      const float* g, const float* dg, int r_sigma,
+                      const float* k, int r_rho,
+                      int normalize, float eps,
+                      float* loss2_out, float* ds_sr,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int srst_stpx_backward(const float* sr, const float* hr, const float* ds,
+                       const float* grad_st, const float* grad_px,
+                       int B, int H, int W,
+                       const float* g, const float* dg, int r_sigma,
+                       const float* k, int r_rho,
+                       float* d_sr, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Best-Buddy loss.   Replaces

@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <type_traits>
+
 #include "st_kernels.cuh"
 #include "st_stream.cuh"
 #include "st_wide.cuh"
@@ -107,18 +109,20 @@ static void fill_taps(StTaps<RG, RK>& t, const float* g, const float* dg, int rs
   for (int u = 0; u <= 2 * RK + 1; ++u) t.kp[u] = make_float2(u <= 2 * RK ? t.k[u] : 0.f, u >= 1 ? t.k[u - 1] : 0.f);
 }
 
-template <class C>
+template <class C> struct PxTag {};  // once-flag tag of the fused-Pixel instantiation of a forward tile shape
+
+template <class C, bool PX = false>
 static int launch_st_forward(StFwdParams<C::RG, C::RK> P, void* stream) {
   P.tiles_x = (P.W + C::TW - 1) / C::TW;
   P.tiles_y = (P.H + C::TH - 1) / C::TH;
   const long long ntiles = (long long)P.B * P.tiles_x * P.tiles_y;
   if (ntiles <= 0 || ntiles > 0x7fffffffLL) return SRST_E_SHAPE;
-  int e = ensure_smem<C>(st_forward_kernel<C>, C::SMEM_BYTES);
+  int e = ensure_smem<std::conditional_t<PX, PxTag<C>, C>>(st_forward_kernel<C, PX>, C::SMEM_BYTES);
   if (e) return e;
   // persistent grid: one wave of resident CTAs, each looping over tiles
   const long long slots = (long long)sm_count() * C::MINB;
   const long long nblk = (C::NP == 0 || ntiles < slots) ? ntiles : slots;
-  SRST_LAUNCH_PDL(st_forward_kernel<C>, dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  SRST_LAUNCH_PDL((st_forward_kernel<C, PX>), dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
   return (int)cudaGetLastError();
 }
 
@@ -168,7 +172,7 @@ static bool make_plane_map(SrstTmap* map, const float* base, long long planes, i
 #endif
 }
 
-template <class C>
+template <class C, bool PX = false>
 static int launch_st_backward(StBwdParams<C::RG, C::RK> P, const float* gray, void* stream) {
   const bool tma_ok = P.vec4 && env_int("SRST_ST_BWD_TMA", 1) != 0;
   P.use_tma = (tma_ok && make_plane_map(&P.ds_map, P.ds, (long long)P.B * 3, P.H, P.W, C::VW, C::SH, 3)) ? 1 : 0;
@@ -177,9 +181,9 @@ static int launch_st_backward(StBwdParams<C::RG, C::RK> P, const float* gray, vo
   P.tiles_y = (P.H + C::TH - 1) / C::TH;
   const long long nblk = (long long)P.B * P.tiles_x * P.tiles_y;
   if (nblk <= 0 || nblk > 0x7fffffffLL) return SRST_E_SHAPE;
-  int e = ensure_smem<C>(st_backward_kernel<C>, C::SMEM_BYTES);
+  int e = ensure_smem<std::conditional_t<PX, PxTag<C>, C>>(st_backward_kernel<C, PX>, C::SMEM_BYTES);
   if (e) return e;
-  SRST_LAUNCH_PDL(st_backward_kernel<C>, dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  SRST_LAUNCH_PDL((st_backward_kernel<C, PX>), dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
   return (int)cudaGetLastError();
 }
 
@@ -228,11 +232,15 @@ const char* srst_error_string(int code) {
 // classes use one generic shape each.
 int srst_st_supported(int r_sigma, int r_rho) { return (r_sigma >= 1 && r_sigma <= 4 && r_rho >= 1 && r_rho <= 12) ? 1 : 0; }
 
-size_t srst_st_workspace_bytes(int B, int H, int W) {
-  if (B <= 0 || H <= 0 || W <= 0) return 0;
+static size_t st_partials_bytes(int B, int H, int W) {
   // one float per CTA of the finest compiled tiling + the ticket counter, rounded to 256 bytes
   const size_t tiles = (size_t)B * ((H + kMinFwdTH - 1) / kMinFwdTH) * ((W + kMinFwdTW - 1) / kMinFwdTW);
   return ((tiles + 4 + 1024) * sizeof(float) + 255) / 256 * 256;  // + room for one partial per persistent CTA
+}
+
+size_t srst_st_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return 2 * st_partials_bytes(B, H, W);  // ST partials + ticket | partials of the fused Pixel term
 }
 
 }  // extern "C"
@@ -244,6 +252,8 @@ struct StCall {
   float *o0, *o1, *loss_out;      // forward: ds_sr, ds_hr ; backward: d_img
   float *gray0, *gray1;           // forward: gray_sr, gray_hr outputs
   const float* gray;              // backward: saved gray planes or null
+  int px;                         // forward: also reduce the fused Pixel (MSE) term into loss_out[1]
+  const float *px_other, *grad_px;  // backward: other image of the pair + upstream gradient of the MSE term
   int B, H, W, normalize, vec4;
   float eps;
   void* workspace;
@@ -295,6 +305,8 @@ static int st_forward_rr(const StCall& c) {
   P.sr = c.a; P.hr = c.b; P.ds_sr = c.o0; P.ds_hr = c.o1; P.gray_sr = c.gray0; P.gray_hr = c.gray1;
   P.ticket = reinterpret_cast<unsigned int*>(c.workspace);
   P.partials = reinterpret_cast<float*>(c.workspace) + 4;
+  P.px_partials = c.px ? reinterpret_cast<float*>(reinterpret_cast<char*>(c.workspace) + st_partials_bytes(c.B, c.H, c.W))
+                       : nullptr;
   P.loss_out = c.loss_out;
   P.B = c.B; P.H = c.H; P.W = c.W; P.tiles_x = P.tiles_y = 0;
   P.normalize = c.normalize; P.vec4 = c.vec4; P.eps = c.eps;
@@ -303,8 +315,12 @@ static int st_forward_rr(const StCall& c) {
   P.debug = env_int("SRST_ST_DEBUG", 0) ? reinterpret_cast<long long*>(reinterpret_cast<char*>(c.workspace) + 4096) : nullptr;
   fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
-    if (c.vec4 && !c.gray0 && !c.gray1 && env_int("SRST_ST_STREAM", 0) == 1) return launch_st_stream<StreamA>(c);
+    if (c.vec4 && !c.gray0 && !c.gray1 && !c.px && env_int("SRST_ST_STREAM", 0) == 1) return launch_st_stream<StreamA>(c);
     const int cfg = pick_fwd_cfg(c.H, c.W);
+    if (c.px) {  // the fused Pixel term is compiled into the two default tile shapes only
+      if (cfg == 2 || (cfg != 3 && c.W <= 96)) return launch_st_forward<FwdC, true>(P, c.stream);
+      return launch_st_forward<FwdD, true>(P, c.stream);
+    }
     if (cfg == 10 && c.vec4 && !c.gray0 && !c.gray1) return launch_st_wide_forward<WideA>(P, c.stream);
     switch (cfg) {
       case 0: return launch_st_forward<FwdA>(P, c.stream);
@@ -319,7 +335,8 @@ static int st_forward_rr(const StCall& c) {
       default: return launch_st_forward<FwdD>(P, c.stream);
     }
   } else {
-    return launch_st_forward<StFwdCfg<32, 64, 16, 4, 0, RG, RK, (RK <= 8 ? 2 : 1)>>(P, c.stream);
+    using G = StFwdCfg<32, 64, 16, 4, 0, RG, RK, (RK <= 8 ? 2 : 1)>;
+    return c.px ? launch_st_forward<G, true>(P, c.stream) : launch_st_forward<G>(P, c.stream);
   }
 }
 
@@ -330,11 +347,16 @@ static int st_backward_rr(const StCall& c) {
   std::memset(&P.gray_map, 0, sizeof(P.gray_map));
   P.use_tma = 0; P.use_gray = 0; P.debug = nullptr;
   P.img = c.a; P.ds = c.b; P.grad_out = c.grad_out; P.d_img = c.o0;
+  P.px_other = c.px_other; P.grad_px = c.grad_px;
   P.B = c.B; P.H = c.H; P.W = c.W; P.tiles_x = P.tiles_y = 0;
   P.vec4 = c.vec4;
   P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
   fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
+    if (c.px_other) {  // the fused Pixel term is compiled into the two default tile shapes only
+      if (pick_bwd_cfg(c.B, c.H, c.W) == 6) return launch_st_backward<BwdG, true>(P, c.gray, c.stream);
+      return launch_st_backward<BwdF, true>(P, c.gray, c.stream);
+    }
     switch (pick_bwd_cfg(c.B, c.H, c.W)) {
       case 1: return launch_st_backward<BwdB>(P, c.gray, c.stream);
       case 2: return launch_st_backward<BwdC>(P, c.gray, c.stream);
@@ -345,7 +367,8 @@ static int st_backward_rr(const StCall& c) {
       default: return launch_st_backward<BwdA>(P, c.gray, c.stream);
     }
   } else {
-    return launch_st_backward<StBwdCfg<24, 64, (24 + 2 * RG) / 2, 256, RG, RK, (RK <= 8 ? 2 : 1)>>(P, c.gray, c.stream);
+    using G = StBwdCfg<24, 64, (24 + 2 * RG) / 2, 256, RG, RK, (RK <= 8 ? 2 : 1)>;
+    return c.px_other ? launch_st_backward<G, true>(P, c.gray, c.stream) : launch_st_backward<G>(P, c.gray, c.stream);
   }
 }
 
@@ -389,6 +412,35 @@ int srst_st_backward(const float* img, const float* gray, const float* ds, const
   c.a = img; c.b = ds; c.grad_out = grad_out; c.o0 = d_img; c.gray = gray;
   c.B = B; c.H = H; c.W = W;
   c.vec4 = (W % 4 == 0 && aligned16(img) && aligned16(d_img) && aligned16(ds)) ? 1 : 0;
+  c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;
+  return st_dispatch(c, false);
+}
+
+int srst_stpx_forward(const float* sr, const float* hr, int B, int H, int W, const float* g, const float* dg,
+                      int r_sigma, const float* k, int r_rho, int normalize, float eps, float* loss2_out, float* ds_sr,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (!sr || !hr || !g || !dg || !k || !loss2_out || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
+  if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
+  if (!workspace || !aligned16(workspace) || workspace_bytes < srst_st_workspace_bytes(B, H, W))
+    return SRST_E_WORKSPACE;
+  StCall c{};
+  c.a = sr; c.b = hr; c.o0 = ds_sr; c.loss_out = loss2_out; c.px = 1;
+  c.B = B; c.H = H; c.W = W; c.normalize = normalize ? 1 : 0; c.eps = eps;
+  c.vec4 = (W % 4 == 0 && aligned16(sr) && aligned16(hr) && (!ds_sr || aligned16(ds_sr))) ? 1 : 0;
+  c.workspace = workspace; c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;
+  return st_dispatch(c, true);
+}
+
+int srst_stpx_backward(const float* sr, const float* hr, const float* ds, const float* grad_st, const float* grad_px,
+                       int B, int H, int W, const float* g, const float* dg, int r_sigma, const float* k, int r_rho,
+                       float* d_sr, void* stream) {
+  if (!sr || !hr || !ds || !grad_st || !grad_px || !g || !dg || !k || !d_sr || B <= 0 || H <= 0 || W <= 0)
+    return SRST_E_INVALID;
+  if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
+  StCall c{};
+  c.a = sr; c.b = ds; c.grad_out = grad_st; c.o0 = d_sr; c.px_other = hr; c.grad_px = grad_px;
+  c.B = B; c.H = H; c.W = W;
+  c.vec4 = (W % 4 == 0 && aligned16(sr) && aligned16(hr) && aligned16(d_sr) && aligned16(ds)) ? 1 : 0;
   c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;
   return st_dispatch(c, false);
 }

@@ -49,8 +49,9 @@ struct StFwdParams {
   float* gray_sr;  // [B,H,W] or null: grayscale planes saved for the backward pass
   float* gray_hr;
   float* partials;
+  float* px_partials;  // null, or per-CTA partials of sum (sr-hr)^2: the fused "Pixel" MSE term (warmup.py:88-96)
   unsigned int* ticket;
-  float* loss_out;
+  float* loss_out;     // [0] = ST loss; [1] = MSE when px_partials is set
   int B, H, W, tiles_x, tiles_y;
   int normalize;
   int vec4;  // 1: W % 4 == 0 and all base pointers 16-byte aligned
@@ -67,6 +68,8 @@ struct StBwdParams {
   const float* img;
   const float* ds;
   const float* grad_out;
+  const float* px_other;  // null, or the other image of the pair: adds grad_px * 2 (img - other) / (3 B H W) to d_img
+  const float* grad_px;   // upstream gradient of the MSE term (device scalar)
   float* d_img;
   int B, H, W, tiles_x, tiles_y;
   int vec4;
@@ -333,10 +336,11 @@ SRST_DEV float st_chain_store(const float2 (&S1)[3][4], const float2 (&S2)[3][4]
 // DEPTH items (6 x LDG.128 each) are in flight per thread before the first conversion.
 // If `gray_out` ([H][W] plane of this image) is given, the pixels of the tile interior
 // rows [iy0, iy1) x cols [ix0, ix1) are also written there (once per pixel across tiles).
-template <int ROWS, int COLS, int PITCH, int NT, int DEPTH>
+template <int ROWS, int COLS, int PITCH, int NT, int DEPTH, bool PX = false>
 SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, int W, int gy0, int gx0,
                              bool vec4, int tid, float* __restrict__ gray_out = nullptr, int iy0 = 0, int iy1 = 0,
-                             int ix0 = 0, int ix1 = 0) {
+                             int ix0 = 0, int ix1 = 0, const float* __restrict__ px_other = nullptr,
+                             float* px_acc = nullptr) {
   constexpr int C4 = COLS / 4;
   constexpr int NITEM = (ROWS / 2) * C4;
   const size_t plane = (size_t)H * W;
@@ -389,6 +393,26 @@ SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, i
               st4(gray_out + (size_t)gy * W + gx, make_float4(v[hf][0], v[hf][1], v[hf][2], v[hf][3]));
           }
         }
+        if (PX && px_other) {  // fused Pixel term: squared RGB difference to the other image, tile interior only
+          const int gx = gx0 + 4 * c4;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int gy = gy0 + 2 * q + hf;
+            if (ok[u][hf] && gy >= iy0 && gy < iy1 && gx >= ix0 && gx < ix1) {
+              const float* po = px_other + (size_t)gy * W + gx;
+              const float4 a = ldg4(po), b = ldg4(po + plane), c = ldg4(po + 2 * plane);
+              float sacc = 0.f;
+              float d;
+              d = R[u][hf].x - a.x; sacc = fmaf(d, d, sacc); d = R[u][hf].y - a.y; sacc = fmaf(d, d, sacc);
+              d = R[u][hf].z - a.z; sacc = fmaf(d, d, sacc); d = R[u][hf].w - a.w; sacc = fmaf(d, d, sacc);
+              d = Gc[u][hf].x - b.x; sacc = fmaf(d, d, sacc); d = Gc[u][hf].y - b.y; sacc = fmaf(d, d, sacc);
+              d = Gc[u][hf].z - b.z; sacc = fmaf(d, d, sacc); d = Gc[u][hf].w - b.w; sacc = fmaf(d, d, sacc);
+              d = Bc[u][hf].x - c.x; sacc = fmaf(d, d, sacc); d = Bc[u][hf].y - c.y; sacc = fmaf(d, d, sacc);
+              d = Bc[u][hf].z - c.z; sacc = fmaf(d, d, sacc); d = Bc[u][hf].w - c.w; sacc = fmaf(d, d, sacc);
+              *px_acc += sacc;
+            }
+          }
+        }
       }
     }
   } else {
@@ -407,6 +431,12 @@ SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, i
             const float* p = base + (size_t)gy * W + x;
             v[hf][j] = gray_of(__ldg(p), __ldg(p + plane), __ldg(p + 2 * plane));
             if (gray_out && gy >= iy0 && gy < iy1 && x >= ix0 && x < ix1) gray_out[(size_t)gy * W + x] = v[hf][j];
+            if (PX && px_other && gy >= iy0 && gy < iy1 && x >= ix0 && x < ix1) {
+              const float* po = px_other + (size_t)gy * W + x;
+              const float d0 = __ldg(p) - __ldg(po), d1 = __ldg(p + plane) - __ldg(po + plane);
+              const float d2 = __ldg(p + 2 * plane) - __ldg(po + 2 * plane);
+              *px_acc += fmaf(d0, d0, fmaf(d1, d1, d2 * d2));
+            }
           }
         }
       }
@@ -656,10 +686,10 @@ struct StFwdCfg {
 // Compute-warp phases B-D for one unit: consumes the gray tile the producer parked in sG and leaves
 // the smoothed tensor (Jxx,Jyy,Jxy) of this thread's 8 pixels (rows 2q, 2q+1; cols ox0..ox0+3 of the
 // tile) in S[3][4] (.x = even row, .y = odd row).
-template <class C, class Taps>
+template <class C, bool PX, class Taps>
 SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float* __restrict__ gray_out, bool vec4, int H,
                              int W, int y0, int x0, const Taps& tp, int tid, int gbuf, bool release_gray,
-                             float2 (&S)[3][4]) {
+                             float2 (&S)[3][4], const float* __restrict__ px_other = nullptr, float* px_acc = nullptr) {
   float* sD0 = smem;
   float* sD1 = sD0 + C::D_FLOATS;
   float* sV = sD1 + C::D_FLOATS;
@@ -675,8 +705,9 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float*
       bar_sync(kBarCompute, C::NC);
       convert_staged_gray<C::GH, C::GW, C::PG, C::NC>(sG, smem, tid);
     } else {
-      load_gray_tile<C::GH, C::GW, C::PG, C::NC, C::LDEPTH>(sG, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, vec4, tid,
-                                                            gray_out, y0, y0 + C::TH, x0, x0 + C::TW);
+      load_gray_tile<C::GH, C::GW, C::PG, C::NC, C::LDEPTH, PX>(sG, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, vec4,
+                                                                tid, gray_out, y0, y0 + C::TH, x0, x0 + C::TW, px_other,
+                                                                px_acc);
     }
     bar_sync(kBarCompute, C::NC);
   }
@@ -778,7 +809,7 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float*
   // orders these sV reads before the next phase C and the sD reads of phase C before the next phase B
 }
 
-template <class C>
+template <class C, bool PX = false>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
   SRST_DYN_SMEM(float, smem);
@@ -821,6 +852,7 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
   const bool norm = P.normalize != 0;
   const int seg = tid / (C::TH / 2), q = tid - seg * (C::TH / 2);
   float lsum = 0.f;
+  [[maybe_unused]] float pxsum = 0.f;
   // NP > 0: persistent loop over tiles (the producer runs one unit ahead); NP == 0: one tile per CTA
   int tile = blockIdx.x;
   do {
@@ -835,10 +867,14 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
 
     float2 S1[3][4], S2[3][4];
     const size_t gray_off = (size_t)b * P.H * P.W;
-    st_unit_tensor<C>(smem, P.sr + img_off, P.gray_sr ? P.gray_sr + gray_off : nullptr, P.vec4 != 0, P.H, P.W, y0, x0,
-                      P.taps, tid, 0, !last_tile, S1);
-    st_unit_tensor<C>(smem, P.hr + img_off, P.gray_hr ? P.gray_hr + gray_off : nullptr, P.vec4 != 0, P.H, P.W, y0, x0,
-                      P.taps, tid, (C::NP > 0 ? 1 : 0), !last_tile, S2);
+    st_unit_tensor<C, false>(smem, P.sr + img_off, P.gray_sr ? P.gray_sr + gray_off : nullptr, P.vec4 != 0, P.H, P.W, y0,
+                             x0, P.taps, tid, 0, !last_tile, S1);
+    if constexpr (PX)  // fused Pixel term: the HR unit's loader also reads the SR pixels of the tile interior
+      st_unit_tensor<C, true>(smem, P.hr + img_off, P.gray_hr ? P.gray_hr + gray_off : nullptr, P.vec4 != 0, P.H, P.W, y0,
+                              x0, P.taps, tid, (C::NP > 0 ? 1 : 0), !last_tile, S2, P.sr + img_off, &pxsum);
+    else
+      st_unit_tensor<C, false>(smem, P.hr + img_off, P.gray_hr ? P.gray_hr + gray_off : nullptr, P.vec4 != 0, P.H, P.W, y0,
+                               x0, P.taps, tid, (C::NP > 0 ? 1 : 0), !last_tile, S2);
 
     // Per-pixel chain on this thread's 2 x 4 pixels, then the ds stores.
     if (want_hr)
@@ -851,13 +887,23 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
 
   // Deterministic loss reduction: block partial -> workspace; the last block to finish sums all
   // partials in a fixed order (double) and re-zeroes the workspace for the next call.
+  [[maybe_unused]] __shared__ float s_red_px[PX ? 32 : 1];
   lsum = warp_sum(lsum);
-  if ((tid & 31) == 0) s_red[tid >> 5] = lsum;
+  if constexpr (PX) pxsum = warp_sum(pxsum);
+  if ((tid & 31) == 0) {
+    s_red[tid >> 5] = lsum;
+    if constexpr (PX) s_red_px[tid >> 5] = pxsum;
+  }
   bar_sync(kBarCompute, C::NC);
   if (tid == 0) {
     float bs = 0.f;
     for (int w = 0; w < C::NC / 32; ++w) bs += s_red[w];
     P.partials[blockIdx.x] = bs;
+    if constexpr (PX) {
+      float bp = 0.f;
+      for (int w = 0; w < C::NC / 32; ++w) bp += s_red_px[w];
+      P.px_partials[blockIdx.x] = bp;
+    }
     __threadfence();
     const unsigned int t = atomicAdd(P.ticket, 1u);
     s_last = (t == gridDim.x - 1) ? 1u : 0u;
@@ -867,14 +913,23 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
     __threadfence();
     if (tid < 32) {
       double acc = 0.0;
+      [[maybe_unused]] double accp = 0.0;
       for (unsigned int i = tid; i < gridDim.x; i += 32) {
         acc += (double)__ldcg(P.partials + i);
         P.partials[i] = 0.f;
+        if constexpr (PX) {
+          accp += (double)__ldcg(P.px_partials + i);
+          P.px_partials[i] = 0.f;
+        }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if constexpr (PX) accp += __shfl_xor_sync(0xffffffffu, accp, o);
+      }
       if (tid == 0) {
         P.loss_out[0] = (float)(acc * (double)P.inv_count);
+        if constexpr (PX) P.loss_out[1] = (float)(accp * (double)P.inv_count / 3.0);  // mean over B*3*H*W
         *P.ticket = 0u;
       }
     }
@@ -915,7 +970,7 @@ struct StBwdCfg {
   static_assert((CSD == 4 || CSD == 8) && EW % CSD == 0, "bad phase-D' item width");
 };
 
-template <class C>
+template <class C, bool PX = false>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   SRST_DYN_SMEM(float, smem);
@@ -1102,6 +1157,7 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   //   dgray = -[ (dIx * dg|) * g-  +  (dIy * g|) * dg- ]
   // i.e. the forward gradient operators applied to dIx and dIy, negated.
   const float scale = -__ldg(P.grad_out) * P.inv_count;
+  [[maybe_unused]] const float px_scale = PX ? __ldg(P.grad_px) * P.inv_count * (2.0f / 3.0f) : 0.f;
   for (int it = tid; it < (C::TH / 2) * (C::TW / 4); it += C::NT) {
     const int seg = it / (C::TH / 2), q = it - seg * (C::TH / 2);
     const int ox0 = 4 * seg;
@@ -1121,11 +1177,25 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         if (P.vec4) {
-          st4(o + c * plane, make_float4(coef[c] * dgr[0], coef[c] * dgr[1], coef[c] * dgr[2], coef[c] * dgr[3]));
+          float4 r = make_float4(coef[c] * dgr[0], coef[c] * dgr[1], coef[c] * dgr[2], coef[c] * dgr[3]);
+          if constexpr (PX) {  // fused Pixel term: d MSE / d img = 2 (img - other) / (3 B H W)
+            const size_t e = img_off + (size_t)(gy + hf) * W + gx0 + c * plane;
+            const float4 a = ldg4(P.img + e), b = ldg4(P.px_other + e);
+            r.x = fmaf(px_scale, a.x - b.x, r.x); r.y = fmaf(px_scale, a.y - b.y, r.y);
+            r.z = fmaf(px_scale, a.z - b.z, r.z); r.w = fmaf(px_scale, a.w - b.w, r.w);
+          }
+          st4(o + c * plane, r);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (gx0 + j < W) o[c * plane + j] = coef[c] * dgr[j];
+            if (gx0 + j < W) {
+              float r = coef[c] * dgr[j];
+              if constexpr (PX) {
+                const size_t e = img_off + (size_t)(gy + hf) * W + gx0 + j + c * plane;
+                r = fmaf(px_scale, __ldg(P.img + e) - __ldg(P.px_other + e), r);
+              }
+              o[c * plane + j] = r;
+            }
         }
       }
     }

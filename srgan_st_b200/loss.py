@@ -151,6 +151,91 @@ class StructureTensorLoss(nn.Module):
         return f"sigma={self.sigma}, rho={self.rho}, normalize={self.normalize}"
 
 
+class _StructureTensorPixelLossFn(torch.autograd.Function):
+    """ST loss and the "Pixel" MSE criterion from ONE pass over (sr, gt) per direction.
+    Returns the two unweighted terms; gt carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, sr, hr, sigma, rho, normalize):
+        lib = _cabi.lib()
+        sr = sr.contiguous()
+        hr = hr.contiguous()
+        B, _, H, W = sr.shape
+        g, dg = _taps.gaussian_taps(float(sigma))
+        k, _ = _taps.gaussian_taps(float(rho))
+        rs, rk = len(g) // 2, len(k) // 2
+        if not lib.srst_st_supported(rs, rk):
+            raise NotImplementedError(
+                f"StructureTensorPixelLoss: filter radii (sigma={sigma} -> {rs}, rho={rho} -> {rk}) are not "
+                "compiled into libsrst.so")
+        need_sr = ctx.needs_input_grad[0]
+        with torch.cuda.device(sr.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            both = torch.empty(2, dtype=torch.float32, device=sr.device)
+            ds_sr = torch.empty_like(sr) if need_sr else None
+            ws = _workspace(sr.device, stream, lib.srst_st_workspace_bytes(B, H, W))
+            rc = lib.srst_stpx_forward(_ptr(sr), _ptr(hr), B, H, W, _taps.as_c(g), _taps.as_c(dg), rs, _taps.as_c(k), rk,
+                                       int(bool(normalize)), 1e-12, _ptr(both), _ptr(ds_sr), _ptr(ws), ws.numel(),
+                                       ctypes.c_void_p(stream))
+        _cabi.check(rc, "srst_stpx_forward")
+        ctx.save_for_backward(sr, hr, ds_sr)
+        ctx.taps = (g, dg, k)
+        return both[0], both[1]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_st, grad_px):
+        lib = _cabi.lib()
+        sr, hr, ds_sr = ctx.saved_tensors
+        g, dg, k = ctx.taps
+        if ds_sr is None or not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        B, _, H, W = sr.shape
+        with torch.cuda.device(sr.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            grad_st = grad_st.to(torch.float32).contiguous()
+            grad_px = grad_px.to(torch.float32).contiguous()
+            d_sr = torch.empty_like(sr)
+            rc = lib.srst_stpx_backward(_ptr(sr), _ptr(hr), _ptr(ds_sr), _ptr(grad_st), _ptr(grad_px), B, H, W,
+                                        _taps.as_c(g), _taps.as_c(dg), len(g) // 2, _taps.as_c(k), len(k) // 2,
+                                        _ptr(d_sr), ctypes.c_void_p(stream))
+        _cabi.check(rc, "srst_stpx_backward")
+        return d_sr, None, None, None, None
+
+
+class StructureTensorPixelLoss(nn.Module):
+    """``st_weight * StructureTensorLoss(sigma, rho, normalize)(x, gt) + pixel_weight * MSELoss()(x, gt)``
+    from one fused pass per direction.
+
+    The reference's warm-up / training loops register "Pixel" (``nn.MSELoss``) and "ST" as two criteria
+    and evaluate them one after the other on the same two tensors (config.py:71-93, warmup.py:88-96,
+    train.py:131-144).  Registering this module once, with weight 1.0, gives the same generator loss
+    and gradient; the two unweighted terms of the last call stay on the device in ``last_terms`` for
+    logging without a synchronisation."""
+
+    def __init__(self, sigma: float = 0.5, rho: float = 2.0, normalize: bool = True, st_weight: float = 1.0,
+                 pixel_weight: float = 1.0):
+        super().__init__()
+        self.sigma = sigma
+        self.rho = rho
+        self.normalize = normalize
+        self.st_weight = st_weight
+        self.pixel_weight = pixel_weight
+        self.last_terms = None
+        _cabi.lib()
+
+    def forward(self, x, gt):
+        _check_pair(x, gt, "StructureTensorPixelLoss")
+        _no_gt_grad(gt, "StructureTensorPixelLoss")
+        st, px = _StructureTensorPixelLossFn.apply(x, gt, self.sigma, self.rho, self.normalize)
+        self.last_terms = (st.detach(), px.detach())
+        return self.st_weight * st + self.pixel_weight * px
+
+    def extra_repr(self) -> str:
+        return (f"sigma={self.sigma}, rho={self.rho}, normalize={self.normalize}, st_weight={self.st_weight}, "
+                f"pixel_weight={self.pixel_weight}")
+
+
 class _BestBuddyLossFn(torch.autograd.Function):
     """autograd boundary of the Best-Buddy loss.  Only the final criterion is differentiable
     (w.r.t. the SR patches): the argmin is not, and gt carries no gradient (reference loss.py:135-139)."""

@@ -122,3 +122,24 @@ def emu_bb(lib, sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion=0, gr
     rc = bwd(_p(sr), _p(gt), _p(gt2), _p(gt4), _p(idx), _p(go), B, H, W, criterion, _p(d_sr), _p(ws), nb, None)
     assert rc == 0, rc
     return dict(loss=float(loss[0]), idx=idx, d_sr=d_sr)
+
+
+def emu_stpx(lib, sr, hr, taps, grad_st=1.0, grad_px=1.0):
+    """Run srst_stpx_forward + srst_stpx_backward of `lib` on host arrays (emulation library only)."""
+    sr = np.ascontiguousarray(sr, np.float32)
+    hr = np.ascontiguousarray(hr, np.float32)
+    B, _, H, W = sr.shape
+    g, dg, k = [np.ascontiguousarray(t, np.float32) for t in taps]
+    nb = lib.srst_st_workspace_bytes(B, H, W)
+    ws = np.zeros(nb // 4 + 4, np.float32)
+    both = np.zeros(2, np.float32)
+    ds_sr = np.full_like(sr, np.nan)
+    rc = lib.srst_stpx_forward(_p(sr), _p(hr), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k), len(k) // 2, 1, 1e-12,
+                               _p(both), _p(ds_sr), _p(ws), nb, None)
+    assert rc == 0, rc
+    gs, gp = np.full(1, grad_st, np.float32), np.full(1, grad_px, np.float32)
+    d_sr = np.full_like(sr, np.nan)
+    rc = lib.srst_stpx_backward(_p(sr), _p(hr), _p(ds_sr), _p(gs), _p(gp), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
+                                len(k) // 2, _p(d_sr), None)
+    assert rc == 0, rc
+    return dict(st=float(both[0]), px=float(both[1]), d_sr=d_sr, ws=ws)

@@ -35,7 +35,7 @@ def test_no_compute_entry_points_that_need_no_gpu():
     """Pure host queries work on the CPU box (no kernel is launched)."""
     from srgan_st_b200 import _cabi
     lib = _cabi.lib()
-    assert lib.srst_version() == 101
+    assert lib.srst_version() == 102
     assert lib.srst_st_supported(2, 8) == 1
     assert lib.srst_st_supported(4, 12) == 1 and lib.srst_st_supported(1, 3) == 1   # padded radius classes
     assert lib.srst_st_supported(5, 8) == 0 and lib.srst_st_supported(2, 13) == 0

@@ -10,7 +10,16 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from srgan_st_b200 import _cabi, taps as T  # noqa: E402
 
-lib = _cabi.bind(os.environ['SRST_LIB']) if os.environ.get('SRST_LIB') else _cabi.lib()  # A/B builds
+def _bind_ab(path):
+    """A/B builds may predate newer entry points: bind only what this tool calls."""
+    l = ctypes.CDLL(path)
+    for name in ("srst_st_forward", "srst_st_backward", "srst_st_workspace_bytes"):
+        fn = getattr(l, name)
+        fn.restype, fn.argtypes = _cabi.SIGNATURES[name]
+    return l
+
+
+lib = _bind_ab(os.environ['SRST_LIB']) if os.environ.get('SRST_LIB') else _cabi.lib()
 g, dg = T.gaussian_taps(0.5)
 k, _ = T.gaussian_taps(2.0)
 dev = torch.device("cuda:0")
