@@ -59,6 +59,22 @@ def _traffic(workload, kernel):
         return None
 
 
+FP32_FLOOR_LANE_OPS_PER_PX = {"fwd": 340, "bwd": 155}
+
+
+def _fp32_context(torch, res, wl):
+    props = torch.cuda.get_device_properties(0)
+    mhz = (res.get("clocks") or {}).get("sm_mhz") or 1965.0
+    peak = props.multi_processor_count * 128 * mhz * 1e6
+    px = wl["B"] * wl["H"] * wl["W"]
+    ops = px * (FP32_FLOOR_LANE_OPS_PER_PX["fwd"] + FP32_FLOOR_LANE_OPS_PER_PX["bwd"])
+    ach = ops / (res["ms_step"] * 1e-3)
+    return {"floor_lane_ops_per_px": FP32_FLOOR_LANE_OPS_PER_PX, "achieved_lane_ops_per_s": ach,
+            "peak_lane_ops_per_s": peak, "frac": ach / peak,
+            "hbm_frac_if_fp32_pipe_saturated": (BYTES_FWD + BYTES_BWD) * peak /
+            (FP32_FLOOR_LANE_OPS_PER_PX["fwd"] + FP32_FLOOR_LANE_OPS_PER_PX["bwd"]) / 1e9 / _peaks()[0]}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -460,7 +476,11 @@ def run_gpu(args):
                                       "frac": main["roofline_bwd"] / hbm_peak, "bytes_per_pixel": BYTES_BWD},
                          "fwd_bwd_pair": {"achieved": main["roofline_pair"], "frac": main["roofline_pair"] / hbm_peak,
                                           "bytes_per_pixel": BYTES_FWD + BYTES_BWD},
-                         "ms_fwd": main["ms_fwd"], "ms_bwd": main["ms_bwd"]},
+                         "ms_fwd": main["ms_fwd"], "ms_bwd": main["ms_bwd"],
+                         # context: the kernels are bound on-chip, not by HBM.  Minimum fp32
+                         # lane-operations of the algorithm (no halo recompute) against the FP32 pipe at the
+                         # sampled SM clock (128 lanes/clk/SM, tools/ubench_fma.cu)
+                         "fp32_pipe": _fp32_context(torch, main, wl)},
             "cpu_baseline": cpu,
             "loss_check": main["loss"],
             "other_workloads": others,
