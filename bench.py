@@ -345,26 +345,24 @@ def run_gpu(args):
                 gen_like = torch.nn.Parameter(torch.zeros(1547350, device=dev))
                 bucket = FlatGradBucket([gen_like])
             n_host = 4
-            host = [(sr.cpu().pin_memory(), hr.cpu().pin_memory()) for sr, hr in pool[:n_host]]
+            # one pinned [2,B,3,H,W] buffer per batch: SR and HR travel in a single copy
+            host = [torch.stack([sr, hr]).cpu().pin_memory() for sr, hr in pool[:n_host]]
             # two device slots: the copy stream fills slot (i+1)%2 while step i computes on slot i%2
             # (the DataLoader pin_memory + non_blocking pattern of train.py:47,119-120); every step's
             # copy is issued and completed inside the timed region
-            slots = [(torch.empty(B, 3, H, W, device=dev), torch.empty(B, 3, H, W, device=dev)) for _ in range(2)]
+            slots = [torch.empty(2, B, 3, H, W, device=dev) for _ in range(2)]
             copy_stream = torch.cuda.Stream(device=dev)
             copied = [torch.cuda.Event(), torch.cuda.Event()]
             consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
             def issue_copy(i):
-                sr_h, hr_h = host[i % n_host]
-                sr_d, hr_d = slots[i % 2]
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(consumed[i % 2])     # slot free (previous user finished)
-                    sr_d.copy_(sr_h, non_blocking=True)
-                    hr_d.copy_(hr_h, non_blocking=True)
+                    slots[i % 2].copy_(host[i % n_host], non_blocking=True)
                     copied[i % 2].record(copy_stream)
 
             def step(i, last):
-                sr_d, hr_d = slots[i % 2]
+                sr_d, hr_d = slots[i % 2][0], slots[i % 2][1]
                 cur = torch.cuda.current_stream()
                 cur.wait_event(copied[i % 2])
                 if not last:
