@@ -304,13 +304,14 @@ class BestBuddyLoss(nn.Module):
     Only the reference's default patch geometry (ksize=3, pad=0, stride=3) and ``dist_norm='l2'``
     have kernels; other values raise ``NotImplementedError``.
 
-    ``pyramid``: "aten" (default) builds the two HR pyramid levels with the reference's own
-    ``F.interpolate`` call; "fused" lets libsrst build them with the same cubic taps.
+    ``pyramid``: "fused" (default) lets libsrst build the two HR pyramid levels with the cubic taps of
+    ``F.interpolate(mode='bicubic', align_corners=False)`` (equal to 2e-7; 0.03 ms instead of 0.43 ms at
+    batch 64 x 192x192); "aten" calls the reference's own op.
     ``last_indices`` holds the argmin indices ``[B,N]`` (int64) of the most recent call.
     """
 
     def __init__(self, alpha: float = 1.0, beta: float = 1.0, ksize: int = 3, pad: int = 0, stride: int = 3,
-                 dist_norm: str = "l2", criterion: str = "l1", pyramid: str = "aten"):
+                 dist_norm: str = "l2", criterion: str = "l1", pyramid: str = "fused"):
         super().__init__()
         self.alpha = alpha
         self.beta = beta
@@ -352,7 +353,7 @@ class GramLoss(nn.Module):
     Only ``ksize=3`` and ``dist_norm='l2'`` have kernels (the reference's defaults)."""
 
     def __init__(self, alpha: float = 1.0, beta: float = 1.0, ksize: int = 3, dist_norm: str = "l2",
-                 criterion: str = "l1", pyramid: str = "aten"):
+                 criterion: str = "l1", pyramid: str = "fused"):
         super().__init__()
         self.alpha = alpha
         self.beta = beta
@@ -451,7 +452,7 @@ class PatchwiseStructureTensorLoss(nn.Module):
     Only ``ksize=3`` and ``dist_norm='l2'`` have kernels (the reference's defaults)."""
 
     def __init__(self, sigma: float = 0.5, rho: float = 2, alpha: float = 1.0, beta: float = 1.0, ksize: int = 3,
-                 dist_norm: str = "l2", criterion: str = "l1", pyramid: str = "aten"):
+                 dist_norm: str = "l2", criterion: str = "l1", pyramid: str = "fused"):
         super().__init__()
         self.alpha = alpha
         self.beta = beta
