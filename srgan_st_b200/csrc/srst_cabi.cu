@@ -39,11 +39,10 @@ using FwdI = StFwdCfg<48, 96, 12, 4, 0, 2, 8, 1>;   // experiment: half a 96x96 
 using FwdJ = StFwdCfg<64, 64, 16, 4, 0, 2, 8, 1>;   // experiment: 512-thread CTA, one per SM
 //                         TH  TW  RS   NT  RG RK MINB
 using BwdA = StBwdCfg<24, 64, 14, 256, 2, 8, 2>;  // large images
-using BwdB = StBwdCfg<16, 96, 10, 256, 2, 8, 2>;  // 96-wide training crops
-using BwdC = StBwdCfg<32, 64, 12, 352, 2, 8, 1>;  // one big CTA per SM
 using BwdD = StBwdCfg<28, 56, 16, 256, 2, 8, 2>;  // 16 row pairs per phase item column: no LDS bank conflicts
-using BwdE = StBwdCfg<28, 88, 16, 384, 2, 8, 1>;  // experiment
 using BwdG = StBwdCfg<16, 96, 10, 256, 2, 8, 2, 8>;  // BwdB with 8-column horizontal-pass items
+using BwdH = StBwdCfg<16, 96, 10, 288, 2, 8, 2, 8>;  // BwdG with 288 threads: the 260 gradient items fit one round
+using BwdI = StBwdCfg<12, 96, 8, 224, 2, 8, 3, 8>;   // shorter strips, three CTAs per SM
 using BwdF = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8>;  // BwdD with 8-column horizontal-pass items (less shared-memory traffic)
 
 //                             TH  TW  RS   NT
@@ -197,10 +196,11 @@ static int pick_fwd_cfg(int H, int W) {
 }
 static int pick_bwd_cfg(int B, int H, int W) {
   const int forced = env_int("SRST_ST_BWD_CFG", -1);
-  if (forced >= 0 && forced <= 6) return forced;
-  // measured on B200 (gpurun sweeps, round 1b): full-width 16x96 strips win on 96-wide crops once
-  // they fill the machine (two CTAs per SM); the conflict-free 28x56 tile wins everywhere else
-  if (W <= 96 && (long long)B * ((H + 15) / 16) >= 2LL * sm_count()) return 6;
+  if (forced >= 0 && forced <= 8) return forced;
+  // measured on B200 (gpurun sweeps, round 1b): on 96-wide crops full-width strips win -- 16x96 with 288
+  // threads once they fill the machine (two CTAs per SM), 12x96 with three CTAs per SM for small
+  // batches; the conflict-free 28x56 tile wins everywhere else
+  if (W <= 96) return ((long long)B * ((H + 15) / 16) >= 2LL * sm_count()) ? 7 : 8;
   return 5;
 }
 
@@ -354,16 +354,15 @@ static int st_backward_rr(const StCall& c) {
   fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
     if (c.px_other) {  // the fused Pixel term is compiled into the two default tile shapes only
-      if (pick_bwd_cfg(c.B, c.H, c.W) == 6) return launch_st_backward<BwdG, true>(P, c.gray, c.stream);
+      if (c.W <= 96) return launch_st_backward<BwdH, true>(P, c.gray, c.stream);
       return launch_st_backward<BwdF, true>(P, c.gray, c.stream);
     }
     switch (pick_bwd_cfg(c.B, c.H, c.W)) {
-      case 1: return launch_st_backward<BwdB>(P, c.gray, c.stream);
-      case 2: return launch_st_backward<BwdC>(P, c.gray, c.stream);
       case 3: return launch_st_backward<BwdD>(P, c.gray, c.stream);
-      case 4: return launch_st_backward<BwdE>(P, c.gray, c.stream);
       case 5: return launch_st_backward<BwdF>(P, c.gray, c.stream);
       case 6: return launch_st_backward<BwdG>(P, c.gray, c.stream);
+      case 7: return launch_st_backward<BwdH>(P, c.gray, c.stream);
+      case 8: return launch_st_backward<BwdI>(P, c.gray, c.stream);
       default: return launch_st_backward<BwdA>(P, c.gray, c.stream);
     }
   } else {

@@ -18,7 +18,7 @@ def lib():
 @pytest.fixture(params=[0, 1, 2, 3, 4, 10])
 def tile_cfg(request, monkeypatch):
     monkeypatch.setenv("SRST_ST_FWD_CFG", str(request.param))
-    monkeypatch.setenv("SRST_ST_BWD_CFG", str({0: 0, 1: 1, 2: 2, 3: 3, 4: 5, 10: 6}[request.param]))
+    monkeypatch.setenv("SRST_ST_BWD_CFG", str({0: 0, 1: 7, 2: 8, 3: 3, 4: 5, 10: 6}[request.param]))
     return request.param
 
 

@@ -40,7 +40,7 @@ def tile_cfg(request, monkeypatch):
         return request.param
     if request.param >= 0:
         monkeypatch.setenv("SRST_ST_FWD_CFG", str(request.param))
-        monkeypatch.setenv("SRST_ST_BWD_CFG", str({0: 0, 1: 1, 2: 2, 3: 3, 4: 5, 10: 6}[request.param]))
+        monkeypatch.setenv("SRST_ST_BWD_CFG", str({0: 0, 1: 7, 2: 8, 3: 3, 4: 5, 10: 6}[request.param]))
     return request.param
 
 

@@ -21,7 +21,7 @@ def _mse(sr, hr):
 def test_emulated_fused_terms_and_gradient(name, cfg, monkeypatch):
     if cfg >= 0:
         monkeypatch.setenv("SRST_ST_FWD_CFG", str(cfg))
-        monkeypatch.setenv("SRST_ST_BWD_CFG", str({0: 0, 2: 6, 3: 5}[cfg]))
+        monkeypatch.setenv("SRST_ST_BWD_CFG", str({0: 0, 2: 7, 3: 5}[cfg]))
     lib = emu_lib()
     z = golden(name)
     taps = (z["g"], z["dg"], z["k"])
