@@ -391,7 +391,11 @@ bb_exact_score(const float* q1, const float* q2, const float* y, const float* xn
   return bb_score(__ldg(xn + qi), __ldg(gn + qi), __ldg(yn + cj), dot1, dot2, alpha, beta);
 }
 
-template <int D>
+// SHARE: the 16 threads that own a query also pool their bound -- every chunk early on, every fourth
+// later, B_i is lowered to the smallest UPPER bound s'_ij + tol_ij any of them saw in the chunk (four
+// shuffle steps).  It costs ~8 % on descriptors whose co-located patch is already a tight seed
+// (BestBuddy, Gram) and saves 25 % on PatchwiseST, whose noisy SR descriptors make the seed loose.
+template <int D, bool SHARE = false>
 __global__ void __launch_bounds__(BB_NT, 1)
 bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, float alpha, float beta,
                  int64_t* __restrict__ idx_out) {
@@ -401,6 +405,9 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
   __shared__ __align__(16) float sYl[2][BB_CT];     // (alpha+beta)|y|^2 - kappa*(|alpha|+|beta|)|y|^2
   __shared__ __align__(16) float sCl[BB_QT];        // c_i - kappa*(|alpha||x|^2 + |beta||g|^2)
   __shared__ __align__(16) float sB0[BB_QT];        // exact score of the co-located candidate j = i
+  // SHARE only: 2*tol of a pair is at most 2 kappa (ca_i + max over the chunk's valid candidates of yt_j)
+  [[maybe_unused]] __shared__ __align__(16) float sCa[SHARE ? BB_QT : 4];   // |alpha||x|^2 + |beta||g|^2
+  [[maybe_unused]] __shared__ __align__(16) float sYtm[2][4];               // per staging warp: max (|alpha|+|beta|)|y|^2
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y, qt = blockIdx.x;
@@ -419,6 +426,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     const int qi = qbase + tid;
     const float xn = __ldg(P.xn + qi), gn = __ldg(P.gn + qi);
     sCl[tid] = fmaf(alpha, xn, beta * gn) - kBbKappa * fmaf(aa, xn, ab * gn);
+    if constexpr (SHARE) sCa[tid] = fmaf(aa, xn, ab * gn);
     // seed of the upper bound; padded queries get -inf so that nothing is ever evaluated for them
     sB0[tid] = (qi < g.N) ? bb_exact_score(P.q1, P.q2, P.y, P.xn, P.gn, P.yn, g.Npad, g.Mpad, D, qi, qi, alpha, beta)
                           : __int_as_float(0xff800000);
@@ -439,7 +447,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     }
     if (tid < BB_CT) pfn = __ldg(P.yn + chunk + tid);
   };
-  auto commit = [&](int buf) {
+  auto commit = [&](int buf, [[maybe_unused]] int chunk) {
 #pragma unroll
     for (int u = 0; u < NLD; ++u) {
       const int it = tid + u * BB_NT;
@@ -449,14 +457,22 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
       }
     }
     // padded candidates carry |y|^2 = +inf: their lower bound is +inf (or NaN) and never passes
-    if (tid < BB_CT) sYl[buf][tid] = (alpha + beta) * pfn - kBbKappa * ((aa + ab) * pfn);
+    if (tid < BB_CT) {
+      sYl[buf][tid] = (alpha + beta) * pfn - kBbKappa * ((aa + ab) * pfn);
+      if constexpr (SHARE) {
+        float m = (chunk + tid < g.M) ? (aa + ab) * pfn : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((tid & 31) == 0) sYtm[buf][tid >> 5] = m;
+      }
+    }
   };
 
   const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads; a half-warp shares ty (its queries)
   // local query l (0..7) -> tile query ty*4 + (l&3) + 64*(l>>2); same for candidates with tx
 
   prefetch(0);
-  commit(0);
+  commit(0, 0);
   __syncthreads();  // queries, bounds and chunk 0 are in shared memory
 
   float best[8], B[8];
@@ -472,6 +488,11 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
 #pragma unroll
   for (int i = 0; i < 8; ++i) { best[i] = __int_as_float(0x7f800000); bidx[i] = 0x7fffffff; }
   const float2 m2 = make_float2(-2.0f, -2.0f);
+  [[maybe_unused]] float ca[8];
+  if constexpr (SHARE) {
+    const float4 a0 = ld4(&sCa[4 * ty]), a1 = ld4(&sCa[64 + 4 * ty]);
+    ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
+  }
 
   for (int chunk = 0, buf = 0; chunk < g.Mpad; chunk += BB_CT, buf ^= 1) {
     const bool more = chunk + BB_CT < g.Mpad;
@@ -500,15 +521,53 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     unsigned long long hit = 0ull;
     const float4 yla = ld4(&sYl[buf][4 * tx]), ylb = ld4(&sYl[buf][64 + 4 * tx]);
     const float yl[8] = {yla.x, yla.y, yla.z, yla.w, ylb.x, ylb.y, ylb.z, ylb.w};
+    if constexpr (!SHARE) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 y2 = make_float2(yl[j], yl[j]);
+      for (int j = 0; j < 8; ++j) {
+        const float2 y2 = make_float2(yl[j], yl[j]);
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float2 lo = __ffma2_rn(m2, acc[p][j], __fadd2_rn(cl[p], y2));
-        if (lo.x <= B[2 * p]) hit |= 1ull << (8 * j + 2 * p);
-        if (lo.y <= B[2 * p + 1]) hit |= 1ull << (8 * j + 2 * p + 1);
+        for (int p = 0; p < 4; ++p) {
+          const float2 lo = __ffma2_rn(m2, acc[p][j], __fadd2_rn(cl[p], y2));
+          if (lo.x <= B[2 * p]) hit |= 1ull << (8 * j + 2 * p);
+          if (lo.y <= B[2 * p + 1]) hit |= 1ull << (8 * j + 2 * p + 1);
+        }
       }
+    } else {
+      // lower bounds L_ij in place; an upper bound of the pair is L_ij + 2 tol_ij <= L_ij + delta_i with
+      // delta_i = 2 kappa (ca_i + max_chunk yt): pool min_j (L_ij) + delta_i over the half-warp into B_i first,
+      // then flag against the pooled bound
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 y2 = make_float2(yl[j], yl[j]);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[p][j] = __ffma2_rn(m2, acc[p][j], __fadd2_rn(cl[p], y2));
+      }
+      const int cidx = chunk / BB_CT;
+      if (cidx < 4 || (cidx & 3) == 0) {
+        const float4 ym = ld4(&sYtm[buf][0]);
+        const float ytmax = fmaxf(fmaxf(ym.x, ym.y), fmaxf(ym.z, ym.w));
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          float mx = acc[p][0].x, my = acc[p][0].y;
+#pragma unroll
+          for (int j = 1; j < 8; ++j) { mx = fminf(mx, acc[p][j].x); my = fminf(my, acc[p][j].y); }
+#pragma unroll
+          for (int o = 1; o <= 8; o <<= 1) {
+            mx = fminf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            my = fminf(my, __shfl_xor_sync(0xffffffffu, my, o));
+          }
+          // 1.0001: the three fp32 roundings of this expression stay far inside the slack of kappa
+          B[2 * p] = fminf(B[2 * p], mx + 2.0002f * kBbKappa * (ca[2 * p] + ytmax));
+          B[2 * p + 1] = fminf(B[2 * p + 1], my + 2.0002f * kBbKappa * (ca[2 * p + 1] + ytmax));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          if (acc[p][j].x <= B[2 * p]) hit |= 1ull << (8 * j + 2 * p);
+          if (acc[p][j].y <= B[2 * p + 1]) hit |= 1ull << (8 * j + 2 * p + 1);
+        }
     }
     if (hit) {  // rare: exact re-scoring, ascending candidate order per query
 #pragma unroll
@@ -525,7 +584,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
         }
       }
     }
-    if (more) commit(buf ^ 1);  // buf^1 was last read before the previous barrier
+    if (more) commit(buf ^ 1, chunk + BB_CT);  // buf^1 was last read before the previous barrier
     __syncthreads();
   }
 

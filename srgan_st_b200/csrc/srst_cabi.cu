@@ -493,7 +493,7 @@ static int bb_forward_impl(const float* sr, const float* gt, const float* gt2, c
   SRST_LAUNCH(bb_pack_kernel<MODE>, dim3((npack + 255) / 256, B), dim3(256), 0, stream, sr, gt, gt2, gt4, w.mats,
               w.per_image, g, tp);
   if ((e = (int)cudaGetLastError()) != 0) return e;
-  SRST_LAUNCH(bb_search_kernel<D>, dim3(g.Npad / BB_QT, B), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, alpha,
+  SRST_LAUNCH((bb_search_kernel<D, MODE == 2>), dim3(g.Npad / BB_QT, B), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, alpha,
               beta, idx_out);
   if ((e = (int)cudaGetLastError()) != 0) return e;
   const unsigned nl = (unsigned)(((size_t)B * g.N + BB_NT - 1) / BB_NT);
