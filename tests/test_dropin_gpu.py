@@ -51,6 +51,52 @@ def test_losses_register_and_train_like_the_reference_loop():
     assert history[-1] < history[0]
 
 
+def test_every_loss_module_trains_in_the_loop_and_under_a_cuda_graph():
+    """All five modules registered at once (incl. the fused ST+Pixel criterion replacing "Pixel" + "ST"), then the
+    whole generator step replayed from ONE CUDA graph without any per-criterion .item(): the
+    loss objects neither allocate outside torch's caching allocator nor synchronise."""
+    from srgan_st_b200 import (BestBuddyLoss, GramLoss, PatchwiseStructureTensorLoss, StructureTensorLoss,
+                               StructureTensorPixelLoss)
+    torch.manual_seed(1)
+    dev = torch.device("cuda:0")
+    crits = {"ST+Pixel": (StructureTensorPixelLoss(st_weight=1 / 3, pixel_weight=1.0), 1.0),
+             "BestBuddy": (BestBuddyLoss(), 50.0), "Gram": (GramLoss(), 10.0),
+             "PatchST": (PatchwiseStructureTensorLoss(), 1.0), "ST": (StructureTensorLoss(rho=1.0), 0.1)}
+    gen = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.PReLU(),
+                              torch.nn.Conv2d(8, 3, 3, padding=1)).to(dev)
+    opt = torch.optim.SGD(gen.parameters(), lr=1e-3)
+    gt = (torch.randint(0, 256, (4, 3, 48, 48), device=dev).float() / 255)
+    lr = (gt + 0.1 * torch.randn_like(gt)).clamp(0, 1)
+
+    def g_step():
+        sr = gen(lr).clamp(0, 1)
+        total = sum(w * m(sr, gt) for m, w in crits.values())
+        opt.zero_grad(set_to_none=False)
+        total.backward()
+        return total
+
+    eager = [g_step().item() for _ in range(3)]          # warm-up on the default stream, also fills .grad
+    assert all(torch.isfinite(p.grad).all() for p in gen.parameters())
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            g_step()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        static_total = g_step()
+    graph.replay()
+    torch.cuda.synchronize()
+    replayed = static_total.item()
+    grads = [p.grad.clone() for p in gen.parameters()]
+    ref = g_step()                                        # same weights, eager
+    torch.cuda.synchronize()
+    assert abs(replayed - ref.item()) <= 1e-5 * abs(ref.item())
+    for a, p in zip(grads, gen.parameters()):
+        assert torch.allclose(a, p.grad, rtol=1e-4, atol=1e-7)
+    assert eager[0] == eager[0]
+
+
 def test_non_contiguous_and_sliced_inputs_are_accepted():
     from srgan_st_b200 import StructureTensorLoss
     x = torch.rand(4, 3, 40, 44, device="cuda").requires_grad_(True)
