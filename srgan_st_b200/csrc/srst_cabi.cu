@@ -50,6 +50,14 @@ using WideA = StWideFwdCfg<48, 96, 12, 384>;  // half a 96x96 training crop per 
 
 constexpr int kMinFwdTH = 24, kMinFwdTW = 32;  // finest compiled forward tiling (workspace sizing)
 
+static bool pdl_enabled_host() {
+#ifdef SRST_EMULATE
+  return false;
+#else
+  return srst::pdl_enabled();
+#endif
+}
+
 static int sm_count() {
 #ifdef SRST_EMULATE
   return 2;  // small persistent grid so the emulation exercises the tile loop
@@ -180,6 +188,7 @@ static int launch_st_backward(StBwdParams<C::RG, C::RK> P, const float* gray, vo
   P.tiles_y = (P.H + C::TH - 1) / C::TH;
   const long long nblk = (long long)P.B * P.tiles_x * P.tiles_y;
   if (nblk <= 0 || nblk > 0x7fffffffLL) return SRST_E_SHAPE;
+  P.early_ctas = (pdl_enabled_host() && env_int("SRST_ST_BWD_EARLY", 1) != 0) ? sm_count() * C::MINB : 0;
   int e = ensure_smem<std::conditional_t<PX, PxTag<C>, C>>(st_backward_kernel<C, PX>, C::SMEM_BYTES);
   if (e) return e;
   SRST_LAUNCH_PDL((st_backward_kernel<C, PX>), dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);

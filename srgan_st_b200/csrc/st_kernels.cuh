@@ -76,6 +76,8 @@ struct StBwdParams {
   int use_tma;
   int use_gray;  // 1: the gray tile comes from gray_map by TMA instead of RGB loads + conversion
   float inv_count;
+  int early_ctas;  // CTAs [0, early_ctas) -- the first wave -- load the image and rebuild Ix, Iy BEFORE waiting for the
+                   // previous kernel of the stream (programmatic dependent launch): that work only reads inputs
   long long* debug;
   StTaps<RG, RK> taps;
 };
@@ -984,7 +986,12 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   float* sdI1 = sX + C::I_FLOATS;
 
   const int tid = threadIdx.x;
-  pdl_wait();     // the forward kernel that wrote ds is complete
+  // First-wave CTAs can become resident while the previous kernel of the stream (the forward, in a
+  // training step's backward pass) is still draining.  Their gray tile and Ix, Iy depend on `img` only,
+  // which that kernel does not write, so they are built first; ds (written by the forward) and
+  // grad_out (written by the autograd op right before this launch) are touched after the wait.
+  const bool early = P.use_tma && !P.use_gray && (int)blockIdx.x < P.early_ctas;
+  if (!early) pdl_wait();
   pdl_trigger();
   int tile = blockIdx.x;
   const int tx = tile % P.tiles_x;
@@ -1008,7 +1015,7 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   if (P.use_gray && tid == 0)
     tma_stage_begin(&s_mbar_g, sG, &P.gray_map, x0 - 2 * C::HXE, y0 - 2 * C::RG, b, C::GW, C::GH, 1);
   if (P.use_tma) {
-    if (tid == 0) tma_stage_begin(&s_mbar, sS, &P.ds_map, xv0, yv0, b * 3, C::VW, C::SH, 3);
+    if (!early && tid == 0) tma_stage_begin(&s_mbar, sS, &P.ds_map, xv0, yv0, b * 3, C::VW, C::SH, 3);
   } else {
     const float* dsb = P.ds + img_off;
     constexpr int C4 = C::VW / 4;
@@ -1080,6 +1087,11 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
     st4(o0 + 4, make_float4(Ix[2].x, Ix[2].y, Ix[3].x, Ix[3].y));
     st4(o1, make_float4(Iy[0].x, Iy[0].y, Iy[1].x, Iy[1].y));
     st4(o1 + 4, make_float4(Iy[2].x, Iy[2].y, Iy[3].x, Iy[3].y));
+  }
+  if (early) {
+    pdl_wait();  // the previous kernel of the stream is complete: ds may be fetched now
+    if (tid == 0) tma_stage_begin(&s_mbar, sS, &P.ds_map, xv0, yv0, b * 3, C::VW, C::SH, 3);
+    __syncthreads();  // the barrier is initialised before anyone polls it
   }
   if (P.use_tma) tma_stage_wait(&s_mbar); else cp_async_wait_all();
   __syncthreads();  // Ix, Iy complete; staged ds planes have landed
