@@ -391,6 +391,14 @@ def run_gpu(args):
 
             for ev in consumed:
                 ev.record()
+            # PCIe links idle down between phases of this script (the CPU arm runs for seconds before this leg on a
+            # fresh box): bring the H2D path to its steady state with an untimed burst of copies first, otherwise
+            # the short timed region (K steps of ~0.3 ms) measures the link's ramp-up (observed: 28 vs 52 GB/s)
+            t_burst = time.perf_counter()
+            while time.perf_counter() - t_burst < 0.3:
+                for j in range(8):
+                    slots[j % 2].copy_(host[j % n_host], non_blocking=True)
+                torch.cuda.synchronize()
             nw = max(Wm, 3)
             issue_copy(0)
             for i in range(nw):
