@@ -285,24 +285,22 @@ def run_gpu(args):
         pool = [make_pair(torch, B, H, W, gen, dev) for _ in range(pool_n)]
         ds = torch.empty(B, 3, H, W, device=dev)
         d_sr = torch.empty(B, 3, H, W, device=dev)
-        gray = torch.empty(B, H, W, device=dev)
+        ixy = torch.empty(lib.srst_st_ixy_floats(B, H, W), device=dev)
         loss = torch.zeros((), device=dev)
         go = torch.ones((), device=dev)
         nws = lib.srst_st_workspace_bytes(B, H, W)
         ws = torch.zeros(max(nws, 4096), dtype=torch.uint8, device=dev)
         vp = lambda t: ctypes.c_void_p(t.data_ptr())
-        GRAY = (lambda t: vp(t)) if os.environ.get("SRST_ST_SAVE_GRAY", "0") == "1" else (lambda t: None)
         s = torch.cuda.Stream(device=dev)
         sp = ctypes.c_void_p(s.cuda_stream)
 
         def fwd(i):
             sr, hr = pool[i % pool_n]
             _cabi.check(lib.srst_st_forward(vp(sr), vp(hr), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8, 1,
-                                            1e-12, vp(loss), vp(ds), None, GRAY(gray), None, vp(ws), ws.numel(), sp), "fwd")
+                                            1e-12, vp(loss), vp(ds), None, vp(ixy), None, vp(ws), ws.numel(), sp), "fwd")
 
         def bwd(i):
-            sr, _ = pool[i % pool_n]
-            _cabi.check(lib.srst_st_backward(vp(sr), GRAY(gray), vp(ds), vp(go), B, H, W, T.as_c(g), T.as_c(dg), 2,
+            _cabi.check(lib.srst_st_backward(vp(ixy), vp(ds), vp(go), B, H, W, T.as_c(g), T.as_c(dg), 2,
                                              T.as_c(k), 8, vp(d_sr), sp), "bwd")
 
         def graph_of(fn_list, n):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRST_VERSION 102 /* major*10000 + minor*100 + patch */
+#define SRST_VERSION 200 /* major*100 + minor: the major number changes whenever an argument list changes */
 
 #define SRST_E_INVALID (-1)     /* null pointer / non-positive size / bad enum */
 #define SRST_E_UNSUPPORTED (-2) /* filter radius or patch geometry not compiled in */
@@ -53,32 +53,47 @@ const char* srst_error_string(int code);
 /* 1 if the (r_sigma, r_rho) pair fits a compiled radius class, else 0. */
 int srst_st_supported(int r_sigma, int r_rho);
 
+/* Tile-shape override for tests and tuning sweeps: force compiled forward / backward tile configuration
+ * fwd_cfg / bwd_cfg (0 .. srst_st_num_cfgs(0|1) - 1) for the default radius class, -1 = the library's own
+ * choice.  Process-wide; the environment variables SRST_ST_FWD_CFG / SRST_ST_BWD_CFG set the initial value
+ * (read once). */
+int srst_st_num_cfgs(int backward);
+int srst_st_force_cfg(int fwd_cfg, int bwd_cfg);
+
 /* Scratch bytes srst_st_forward / srst_stpx_forward need for a [B,3,H,W] problem (per-CTA partial sums + ticket).
- * The workspace must be 16-byte aligned and ZERO-FILLED ONCE before its first use; the kernels
- * leave it zeroed again, so it can be reused by later calls on the same stream. */
+ * The workspace must be 16-byte aligned; its first 16 bytes (the ticket counter) must be ZERO before the
+ * first use.  Every launch writes its partial sums before reading them and hands the ticket back zeroed,
+ * so the buffer can be reused by later calls on the same stream; do not share one buffer between
+ * streams, or between this entry point and the patch-loss entry points (they lay it out differently). */
 size_t srst_st_workspace_bytes(int B, int H, int W);
+
+/* Number of floats of a saved-gradient buffer ("ixy") for a [B,3,H,W] problem: [B][2][ceil(H/2)][W][2],
+ * plane 0 = Ix (derivative along H), plane 1 = Iy, rows 2p / 2p+1 of a column interleaved (the layout the
+ * kernels use in shared memory, so the backward fetches its tile with one TMA box copy). */
+size_t srst_st_ixy_floats(int B, int H, int W);
 
 /* Forward.  sr, hr: device [B,3,H,W] fp32.  Writes
  *   loss_out[0]  = mean over B*H*W pixels of the Riemannian distance   (device, 1 float)
  *   ds_sr        = d(sum of distances)/d(Jxx,Jyy,Jxy of SR), device [B,3,H,W], or NULL to skip
  *   ds_hr        = same w.r.t. the HR tensor, or NULL (only needed when hr requires grad)
- *   gray_sr/_hr  = grayscale planes, device [B,H,W], or NULL; when given, srst_st_backward can
- *                  fetch its gray tile with one TMA copy instead of re-reading and converting RGB
- * The ds_* planes are the "saved intermediates" the backward pass consumes; they are unscaled
+ *   ixy_sr/_hr   = the Gaussian-derivative gradients Ix, Iy of the grayscale image (utils.py:219-222),
+ *                  srst_st_ixy_floats() floats each, or NULL; required next to the matching ds_*
+ * ds_* and ixy_* are the "saved intermediates" the backward pass consumes (20 B/pixel); ds is unscaled
  * (neither 1/(B*H*W) nor the upstream gradient is applied yet). */
 int srst_st_forward(const float* sr, const float* hr, int B, int H, int W,
                     const float* g, const float* dg, int r_sigma,
                     const float* k, int r_rho,
                     int normalize, float eps,
-                    float* loss_out, float* ds_sr, float* ds_hr, float* gray_sr, float* gray_hr,
+                    float* loss_out, float* ds_sr, float* ds_hr, float* ixy_sr, float* ixy_hr,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* Backward for one image tensor.  img: the same [B,3,H,W] tensor the forward saw (sr or hr);
- * gray: the matching gray_* planes the forward saved, or NULL (then img is re-read and converted);
- * ds: the matching ds_* planes; grad_out: device pointer to the upstream scalar gradient.
+/* Backward for one image tensor (sr or hr): ixy, ds = the matching ixy_* / ds_* buffers the forward
+ * wrote; grad_out: device pointer to the upstream scalar gradient.  The image itself is not read again.
  * Writes d_img[B,3,H,W] = grad_out/(B*H*W) * dLoss_sum/dimg (adjoint smoothing, product rule,
- * adjoint Gaussian-derivative filters, grayscale weights). */
-int srst_st_backward(const float* img, const float* gray, const float* ds, const float* grad_out,
+ * adjoint Gaussian-derivative filters, grayscale weights).
+ * Ordering: plain stream order -- every input may be produced by the kernel enqueued immediately before
+ * this call on `stream` (the kernel waits for its predecessor before its first global read). */
+int srst_st_backward(const float* ixy, const float* ds, const float* grad_out,
                      int B, int H, int W,
                      const float* g, const float* dg, int r_sigma,
                      const float* k, int r_rho,
@@ -99,9 +114,9 @@ int srst_stpx_forward(const float* sr, const float* hr, int B, int H, int W,
                       const float* g, const float* dg, int r_sigma,
                       const float* k, int r_rho,
                       int normalize, float eps,
-                      float* loss2_out, float* ds_sr,
+                      float* loss2_out, float* ds_sr, float* ixy_sr,
                       void* workspace, size_t workspace_bytes, void* stream);
-int srst_stpx_backward(const float* sr, const float* hr, const float* ds,
+int srst_stpx_backward(const float* sr, const float* hr, const float* ixy, const float* ds,
                        const float* grad_st, const float* grad_px,
                        int B, int H, int W,
                        const float* g, const float* dg, int r_sigma,

@@ -11,6 +11,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsrst.so")
 
+ABI_MAJOR = 2  # include/srst.h SRST_VERSION // 100
+
 c_float_p = ctypes.POINTER(ctypes.c_float)
 c_i64_p = ctypes.POINTER(ctypes.c_int64)
 vp = ctypes.c_void_p
@@ -20,18 +22,21 @@ SIGNATURES = {
     "srst_version": (ctypes.c_int, []),
     "srst_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "srst_st_supported": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "srst_st_num_cfgs": (ctypes.c_int, [ctypes.c_int]),
+    "srst_st_force_cfg": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "srst_st_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
+    "srst_st_ixy_floats": (ctypes.c_size_t, [ctypes.c_int] * 3),
     "srst_st_forward": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_float, vp, vp, vp, vp, vp,
                                        vp, ctypes.c_size_t, vp]),
-    "srst_st_backward": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+    "srst_st_backward": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
                                         vp, vp]),
     "srst_stpx_forward": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
-                                         ctypes.c_int, ctypes.c_float, vp, vp, vp, ctypes.c_size_t, vp]),
-    "srst_stpx_backward": (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_float, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+    "srst_stpx_backward": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, vp, vp]),
     "srst_bb_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
     "srst_bb_forward": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -80,7 +85,7 @@ def lib() -> ctypes.CDLL:
                 f"{LIB_PATH} not found. srgan_st_b200 has no CPU or PyTorch fallback: build the "
                 "sm_100a library first with `python -m srgan_st_b200.build`.")
         _lib = bind(LIB_PATH)
-        if _lib.srst_version() // 100 != 1:
+        if _lib.srst_version() // 100 != ABI_MAJOR:
             raise SrstError(f"libsrst.so ABI version {_lib.srst_version()} does not match this package")
     return _lib
 

@@ -12,55 +12,53 @@
 #include <type_traits>
 
 #include "st_kernels.cuh"
-#include "st_stream.cuh"
-#include "st_wide.cuh"
 #include "bb_kernels.cuh"
 
 namespace srst {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-static int env_int(const char* name, int dflt) {
+// Tuning knobs are read from the environment ONCE (first use); srst_st_force_cfg() overrides the
+// tile choice at run time (tests cover every compiled shape through it).
+static int env_int_once(const char* name, int dflt) {
   const char* s = std::getenv(name);
   return (s && *s) ? std::atoi(s) : dflt;
 }
-
-// ---- compiled structure-tensor tile configurations ------------------------------------------
-//                         TH  TW  RS CSB NP RG RK MINB
-using FwdA = StFwdCfg<40, 64, 10, 4, 0, 2, 8, 2>;   // large images (DIV2K-sized validation)
-using FwdB = StFwdCfg<32, 96, 8, 4, 0, 2, 8, 2>;    // 96-wide training crops: a tile spans the row
-using FwdC = StFwdCfg<48, 48, 12, 4, 0, 2, 8, 2>;   // square quarter of a 96x96 crop
-using FwdD = StFwdCfg<32, 64, 16, 4, 0, 2, 8, 3>;   // small footprint: three CTAs per SM
-using FwdE = StFwdCfg<32, 64, 16, 4, 64, 2, 8, 2>;  // FwdD + two producer warps, double-buffered gray tile (persistent)
-using FwdF = StFwdCfg<24, 64, 12, 4, 0, 2, 8, 4>;   // experiment: four small CTAs per SM
-using FwdG = StFwdCfg<32, 32, 16, 4, 0, 2, 8, 4>;   // experiment: four 128-thread CTAs per SM
-using FwdH = StFwdCfg<48, 64, 12, 4, 0, 2, 8, 2>;   // experiment: taller tile, two CTAs per SM
-using FwdI = StFwdCfg<48, 96, 12, 4, 0, 2, 8, 1>;   // experiment: half a 96x96 crop per CTA, one 576-thread CTA per SM
-using FwdJ = StFwdCfg<64, 64, 16, 4, 0, 2, 8, 1>;   // experiment: 512-thread CTA, one per SM
-//                         TH  TW  RS   NT  RG RK MINB
-using BwdA = StBwdCfg<24, 64, 14, 256, 2, 8, 2>;  // large images
-using BwdD = StBwdCfg<28, 56, 16, 256, 2, 8, 2>;  // 16 row pairs per phase item column: no LDS bank conflicts
-using BwdG = StBwdCfg<16, 96, 10, 256, 2, 8, 2, 8>;  // BwdB with 8-column horizontal-pass items
-using BwdH = StBwdCfg<16, 96, 10, 288, 2, 8, 2, 8>;  // BwdG with 288 threads: the 260 gradient items fit one round
-using BwdI = StBwdCfg<12, 96, 8, 224, 2, 8, 3, 8>;   // shorter strips, three CTAs per SM
-using BwdF = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8>;  // BwdD with 8-column horizontal-pass items (less shared-memory traffic)
-
-//                             TH  TW  RS   NT
-using WideA = StWideFwdCfg<48, 96, 12, 384>;  // half a 96x96 training crop per CTA, one CTA per SM
-
-constexpr int kMinFwdTH = 24, kMinFwdTW = 32;  // finest compiled forward tiling (workspace sizing)
-
-static bool pdl_enabled_host() {
-#ifdef SRST_EMULATE
-  return false;
-#else
-  return srst::pdl_enabled();
-#endif
+static int g_force_fwd = -2, g_force_bwd = -2;  // -2: not initialised, -1: library's own choice
+static int forced_fwd() {
+  if (g_force_fwd == -2) g_force_fwd = env_int_once("SRST_ST_FWD_CFG", -1);
+  return g_force_fwd;
 }
+static int forced_bwd() {
+  if (g_force_bwd == -2) g_force_bwd = env_int_once("SRST_ST_BWD_CFG", -1);
+  return g_force_bwd;
+}
+
+// ---- compiled structure-tensor tile configurations (reference default radii: r_sigma 2, r_rho 8) ----
+//                       TH  TW  RS CSB RG RK MINB CHU
+using Fwd0 = StFwdCfg<48, 48, 12, 4, 2, 8, 2>;  // square quarter of a 96x96 crop, 288 threads
+using Fwd1 = StFwdCfg<32, 64, 16, 4, 2, 8, 2>;  // large images, 256 threads
+using Fwd2 = StFwdCfg<24, 96, 8, 4, 2, 8, 2>;   // full-width strip of a 96-wide crop (no horizontal halo), 288 threads
+using Fwd3 = StFwdCfg<32, 48, 16, 4, 2, 8, 3>;  // small footprint: three 192-thread CTAs per SM
+using Fwd4 = StFwdCfg<40, 64, 10, 4, 2, 8, 2>;  // taller tile, 320 threads
+using Fwd5 = StFwdCfg<24, 64, 12, 4, 2, 8, 3>;  // three 192-thread CTAs per SM
+using Fwd6 = StFwdCfg<48, 48, 12, 4, 2, 8, 2, 2>;  // Fwd0 with two chain iterations in flight
+using Fwd7 = StFwdCfg<32, 64, 16, 4, 2, 8, 2, 2>;  // Fwd1 with two chain iterations in flight
+constexpr int kNumFwdCfg = 8;
+//                       TH  TW  RS   NT RG RK MINB CSD
+using Bwd0 = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8>;  // large images: 16 row pairs per horizontal-pass column
+using Bwd1 = StBwdCfg<16, 96, 10, 288, 2, 8, 2, 8>;  // full-width strips of 96-wide crops
+using Bwd2 = StBwdCfg<12, 96, 8, 224, 2, 8, 2, 8>;   // shorter strips for small batches (more CTAs)
+using Bwd3 = StBwdCfg<20, 56, 12, 192, 2, 8, 3, 8>;  // three CTAs per SM
+using Bwd4 = StBwdCfg<24, 64, 14, 256, 2, 8, 2, 8>;
+using Bwd5 = StBwdCfg<28, 96, 16, 384, 2, 8, 1, 8>;  // 96-wide crops, one large CTA per SM
+constexpr int kNumBwdCfg = 6;
+
+constexpr int kMinFwdTH = 24, kMinFwdTW = 48;  // finest compiled forward tiling (workspace sizing)
 
 static int sm_count() {
 #ifdef SRST_EMULATE
-  return 2;  // small persistent grid so the emulation exercises the tile loop
+  return 2;
 #else
   static int cached[64] = {};
   int dev = 0;
@@ -116,43 +114,56 @@ static void fill_taps(StTaps<RG, RK>& t, const float* g, const float* dg, int rs
   for (int u = 0; u <= 2 * RK + 1; ++u) t.kp[u] = make_float2(u <= 2 * RK ? t.k[u] : 0.f, u >= 1 ? t.k[u - 1] : 0.f);
 }
 
-template <class C> struct PxTag {};  // once-flag tag of the fused-Pixel instantiation of a forward tile shape
+// The filled tap block depends on the caller's tap values only: keep the last one per radius class
+// and thread (a training loop calls with the same sigma / rho every step).
+template <int RG, int RK>
+static const StTaps<RG, RK>& cached_taps(const float* g, const float* dg, int rs, const float* k, int rk) {
+  struct Entry { bool valid = false; int rs = 0, rk = 0; float g[2 * RG + 1], dg[2 * RG + 1], k[2 * RK + 1]; StTaps<RG, RK> taps; };
+  static thread_local Entry e;
+  const bool hit = e.valid && e.rs == rs && e.rk == rk && std::memcmp(e.g, g, sizeof(float) * (2 * rs + 1)) == 0 &&
+                   std::memcmp(e.dg, dg, sizeof(float) * (2 * rs + 1)) == 0 &&
+                   std::memcmp(e.k, k, sizeof(float) * (2 * rk + 1)) == 0;
+  if (!hit) {
+    e.rs = rs; e.rk = rk;
+    std::memcpy(e.g, g, sizeof(float) * (2 * rs + 1));
+    std::memcpy(e.dg, dg, sizeof(float) * (2 * rs + 1));
+    std::memcpy(e.k, k, sizeof(float) * (2 * rk + 1));
+    fill_taps(e.taps, g, dg, rs, k, rk);
+    e.valid = true;
+  }
+  return e.taps;
+}
+
+template <class C, bool PX, bool HR> struct FwdTag {};  // once-flag tag per forward instantiation
+template <class C, bool PX> struct BwdTag {};
 
 template <class C, bool PX = false>
-static int launch_st_forward(StFwdParams<C::RG, C::RK> P, void* stream) {
+static int launch_st_forward(StFwdParams<C::RG, C::RK>& P, void* stream) {
   P.tiles_x = (P.W + C::TW - 1) / C::TW;
   P.tiles_y = (P.H + C::TH - 1) / C::TH;
   const long long ntiles = (long long)P.B * P.tiles_x * P.tiles_y;
   if (ntiles <= 0 || ntiles > 0x7fffffffLL) return SRST_E_SHAPE;
-  int e = ensure_smem<std::conditional_t<PX, PxTag<C>, C>>(st_forward_kernel<C, PX>, C::SMEM_BYTES);
-  if (e) return e;
-  // persistent grid: one wave of resident CTAs, each looping over tiles
-  const long long slots = (long long)sm_count() * C::MINB;
-  const long long nblk = (C::NP == 0 || ntiles < slots) ? ntiles : slots;
-  SRST_LAUNCH_PDL((st_forward_kernel<C, PX>), dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  int e;
+  if (P.ds_hr) {
+    if ((e = ensure_smem<FwdTag<C, PX, true>>(st_forward_kernel<C, PX, true>, C::SMEM_BYTES)) != 0) return e;
+    SRST_LAUNCH_PDL((st_forward_kernel<C, PX, true>), dim3((unsigned)ntiles), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  } else {
+    if ((e = ensure_smem<FwdTag<C, PX, false>>(st_forward_kernel<C, PX, false>, C::SMEM_BYTES)) != 0) return e;
+    SRST_LAUNCH_PDL((st_forward_kernel<C, PX, false>), dim3((unsigned)ntiles), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  }
   return (int)cudaGetLastError();
 }
 
-template <class C>
-static int launch_st_wide_forward(StFwdParams<C::RG, C::RK> P, void* stream) {
-  P.tiles_x = (P.W + C::TW - 1) / C::TW;
-  P.tiles_y = (P.H + C::TH - 1) / C::TH;
-  const long long ntiles = (long long)P.B * P.tiles_x * P.tiles_y;
-  if (ntiles <= 0 || ntiles > 0x7fffffffLL) return SRST_E_SHAPE;
-  int e = ensure_smem<C>(st_wide_forward_kernel<C>, C::SMEM_BYTES);
-  if (e) return e;
-  SRST_LAUNCH_PDL(st_wide_forward_kernel<C>, dim3((unsigned)ntiles), dim3(C::NT), C::SMEM_BYTES, stream, P);
-  return (int)cudaGetLastError();
-}
-
-// Tensor map of a [planes][H][W] fp32 tensor with a [3][box_h][box_w] box (no swizzle, zero OOB fill).
-// Returns false when TMA cannot be used (unaligned tensor, driver entry point missing): the kernel
-// then stages with cp.async instead.
-static bool make_plane_map(SrstTmap* map, const float* base, long long planes, int H, int W, int box_w, int box_h,
+// Tensor map of an fp32 tensor viewed as [planes][rows][cols] with a [box_p][box_h][box_w] box (no
+// swizzle, zero OOB fill).  Returns false when TMA cannot be used (unaligned tensor, row pitch not a
+// multiple of 16 bytes, driver entry point missing): the kernel then stages with plain loads.
+// Encoding costs a driver call, so the last few maps are kept per thread, keyed by everything that
+// goes into them (a training loop re-uses the same saved-tensor addresses step after step).
+static bool make_plane_map(SrstTmap* map, const float* base, long long planes, int rows, int cols, int box_w, int box_h,
                            int box_p) {
 #ifdef SRST_EMULATE
   (void)box_w; (void)box_h; (void)box_p;
-  map->base = base; map->W = W; map->H = H; map->P = (int)planes;
+  map->base = base; map->W = cols; map->H = rows; map->P = (int)planes;
   return true;
 #else
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -168,49 +179,65 @@ static bool make_plane_map(SrstTmap* map, const float* base, long long planes, i
       encode = reinterpret_cast<EncodeFn>(fn);
     looked_up = true;
   }
-  if (!encode || !aligned16(base) || (W % 4) != 0 || box_w > 256 || box_h > 256) return false;
-  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
-  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+  if (!encode || !aligned16(base) || (cols % 4) != 0 || box_w > 256 || box_h > 256 || (box_w % 4) != 0) return false;
+  struct Key { const float* base; long long planes; int rows, cols, bw, bh, bp; };
+  struct Entry { Key key; CUtensorMap map; bool valid; };
+  constexpr int kSlots = 16;
+  static thread_local Entry cache[kSlots] = {};
+  static thread_local int next = 0;
+  const Key key{base, planes, rows, cols, box_w, box_h, box_p};
+  for (int i = 0; i < kSlots; ++i) {
+    const Entry& c = cache[i];
+    if (c.valid && c.key.base == key.base && c.key.planes == key.planes && c.key.rows == key.rows &&
+        c.key.cols == key.cols && c.key.bw == key.bw && c.key.bh == key.bh && c.key.bp == key.bp) {
+      *map = c.map;
+      return true;
+    }
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * rows * 4};
   const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_p};
   const cuuint32_t estr[3] = {1, 1, 1};
-  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  Entry& slot = cache[next];
+  next = (next + 1) % kSlots;
+  slot.key = key; slot.map = *map; slot.valid = true;
+  return true;
 #endif
 }
 
 template <class C, bool PX = false>
-static int launch_st_backward(StBwdParams<C::RG, C::RK> P, const float* gray, void* stream) {
-  const bool tma_ok = P.vec4 && env_int("SRST_ST_BWD_TMA", 1) != 0;
-  P.use_tma = (tma_ok && make_plane_map(&P.ds_map, P.ds, (long long)P.B * 3, P.H, P.W, C::VW, C::SH, 3)) ? 1 : 0;
-  P.use_gray = (tma_ok && gray && make_plane_map(&P.gray_map, gray, (long long)P.B, P.H, P.W, C::GW, C::GH, 1)) ? 1 : 0;
+static int launch_st_backward(StBwdParams<C::RG, C::RK>& P, void* stream) {
+  static const bool tma_env = env_int_once("SRST_ST_BWD_TMA", 1) != 0;
+  const int Hp = (P.H + 1) / 2;
+  P.use_tma = (tma_env && P.vec4 && aligned16(P.ixy) &&
+               make_plane_map(&P.ds_map, P.ds, (long long)P.B * 3, P.H, P.W, C::VW, C::SH, 3) &&
+               make_plane_map(&P.ixy_map, P.ixy, (long long)P.B * 2, Hp, 2 * P.W, C::PI, C::EH / 2, 2)) ? 1 : 0;
   P.tiles_x = (P.W + C::TW - 1) / C::TW;
   P.tiles_y = (P.H + C::TH - 1) / C::TH;
   const long long nblk = (long long)P.B * P.tiles_x * P.tiles_y;
   if (nblk <= 0 || nblk > 0x7fffffffLL) return SRST_E_SHAPE;
-  P.early_ctas = (pdl_enabled_host() && env_int("SRST_ST_BWD_EARLY", 1) != 0) ? sm_count() * C::MINB : 0;
-  int e = ensure_smem<std::conditional_t<PX, PxTag<C>, C>>(st_backward_kernel<C, PX>, C::SMEM_BYTES);
+  int e = ensure_smem<BwdTag<C, PX>>(st_backward_kernel<C, PX>, C::SMEM_BYTES);
   if (e) return e;
   SRST_LAUNCH_PDL((st_backward_kernel<C, PX>), dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
   return (int)cudaGetLastError();
 }
 
 static int pick_fwd_cfg(int H, int W) {
-  const int forced = env_int("SRST_ST_FWD_CFG", -1);
-  if (forced >= 0 && forced <= 10) return forced;
-  // measured on B200 (profiles/r01_v2_tile_sweep.log): square 48x48 tiles win on 96-wide crops,
-  // the 3-CTA/SM 32x64 tile wins on large images
-  if (W <= 96) return 2;
-  return 3;
+  const int forced = forced_fwd();
+  if (forced >= 0 && forced < kNumFwdCfg) return forced;
+  (void)H;
+  if (W <= 96) return 0;
+  return 1;
 }
 static int pick_bwd_cfg(int B, int H, int W) {
-  const int forced = env_int("SRST_ST_BWD_CFG", -1);
-  if (forced >= 0 && forced <= 8) return forced;
-  // measured on B200 (gpurun sweeps, round 1b): on 96-wide crops full-width strips win -- 16x96 with 288
-  // threads once they fill the machine (two CTAs per SM), 12x96 with three CTAs per SM for small
-  // batches; the conflict-free 28x56 tile wins everywhere else
-  if (W <= 96) return ((long long)B * ((H + 15) / 16) >= 2LL * sm_count()) ? 7 : 8;
-  return 5;
+  const int forced = forced_bwd();
+  if (forced >= 0 && forced < kNumBwdCfg) return forced;
+  if (W <= 96) return ((long long)B * ((H + 15) / 16) >= 2LL * sm_count()) ? 1 : 2;
+  return 0;
 }
 
 }  // namespace srst
@@ -241,10 +268,19 @@ const char* srst_error_string(int code) {
 // classes use one generic shape each.
 int srst_st_supported(int r_sigma, int r_rho) { return (r_sigma >= 1 && r_sigma <= 4 && r_rho >= 1 && r_rho <= 12) ? 1 : 0; }
 
+int srst_st_num_cfgs(int backward) { return backward ? kNumBwdCfg : kNumFwdCfg; }
+
+int srst_st_force_cfg(int fwd_cfg, int bwd_cfg) {
+  if (fwd_cfg < -1 || fwd_cfg >= kNumFwdCfg || bwd_cfg < -1 || bwd_cfg >= kNumBwdCfg) return SRST_E_INVALID;
+  g_force_fwd = fwd_cfg;
+  g_force_bwd = bwd_cfg;
+  return 0;
+}
+
 static size_t st_partials_bytes(int B, int H, int W) {
   // one float per CTA of the finest compiled tiling + the ticket counter, rounded to 256 bytes
   const size_t tiles = (size_t)B * ((H + kMinFwdTH - 1) / kMinFwdTH) * ((W + kMinFwdTW - 1) / kMinFwdTW);
-  return ((tiles + 4 + 1024) * sizeof(float) + 255) / 256 * 256;  // + room for one partial per persistent CTA
+  return ((tiles + 4) * sizeof(float) + 255) / 256 * 256;
 }
 
 size_t srst_st_workspace_bytes(int B, int H, int W) {
@@ -252,66 +288,33 @@ size_t srst_st_workspace_bytes(int B, int H, int W) {
   return 2 * st_partials_bytes(B, H, W);  // ST partials + ticket | partials of the fused Pixel term
 }
 
+size_t srst_st_ixy_floats(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)B * 2 * ((H + 1) / 2) * (size_t)W * 2;
+}
+
 }  // extern "C"
 
 namespace srst {
 
 struct StCall {
-  const float *a, *b, *grad_out;  // forward: sr, hr ; backward: img, ds, grad_out
-  float *o0, *o1, *loss_out;      // forward: ds_sr, ds_hr ; backward: d_img
-  float *gray0, *gray1;           // forward: gray_sr, gray_hr outputs
-  const float* gray;              // backward: saved gray planes or null
-  int px;                         // forward: also reduce the fused Pixel (MSE) term into loss_out[1]
-  const float *px_other, *grad_px;  // backward: other image of the pair + upstream gradient of the MSE term
-  int B, H, W, normalize, vec4;
-  float eps;
-  void* workspace;
-  const float *g, *dg, *k;
-  int rs, rk;
-  void* stream;
+  // forward: sr, hr -> ds_sr, ds_hr, ixy_sr, ixy_hr, loss_out ; backward: ixy, ds, grad_out -> d_img
+  const float *sr = nullptr, *hr = nullptr, *ixy = nullptr, *ds = nullptr, *grad_out = nullptr;
+  float *ds_sr = nullptr, *ds_hr = nullptr, *ixy_sr = nullptr, *ixy_hr = nullptr, *loss_out = nullptr, *d_img = nullptr;
+  int px = 0;                                            // forward: also reduce the fused Pixel (MSE) term into loss_out[1]
+  const float *px_img = nullptr, *px_other = nullptr, *grad_px = nullptr;  // backward: image pair + upstream gradient of the MSE term
+  int B = 0, H = 0, W = 0, normalize = 1, vec4 = 0;
+  float eps = 0.f;
+  void* workspace = nullptr;
+  const float *g = nullptr, *dg = nullptr, *k = nullptr;
+  int rs = 0, rk = 0;
+  void* stream = nullptr;
 };
-
-//                            TW  LG GR VS HC (warps per role)
-using StreamA = StStreamCfg<64, 4, 4, 5, 8>;
-
-// Streaming forward: auto-selected for (2, 8) filters on 16-byte aligned tensors when the problem
-// has enough rows per SM to keep the pipeline full; SRST_ST_STREAM=0/1 forces it off/on.
-template <class C>
-static int launch_st_stream(const StCall& c) {
-  StStreamParams P;
-  P.sr = c.a; P.hr = c.b; P.ds_sr = c.o0; P.ds_hr = c.o1;
-  P.ticket = reinterpret_cast<unsigned int*>(c.workspace);
-  P.partials = reinterpret_cast<float*>(c.workspace) + 4;
-  P.loss_out = c.loss_out;
-  P.B = c.B; P.H = c.H; P.W = c.W;
-  P.normalize = c.normalize; P.eps = c.eps;
-  P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
-  // SRST_ST_STREAM_DEBUG=1: CTA 0 dumps per-warp (work, wait) cycles at byte 2048 of the workspace
-  P.debug = env_int("SRST_ST_STREAM_DEBUG", 0) ? reinterpret_cast<long long*>(reinterpret_cast<char*>(c.workspace) + 2048) : nullptr;
-  fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
-  const int nsm = sm_count();
-  P.nstrips = (c.W + C::TW - 1) / C::TW;
-  const long long cols = (long long)c.B * P.nstrips;
-  long long want = (2LL * nsm + cols - 1) / cols;           // row segments per strip for ~2 units per SM
-  const long long max_segs = c.H / 32 > 0 ? c.H / 32 : 1;
-  if (want > max_segs) want = max_segs;
-  if (want < 1) want = 1;
-  P.segh = (int)(((c.H + want - 1) / want + 15) / 16 * 16);
-  P.nsegs = (c.H + P.segh - 1) / P.segh;
-  const long long nunits = cols * P.nsegs;
-  if (nunits > 0x7fffffffLL) return SRST_E_SHAPE;
-  P.nunits = (int)nunits;
-  int e = ensure_smem<C>(st_stream_forward_kernel<C>, C::SMEM_BYTES);
-  if (e) return e;
-  const int grid = nunits < nsm ? (int)nunits : nsm;
-  SRST_LAUNCH(st_stream_forward_kernel<C>, dim3(grid), dim3(C::NT), C::SMEM_BYTES, c.stream, P);
-  return (int)cudaGetLastError();
-}
 
 template <int RG, int RK>
 static int st_forward_rr(const StCall& c) {
-  StFwdParams<RG, RK> P;
-  P.sr = c.a; P.hr = c.b; P.ds_sr = c.o0; P.ds_hr = c.o1; P.gray_sr = c.gray0; P.gray_hr = c.gray1;
+  static thread_local StFwdParams<RG, RK> P;  // ~0.5 KB of taps: filled in place, passed by reference to the launcher
+  P.sr = c.sr; P.hr = c.hr; P.ds_sr = c.ds_sr; P.ds_hr = c.ds_hr; P.ixy_sr = c.ixy_sr; P.ixy_hr = c.ixy_hr;
   P.ticket = reinterpret_cast<unsigned int*>(c.workspace);
   P.partials = reinterpret_cast<float*>(c.workspace) + 4;
   P.px_partials = c.px ? reinterpret_cast<float*>(reinterpret_cast<char*>(c.workspace) + st_partials_bytes(c.B, c.H, c.W))
@@ -320,63 +323,55 @@ static int st_forward_rr(const StCall& c) {
   P.B = c.B; P.H = c.H; P.W = c.W; P.tiles_x = P.tiles_y = 0;
   P.normalize = c.normalize; P.vec4 = c.vec4; P.eps = c.eps;
   P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
-  // SRST_ST_DEBUG=1: CTA 0 writes per-warp phase time stamps at byte 4096 of the workspace (tools/wide_debug.py)
-  P.debug = env_int("SRST_ST_DEBUG", 0) ? reinterpret_cast<long long*>(reinterpret_cast<char*>(c.workspace) + 4096) : nullptr;
-  fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
+  P.taps = cached_taps<RG, RK>(c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
-    if (c.vec4 && !c.gray0 && !c.gray1 && !c.px && env_int("SRST_ST_STREAM", 0) == 1) return launch_st_stream<StreamA>(c);
     const int cfg = pick_fwd_cfg(c.H, c.W);
     if (c.px) {  // the fused Pixel term is compiled into the two default tile shapes only
-      if (cfg == 2 || (cfg != 3 && c.W <= 96)) return launch_st_forward<FwdC, true>(P, c.stream);
-      return launch_st_forward<FwdD, true>(P, c.stream);
+      if (cfg == 0 || (cfg != 1 && c.W <= 96)) return launch_st_forward<Fwd0, true>(P, c.stream);
+      return launch_st_forward<Fwd1, true>(P, c.stream);
     }
-    if (cfg == 10 && c.vec4 && !c.gray0 && !c.gray1) return launch_st_wide_forward<WideA>(P, c.stream);
     switch (cfg) {
-      case 0: return launch_st_forward<FwdA>(P, c.stream);
-      case 1: return launch_st_forward<FwdB>(P, c.stream);
-      case 2: return launch_st_forward<FwdC>(P, c.stream);
-      case 4: return launch_st_forward<FwdE>(P, c.stream);
-      case 5: return launch_st_forward<FwdF>(P, c.stream);
-      case 6: return launch_st_forward<FwdG>(P, c.stream);
-      case 7: return launch_st_forward<FwdH>(P, c.stream);
-      case 8: return launch_st_forward<FwdI>(P, c.stream);
-      case 9: return launch_st_forward<FwdJ>(P, c.stream);
-      default: return launch_st_forward<FwdD>(P, c.stream);
+      case 0: return launch_st_forward<Fwd0>(P, c.stream);
+      case 2: return launch_st_forward<Fwd2>(P, c.stream);
+      case 3: return launch_st_forward<Fwd3>(P, c.stream);
+      case 4: return launch_st_forward<Fwd4>(P, c.stream);
+      case 5: return launch_st_forward<Fwd5>(P, c.stream);
+      case 6: return launch_st_forward<Fwd6>(P, c.stream);
+      case 7: return launch_st_forward<Fwd7>(P, c.stream);
+      default: return launch_st_forward<Fwd1>(P, c.stream);
     }
   } else {
-    using G = StFwdCfg<32, 64, 16, 4, 0, RG, RK, (RK <= 8 ? 2 : 1)>;
+    using G = StFwdCfg<32, 64, 16, 4, RG, RK, (RK <= 8 ? 2 : 1)>;
     return c.px ? launch_st_forward<G, true>(P, c.stream) : launch_st_forward<G>(P, c.stream);
   }
 }
 
 template <int RG, int RK>
 static int st_backward_rr(const StCall& c) {
-  StBwdParams<RG, RK> P;
-  std::memset(&P.ds_map, 0, sizeof(P.ds_map));
-  std::memset(&P.gray_map, 0, sizeof(P.gray_map));
-  P.use_tma = 0; P.use_gray = 0; P.debug = nullptr;
-  P.img = c.a; P.ds = c.b; P.grad_out = c.grad_out; P.d_img = c.o0;
-  P.px_other = c.px_other; P.grad_px = c.grad_px;
+  static thread_local StBwdParams<RG, RK> P;
+  P.use_tma = 0;
+  P.ds = c.ds; P.ixy = c.ixy; P.grad_out = c.grad_out; P.d_img = c.d_img;
+  P.img = c.px_img; P.px_other = c.px_other; P.grad_px = c.grad_px;
   P.B = c.B; P.H = c.H; P.W = c.W; P.tiles_x = P.tiles_y = 0;
   P.vec4 = c.vec4;
   P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
-  fill_taps(P.taps, c.g, c.dg, c.rs, c.k, c.rk);
+  P.taps = cached_taps<RG, RK>(c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
     if (c.px_other) {  // the fused Pixel term is compiled into the two default tile shapes only
-      if (c.W <= 96) return launch_st_backward<BwdH, true>(P, c.gray, c.stream);
-      return launch_st_backward<BwdF, true>(P, c.gray, c.stream);
+      if (c.W <= 96) return launch_st_backward<Bwd1, true>(P, c.stream);
+      return launch_st_backward<Bwd0, true>(P, c.stream);
     }
     switch (pick_bwd_cfg(c.B, c.H, c.W)) {
-      case 3: return launch_st_backward<BwdD>(P, c.gray, c.stream);
-      case 5: return launch_st_backward<BwdF>(P, c.gray, c.stream);
-      case 6: return launch_st_backward<BwdG>(P, c.gray, c.stream);
-      case 7: return launch_st_backward<BwdH>(P, c.gray, c.stream);
-      case 8: return launch_st_backward<BwdI>(P, c.gray, c.stream);
-      default: return launch_st_backward<BwdA>(P, c.gray, c.stream);
+      case 1: return launch_st_backward<Bwd1>(P, c.stream);
+      case 2: return launch_st_backward<Bwd2>(P, c.stream);
+      case 3: return launch_st_backward<Bwd3>(P, c.stream);
+      case 4: return launch_st_backward<Bwd4>(P, c.stream);
+      case 5: return launch_st_backward<Bwd5>(P, c.stream);
+      default: return launch_st_backward<Bwd0>(P, c.stream);
     }
   } else {
-    using G = StBwdCfg<24, 64, (24 + 2 * RG) / 2, 256, RG, RK, (RK <= 8 ? 2 : 1)>;
-    return c.px_other ? launch_st_backward<G, true>(P, c.gray, c.stream) : launch_st_backward<G>(P, c.gray, c.stream);
+    using G = StBwdCfg<24, 64, (24 + 2 * RG) / 2, 256, RG, RK, (RK <= 8 ? 2 : 1), 4>;
+    return c.px_other ? launch_st_backward<G, true>(P, c.stream) : launch_st_backward<G>(P, c.stream);
   }
 }
 
@@ -396,57 +391,58 @@ extern "C" {
 
 int srst_st_forward(const float* sr, const float* hr, int B, int H, int W, const float* g, const float* dg,
                     int r_sigma, const float* k, int r_rho, int normalize, float eps, float* loss_out,
-                    float* ds_sr, float* ds_hr, float* gray_sr, float* gray_hr, void* workspace,
+                    float* ds_sr, float* ds_hr, float* ixy_sr, float* ixy_hr, void* workspace,
                     size_t workspace_bytes, void* stream) {
   if (!sr || !hr || !g || !dg || !k || !loss_out || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
   if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
   if (!workspace || !aligned16(workspace) || workspace_bytes < srst_st_workspace_bytes(B, H, W))
     return SRST_E_WORKSPACE;
-  StCall c{};
-  c.a = sr; c.b = hr; c.o0 = ds_sr; c.o1 = ds_hr; c.loss_out = loss_out; c.gray0 = gray_sr; c.gray1 = gray_hr;
+  StCall c;
+  c.sr = sr; c.hr = hr; c.ds_sr = ds_sr; c.ds_hr = ds_hr; c.ixy_sr = ixy_sr; c.ixy_hr = ixy_hr; c.loss_out = loss_out;
   c.B = B; c.H = H; c.W = W; c.normalize = normalize ? 1 : 0; c.eps = eps;
   c.vec4 = (W % 4 == 0 && aligned16(sr) && aligned16(hr) && (!ds_sr || aligned16(ds_sr)) &&
-            (!ds_hr || aligned16(ds_hr)) && (!gray_sr || aligned16(gray_sr)) && (!gray_hr || aligned16(gray_hr))) ? 1 : 0;
+            (!ds_hr || aligned16(ds_hr)) && (!ixy_sr || aligned16(ixy_sr)) && (!ixy_hr || aligned16(ixy_hr))) ? 1 : 0;
   c.workspace = workspace; c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;
   return st_dispatch(c, true);
 }
 
-int srst_st_backward(const float* img, const float* gray, const float* ds, const float* grad_out, int B, int H, int W,
+int srst_st_backward(const float* ixy, const float* ds, const float* grad_out, int B, int H, int W,
                      const float* g, const float* dg, int r_sigma, const float* k, int r_rho, float* d_img,
                      void* stream) {
-  if (!img || !ds || !grad_out || !g || !dg || !k || !d_img || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
+  if (!ixy || !ds || !grad_out || !g || !dg || !k || !d_img || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
   if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
-  StCall c{};
-  c.a = img; c.b = ds; c.grad_out = grad_out; c.o0 = d_img; c.gray = gray;
+  StCall c;
+  c.ixy = ixy; c.ds = ds; c.grad_out = grad_out; c.d_img = d_img;
   c.B = B; c.H = H; c.W = W;
-  c.vec4 = (W % 4 == 0 && aligned16(img) && aligned16(d_img) && aligned16(ds)) ? 1 : 0;
+  c.vec4 = (W % 4 == 0 && aligned16(d_img) && aligned16(ds)) ? 1 : 0;
   c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;
   return st_dispatch(c, false);
 }
 
 int srst_stpx_forward(const float* sr, const float* hr, int B, int H, int W, const float* g, const float* dg,
                       int r_sigma, const float* k, int r_rho, int normalize, float eps, float* loss2_out, float* ds_sr,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      float* ixy_sr, void* workspace, size_t workspace_bytes, void* stream) {
   if (!sr || !hr || !g || !dg || !k || !loss2_out || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
   if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
   if (!workspace || !aligned16(workspace) || workspace_bytes < srst_st_workspace_bytes(B, H, W))
     return SRST_E_WORKSPACE;
-  StCall c{};
-  c.a = sr; c.b = hr; c.o0 = ds_sr; c.loss_out = loss2_out; c.px = 1;
+  StCall c;
+  c.sr = sr; c.hr = hr; c.ds_sr = ds_sr; c.ixy_sr = ixy_sr; c.loss_out = loss2_out; c.px = 1;
   c.B = B; c.H = H; c.W = W; c.normalize = normalize ? 1 : 0; c.eps = eps;
-  c.vec4 = (W % 4 == 0 && aligned16(sr) && aligned16(hr) && (!ds_sr || aligned16(ds_sr))) ? 1 : 0;
+  c.vec4 = (W % 4 == 0 && aligned16(sr) && aligned16(hr) && (!ds_sr || aligned16(ds_sr)) &&
+            (!ixy_sr || aligned16(ixy_sr))) ? 1 : 0;
   c.workspace = workspace; c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;
   return st_dispatch(c, true);
 }
 
-int srst_stpx_backward(const float* sr, const float* hr, const float* ds, const float* grad_st, const float* grad_px,
-                       int B, int H, int W, const float* g, const float* dg, int r_sigma, const float* k, int r_rho,
-                       float* d_sr, void* stream) {
-  if (!sr || !hr || !ds || !grad_st || !grad_px || !g || !dg || !k || !d_sr || B <= 0 || H <= 0 || W <= 0)
+int srst_stpx_backward(const float* sr, const float* hr, const float* ixy, const float* ds, const float* grad_st,
+                       const float* grad_px, int B, int H, int W, const float* g, const float* dg, int r_sigma,
+                       const float* k, int r_rho, float* d_sr, void* stream) {
+  if (!sr || !hr || !ixy || !ds || !grad_st || !grad_px || !g || !dg || !k || !d_sr || B <= 0 || H <= 0 || W <= 0)
     return SRST_E_INVALID;
   if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
-  StCall c{};
-  c.a = sr; c.b = ds; c.grad_out = grad_st; c.o0 = d_sr; c.px_other = hr; c.grad_px = grad_px;
+  StCall c;
+  c.ixy = ixy; c.ds = ds; c.grad_out = grad_st; c.d_img = d_sr; c.px_img = sr; c.px_other = hr; c.grad_px = grad_px;
   c.B = B; c.H = H; c.W = W;
   c.vec4 = (W % 4 == 0 && aligned16(sr) && aligned16(hr) && aligned16(d_sr) && aligned16(ds)) ? 1 : 0;
   c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;

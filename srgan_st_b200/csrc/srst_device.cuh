@@ -45,8 +45,8 @@ namespace srst {
 
 #ifndef SRST_EMULATE
 inline bool pdl_enabled() {
-  const char* e = std::getenv("SRST_PDL");
-  return !(e && e[0] == '0');
+  static const bool on = [] { const char* e = std::getenv("SRST_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 #endif
 // Programmatic dependent launch hooks (no-ops for kernels launched without the PDL attribute):
@@ -117,8 +117,10 @@ SRST_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "m
 // mbarrier that every consumer thread polls.
 #ifdef SRST_EMULATE
 struct SrstTmap { const float* base; int W, H, P; };
-SRST_DEV void tma_stage_begin(unsigned long long* mbar, float* dst, const SrstTmap* m, int x, int y, int z, int bw,
-                              int bh, int bp) {
+SRST_DEV void tma_barrier_init(unsigned long long* mbar) { (void)mbar; }
+SRST_DEV void tma_expect(unsigned long long* mbar, unsigned bytes) { (void)mbar; (void)bytes; }
+SRST_DEV void tma_load_3d(unsigned long long* mbar, float* dst, const SrstTmap* m, int x, int y, int z, int bw,
+                          int bh, int bp) {
   (void)mbar;
   for (int p = 0; p < bp; ++p)
     for (int r = 0; r < bh; ++r)
@@ -128,27 +130,36 @@ SRST_DEV void tma_stage_begin(unsigned long long* mbar, float* dst, const SrstTm
         dst[(p * bh + r) * bw + c] = ok ? m->base[((size_t)gp * m->H + gy) * m->W + gx] : 0.f;
       }
 }
-SRST_DEV void tma_stage_wait(unsigned long long* mbar) { (void)mbar; }
+SRST_DEV void tma_wait(unsigned long long* mbar) { (void)mbar; }
 #else
 }  // namespace srst
 #include <cuda.h>
 namespace srst {
 typedef CUtensorMap SrstTmap;
-SRST_DEV void tma_stage_begin(unsigned long long* mbar, float* dst, const SrstTmap* m, int x, int y, int z, int bw,
-                              int bh, int bp) {
+// One mbarrier can collect several box copies: init (one arriving thread), announce the total byte
+// count once, then issue the copies.  (bw, bh, bp) repeat the box dimensions encoded in the tensor
+// map; only the emulation reads them.
+SRST_DEV void tma_barrier_init(unsigned long long* mbar) {
   const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
-  const unsigned sdst = (unsigned)__cvta_generic_to_shared(dst);
-  const unsigned bytes = (unsigned)(bw * bh * bp * 4);
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+SRST_DEV void tma_expect(unsigned long long* mbar, unsigned bytes) {
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+SRST_DEV void tma_load_3d(unsigned long long* mbar, float* dst, const SrstTmap* m, int x, int y, int z, int bw,
+                          int bh, int bp) {
+  (void)bw; (void)bh; (void)bp;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
+  const unsigned sdst = (unsigned)__cvta_generic_to_shared(dst);
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(sdst), "l"(reinterpret_cast<unsigned long long>(m)), "r"(x), "r"(y), "r"(z), "r"(bar)
       : "memory");
 }
-SRST_DEV void tma_stage_wait(unsigned long long* mbar) {
+SRST_DEV void tma_wait(unsigned long long* mbar) {
   const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
   unsigned done = 0;
   while (!done) {

@@ -6,9 +6,10 @@
 //   st_forward_kernel : RGB tile (+halo) of SR and HR -> grayscale -> Gaussian-derivative
 //                       gradients Ix, Iy -> products -> separable rho-smoothing -> per-pixel
 //                       det-normalise, adj(S1)*S2, eigenvalues, log-distance  -> block partial of
-//                       the loss AND the per-pixel d(distance)/d(Jxx,Jyy,Jxy) ("ds" planes).
-//   st_backward_kernel: ds planes -> adjoint rho-smoothing -> product rule with recomputed Ix, Iy
-//                       -> adjoint derivative filters -> grayscale weights -> d_img.
+//                       the loss, the per-pixel d(distance)/d(Jxx,Jyy,Jxy) ("ds" planes) AND the
+//                       gradient planes Ix, Iy ("ixy", row-pair interleaved) the backward re-uses.
+//   st_backward_kernel: ds planes + saved Ix, Iy (two TMA box copies) -> adjoint rho-smoothing ->
+//                       product rule -> adjoint derivative filters -> grayscale weights -> d_img.
 //
 // Both are FP32 CUDA-core stencils (no tensor cores by design: see DESIGN.md).  The measured
 // bound on B200 is the FP32 pipe (128 lane-FMA/clk/SM, tools/ubench_fma.cu), not HBM, so the
@@ -20,9 +21,13 @@
 //     multiply one value (broadcast) by the tap PAIR (k[t], k[t-1]) that maps it onto the two
 //     output rows.  Both operand forms are native (FFMA2 Rd, Ra.F32, URb.F32x2, Rc), so a 17-tap
 //     pass costs 17 issue slots per pixel pair and no register moves;
-//   * horizontal passes are register-blocked (4 columns x 2 rows per thread, LDS.128 on a pitch
-//     == 4 mod 8), vertical passes own one column and RS rows (conflict-free LDS.64/STS.64);
-//   * taps live in kernel parameters and every tap index is a compile-time constant.
+//   * horizontal passes are register-blocked (4 or 8 columns x 2 rows per thread, LDS.128 on a pitch
+//     == 4 mod 8, lanes grouped so that every quarter-warp hits eight distinct 16-byte bank groups:
+//     ItemMap), vertical passes own one column and RS rows (conflict-free LDS.64/STS.64);
+//   * taps live in kernel parameters and every tap index is a compile-time constant;
+//   * the forward runs the SR and the HR image through ONE copy of the filter code (a rolled loop)
+//     and parks each image's smoothed tensor in a thread-private shared-memory slot, so the
+//     per-pixel chain starts with an empty register file (no spills) and is itself a rolled loop.
 #pragma once
 #include "srst_device.cuh"
 
@@ -40,14 +45,21 @@ struct StTaps {
   float2 kp[2 * RK + 2];
 };
 
+// Saved gradient planes ("ixy"): [B][2][ceil(H/2)][W][2] fp32 -- plane 0 = Ix, plane 1 = Iy, each stored
+// row-pair interleaved exactly like the shared-memory planes (rows 2p and 2p+1 of column c are the
+// two floats at ((b*2+plane)*Hp + p)*2W + 2c), so that the backward fetches its tile with one TMA box.
+SRST_DEV size_t ixy_offset(int b, int plane, int Hp, int W, int rowpair, int col) {
+  return (((size_t)b * 2 + plane) * Hp + rowpair) * (size_t)(2 * W) + 2 * (size_t)col;
+}
+
 template <int RG, int RK>
 struct StFwdParams {
   const float* sr;
   const float* hr;
-  float* ds_sr;  // [B,3,H,W] or null
-  float* ds_hr;  // [B,3,H,W] or null
-  float* gray_sr;  // [B,H,W] or null: grayscale planes saved for the backward pass
-  float* gray_hr;
+  float* ds_sr;   // [B,3,H,W] or null
+  float* ds_hr;   // [B,3,H,W] or null
+  float* ixy_sr;  // saved gradient planes of SR (see ixy_offset) or null
+  float* ixy_hr;
   float* partials;
   float* px_partials;  // null, or per-CTA partials of sum (sr-hr)^2: the fused "Pixel" MSE term (warmup.py:88-96)
   unsigned int* ticket;
@@ -57,35 +69,33 @@ struct StFwdParams {
   int vec4;  // 1: W % 4 == 0 and all base pointers 16-byte aligned
   float eps;
   float inv_count;
-  long long* debug;  // optional (SRST_ST_DEBUG=1): per-warp phase time stamps of CTA 0
   StTaps<RG, RK> taps;
 };
 
 template <int RG, int RK>
 struct StBwdParams {
-  SrstTmap ds_map;    // tensor map of ds viewed as [B*3][H][W] (valid when use_tma)
-  SrstTmap gray_map;  // tensor map of the saved gray planes [B][H][W] (valid when use_gray)
-  const float* img;
+  SrstTmap ds_map;   // tensor map of ds viewed as [B*3][H][W]            (valid when use_tma)
+  SrstTmap ixy_map;  // tensor map of ixy viewed as [B*2][ceil(H/2)][2W]  (valid when use_tma)
   const float* ds;
+  const float* ixy;
   const float* grad_out;
-  const float* px_other;  // null, or the other image of the pair: adds grad_px * 2 (img - other) / (3 B H W) to d_img
+  const float* img;       // fused Pixel term only: the image d_img belongs to ...
+  const float* px_other;  // ... and the other image of the pair: adds grad_px * 2 (img - other) / (3 B H W) to d_img
   const float* grad_px;   // upstream gradient of the MSE term (device scalar)
   float* d_img;
   int B, H, W, tiles_x, tiles_y;
   int vec4;
   int use_tma;
-  int use_gray;  // 1: the gray tile comes from gray_map by TMA instead of RGB loads + conversion
   float inv_count;
-  int early_ctas;  // CTAs [0, early_ctas) -- the first wave -- load the image and rebuild Ix, Iy BEFORE waiting for the
-                   // previous kernel of the stream (programmatic dependent launch): that work only reads inputs
-  long long* debug;
   StTaps<RG, RK> taps;
 };
+
 
 SRST_DEV float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 SRST_DEV float2 bcast2(float v) { return make_float2(v, v); }
 SRST_DEV float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 SRST_DEV void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+
 
 // ------------------------------------------------------------------------------------------------
 // Per-pixel chain: utils.py:236-279 forward and its adjoint.
@@ -105,81 +115,6 @@ struct StPixelGrad {
 SRST_DEV float rsqrt_nr(float x) {
   const float y = fast_rsqrt(x);
   return y * fmaf(-0.5f * x, y * y, 1.5f);  // one Newton step; NaN for x < 0 like 1/sqrt(x)
-}
-
-template <bool WANT_SR, bool WANT_HR>
-SRST_DEV float st_pixel(float a, float b, float c, float e, float f, float h, bool normalize, float eps,
-                        StPixelGrad& G) {
-  constexpr float kLn2 = 0.6931471805599453f;
-  float iq1 = 1.0f, iq2 = 1.0f;
-  if (normalize) {
-    iq1 = rsqrt_nr(fmaf(a, b, -c * c) + eps);
-    iq2 = rsqrt_nr(fmaf(e, f, -h * h) + eps);
-  }
-  const float ah = a * iq1, bh = b * iq1, ch = c * iq1;
-  const float eh = e * iq2, fh = f * iq2, hh = h * iq2;
-  const float chh = ch * hh;
-  const float A = fmaf(bh, eh, -chh);
-  const float Bm = fmaf(ah, fh, -chh);
-  const float Cc = fmaf(bh, hh, -ch * fh);
-  const float Dd = fmaf(ah, hh, -ch * eh);
-  const float T = A + Bm;
-  const float amb = A - Bm;
-  const float disc_raw = fmaf(amb, amb, 4.0f * (Cc * Dd));
-  const float disc = (disc_raw < eps) ? eps : disc_raw;
-  const float ir = fast_rsqrt(disc);
-  const float r = disc * ir;
-  const float hT = 0.5f * T;
-  const float l1r = fmaf(-0.5f, r, hT), l2r = fmaf(0.5f, r, hT);
-  const float l1 = (l1r < 1.0f) ? 1.0f : l1r;
-  const float l2 = (l2r < 1.0f) ? 1.0f : l2r;
-  // natural logs: det M == 1 makes l1 <= 1 <= l2, so L1 is 0 except for rounding stragglers
-  const float L1 = kLn2 * fast_lg2(l1), L2 = kLn2 * fast_lg2(l2);
-  const float arg = fmaf(L1, L1, fmaf(L2, L2, eps));
-  const float inv_d = fast_rsqrt(arg);
-  const float d = arg * inv_d;
-  if (WANT_SR || WANT_HR) {
-    const float dl1 = (l1r >= 1.0f) ? (L1 * inv_d) * fast_rcp(l1) : (l1r * 0.0f);  // x*0 keeps NaN
-    const float dl2 = (l2r >= 1.0f) ? (L2 * inv_d) * fast_rcp(l2) : (l2r * 0.0f);
-    const float dr = 0.5f * (dl2 - dl1);
-    const float ddisc = (disc_raw >= eps) ? (0.5f * dr * ir) : (disc_raw * 0.0f);
-    const float dT = fmaf(2.0f * T, ddisc, 0.5f * (dl1 + dl2));
-    const float dd4 = 4.0f * ddisc;
-    const float dA = fmaf(-dd4, Bm, dT);
-    const float dB = fmaf(-dd4, A, dT);
-    const float dC = dd4 * Dd;
-    const float dD = dd4 * Cc;
-    if (WANT_SR) {
-      const float dah = fmaf(dB, fh, dD * hh);
-      const float dbh = fmaf(dA, eh, dC * hh);
-      const float dch = -fmaf(dA + dB, hh, fmaf(dC, fh, dD * eh));
-      if (normalize) {
-        // S^ = S/q, q = sqrt(det+eps): dS = dS^/q - S * <S,dS^>/(2 q^3) * d(det)/dS
-        const float s = fmaf(a, dah, fmaf(b, dbh, c * dch));
-        const float ddet = (-0.5f * s) * (iq1 * iq1) * iq1;
-        G.da = fmaf(dah, iq1, ddet * b);
-        G.db = fmaf(dbh, iq1, ddet * a);
-        G.dc = fmaf(dch, iq1, -2.0f * ddet * c);
-      } else {
-        G.da = dah; G.db = dbh; G.dc = dch;
-      }
-    }
-    if (WANT_HR) {
-      const float deh = fmaf(dA, bh, -dD * ch);
-      const float dfh = fmaf(dB, ah, -dC * ch);
-      const float dhh = fmaf(-(dA + dB), ch, fmaf(dC, bh, dD * ah));
-      if (normalize) {
-        const float s = fmaf(e, deh, fmaf(f, dfh, h * dhh));
-        const float ddet = (-0.5f * s) * (iq2 * iq2) * iq2;
-        G.de = fmaf(deh, iq2, ddet * f);
-        G.df = fmaf(dfh, iq2, ddet * e);
-        G.dh = fmaf(dhh, iq2, -2.0f * ddet * h);
-      } else {
-        G.de = deh; G.df = dfh; G.dh = dhh;
-      }
-    }
-  }
-  return d;
 }
 
 // Packed form of st_pixel: the same chain on TWO pixels at once (.x = even row, .y = odd row of a
@@ -277,57 +212,6 @@ SRST_DEV float2 st_pixel2(float2 a, float2 b, float2 c, float2 e, float2 f, floa
   return d;
 }
 
-// Chain + stores for one thread's 2 x 4 pixels; returns the sum of the valid distances.
-template <bool WANT_HR>
-SRST_DEV float st_chain_store(const float2 (&S1)[3][4], const float2 (&S2)[3][4], bool norm, float eps,
-                              float* __restrict__ ds_sr, float* __restrict__ ds_hr, size_t img_off, int H, int W,
-                              int gy0, int gx0, bool vec4) {
-  float lsum = 0.f;
-  float2 gs[3][4], gh[3][4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    StPixelGrad2 G;
-    G.da = G.db = G.dc = G.de = G.df = G.dh = make_float2(0.f, 0.f);
-    const float2 d = st_pixel2<true, WANT_HR>(S1[0][j], S1[1][j], S1[2][j], S2[0][j], S2[1][j], S2[2][j], norm, eps, G);
-    const bool okx = gx0 + j < W;
-    lsum += (okx && gy0 < H) ? d.x : 0.f;
-    lsum += (okx && gy0 + 1 < H) ? d.y : 0.f;
-    gs[0][j] = G.da; gs[1][j] = G.db; gs[2][j] = G.dc;
-    if (WANT_HR) { gh[0][j] = G.de; gh[1][j] = G.df; gh[2][j] = G.dh; }
-  }
-  if (gx0 >= W) return lsum;
-  const size_t plane = (size_t)H * W;
-#pragma unroll
-  for (int hf = 0; hf < 2; ++hf) {
-    if (gy0 + hf >= H) continue;
-    const size_t o = img_off + (size_t)(gy0 + hf) * W + gx0;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float v0 = hf ? gs[c][0].y : gs[c][0].x, v1 = hf ? gs[c][1].y : gs[c][1].x;
-      const float v2 = hf ? gs[c][2].y : gs[c][2].x, v3 = hf ? gs[c][3].y : gs[c][3].x;
-      float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-      if (WANT_HR) {
-        w0 = hf ? gh[c][0].y : gh[c][0].x; w1 = hf ? gh[c][1].y : gh[c][1].x;
-        w2 = hf ? gh[c][2].y : gh[c][2].x; w3 = hf ? gh[c][3].y : gh[c][3].x;
-      }
-      if (vec4) {
-        if (ds_sr) st4(ds_sr + o + c * plane, make_float4(v0, v1, v2, v3));
-        if (WANT_HR) st4(ds_hr + o + c * plane, make_float4(w0, w1, w2, w3));
-      } else {
-        const float vv[4] = {v0, v1, v2, v3}, ww[4] = {w0, w1, w2, w3};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (gx0 + j < W) {
-            if (ds_sr) ds_sr[o + c * plane + j] = vv[j];
-            if (WANT_HR) ds_hr[o + c * plane + j] = ww[j];
-          }
-        }
-      }
-    }
-  }
-  return lsum;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Shared building blocks (row-pair interleaved planes: float2 at rp*PITCH + 2*col)
 // ------------------------------------------------------------------------------------------------
@@ -336,13 +220,12 @@ SRST_DEV float st_chain_store(const float2 (&S1)[3][4], const float2 (&S2)[3][4]
 // convert to grayscale, store row-pair interleaved into sG; zero outside the image (the reference
 // zero-pads: padding='same', utils.py:219-222).  ROWS even; gx0 and COLS multiples of 4.
 // DEPTH items (6 x LDG.128 each) are in flight per thread before the first conversion.
-// If `gray_out` ([H][W] plane of this image) is given, the pixels of the tile interior
-// rows [iy0, iy1) x cols [ix0, ix1) are also written there (once per pixel across tiles).
+// PX: the fused Pixel term -- when `px_other` (the other image of the pair) is given, the squared RGB
+// difference over the tile interior rows [iy0, iy1) x cols [ix0, ix1) is accumulated into *px_acc.
 template <int ROWS, int COLS, int PITCH, int NT, int DEPTH, bool PX = false>
 SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, int W, int gy0, int gx0,
-                             bool vec4, int tid, float* __restrict__ gray_out = nullptr, int iy0 = 0, int iy1 = 0,
-                             int ix0 = 0, int ix1 = 0, const float* __restrict__ px_other = nullptr,
-                             float* px_acc = nullptr) {
+                             bool vec4, int tid, int iy0 = 0, int iy1 = 0, int ix0 = 0, int ix1 = 0,
+                             const float* __restrict__ px_other = nullptr, float* px_acc = nullptr) {
   constexpr int C4 = COLS / 4;
   constexpr int NITEM = (ROWS / 2) * C4;
   const size_t plane = (size_t)H * W;
@@ -386,15 +269,6 @@ SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, i
         float* o = sG + q * PITCH + 8 * c4;
         st4(o, make_float4(v[0][0], v[1][0], v[0][1], v[1][1]));
         st4(o + 4, make_float4(v[0][2], v[1][2], v[0][3], v[1][3]));
-        if (gray_out) {
-          const int gx = gx0 + 4 * c4;
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int gy = gy0 + 2 * q + hf;
-            if (ok[u][hf] && gy >= iy0 && gy < iy1 && gx >= ix0 && gx < ix1)
-              st4(gray_out + (size_t)gy * W + gx, make_float4(v[hf][0], v[hf][1], v[hf][2], v[hf][3]));
-          }
-        }
         if (PX && px_other) {  // fused Pixel term: squared RGB difference to the other image, tile interior only
           const int gx = gx0 + 4 * c4;
 #pragma unroll
@@ -432,7 +306,6 @@ SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, i
           if (gy >= 0 && gy < H && x >= 0 && x < W) {
             const float* p = base + (size_t)gy * W + x;
             v[hf][j] = gray_of(__ldg(p), __ldg(p + plane), __ldg(p + 2 * plane));
-            if (gray_out && gy >= iy0 && gy < iy1 && x >= ix0 && x < ix1) gray_out[(size_t)gy * W + x] = v[hf][j];
             if (PX && px_other && gy >= iy0 && gy < iy1 && x >= ix0 && x < ix1) {
               const float* po = px_other + (size_t)gy * W + x;
               const float d0 = __ldg(p) - __ldg(po), d1 = __ldg(p + plane) - __ldg(po + plane);
@@ -447,65 +320,6 @@ SRST_DEV void load_gray_tile(float* sG, const float* __restrict__ base, int H, i
       st4(o + 4, make_float4(v[0][2], v[1][2], v[0][3], v[1][3]));
     }
   }
-}
-
-// Asynchronous staging of the raw RGB rows [gy0, gy0+ROWS) x cols [gx0, gx0+COLS) of one image
-// into shared memory ([3][ROWS][COLS] row-major) with 16-byte LDGSTS copies: no registers are
-// held while the data is in flight, every copy of the tile is outstanding at once (one exposed
-// round trip per tile), and pixels outside the image are zero-filled by the copy itself.
-template <int ROWS, int COLS, int NT>
-SRST_DEV void stage_rgb_async(float* sS, const float* __restrict__ base, int H, int W, int gy0, int gx0, int tid) {
-  constexpr int C4 = COLS / 4;
-  const size_t plane = (size_t)H * W;
-  for (int it = tid; it < 3 * ROWS * C4; it += NT) {
-    const int c4 = it % C4, rc = it / C4;
-    const int r = rc % ROWS, c = rc / ROWS;
-    const int gy = gy0 + r, gx = gx0 + 4 * c4;
-    const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;  // W % 4 == 0: all-in or all-out
-    cp_async16(sS + (c * ROWS + r) * COLS + 4 * c4, ok ? base + c * plane + (size_t)gy * W + gx : base, ok);
-  }
-  cp_async_commit();
-}
-
-// Staged RGB -> grayscale, row-pair interleaved (loss.py:400-401).
-template <int ROWS, int COLS, int PITCH, int NT>
-SRST_DEV void convert_staged_gray(float* sG, const float* sS, int tid) {
-  constexpr int C4 = COLS / 4;
-  for (int it = tid; it < (ROWS / 2) * C4; it += NT) {
-    const int q = it / C4, c4 = it - q * C4;
-    float v[2][4];
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const float* p = sS + (2 * q + hf) * COLS + 4 * c4;
-      const float4 R = ld4(p), Gc = ld4(p + ROWS * COLS), Bc = ld4(p + 2 * ROWS * COLS);
-      v[hf][0] = gray_of(R.x, Gc.x, Bc.x);
-      v[hf][1] = gray_of(R.y, Gc.y, Bc.y);
-      v[hf][2] = gray_of(R.z, Gc.z, Bc.z);
-      v[hf][3] = gray_of(R.w, Gc.w, Bc.w);
-    }
-    float* o = sG + q * PITCH + 8 * c4;
-    st4(o, make_float4(v[0][0], v[1][0], v[0][1], v[1][1]));
-    st4(o + 4, make_float4(v[0][2], v[1][2], v[0][3], v[1][3]));
-  }
-}
-
-// L2 prefetch of the rows [gy0, gy0+ROWS) x cols [gx0, gx0+COLS) of the three planes of an image
-// (one prefetch per 128-byte line): issued for the HR tile before the SR tile is processed.
-template <int ROWS, int COLS, int NT>
-SRST_DEV void prefetch_tile_l2(const float* __restrict__ base, int H, int W, int gy0, int gx0, int tid) {
-#ifndef SRST_EMULATE
-  constexpr int L = (COLS + 31) / 32 + 1;
-  const size_t plane = (size_t)H * W;
-  for (int it = tid; it < ROWS * 3 * L; it += NT) {
-    const int l = it % L, rc = it / L;
-    const int c = rc % 3, r = rc / 3;
-    const int gy = gy0 + r, gx = gx0 + 32 * l;
-    if (gy >= 0 && gy < H && gx < W && gx + 31 >= 0) {
-      const float* p = base + c * plane + (size_t)gy * W + max(gx, 0);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
-  }
-#endif
 }
 
 // Gaussian-derivative filter pair on a row pair, CS output columns:
@@ -557,44 +371,6 @@ SRST_DEV void grad_rowpair_rows(const float* const (&pa)[RG + 1], const float* c
   }
 }
 
-// Same filter pair from a ROW-MAJOR plane (row pitch PITCH floats): `p` points at (first input row,
-// window start column); rows 2q and 2q+1 are loaded separately and used as broadcast scalars.
-template <int RG, int CS, int WIN, int CEN, int PITCH, class Taps>
-SRST_DEV void grad_rowpair_rm(const float* p, const Taps& tp, float2 (&ox)[CS], float2 (&oy)[CS]) {
-  static_assert(RG % 2 == 0 && WIN % 4 == 0, "row-major gradient window must be a multiple of 4 columns");
-  float2 tA[WIN], tB[WIN];
-#pragma unroll
-  for (int j = 0; j < WIN; ++j) { tA[j] = make_float2(0.f, 0.f); tB[j] = make_float2(0.f, 0.f); }
-#pragma unroll
-  for (int q = 0; q <= RG; ++q) {
-    float r0[WIN], r1[WIN];
-#pragma unroll
-    for (int m = 0; m < WIN / 4; ++m) {
-      const float4 a = ld4(p + (2 * q) * PITCH + 4 * m), b = ld4(p + (2 * q + 1) * PITCH + 4 * m);
-      r0[4 * m] = a.x; r0[4 * m + 1] = a.y; r0[4 * m + 2] = a.z; r0[4 * m + 3] = a.w;
-      r1[4 * m] = b.x; r1[4 * m + 1] = b.y; r1[4 * m + 2] = b.z; r1[4 * m + 3] = b.w;
-    }
-#pragma unroll
-    for (int j = CEN - RG; j < CEN + CS + RG; ++j) {
-      tA[j] = ffma2(bcast2(r0[j]), tp.dgp[2 * q], tA[j]);
-      tA[j] = ffma2(bcast2(r1[j]), tp.dgp[2 * q + 1], tA[j]);
-      tB[j] = ffma2(bcast2(r0[j]), tp.gp[2 * q], tB[j]);
-      tB[j] = ffma2(bcast2(r1[j]), tp.gp[2 * q + 1], tB[j]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < CS; ++j) {
-    float2 sx = make_float2(0.f, 0.f), sy = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int t = 0; t <= 2 * RG; ++t) {
-      sx = ffma2(tA[CEN + j + t - RG], bcast2(tp.g[t]), sx);
-      if (t != RG) sy = ffma2(tB[CEN + j + t - RG], bcast2(tp.dg[t]), sy);
-    }
-    ox[j] = sx;
-    oy[j] = sy;
-  }
-}
-
 // Same, for planes whose RG+1 input row pairs are PITCH floats apart.
 template <int RG, int CS, int WIN, int CEN, int PITCH, bool SAME, class Taps>
 SRST_DEV void grad_rowpair(const float* pa, const float* pb, const Taps& tp, float2 (&ox)[CS], float2 (&oy)[CS]) {
@@ -623,44 +399,40 @@ SRST_DEV void smooth_h_rowpair_n(const float* row, const Taps& tp, float2 (&out)
     out[j] = s;
   }
 }
-
-template <int RK, int WIN, int CEN, class Taps>
-SRST_DEV void smooth_h_rowpair(const float* row, const Taps& tp, float2 (&out)[4]) {
-  float2 v[WIN];
-#pragma unroll
-  for (int m = 0; m < WIN / 2; ++m) {
-    const float4 t = ld4(row + 4 * m);
-    v[2 * m] = make_float2(t.x, t.y);
-    v[2 * m + 1] = make_float2(t.z, t.w);
+// ------------------------------------------------------------------------------------------------
+// Lane -> item mapping of the register-blocked (row pair x CS columns) phases.  An item reads
+// LDS.128 windows at q*PITCH + 2*CS*seg + const with PITCH == 4 mod 8, i.e. 16-byte bank group
+// (q*odd + (CS/2)*seg) mod 8.  A quarter-warp (the unit one LDS.128 wavefront serves) is conflict
+// free when its eight lanes are 8 consecutive q of one seg, or 2 q x 4 seg (CS == 4), or 4 q x 2 seg
+// (CS == 8).  The group shape is picked from the row-pair count so that no lane pattern straddles a
+// segment boundary the way a plain it -> (it / NQ, it % NQ) split does when NQ % 8 != 0 (round 1:
+// 16 % of the backward's shared-memory wavefronts were such conflicts).
+// ------------------------------------------------------------------------------------------------
+template <int NQ_, int NSEG_, int CS_>
+struct ItemMap {
+  static constexpr int NQ = NQ_, NSEG = NSEG_, CS = CS_;
+  static constexpr int GQ = (NQ % 8 == 0) ? 8 : (CS == 4 ? 2 : 4);
+  static constexpr int GS = 8 / GQ;
+  static constexpr int NQG = (NQ + GQ - 1) / GQ, NSG = (NSEG + GS - 1) / GS;
+  static constexpr int SLOTS = NQG * NSG * 8;
+  static_assert(CS == 4 || CS == 8, "ItemMap: 4- or 8-column items");
+  SRST_DEV static bool decode(int it, int& q, int& seg) {
+    const int g = it >> 3, l = it & 7;
+    const int gs = g / NQG, gq = g - gs * NQG;
+    q = gq * GQ + (l % GQ);
+    seg = gs * GS + (l / GQ);
+    return q < NQ && seg < NSEG;
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float2 s = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int t = 0; t <= 2 * RK; ++t) s = ffma2(v[CEN + j + t - RK], bcast2(tp.k[t]), s);
-    out[j] = s;
-  }
-}
+};
 
 // ------------------------------------------------------------------------------------------------
 // Forward
-//
-// Persistent, warp-specialised CTA.  NC compute threads run the filter phases; NP producer threads
-// (one or two warps) only move data: they read the RGB tile (+halo) of the NEXT unit -- a unit is
-// one image of one tile, SR then HR -- convert it to grayscale and park it in shared memory while
-// the compute warps are still smoothing the current unit, so no compute warp ever waits on HBM/L2.
-// Hand-off uses named barriers: FULL (producer arrives, consumers sync) and EMPTY (consumers
-// arrive once the gradient phase has consumed the gray tile, producer syncs).
 // ------------------------------------------------------------------------------------------------
-constexpr int kBarFull = 1 /* +buffer (1,2) */, kBarCompute = 3, kBarEmpty = 4 /* +buffer (4,5) */;
-
-template <int TH_, int TW_, int RS_, int CSB_, int NP_, int RG_, int RK_, int MINB_, bool STAGE_ = false>
+template <int TH_, int TW_, int RS_, int CSB_, int RG_, int RK_, int MINB_, int CHU_ = 1>
 struct StFwdCfg {
-  static constexpr int TH = TH_, TW = TW_, RS = RS_, CSB = CSB_, NP = NP_, RG = RG_, RK = RK_, MINB = MINB_;
-  static constexpr bool STAGE = STAGE_;  // stage raw RGB with cp.async over D|V instead of LDG -> registers
+  static constexpr int TH = TH_, TW = TW_, RS = RS_, CSB = CSB_, RG = RG_, RK = RK_, MINB = MINB_;
+  static constexpr int CHU = CHU_;       // pixel pairs of the per-pixel chain in flight per thread (loop unroll)
   static constexpr int LDEPTH = 2;       // gray-tile items (6 x LDG.128 each) in flight per thread
-  static constexpr int NC = TH * TW / 8;     // one horizontal-pass item (2 rows x 4 cols) per compute thread
-  static constexpr int NT = NC + NP;
   static constexpr int HXD = round_up4(RK);  // x halo of the gradient (D) and V regions
   static constexpr int OFF = round_up4(RG);
   static constexpr int HXG = HXD + OFF;      // x halo of the gray (G) region
@@ -670,54 +442,48 @@ struct StFwdCfg {
   static constexpr int NSEG = TH / RS;
   static constexpr int BW_LO = (OFF - RG) / 2 * 2, BW_HI = (OFF + CSB + RG + 1) / 2 * 2, BWIN = BW_HI - BW_LO;
   static constexpr int DW_LO = (HXD - RK) / 2 * 2, DW_HI = (HXD + 4 + RK + 1) / 2 * 2, DWIN = DW_HI - DW_LO;
+  using MapB = ItemMap<DH / 2, DW / CSB, CSB>;  // gradient items
+  using MapD = ItemMap<TH / 2, TW / 4, 4>;      // horizontal-pass items == the thread's 2 x 4 output pixels
+  static constexpr int NT = MapD::SLOTS;         // one horizontal-pass item per thread
   static constexpr int D_FLOATS = (DH / 2) * PD, V_FLOATS = (TH / 2) * PV, G_FLOATS = (GH / 2) * PG;
-  // smem: D (Ix, Iy) | V (3 planes) | G (gray).  With producer warps or RGB staging the gray tile
-  // needs its own buffer; otherwise it aliases V (it is dead once the gradient phase is done).
-  static constexpr bool G_ALIAS = (NP == 0) && !STAGE;
-  static constexpr int G_OFF = 2 * D_FLOATS + (G_ALIAS ? 0 : 3 * V_FLOATS);
-  static constexpr int NGBUF = NP > 0 ? 2 : 1;  // the producer runs a whole unit ahead: two gray buffers
-  static constexpr int SMEM_FLOATS = G_ALIAS ? 2 * D_FLOATS + cmax(3 * V_FLOATS, G_FLOATS) : G_OFF + NGBUF * G_FLOATS;
+  static constexpr int SP_FLOATS = 24 * NT;  // a parked tensor: 3 channels x 4 columns x float2 per thread
+  // smem: D (Ix, Iy) | V (3 planes; the gray tile aliases it: dead once the gradient phase is done) | SP1.
+  // The HR tensor is parked over D (SP2): dead once the vertical pass is done.
+  static constexpr int VG_FLOATS = cmax(3 * V_FLOATS, G_FLOATS);
+  static constexpr int SP_OFF = 2 * D_FLOATS + VG_FLOATS;
+  static constexpr int SP2_OFF = (SP_FLOATS <= 2 * D_FLOATS) ? 0 : SP_OFF + SP_FLOATS;  // small radii: D is too small
+  static constexpr int SMEM_FLOATS = SP_OFF + SP_FLOATS + (SP2_OFF ? SP_FLOATS : 0);
   static constexpr size_t SMEM_BYTES = sizeof(float) * SMEM_FLOATS;
-  static_assert(!STAGE || 3 * GH * GW <= 2 * D_FLOATS + 3 * V_FLOATS, "RGB staging does not fit over the D|V region");
   static_assert((CSB == 4 || CSB == 8) && DW % CSB == 0, "bad gradient segment width");
   static_assert(TH % RS == 0 && RS % 2 == 0 && TH % 2 == 0 && TW % 4 == 0 && RG % 2 == 0 && RK % 2 == 0,
                 "bad forward tile");
-  static_assert(NC % 32 == 0 && NP % 32 == 0 && NT <= 1024, "bad forward block size");
+  static_assert(NT % 32 == 0 && NT <= 1024, "bad forward block size");
+  static_assert(CHU == 1 || CHU == 2 || CHU == 4, "chain unroll");
 };
 
-// Compute-warp phases B-D for one unit: consumes the gray tile the producer parked in sG and leaves
-// the smoothed tensor (Jxx,Jyy,Jxy) of this thread's 8 pixels (rows 2q, 2q+1; cols ox0..ox0+3 of the
-// tile) in S[3][4] (.x = even row, .y = odd row).
+// Phases A-D for one image of the tile: leaves the smoothed tensor (Jxx,Jyy,Jxy) of this thread's
+// 8 pixels (rows 2q, 2q+1; cols 4*seg..4*seg+3 of the tile) in S[3][4] (.x = even row, .y = odd row).
 template <class C, bool PX, class Taps>
-SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float* __restrict__ gray_out, bool vec4, int H,
-                             int W, int y0, int x0, const Taps& tp, int tid, int gbuf, bool release_gray,
-                             float2 (&S)[3][4], const float* __restrict__ px_other = nullptr, float* px_acc = nullptr) {
+SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float* __restrict__ ixy, int b, bool vec4,
+                             int H, int W, int y0, int x0, const Taps& tp, int tid, bool dvalid, int dq, int dseg,
+                             float2 (&S)[3][4], const float* __restrict__ px_other, float* px_acc) {
   float* sD0 = smem;
   float* sD1 = sD0 + C::D_FLOATS;
   float* sV = sD1 + C::D_FLOATS;
-  float* sG = smem + C::G_OFF + gbuf * C::G_FLOATS;
+  float* sG = sV;
 
-  if (C::NP > 0) {
-    bar_sync(kBarFull + gbuf, C::NT);  // gray tile of this unit is in sG (also: every compute thread is done with sV)
-  } else {
-    bar_sync(kBarCompute, C::NC);  // every thread is done with sD / sV of the previous unit
-    if (C::STAGE && vec4) {
-      stage_rgb_async<C::GH, C::GW, C::NC>(smem, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, tid);
-      cp_async_wait_all();
-      bar_sync(kBarCompute, C::NC);
-      convert_staged_gray<C::GH, C::GW, C::PG, C::NC>(sG, smem, tid);
-    } else {
-      load_gray_tile<C::GH, C::GW, C::PG, C::NC, C::LDEPTH, PX>(sG, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, vec4,
-                                                                tid, gray_out, y0, y0 + C::TH, x0, x0 + C::TW, px_other,
-                                                                px_acc);
-    }
-    bar_sync(kBarCompute, C::NC);
-  }
+  __syncthreads();  // every thread is done with sV / sD (SP2) of the previous unit
+  load_gray_tile<C::GH, C::GW, C::PG, C::NT, C::LDEPTH, PX>(sG, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, vec4,
+                                                            tid, y0, y0 + C::TH, x0, x0 + C::TW, px_other, px_acc);
+  __syncthreads();
 
   // Phase B: Ix, Iy on the D region; forced to zero outside the image because the reference
-  // zero-pads the *products* for the rho-smoothing (utils.py:225-230).
-  for (int it = tid; it < (C::DH / 2) * (C::DW / C::CSB); it += C::NC) {
-    const int seg = it / (C::DH / 2), q = it - seg * (C::DH / 2);
+  // zero-pads the *products* for the rho-smoothing (utils.py:225-230).  Tile-interior items also
+  // save their values for the backward pass (ixy planes).
+  const int Hp = (H + 1) >> 1;
+  for (int it = tid; it < C::MapB::SLOTS; it += C::NT) {
+    int q, seg;
+    if (!C::MapB::decode(it, q, seg)) continue;
     const int dx0 = C::CSB * seg;
     const int gy = y0 - C::RK + 2 * q, gx0 = x0 - C::HXD + dx0;
     float2 Ix[C::CSB], Iy[C::CSB];
@@ -733,6 +499,21 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float*
         Iy[j].x = (ok && r0) ? Iy[j].x : 0.f;
         Iy[j].y = (ok && r1) ? Iy[j].y : 0.f;
       }
+      if (ixy && gy >= y0 && gy < y0 + C::TH && gx0 >= x0 && gx0 < x0 + C::TW) {  // tile interior, inside the image
+        float* ox = ixy + ixy_offset(b, 0, Hp, W, gy >> 1, gx0);
+        float* oy = ixy + ixy_offset(b, 1, Hp, W, gy >> 1, gx0);
+        if (vec4) {
+#pragma unroll
+          for (int j = 0; j < C::CSB; j += 2) {
+            st4(ox + 2 * j, make_float4(Ix[j].x, Ix[j].y, Ix[j + 1].x, Ix[j + 1].y));
+            st4(oy + 2 * j, make_float4(Iy[j].x, Iy[j].y, Iy[j + 1].x, Iy[j + 1].y));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < C::CSB; ++j)
+            if (gx0 + j < W) { st2(ox + 2 * j, Ix[j]); st2(oy + 2 * j, Iy[j]); }
+        }
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < C::CSB; ++j) { Ix[j] = make_float2(0.f, 0.f); Iy[j] = make_float2(0.f, 0.f); }
@@ -745,8 +526,7 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float*
       st4(o1 + 2 * j, make_float4(Iy[j].x, Iy[j].y, Iy[j + 1].x, Iy[j + 1].y));
     }
   }
-  if (C::NP > 0 && release_gray) bar_arrive(kBarEmpty + gbuf, C::NT);  // this gray buffer may be refilled (unit + 2)
-  bar_sync(kBarCompute, C::NC);
+  __syncthreads();
 
   // Phase C: vertical rho-pass of the three products; a lane owns one column and RS output rows
   // (RS/2 row pairs).  Columns outside the image hold zeros and are only cleared.
@@ -754,13 +534,13 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float*
     const int c_lo = max(0, C::HXD - x0), c_hi = min(C::DW, W + C::HXD - x0);  // valid D columns
     const int ncol = c_hi - c_lo;
     const int nclr = C::DW - ncol;
-    for (int it = tid; it < nclr * (C::TH / 2); it += C::NC) {
+    for (int it = tid; it < nclr * (C::TH / 2); it += C::NT) {
       const int q = it / nclr, u = it - q * nclr;
       const int dx = (u < c_lo) ? u : (c_hi + (u - c_lo));
 #pragma unroll
       for (int c = 0; c < 3; ++c) st2(sV + c * C::V_FLOATS + q * C::PV + 2 * dx, make_float2(0.f, 0.f));
     }
-    for (int it = tid; it < ncol * C::NSEG; it += C::NC) {
+    for (int it = tid; it < ncol * C::NSEG; it += C::NT) {
       const int seg = it / ncol, dx = c_lo + (it - seg * ncol);
       float2 acc[3][C::RS / 2];
 #pragma unroll
@@ -796,121 +576,138 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float*
       }
     }
   }
-  bar_sync(kBarCompute, C::NC);
+  __syncthreads();
 
   // Phase D: horizontal rho-pass; a lane owns 4 consecutive columns of one row pair.
-  {
-    const int seg = tid / (C::TH / 2), q = tid - seg * (C::TH / 2);
-    const int ox0 = 4 * seg;
+  if (dvalid) {
+    const int ox0 = 4 * dseg;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-      smooth_h_rowpair<C::RK, C::DWIN, C::HXD - C::DW_LO>(sV + c * C::V_FLOATS + q * C::PV + 2 * (ox0 + C::DW_LO), tp,
-                                                          S[c]);
+      smooth_h_rowpair_n<C::RK, 4, C::DWIN, C::HXD - C::DW_LO>(sV + c * C::V_FLOATS + dq * C::PV + 2 * (ox0 + C::DW_LO), tp,
+                                                              S[c]);
   }
-  // no barrier here: the next unit starts with bar_sync(kBarFull) over all compute threads, which
-  // orders these sV reads before the next phase C and the sD reads of phase C before the next phase B
 }
 
-template <class C, bool PX = false>
+template <class C, bool PX = false, bool WANT_HR = false>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
   SRST_DYN_SMEM(float, smem);
   __shared__ float s_red[32];
   __shared__ unsigned int s_last;
+  [[maybe_unused]] __shared__ float s_red_px[PX ? 32 : 1];
   const int tid = threadIdx.x;
-  const int ntiles = P.B * P.tiles_y * P.tiles_x;
   pdl_wait();     // previous kernel of the stream is complete (it may have produced sr or used the workspace)
   pdl_trigger();  // the next PDL-launched kernel may start launching; it waits for this grid itself
 
-  if (C::NP > 0 && tid >= C::NC) {
-    // ---- producer warps: RGB tile (+halo) -> gray -> sG, one unit ahead of the compute warps ----
-    const int ptid = tid - C::NC;
-    int u = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      int t = tile;
-      const int tx = t % P.tiles_x;
-      t /= P.tiles_x;
-      const int ty = t % P.tiles_y;
-      const int b = t / P.tiles_y;
-      const size_t img_off = (size_t)b * 3 * P.H * P.W;
+  int t = blockIdx.x;
+  const int tx = t % P.tiles_x;
+  t /= P.tiles_x;
+  const int ty = t % P.tiles_y;
+  const int b = t / P.tiles_y;
+  const int y0 = ty * C::TH, x0 = tx * C::TW;
+  const int H = P.H, W = P.W;
+  const size_t img_off = (size_t)b * 3 * H * W;
+  const bool vec4 = P.vec4 != 0;
+  const bool norm = P.normalize != 0;
+  int q, seg;
+  const bool dvalid = C::MapD::decode(tid, q, seg);
+  float* sp1 = smem + C::SP_OFF + 2 * tid;   // slot (c, j) of this thread: + 2 * NT * (c * 4 + j)
+  float* sp2 = smem + C::SP2_OFF + 2 * tid;  // HR tensor, parked over the (dead) D region when it fits there
+  [[maybe_unused]] float pxsum = 0.f;
+
+  // SR, then HR, through one copy of the filter code
 #pragma unroll 1
-      for (int img = 0; img < 2; ++img, ++u) {
-        const int gb = u & 1;
-        if (u >= 2) bar_sync(kBarEmpty + gb, C::NT);  // compute warps consumed the tile of unit u-2
-        load_gray_tile<C::GH, C::GW, C::PG, (C::NP > 0 ? C::NP : 32), 3>(
-            smem + C::G_OFF + gb * C::G_FLOATS, (img ? P.hr : P.sr) + img_off, P.H, P.W,
-            ty * C::TH - (C::RG + C::RK), tx * C::TW - C::HXG, P.vec4 != 0, ptid,
-            (img ? P.gray_hr : P.gray_sr) ? (img ? P.gray_hr : P.gray_sr) + (size_t)b * P.H * P.W : nullptr, ty * C::TH,
-            ty * C::TH + C::TH, tx * C::TW, tx * C::TW + C::TW);
-        __threadfence_block();
-        bar_arrive(kBarFull + gb, C::NT);
-      }
+  for (int img = 0; img < 2; ++img) {
+    float2 S[3][4];
+    const float* base = (img ? P.hr : P.sr) + img_off;
+    float* ixy = img ? P.ixy_hr : P.ixy_sr;
+    st_unit_tensor<C, PX>(smem, base, ixy, b, vec4, H, W, y0, x0, P.taps, tid, dvalid, q, seg, S,
+                          (PX && img) ? P.sr + img_off : nullptr, &pxsum);
+    if (dvalid) {
+      float* sp = img ? sp2 : sp1;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st2(sp + 2 * C::NT * (c * 4 + j), S[c][j]);
     }
-    return;
   }
 
-  // ---- compute warps ----
-  const bool want_hr = P.ds_hr != nullptr;
-  const bool norm = P.normalize != 0;
-  const int seg = tid / (C::TH / 2), q = tid - seg * (C::TH / 2);
+  // Per-pixel chain on this thread's 2 x 4 pixels, one pixel pair (two rows of one column) per
+  // iteration; operands come from the thread's parked slots and the results go back into them.
   float lsum = 0.f;
-  [[maybe_unused]] float pxsum = 0.f;
-  // NP > 0: persistent loop over tiles (the producer runs one unit ahead); NP == 0: one tile per CTA
-  int tile = blockIdx.x;
-  do {
-    int t = tile;
-    const int tx = t % P.tiles_x;
-    t /= P.tiles_x;
-    const int ty = t % P.tiles_y;
-    const int b = t / P.tiles_y;
-    const int y0 = ty * C::TH, x0 = tx * C::TW;
-    const size_t img_off = (size_t)b * 3 * P.H * P.W;
-    const bool last_tile = tile + (int)gridDim.x >= ntiles;  // units of the last tile have no unit + 2
-
-    float2 S1[3][4], S2[3][4];
-    const size_t gray_off = (size_t)b * P.H * P.W;
-    st_unit_tensor<C, false>(smem, P.sr + img_off, P.gray_sr ? P.gray_sr + gray_off : nullptr, P.vec4 != 0, P.H, P.W, y0,
-                             x0, P.taps, tid, 0, !last_tile, S1);
-    if constexpr (PX)  // fused Pixel term: the HR unit's loader also reads the SR pixels of the tile interior
-      st_unit_tensor<C, true>(smem, P.hr + img_off, P.gray_hr ? P.gray_hr + gray_off : nullptr, P.vec4 != 0, P.H, P.W, y0,
-                              x0, P.taps, tid, (C::NP > 0 ? 1 : 0), !last_tile, S2, P.sr + img_off, &pxsum);
-    else
-      st_unit_tensor<C, false>(smem, P.hr + img_off, P.gray_hr ? P.gray_hr + gray_off : nullptr, P.vec4 != 0, P.H, P.W, y0,
-                               x0, P.taps, tid, (C::NP > 0 ? 1 : 0), !last_tile, S2);
-
-    // Per-pixel chain on this thread's 2 x 4 pixels, then the ds stores.
-    if (want_hr)
-      lsum += st_chain_store<true>(S1, S2, norm, P.eps, P.ds_sr, P.ds_hr, img_off, P.H, P.W, y0 + 2 * q, x0 + 4 * seg,
-                                   P.vec4 != 0);
-    else
-      lsum += st_chain_store<false>(S1, S2, norm, P.eps, P.ds_sr, P.ds_hr, img_off, P.H, P.W, y0 + 2 * q, x0 + 4 * seg,
-                                    P.vec4 != 0);
-  } while (C::NP > 0 && (tile += (int)gridDim.x) < ntiles);
+  const int gy0 = y0 + 2 * q, gx0 = x0 + 4 * seg;
+  if (dvalid) {
+#pragma unroll C::CHU
+    for (int j = 0; j < 4; ++j) {
+      float* a1 = sp1 + 2 * C::NT * j;
+      float* a2 = sp2 + 2 * C::NT * j;
+      StPixelGrad2 G;
+      G.da = G.db = G.dc = G.de = G.df = G.dh = make_float2(0.f, 0.f);
+      const float2 d = st_pixel2<true, WANT_HR>(ld2(a1), ld2(a1 + 8 * C::NT), ld2(a1 + 16 * C::NT), ld2(a2),
+                                                ld2(a2 + 8 * C::NT), ld2(a2 + 16 * C::NT), norm, P.eps, G);
+      const bool okx = gx0 + j < W;
+      lsum += (okx && gy0 < H) ? d.x : 0.f;
+      lsum += (okx && gy0 + 1 < H) ? d.y : 0.f;
+      st2(a1, G.da); st2(a1 + 8 * C::NT, G.db); st2(a1 + 16 * C::NT, G.dc);
+      if (WANT_HR) { st2(a2, G.de); st2(a2 + 8 * C::NT, G.df); st2(a2 + 16 * C::NT, G.dh); }
+    }
+    // ds stores: rows of 4 consecutive columns per channel (STG.128)
+    if (gx0 < W && (P.ds_sr || WANT_HR)) {
+      const size_t plane = (size_t)H * W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float2 v[4], w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = ld2(sp1 + 2 * C::NT * (c * 4 + j));
+          if (WANT_HR) w[j] = ld2(sp2 + 2 * C::NT * (c * 4 + j));
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          if (gy0 + hf >= H) continue;
+          const size_t o = img_off + c * plane + (size_t)(gy0 + hf) * W + gx0;
+          if (vec4) {
+            if (P.ds_sr) st4(P.ds_sr + o, hf ? make_float4(v[0].y, v[1].y, v[2].y, v[3].y)
+                                           : make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
+            if (WANT_HR) st4(P.ds_hr + o, hf ? make_float4(w[0].y, w[1].y, w[2].y, w[3].y)
+                                             : make_float4(w[0].x, w[1].x, w[2].x, w[3].x));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (gx0 + j < W) {
+                if (P.ds_sr) P.ds_sr[o + j] = hf ? v[j].y : v[j].x;
+                if (WANT_HR) P.ds_hr[o + j] = hf ? w[j].y : w[j].x;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
 
   // Deterministic loss reduction: block partial -> workspace; the last block to finish sums all
   // partials in a fixed order (double) and re-zeroes the workspace for the next call.
-  [[maybe_unused]] __shared__ float s_red_px[PX ? 32 : 1];
   lsum = warp_sum(lsum);
   if constexpr (PX) pxsum = warp_sum(pxsum);
   if ((tid & 31) == 0) {
     s_red[tid >> 5] = lsum;
     if constexpr (PX) s_red_px[tid >> 5] = pxsum;
   }
-  bar_sync(kBarCompute, C::NC);
+  __syncthreads();
   if (tid == 0) {
     float bs = 0.f;
-    for (int w = 0; w < C::NC / 32; ++w) bs += s_red[w];
+    for (int w = 0; w < C::NT / 32; ++w) bs += s_red[w];
     P.partials[blockIdx.x] = bs;
     if constexpr (PX) {
       float bp = 0.f;
-      for (int w = 0; w < C::NC / 32; ++w) bp += s_red_px[w];
+      for (int w = 0; w < C::NT / 32; ++w) bp += s_red_px[w];
       P.px_partials[blockIdx.x] = bp;
     }
     __threadfence();
-    const unsigned int t = atomicAdd(P.ticket, 1u);
-    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    const unsigned int tk = atomicAdd(P.ticket, 1u);
+    s_last = (tk == gridDim.x - 1) ? 1u : 0u;
   }
-  bar_sync(kBarCompute, C::NC);
+  __syncthreads();
   if (s_last) {
     __threadfence();
     if (tid < 32) {
@@ -941,7 +738,7 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
 // ------------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------------
-template <int TH_, int TW_, int RS_, int NT_, int RG_, int RK_, int MINB_, int CSD_ = 4>
+template <int TH_, int TW_, int RS_, int NT_, int RG_, int RK_, int MINB_, int CSD_ = 8>
 struct StBwdCfg {
   static constexpr int TH = TH_, TW = TW_, RS = RS_, NT = NT_, RG = RG_, RK = RK_, MINB = MINB_;
   static constexpr int CSD = CSD_;  // output columns per phase-D' item: 8 reads a 24-column window per 8 outputs
@@ -949,23 +746,26 @@ struct StBwdCfg {
   static constexpr int HXE = round_up4(RG);  // x halo of the E region (where dIx, dIy are needed)
   static constexpr int HXK = round_up4(RK);
   static constexpr int EH = TH + 2 * RG, EW = TW + 2 * HXE, PE = smem_pitch(2 * EW);
-  static constexpr int GH = EH + 2 * RG, GW = EW + 2 * HXE, PG = smem_pitch(2 * GW);  // gray region
-  static constexpr int VW = EW + 2 * HXK, PV = smem_pitch(2 * VW);                     // vertical-pass output
-  static constexpr int SH = EH + 2 * RK;                                              // staged ds rows
+  static constexpr int VW = EW + 2 * HXK, PV = smem_pitch(2 * VW);  // vertical-pass output
+  static constexpr int SH = EH + 2 * RK;                            // staged ds rows
   static constexpr int NSEG = EH / RS;
+  // saved Ix, Iy tile: TMA box of EH/2 row pairs x EWB columns (x 2 floats); EWB = EW + 2 makes the
+  // pitch 2*EWB == 4 mod 8 floats (conflict-free LDS.128 across row pairs) and a multiple of 16 bytes
+  static constexpr int EWB = EW + 2, PI = 2 * EWB;
   static constexpr int BW_LO = (HXE - RG) / 2 * 2, BW_HI = (HXE + 4 + RG + 1) / 2 * 2, BWIN = BW_HI - BW_LO;
   static constexpr int DW_LO = (HXK - RK) / 2 * 2, DW_HI = (HXK + CSD + RK + 1) / 2 * 2, DWIN = DW_HI - DW_LO;
-  // smem: V (3 planes) | I (Ix, Iy) | G (gray) | X: staged ds planes [3][SH][VW] row-major, later
-  // dIx|dIy (the staging is dead once the vertical pass has consumed it)
-  static constexpr int V_FLOATS = (EH / 2) * PV, I_FLOATS = (EH / 2) * PE, G_FLOATS = (GH / 2) * PG;
+  using MapD = ItemMap<EH / 2, EW / CSD, CSD>;  // horizontal pass + product rule
+  using MapE = ItemMap<TH / 2, TW / 4, 4>;      // adjoint derivative filters + stores
+  // smem: X: staged ds planes [3][SH][VW] row-major (TMA destination), later dIx|dIy (the staging is
+  // dead once the vertical pass has consumed it) | I: saved Ix, Iy [2][EH/2][PI] (TMA destination) | V (3 planes)
+  static constexpr int V_FLOATS = (EH / 2) * PV, I_FLOATS = (EH / 2) * PI, DI_FLOATS = (EH / 2) * PE;
   static constexpr int S_FLOATS = SH * VW;
-  static constexpr int X_FLOATS = cmax(2 * I_FLOATS, 3 * S_FLOATS);
-  static constexpr int G_OFF = (3 * V_FLOATS + 2 * I_FLOATS + 31) / 32 * 32;             // 128-byte aligned (TMA destination)
-  static constexpr int X_OFF = (G_OFF + G_FLOATS + 31) / 32 * 32;
-  static constexpr int RMW_LO = (HXE - RG) / 4 * 4, RMWIN = (HXE + 4 + RG + 3) / 4 * 4 - RMW_LO;  // row-major gradient window
-  static_assert(GH * GW <= G_FLOATS, "row-major gray tile must fit the gray region");
-  static constexpr int SMEM_FLOATS = X_OFF + X_FLOATS;
+  static constexpr int X_FLOATS = cmax(2 * DI_FLOATS, 3 * S_FLOATS);
+  static constexpr int I_OFF = (X_FLOATS + 31) / 32 * 32;               // 128-byte aligned (TMA destination)
+  static constexpr int V_OFF = (I_OFF + 2 * I_FLOATS + 31) / 32 * 32;
+  static constexpr int SMEM_FLOATS = V_OFF + 3 * V_FLOATS;
   static constexpr size_t SMEM_BYTES = sizeof(float) * SMEM_FLOATS;
+  static_assert(PI % 8 == 4 && PE % 8 == 4 && PV % 8 == 4, "row-pair pitches must be == 4 mod 8");
   static_assert(EH % RS == 0 && RS % 2 == 0 && TH % 2 == 0 && TW % 4 == 0 && RG % 2 == 0 && RK % 2 == 0,
                 "bad backward tile");
   static_assert(NT % 32 == 0 && NT <= 1024, "bad backward block size");
@@ -976,23 +776,15 @@ template <class C, bool PX = false>
 __global__ void __launch_bounds__(C::NT, C::MINB)
 st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   SRST_DYN_SMEM(float, smem);
-  float* sV = smem;                    // [3][EH/2][PV]  vertical rho-pass of ds
-  float* sI0 = sV + 3 * C::V_FLOATS;   // Ix [EH/2][PE]
-  float* sI1 = sI0 + C::I_FLOATS;      // Iy
-  float* sG = smem + C::G_OFF;         // gray [GH/2][PG] (row pairs), or [GH][GW] row-major when it comes by TMA
-  float* sX = smem + C::X_OFF;         // staged ds [3][SH][VW], later dIx|dIy
-  float* sS = sX;
-  float* sdI0 = sX;
-  float* sdI1 = sX + C::I_FLOATS;
+  float* sS = smem;                     // staged ds [3][SH][VW]
+  float* sdI0 = smem;                   // later: dIx [EH/2][PE]
+  float* sdI1 = smem + C::DI_FLOATS;    //        dIy
+  float* sI0 = smem + C::I_OFF;         // saved Ix [EH/2][PI]
+  float* sI1 = sI0 + C::I_FLOATS;       // saved Iy
+  float* sV = smem + C::V_OFF;          // [3][EH/2][PV]  vertical rho-pass of ds
+  __shared__ __align__(8) unsigned long long s_mbar;
 
   const int tid = threadIdx.x;
-  // First-wave CTAs can become resident while the previous kernel of the stream (the forward, in a
-  // training step's backward pass) is still draining.  Their gray tile and Ix, Iy depend on `img` only,
-  // which that kernel does not write, so they are built first; ds (written by the forward) and
-  // grad_out (written by the autograd op right before this launch) are touched after the wait.
-  const bool early = P.use_tma && !P.use_gray && (int)blockIdx.x < P.early_ctas;
-  if (!early) pdl_wait();
-  pdl_trigger();
   int tile = blockIdx.x;
   const int tx = tile % P.tiles_x;
   tile /= P.tiles_x;
@@ -1003,98 +795,43 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   const size_t plane = (size_t)H * W;
   const size_t img_off = (size_t)b * 3 * plane;
   const auto& tp = P.taps;
-  const int xv0 = x0 - C::HXE - C::HXK;        // first staged / V column
-  const int yv0 = y0 - C::RG - C::RK;          // first staged row
+  const int xv0 = x0 - C::HXE - C::HXK;  // first staged / V column
+  const int yv0 = y0 - C::RG - C::RK;    // first staged row
+  const int xe0 = x0 - C::HXE;           // first E-region column
+  const int qe0 = (y0 - C::RG) / 2;      // first E-region row pair (y0 - RG is even; may be -RG/2)
 
-  // Stage the three ds planes (+halo).  Preferred path: ONE TMA box copy issued by one thread
-  // (rows/columns outside the image are zero-filled by the hardware = the zero padding of the
-  // adjoint smoothing); otherwise 16-byte cp.async copies, or scalar loads for unaligned tensors.
-  __shared__ __align__(8) unsigned long long s_mbar;
-  __shared__ __align__(8) unsigned long long s_mbar_g;
-  // the gray box is needed first (phase B'): queue it ahead of the much larger ds box
-  if (P.use_gray && tid == 0)
-    tma_stage_begin(&s_mbar_g, sG, &P.gray_map, x0 - 2 * C::HXE, y0 - 2 * C::RG, b, C::GW, C::GH, 1);
+  if (P.use_tma && tid == 0) tma_barrier_init(&s_mbar);
+  pdl_wait();  // ds and ixy come from the forward kernel, grad_out from the autograd op before this launch
+  pdl_trigger();
+
+  // Stage the three ds planes (+halo) and the saved Ix, Iy tile.  Preferred path: two TMA box copies
+  // issued by one thread (elements outside the tensors are zero-filled by the hardware = the zero padding
+  // of the adjoint smoothing, and Ix = Iy = 0 outside the image); otherwise plain loads.
   if (P.use_tma) {
-    if (!early && tid == 0) tma_stage_begin(&s_mbar, sS, &P.ds_map, xv0, yv0, b * 3, C::VW, C::SH, 3);
+    if (tid == 0) {
+      tma_expect(&s_mbar, (unsigned)((3 * C::S_FLOATS + 2 * C::I_FLOATS) * sizeof(float)));
+      tma_load_3d(&s_mbar, sS, &P.ds_map, xv0, yv0, b * 3, C::VW, C::SH, 3);
+      tma_load_3d(&s_mbar, sI0, &P.ixy_map, 2 * xe0, qe0, b * 2, C::PI, C::EH / 2, 2);
+    }
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    tma_wait(&s_mbar);
   } else {
     const float* dsb = P.ds + img_off;
-    constexpr int C4 = C::VW / 4;
-    if (P.vec4) {
-      // (plane c, row r, 16-byte column group c4) walked incrementally: no div/mod in the loop
-      constexpr int DC4 = C::NT % C4, DR = C::NT / C4;
-      static_assert(DR + 1 < C::SH, "staging walk assumes at most one row wrap per step");
-      int c4 = tid % C4, r = tid / C4, c = 0;
-      while (r >= C::SH) { r -= C::SH; ++c; }
-      while (c < 3) {
-        const int gy = yv0 + r, gx = xv0 + 4 * c4;
-        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        cp_async16(sS + (c * C::SH + r) * C::VW + 4 * c4, ok ? dsb + c * plane + (size_t)gy * W + gx : dsb, ok);
-        c4 += DC4; r += DR;
-        if (c4 >= C4) { c4 -= C4; ++r; }
-        if (r >= C::SH) { r -= C::SH; ++c; }
-      }
-      cp_async_commit();
-    } else {
-      for (int it = tid; it < 3 * C::SH * C::VW; it += C::NT) {
-        const int vx = it % C::VW, rc = it / C::VW;
-        const int r = rc % C::SH, c = rc / C::SH;
-        const int gy = yv0 + r, gx = xv0 + vx;
-        sS[it] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(dsb + c * plane + (size_t)gy * W + gx) : 0.f;
-      }
+    for (int it = tid; it < 3 * C::SH * C::VW; it += C::NT) {
+      const int vx = it % C::VW, rc = it / C::VW;
+      const int r = rc % C::SH, c = rc / C::SH;
+      const int gy = yv0 + r, gx = xv0 + vx;
+      sS[it] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(dsb + c * plane + (size_t)gy * W + gx) : 0.f;
     }
-  }
-
-  // Phase A': gray tile of the image (halo 2*RG rows, 2*HXE cols): one TMA box of the gray plane
-  // the forward saved, or RGB loads + conversion.
-  if (P.use_gray) {
-    __syncthreads();  // the barrier is initialised before anyone polls it
-    tma_stage_wait(&s_mbar_g);
-  } else {
-    load_gray_tile<C::GH, C::GW, C::PG, C::NT, 1>(sG, P.img + img_off, H, W, y0 - 2 * C::RG, x0 - 2 * C::HXE,
-                                                  P.vec4 != 0, tid);
+    const int Hp = (H + 1) >> 1;
+    for (int it = tid; it < 2 * (C::EH / 2) * C::PI; it += C::NT) {
+      const int e = it % C::PI, rc = it / C::PI;
+      const int qq = rc % (C::EH / 2), pl = rc / (C::EH / 2);
+      const int gp = qe0 + qq, gx = xe0 + (e >> 1);
+      sI0[it] = (gp >= 0 && gp < Hp && gx >= 0 && gx < W) ? __ldg(P.ixy + ixy_offset(b, pl, Hp, W, gp, gx) + (e & 1)) : 0.f;
+    }
     __syncthreads();
   }
-
-  // Phase B': recompute Ix, Iy on the E region (zero outside the image).
-  for (int it = tid; it < (C::EH / 2) * (C::EW / 4); it += C::NT) {
-    const int seg = it / (C::EH / 2), q = it - seg * (C::EH / 2);
-    const int ex0 = 4 * seg;
-    const int gy = y0 - C::RG + 2 * q, gx0 = x0 - C::HXE + ex0;
-    float2 Ix[4], Iy[4];
-    if (gy + 1 >= 0 && gy < H && gx0 + 3 >= 0 && gx0 < W) {
-      if (P.use_gray) {
-        grad_rowpair_rm<C::RG, 4, C::RMWIN, C::HXE - C::RMW_LO, C::GW>(sG + (2 * q) * C::GW + ex0 + C::RMW_LO, tp, Ix, Iy);
-      } else {
-        const float* p = sG + q * C::PG + 2 * (ex0 + C::BW_LO);
-        grad_rowpair<C::RG, 4, C::BWIN, C::HXE - C::BW_LO, C::PG, true>(p, p, tp, Ix, Iy);
-      }
-      const bool r0 = gy >= 0, r1 = gy + 1 < H;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const bool ok = (gx0 + j >= 0) && (gx0 + j < W);
-        Ix[j].x = (ok && r0) ? Ix[j].x : 0.f;
-        Ix[j].y = (ok && r1) ? Ix[j].y : 0.f;
-        Iy[j].x = (ok && r0) ? Iy[j].x : 0.f;
-        Iy[j].y = (ok && r1) ? Iy[j].y : 0.f;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { Ix[j] = make_float2(0.f, 0.f); Iy[j] = make_float2(0.f, 0.f); }
-    }
-    float* o0 = sI0 + q * C::PE + 2 * ex0;
-    float* o1 = sI1 + q * C::PE + 2 * ex0;
-    st4(o0, make_float4(Ix[0].x, Ix[0].y, Ix[1].x, Ix[1].y));
-    st4(o0 + 4, make_float4(Ix[2].x, Ix[2].y, Ix[3].x, Ix[3].y));
-    st4(o1, make_float4(Iy[0].x, Iy[0].y, Iy[1].x, Iy[1].y));
-    st4(o1 + 4, make_float4(Iy[2].x, Iy[2].y, Iy[3].x, Iy[3].y));
-  }
-  if (early) {
-    pdl_wait();  // the previous kernel of the stream is complete: ds may be fetched now
-    if (tid == 0) tma_stage_begin(&s_mbar, sS, &P.ds_map, xv0, yv0, b * 3, C::VW, C::SH, 3);
-    __syncthreads();  // the barrier is initialised before anyone polls it
-  }
-  if (P.use_tma) tma_stage_wait(&s_mbar); else cp_async_wait_all();
-  __syncthreads();  // Ix, Iy complete; staged ds planes have landed
 
   // Phase C': vertical rho-pass of the three staged ds planes; a lane owns one column and RS rows.
   // The adjoint of the zero-padded symmetric smoothing is the same zero-padded smoothing.
@@ -1135,8 +872,9 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
 
   // Phase D': horizontal rho-pass -> E = K*ds at the E-region pixels, then the product rule
   //   dIx = 2 Ix Exx + Iy Exy ,  dIy = 2 Iy Eyy + Ix Exy      (adjoint of utils.py:225-229)
-  for (int it = tid; it < (C::EH / 2) * (C::EW / C::CSD); it += C::NT) {
-    const int seg = it / (C::EH / 2), q = it - seg * (C::EH / 2);
+  for (int it = tid; it < C::MapD::SLOTS; it += C::NT) {
+    int q, seg;
+    if (!C::MapD::decode(it, q, seg)) continue;
     const int ex0 = C::CSD * seg;
     float2 E[3][C::CSD];
 #pragma unroll
@@ -1147,7 +885,7 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
     float* o1 = sdI1 + q * C::PE + 2 * ex0;
 #pragma unroll
     for (int m = 0; m < C::CSD / 2; ++m) {  // two columns per LDS.128 / STS.128
-      const float4 ixv = ld4(sI0 + q * C::PE + 2 * ex0 + 4 * m), iyv = ld4(sI1 + q * C::PE + 2 * ex0 + 4 * m);
+      const float4 ixv = ld4(sI0 + q * C::PI + 2 * ex0 + 4 * m), iyv = ld4(sI1 + q * C::PI + 2 * ex0 + 4 * m);
       const float2 ix[2] = {make_float2(ixv.x, ixv.y), make_float2(ixv.z, ixv.w)};
       const float2 iy[2] = {make_float2(iyv.x, iyv.y), make_float2(iyv.z, iyv.w)};
       float2 dx[2], dy[2];
@@ -1170,8 +908,9 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   // i.e. the forward gradient operators applied to dIx and dIy, negated.
   const float scale = -__ldg(P.grad_out) * P.inv_count;
   [[maybe_unused]] const float px_scale = PX ? __ldg(P.grad_px) * P.inv_count * (2.0f / 3.0f) : 0.f;
-  for (int it = tid; it < (C::TH / 2) * (C::TW / 4); it += C::NT) {
-    const int seg = it / (C::TH / 2), q = it - seg * (C::TH / 2);
+  for (int it = tid; it < C::MapE::SLOTS; it += C::NT) {
+    int q, seg;
+    if (!C::MapE::decode(it, q, seg)) continue;
     const int ox0 = 4 * seg;
     const int gy = y0 + 2 * q, gx0 = x0 + ox0;
     if (gy >= H || gx0 >= W) continue;
@@ -1192,9 +931,9 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
           float4 r = make_float4(coef[c] * dgr[0], coef[c] * dgr[1], coef[c] * dgr[2], coef[c] * dgr[3]);
           if constexpr (PX) {  // fused Pixel term: d MSE / d img = 2 (img - other) / (3 B H W)
             const size_t e = img_off + (size_t)(gy + hf) * W + gx0 + c * plane;
-            const float4 a = ldg4(P.img + e), b = ldg4(P.px_other + e);
-            r.x = fmaf(px_scale, a.x - b.x, r.x); r.y = fmaf(px_scale, a.y - b.y, r.y);
-            r.z = fmaf(px_scale, a.z - b.z, r.z); r.w = fmaf(px_scale, a.w - b.w, r.w);
+            const float4 a = ldg4(P.img + e), b4 = ldg4(P.px_other + e);
+            r.x = fmaf(px_scale, a.x - b4.x, r.x); r.y = fmaf(px_scale, a.y - b4.y, r.y);
+            r.z = fmaf(px_scale, a.z - b4.z, r.z); r.w = fmaf(px_scale, a.w - b4.w, r.w);
           }
           st4(o + c * plane, r);
         } else {

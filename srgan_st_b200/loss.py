@@ -11,8 +11,6 @@ No CPU path, no PyTorch fallback: CPU tensors, non-fp32 dtypes and unsupported f
 """
 from __future__ import annotations
 
-import ctypes
-import os
 from typing import Dict, Tuple
 
 import torch
@@ -21,16 +19,21 @@ from torch.autograd.function import once_differentiable
 
 from . import _cabi, taps as _taps
 
-_WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
+_WORKSPACES: Dict[Tuple[str, int, int], torch.Tensor] = {}
 
 
-def _workspace(device: torch.device, stream_ptr: int, nbytes: int) -> torch.Tensor:
-    """Zero-initialised scratch, cached per (device, stream).  The kernels leave it zeroed, so it
-    is safe to reuse for later launches on the same stream (srst.h, srst_st_workspace_bytes)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr)
+def _workspace(kind: str, device: torch.device, stream_ptr: int, nbytes: int) -> torch.Tensor:
+    """Scratch for one family of entry points (`kind`: "st" or "bb" -- they lay the buffer out differently,
+    so they never share one), cached per (kind, device, stream).  Only the 16-byte ticket header has to be
+    zero before the first launch; the kernels hand it back zeroed (srst.h, srst_st_workspace_bytes).
+    Nothing is cached while a CUDA graph is being captured: an allocation made then belongs to the graph's
+    private pool and must not be handed to eager code later."""
+    key = (kind, device.index if device.index is not None else torch.cuda.current_device(), stream_ptr)
     ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.zeros(max(nbytes, 4096), dtype=torch.uint8, device=device)
+    if ws is not None and ws.numel() >= nbytes:
+        return ws
+    ws = torch.zeros(max(nbytes, 4096), dtype=torch.uint8, device=device)
+    if not torch.cuda.is_current_stream_capturing():
         _WORKSPACES[key] = ws
     return ws
 
@@ -58,12 +61,51 @@ def _no_gt_grad(gt: torch.Tensor, who: str) -> None:
 
 
 def _ptr(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    return t.data_ptr() if t is not None else None
+
+
+class _on_device:
+    """`with torch.cuda.device(d)` costs ~10 us per call even when d is already current (the normal case in a
+    training loop); this enters the context only when the tensor lives on another device."""
+    __slots__ = ("_ctx",)
+
+    def __init__(self, device: torch.device):
+        self._ctx = None if device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+        return False
+
+
+_ST_TAPS: Dict[Tuple[float, float], tuple] = {}
+
+
+def _st_taps(sigma: float, rho: float, who: str):
+    """(g*, dg*, r_sigma, k*, r_rho) as ready-made ctypes arguments, cached per (sigma, rho); raises for
+    radii outside the compiled classes."""
+    key = (float(sigma), float(rho))
+    t = _ST_TAPS.get(key)
+    if t is None:
+        g, dg = _taps.gaussian_taps(key[0])
+        k, _ = _taps.gaussian_taps(key[1])
+        rs, rk = len(g) // 2, len(k) // 2
+        if not _cabi.lib().srst_st_supported(rs, rk):
+            raise NotImplementedError(
+                f"{who}: filter radii (sigma={sigma} -> {rs}, rho={rho} -> {rk}) are not compiled into libsrst.so")
+        t = (_taps.as_c(g), _taps.as_c(dg), rs, _taps.as_c(k), rk, (g, dg, k))  # keep the arrays alive
+        _ST_TAPS[key] = t
+    return t
 
 
 class _StructureTensorLossFn(torch.autograd.Function):
     """autograd boundary of the fused ST loss (the reference lets autograd differentiate ~100
-    ATen ops instead; loss.py:399-413)."""
+    ATen ops instead; loss.py:399-413).  Saved for backward: per image that needs a gradient, ONE buffer
+    holding the ds planes (12 B/px) followed by the Ix, Iy planes (8 B/px); the images themselves are not."""
 
     @staticmethod
     def forward(ctx, sr, hr, sigma, rho, normalize):
@@ -71,56 +113,45 @@ class _StructureTensorLossFn(torch.autograd.Function):
         sr = sr.contiguous()
         hr = hr.contiguous()
         B, _, H, W = sr.shape
-        g, dg = _taps.gaussian_taps(float(sigma))
-        k, _ = _taps.gaussian_taps(float(rho))
-        rs, rk = len(g) // 2, len(k) // 2
-        if not lib.srst_st_supported(rs, rk):
-            raise NotImplementedError(
-                f"StructureTensorLoss: filter radii (sigma={sigma} -> {rs}, rho={rho} -> {rk}) are not "
-                "compiled into libsrst.so")
-        need_sr, need_hr = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        with torch.cuda.device(sr.device):
+        tp = _st_taps(sigma, rho, "StructureTensorLoss")
+        need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        n_ds = (B * 3 * H * W + 3) // 4 * 4          # keeps the ixy part 16-byte aligned
+        n_ixy = lib.srst_st_ixy_floats(B, H, W) if (need[0] or need[1]) else 0
+        with _on_device(sr.device):
             stream = torch.cuda.current_stream().cuda_stream
             loss = torch.empty((), dtype=torch.float32, device=sr.device)
-            ds_sr = torch.empty_like(sr) if need_sr else None
-            ds_hr = torch.empty_like(hr) if need_hr else None
-            # The C ABI can also save gray planes for a TMA-fed backward gray tile; measured on B200 it
-            # is slower than re-reading RGB (extra forward stores, bank-conflicted row-major tile), so
-            # the module does not use it (SRST_ST_SAVE_GRAY=1 turns it on for experiments).
-            save_gray = os.environ.get("SRST_ST_SAVE_GRAY", "0") == "1"
-            gray_sr = torch.empty((B, H, W), dtype=torch.float32, device=sr.device) if (need_sr and save_gray) else None
-            gray_hr = torch.empty((B, H, W), dtype=torch.float32, device=sr.device) if (need_hr and save_gray) else None
-            nbytes = lib.srst_st_workspace_bytes(B, H, W)
-            ws = _workspace(sr.device, stream, nbytes)
-            rc = lib.srst_st_forward(_ptr(sr), _ptr(hr), B, H, W, _taps.as_c(g), _taps.as_c(dg), rs,
-                                     _taps.as_c(k), rk, int(bool(normalize)), 1e-12, _ptr(loss),
-                                     _ptr(ds_sr), _ptr(ds_hr), _ptr(gray_sr), _ptr(gray_hr), _ptr(ws), ws.numel(),
-                                     ctypes.c_void_p(stream))
-        _cabi.check(rc, "srst_st_forward")
-        ctx.save_for_backward(sr, hr, ds_sr, ds_hr, gray_sr, gray_hr)
-        ctx.taps = (g, dg, k)
+            saved = [torch.empty(n_ds + n_ixy, dtype=torch.float32, device=sr.device) if n else None for n in need]
+            ds = [t.data_ptr() if t is not None else None for t in saved]
+            ixy = [t.data_ptr() + 4 * n_ds if t is not None else None for t in saved]
+            ws = _workspace("st", sr.device, stream, lib.srst_st_workspace_bytes(B, H, W))
+            rc = lib.srst_st_forward(sr.data_ptr(), hr.data_ptr(), B, H, W, tp[0], tp[1], tp[2], tp[3], tp[4],
+                                     int(bool(normalize)), 1e-12, loss.data_ptr(), ds[0], ds[1], ixy[0], ixy[1],
+                                     ws.data_ptr(), ws.numel(), stream)
+        if rc:
+            _cabi.check(rc, "srst_st_forward")
+        ctx.save_for_backward(saved[0], saved[1])
+        ctx.meta = (tp, B, H, W, n_ds)
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_out):
         lib = _cabi.lib()
-        sr, hr, ds_sr, ds_hr, gray_sr, gray_hr = ctx.saved_tensors
-        g, dg, k = ctx.taps
-        rs, rk = len(g) // 2, len(k) // 2
-        B, _, H, W = sr.shape
-        grad_out = grad_out.to(torch.float32).contiguous()
+        tp, B, H, W, n_ds = ctx.meta
+        if grad_out.dtype != torch.float32 or not grad_out.is_contiguous():
+            grad_out = grad_out.to(torch.float32).contiguous()
         outs = [None, None]
-        with torch.cuda.device(sr.device):
+        dev = grad_out.device
+        with _on_device(dev):
             stream = torch.cuda.current_stream().cuda_stream
-            for i, (img, ds, gray) in enumerate(((sr, ds_sr, gray_sr), (hr, ds_hr, gray_hr))):
-                if ds is None or not ctx.needs_input_grad[i]:
+            for i, saved in enumerate(ctx.saved_tensors):
+                if saved is None or not ctx.needs_input_grad[i]:
                     continue
-                d_img = torch.empty_like(img)
-                rc = lib.srst_st_backward(_ptr(img), _ptr(gray), _ptr(ds), _ptr(grad_out), B, H, W, _taps.as_c(g),
-                                          _taps.as_c(dg), rs, _taps.as_c(k), rk, _ptr(d_img),
-                                          ctypes.c_void_p(stream))
-                _cabi.check(rc, "srst_st_backward")
+                d_img = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+                rc = lib.srst_st_backward(saved.data_ptr() + 4 * n_ds, saved.data_ptr(), grad_out.data_ptr(), B, H, W,
+                                          tp[0], tp[1], tp[2], tp[3], tp[4], d_img.data_ptr(), stream)
+                if rc:
+                    _cabi.check(rc, "srst_st_backward")
                 outs[i] = d_img
         return outs[0], outs[1], None, None, None
 
@@ -161,45 +192,45 @@ class _StructureTensorPixelLossFn(torch.autograd.Function):
         sr = sr.contiguous()
         hr = hr.contiguous()
         B, _, H, W = sr.shape
-        g, dg = _taps.gaussian_taps(float(sigma))
-        k, _ = _taps.gaussian_taps(float(rho))
-        rs, rk = len(g) // 2, len(k) // 2
-        if not lib.srst_st_supported(rs, rk):
-            raise NotImplementedError(
-                f"StructureTensorPixelLoss: filter radii (sigma={sigma} -> {rs}, rho={rho} -> {rk}) are not "
-                "compiled into libsrst.so")
+        tp = _st_taps(sigma, rho, "StructureTensorPixelLoss")
         need_sr = ctx.needs_input_grad[0]
-        with torch.cuda.device(sr.device):
+        n_ds = (B * 3 * H * W + 3) // 4 * 4
+        n_ixy = lib.srst_st_ixy_floats(B, H, W)
+        with _on_device(sr.device):
             stream = torch.cuda.current_stream().cuda_stream
             both = torch.empty(2, dtype=torch.float32, device=sr.device)
-            ds_sr = torch.empty_like(sr) if need_sr else None
-            ws = _workspace(sr.device, stream, lib.srst_st_workspace_bytes(B, H, W))
-            rc = lib.srst_stpx_forward(_ptr(sr), _ptr(hr), B, H, W, _taps.as_c(g), _taps.as_c(dg), rs, _taps.as_c(k), rk,
-                                       int(bool(normalize)), 1e-12, _ptr(both), _ptr(ds_sr), _ptr(ws), ws.numel(),
-                                       ctypes.c_void_p(stream))
-        _cabi.check(rc, "srst_stpx_forward")
-        ctx.save_for_backward(sr, hr, ds_sr)
-        ctx.taps = (g, dg, k)
+            saved = torch.empty(n_ds + n_ixy, dtype=torch.float32, device=sr.device) if need_sr else None
+            ws = _workspace("st", sr.device, stream, lib.srst_st_workspace_bytes(B, H, W))
+            rc = lib.srst_stpx_forward(sr.data_ptr(), hr.data_ptr(), B, H, W, tp[0], tp[1], tp[2], tp[3], tp[4],
+                                       int(bool(normalize)), 1e-12, both.data_ptr(),
+                                       saved.data_ptr() if need_sr else None,
+                                       saved.data_ptr() + 4 * n_ds if need_sr else None,
+                                       ws.data_ptr(), ws.numel(), stream)
+        if rc:
+            _cabi.check(rc, "srst_stpx_forward")
+        ctx.save_for_backward(sr, hr, saved)
+        ctx.meta = (tp, n_ds)
         return both[0], both[1]
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_st, grad_px):
         lib = _cabi.lib()
-        sr, hr, ds_sr = ctx.saved_tensors
-        g, dg, k = ctx.taps
-        if ds_sr is None or not ctx.needs_input_grad[0]:
+        sr, hr, saved = ctx.saved_tensors
+        tp, n_ds = ctx.meta
+        if saved is None or not ctx.needs_input_grad[0]:
             return None, None, None, None, None
         B, _, H, W = sr.shape
-        with torch.cuda.device(sr.device):
+        with _on_device(sr.device):
             stream = torch.cuda.current_stream().cuda_stream
             grad_st = grad_st.to(torch.float32).contiguous()
             grad_px = grad_px.to(torch.float32).contiguous()
             d_sr = torch.empty_like(sr)
-            rc = lib.srst_stpx_backward(_ptr(sr), _ptr(hr), _ptr(ds_sr), _ptr(grad_st), _ptr(grad_px), B, H, W,
-                                        _taps.as_c(g), _taps.as_c(dg), len(g) // 2, _taps.as_c(k), len(k) // 2,
-                                        _ptr(d_sr), ctypes.c_void_p(stream))
-        _cabi.check(rc, "srst_stpx_backward")
+            rc = lib.srst_stpx_backward(sr.data_ptr(), hr.data_ptr(), saved.data_ptr() + 4 * n_ds, saved.data_ptr(),
+                                        grad_st.data_ptr(), grad_px.data_ptr(), B, H, W, tp[0], tp[1], tp[2], tp[3],
+                                        tp[4], d_sr.data_ptr(), stream)
+        if rc:
+            _cabi.check(rc, "srst_stpx_backward")
         return d_sr, None, None, None, None
 
 
@@ -249,7 +280,7 @@ class _BestBuddyLossFn(torch.autograd.Function):
         B, _, H, W = sr.shape
         if H < 12 or W < 12:
             raise ValueError(f"BestBuddyLoss: images must be at least 12x12 (got {H}x{W})")
-        with torch.cuda.device(sr.device):
+        with _on_device(sr.device):
             stream = torch.cuda.current_stream().cuda_stream
             if pyramid == "aten":
                 # the reference's own op for the HR pyramid (loss.py:123,127)
@@ -264,10 +295,10 @@ class _BestBuddyLossFn(torch.autograd.Function):
             idx = torch.empty((B, N), dtype=torch.int64, device=sr.device)
             loss = torch.empty((), dtype=torch.float32, device=sr.device)
             nbytes = lib.srst_bb_workspace_bytes(B, H, W)
-            ws = _workspace(sr.device, stream, nbytes)
+            ws = _workspace("bb", sr.device, stream, nbytes)
             rc = fwd(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), B, H, W, float(alpha), float(beta),
                                      int(criterion), _ptr(idx), _ptr(loss), _ptr(ws), ws.numel(),
-                                     ctypes.c_void_p(stream))
+                                     stream)
         _cabi.check(rc, "srst_bb_forward" if mode == "patch" else "srst_gram_forward")
         ctx.save_for_backward(sr, gt, gt2, gt4, idx)
         ctx.criterion = int(criterion)
@@ -285,13 +316,13 @@ class _BestBuddyLossFn(torch.autograd.Function):
         if not ctx.needs_input_grad[0]:
             return None, None, None, None, None, None, None
         grad_out = grad_out.to(torch.float32).contiguous()
-        with torch.cuda.device(sr.device):
+        with _on_device(sr.device):
             stream = torch.cuda.current_stream().cuda_stream
             d_sr = torch.empty_like(sr)
             nbytes = lib.srst_bb_workspace_bytes(B, H, W)
-            ws = _workspace(sr.device, stream, nbytes)
+            ws = _workspace("bb", sr.device, stream, nbytes)
             rc = bwd(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
-                                      ctx.criterion, _ptr(d_sr), _ptr(ws), ws.numel(), ctypes.c_void_p(stream))
+                                      ctx.criterion, _ptr(d_sr), _ptr(ws), ws.numel(), stream)
         _cabi.check(rc, "srst_bb_backward" if ctx.mode == "patch" else "srst_gram_backward")
         return d_sr, None, None, None, None, None, None
 
@@ -399,7 +430,7 @@ class _PatchwiseStLossFn(torch.autograd.Function):
             raise ValueError(f"PatchwiseStructureTensorLoss: images must be at least 12x12 (got {H}x{W})")
         g, dg = _taps.gaussian_taps(float(sigma))
         k, _ = _taps.gaussian_taps(float(rho))
-        with torch.cuda.device(sr.device):
+        with _on_device(sr.device):
             stream = torch.cuda.current_stream().cuda_stream
             if pyramid == "aten":
                 with torch.no_grad():  # the reference's own op for the HR pyramid (loss.py:353,356)
@@ -412,11 +443,11 @@ class _PatchwiseStLossFn(torch.autograd.Function):
             N = (H // 3) * (W // 3)
             idx = torch.empty((B, N), dtype=torch.int64, device=sr.device)
             loss = torch.empty((), dtype=torch.float32, device=sr.device)
-            ws = _workspace(sr.device, stream, lib.srst_bb_workspace_bytes(B, H, W))
+            ws = _workspace("bb", sr.device, stream, lib.srst_bb_workspace_bytes(B, H, W))
             rc = lib.srst_pst_forward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), B, H, W, _taps.as_c(g), _taps.as_c(dg),
                                       len(g) // 2, _taps.as_c(k), len(k) // 2, float(alpha), float(beta),
                                       int(criterion), _ptr(idx), _ptr(loss), _ptr(ws), ws.numel(),
-                                      ctypes.c_void_p(stream))
+                                      stream)
         _cabi.check(rc, "srst_pst_forward")
         ctx.save_for_backward(sr, gt, gt2, gt4, idx)
         ctx.taps = (g, dg, k)
@@ -434,13 +465,13 @@ class _PatchwiseStLossFn(torch.autograd.Function):
         if not ctx.needs_input_grad[0]:
             return (None,) * 8
         grad_out = grad_out.to(torch.float32).contiguous()
-        with torch.cuda.device(sr.device):
+        with _on_device(sr.device):
             stream = torch.cuda.current_stream().cuda_stream
             d_sr = torch.empty_like(sr)
-            ws = _workspace(sr.device, stream, lib.srst_bb_workspace_bytes(B, H, W))
+            ws = _workspace("bb", sr.device, stream, lib.srst_bb_workspace_bytes(B, H, W))
             rc = lib.srst_pst_backward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
                                        _taps.as_c(g), _taps.as_c(dg), len(g) // 2, _taps.as_c(k), len(k) // 2,
-                                       ctx.criterion, _ptr(d_sr), _ptr(ws), ws.numel(), ctypes.c_void_p(stream))
+                                       ctx.criterion, _ptr(d_sr), _ptr(ws), ws.numel(), stream)
         _cabi.check(rc, "srst_pst_backward")
         return (d_sr,) + (None,) * 7
 

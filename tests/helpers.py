@@ -57,7 +57,7 @@ def _fp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
 
 
-def emu_st(lib, sr, hr, taps, normalize=True, want_hr=False, grad_out=1.0, save_gray=True):
+def emu_st(lib, sr, hr, taps, normalize=True, want_hr=False, grad_out=1.0):
     """Run srst_st_forward + srst_st_backward of `lib` on host arrays (emulation library only)."""
     sr = np.ascontiguousarray(sr, np.float32)
     hr = np.ascontiguousarray(hr, np.float32)
@@ -66,24 +66,25 @@ def emu_st(lib, sr, hr, taps, normalize=True, want_hr=False, grad_out=1.0, save_
     nb = lib.srst_st_workspace_bytes(B, H, W)
     ws = np.zeros(nb // 4 + 4, np.float32)
     loss = np.zeros(1, np.float32)
+    n_ixy = lib.srst_st_ixy_floats(B, H, W)
     ds_sr = np.full_like(sr, np.nan)
     ds_hr = np.full_like(sr, np.nan) if want_hr else None
-    gray_sr = np.full((B, H, W), np.nan, np.float32) if save_gray else None
-    gray_hr = np.full((B, H, W), np.nan, np.float32) if (save_gray and want_hr) else None
+    ixy_sr = np.full(n_ixy, np.nan, np.float32)
+    ixy_hr = np.full(n_ixy, np.nan, np.float32) if want_hr else None
     rc = lib.srst_st_forward(_p(sr), _p(hr), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k), len(k) // 2,
-                             int(normalize), 1e-12, _p(loss), _p(ds_sr), _p(ds_hr), _p(gray_sr), _p(gray_hr), _p(ws), nb,
+                             int(normalize), 1e-12, _p(loss), _p(ds_sr), _p(ds_hr), _p(ixy_sr), _p(ixy_hr), _p(ws), nb,
                              None)
     assert rc == 0, rc
     go = np.full(1, grad_out, np.float32)
-    out = dict(loss=float(loss[0]), ds_sr=ds_sr, ws=ws, gray_sr=gray_sr)
+    out = dict(loss=float(loss[0]), ds_sr=ds_sr, ws=ws, ixy_sr=ixy_sr.reshape(B, 2, (H + 1) // 2, W, 2))
     d_sr = np.full_like(sr, np.nan)
-    rc = lib.srst_st_backward(_p(sr), _p(gray_sr), _p(ds_sr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
+    rc = lib.srst_st_backward(_p(ixy_sr), _p(ds_sr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
                               len(k) // 2, _p(d_sr), None)
     assert rc == 0, rc
     out["d_sr"] = d_sr
     if want_hr:
         d_hr = np.full_like(sr, np.nan)
-        rc = lib.srst_st_backward(_p(hr), _p(gray_hr), _p(ds_hr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
+        rc = lib.srst_st_backward(_p(ixy_hr), _p(ds_hr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
                                   len(k) // 2, _p(d_hr), None)
         assert rc == 0, rc
         out["d_hr"] = d_hr
@@ -134,12 +135,13 @@ def emu_stpx(lib, sr, hr, taps, grad_st=1.0, grad_px=1.0):
     ws = np.zeros(nb // 4 + 4, np.float32)
     both = np.zeros(2, np.float32)
     ds_sr = np.full_like(sr, np.nan)
+    ixy_sr = np.full(lib.srst_st_ixy_floats(B, H, W), np.nan, np.float32)
     rc = lib.srst_stpx_forward(_p(sr), _p(hr), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k), len(k) // 2, 1, 1e-12,
-                               _p(both), _p(ds_sr), _p(ws), nb, None)
+                               _p(both), _p(ds_sr), _p(ixy_sr), _p(ws), nb, None)
     assert rc == 0, rc
     gs, gp = np.full(1, grad_st, np.float32), np.full(1, grad_px, np.float32)
     d_sr = np.full_like(sr, np.nan)
-    rc = lib.srst_stpx_backward(_p(sr), _p(hr), _p(ds_sr), _p(gs), _p(gp), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
-                                len(k) // 2, _p(d_sr), None)
+    rc = lib.srst_stpx_backward(_p(sr), _p(hr), _p(ixy_sr), _p(ds_sr), _p(gs), _p(gp), B, H, W, _fp(g), _fp(dg),
+                                len(g) // 2, _fp(k), len(k) // 2, _p(d_sr), None)
     assert rc == 0, rc
     return dict(st=float(both[0]), px=float(both[1]), d_sr=d_sr, ws=ws)

@@ -35,13 +35,17 @@ def test_no_compute_entry_points_that_need_no_gpu():
     """Pure host queries work on the CPU box (no kernel is launched)."""
     from srgan_st_b200 import _cabi
     lib = _cabi.lib()
-    assert lib.srst_version() == 102
+    assert lib.srst_version() // 100 == _cabi.ABI_MAJOR == 2
     assert lib.srst_st_supported(2, 8) == 1
     assert lib.srst_st_supported(4, 12) == 1 and lib.srst_st_supported(1, 3) == 1   # padded radius classes
     assert lib.srst_st_supported(5, 8) == 0 and lib.srst_st_supported(2, 13) == 0
     assert lib.srst_st_workspace_bytes(16, 96, 96) >= 16 * 3 * 2 * 4
     assert lib.srst_st_workspace_bytes(0, 96, 96) == 0
     assert b"workspace" in lib.srst_error_string(-3)
+    assert lib.srst_st_ixy_floats(2, 5, 8) == 2 * 2 * 3 * 8 * 2       # [B][2][ceil(H/2)][W][2]
+    assert lib.srst_st_num_cfgs(0) >= 2 and lib.srst_st_num_cfgs(1) >= 2
+    assert lib.srst_st_force_cfg(99, 0) == -1 and lib.srst_st_force_cfg(-1, -1) == 0
     # argument validation happens before any CUDA call
     assert lib.srst_st_forward(None, None, 1, 8, 8, None, None, 2, None, 8, 1, 1e-12, None, None, None,
                                None, None, None, 0, None) == -1
+    assert lib.srst_st_backward(None, None, None, 1, 8, 8, None, None, 2, None, 8, None, None) == -1

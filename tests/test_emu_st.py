@@ -15,11 +15,13 @@ def lib():
     return emu_lib()
 
 
-@pytest.fixture(params=[0, 1, 2, 3, 4, 10])
-def tile_cfg(request, monkeypatch):
-    monkeypatch.setenv("SRST_ST_FWD_CFG", str(request.param))
-    monkeypatch.setenv("SRST_ST_BWD_CFG", str({0: 0, 1: 7, 2: 8, 3: 3, 4: 5, 10: 6}[request.param]))
-    return request.param
+@pytest.fixture(params=[0, 1, 2, 3, 4, 5])
+def tile_cfg(request, lib):
+    """Every compiled forward tile shape, paired with a backward shape (srst_st_force_cfg)."""
+    assert lib.srst_st_num_cfgs(0) >= 6 and lib.srst_st_num_cfgs(1) >= 6
+    assert lib.srst_st_force_cfg(request.param, request.param) == 0
+    yield request.param
+    lib.srst_st_force_cfg(-1, -1)
 
 
 @pytest.mark.parametrize("name", ["st_rand_2x24x36", "st_srlike_2x40x52", "st_rand_ragged_1x37x53"])
@@ -81,15 +83,22 @@ def test_emulated_golden_sigma1_rho25(lib):
     assert maxnorm_err(out["d_sr"], ref["d_sr"]) < 1e-4 and maxnorm_err(out["d_hr"], ref["d_hr"]) < 1e-4
 
 
-def test_emulated_backward_without_saved_gray(lib):
-    """gray = NULL: the backward re-reads RGB and converts (same result as the TMA gray-tile path)."""
-    z = golden("st_srlike_2x40x52")
+def test_emulated_saved_gradient_planes(lib):
+    """The ixy planes the forward saves are the oracle's Ix, Iy, row-pair interleaved, zero in the padding row of an
+    odd-height image -- and fully written (no NaN left from the poison fill)."""
+    z = golden("st_rand_ragged_1x37x53")
     taps = (z["g"], z["dg"], z["k"])
-    a = emu_st(lib, z["sr"], z["hr"], taps, save_gray=True)
-    b = emu_st(lib, z["sr"], z["hr"], taps, save_gray=False)
-    assert np.allclose(a["d_sr"], b["d_sr"], rtol=1e-5, atol=1e-9)
-    gray = 0.2989 * z["sr"][:, 0] + 0.587 * z["sr"][:, 1] + 0.114 * z["sr"][:, 2]
-    assert np.allclose(a["gray_sr"], gray, rtol=1e-6, atol=1e-7)
+    out = emu_st(lib, z["sr"], z["hr"], taps)
+    gray = (0.2989 * z["sr"][:, 0] + 0.587 * z["sr"][:, 1]) + 0.114 * z["sr"][:, 2]
+    Ix = O._corr_axis(O._corr_axis(gray.astype(np.float64), z["dg"].astype(np.float64), 1), z["g"].astype(np.float64), 2)
+    Iy = O._corr_axis(O._corr_axis(gray.astype(np.float64), z["g"].astype(np.float64), 1), z["dg"].astype(np.float64), 2)
+    ixy = out["ixy_sr"]                                  # [B, 2, Hp, W, 2]
+    H = gray.shape[1]
+    got_x = ixy[:, 0].transpose(0, 1, 3, 2).reshape(1, -1, gray.shape[2])[:, :H]   # rows 2p, 2p+1 de-interleaved
+    got_y = ixy[:, 1].transpose(0, 1, 3, 2).reshape(1, -1, gray.shape[2])[:, :H]
+    assert not np.isnan(ixy).any()
+    assert np.allclose(got_x, Ix, rtol=1e-5, atol=1e-6) and np.allclose(got_y, Iy, rtol=1e-5, atol=1e-6)
+    assert np.all(ixy[:, :, -1, :, 1] == 0)             # H = 37 is odd: the pair partner of the last row
 
 
 @pytest.mark.parametrize("shape", [(1, 3, 1, 1), (1, 3, 5, 7), (2, 3, 17, 4), (1, 3, 2, 130), (1, 3, 9, 9)])

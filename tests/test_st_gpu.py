@@ -31,17 +31,18 @@ def _run(sr, hr, normalize=True, want_hr=True, sigma=0.5, rho=2.0):
     return loss.item(), x.grad.cpu().numpy(), (y.grad.cpu().numpy() if want_hr else None)
 
 
-@pytest.fixture(params=[-1, 0, 1, 2, 3, 4, 10, "stream"])
-def tile_cfg(request, monkeypatch):
-    """-1 = the library's own choice; 0..4 force a compiled tile shape, 10 the wide-strip kernels; "stream" forces the
-    row-marching forward kernel."""
-    if request.param == "stream":
-        monkeypatch.setenv("SRST_ST_STREAM", "1")
-        return request.param
-    if request.param >= 0:
-        monkeypatch.setenv("SRST_ST_FWD_CFG", str(request.param))
-        monkeypatch.setenv("SRST_ST_BWD_CFG", str({0: 0, 1: 7, 2: 8, 3: 3, 4: 5, 10: 6}[request.param]))
-    return request.param
+N_CFG = 6   # compiled tile shapes exercised per direction (srst_st_num_cfgs() >= this)
+
+
+@pytest.fixture(params=[-1, 0, 1, 2, 3, 4, 5])
+def tile_cfg(request):
+    """-1 = the library's own choice; 0.. force a compiled forward / backward tile shape (srst_st_force_cfg)."""
+    from srgan_st_b200 import _cabi
+    lib = _cabi.lib()
+    assert lib.srst_st_num_cfgs(0) >= N_CFG and lib.srst_st_num_cfgs(1) >= N_CFG
+    assert lib.srst_st_force_cfg(request.param, request.param) == 0
+    yield request.param
+    lib.srst_st_force_cfg(-1, -1)
 
 
 @pytest.mark.parametrize("name", DEFAULT_CASES)

@@ -17,12 +17,10 @@ def _mse(sr, hr):
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("cfg", [-1, 0, 2, 3])
-def test_emulated_fused_terms_and_gradient(name, cfg, monkeypatch):
-    if cfg >= 0:
-        monkeypatch.setenv("SRST_ST_FWD_CFG", str(cfg))
-        monkeypatch.setenv("SRST_ST_BWD_CFG", str({0: 0, 2: 7, 3: 5}[cfg]))
+@pytest.mark.parametrize("cfg", [-1, 0, 1])
+def test_emulated_fused_terms_and_gradient(name, cfg):
     lib = emu_lib()
+    assert lib.srst_st_force_cfg(cfg, cfg) == 0   # the fused term is compiled into the two default tile shapes
     z = golden(name)
     taps = (z["g"], z["dg"], z["k"])
     w_st, w_px = 1.0 / 3.0, 1.7
@@ -34,6 +32,7 @@ def test_emulated_fused_terms_and_gradient(name, cfg, monkeypatch):
     want = w_st * ref["d_sr"] + w_px * dmse
     assert maxnorm_err(out["d_sr"], want) < 1e-4
     assert np.all(out["ws"] == 0), "workspace must be left zeroed (both partial arrays)"
+    lib.srst_st_force_cfg(-1, -1)
 
 
 @pytest.mark.gpu

@@ -13,7 +13,8 @@ from srgan_st_b200 import _cabi, taps as T  # noqa: E402
 def _bind_ab(path):
     """A/B builds may predate newer entry points: bind only what this tool calls."""
     l = ctypes.CDLL(path)
-    for name in ("srst_st_forward", "srst_st_backward", "srst_st_workspace_bytes"):
+    for name in ("srst_st_forward", "srst_st_backward", "srst_st_workspace_bytes", "srst_st_ixy_floats",
+                 "srst_st_force_cfg", "srst_st_num_cfgs"):
         fn = getattr(l, name)
         fn.restype, fn.argtypes = _cabi.SIGNATURES[name]
     return l
@@ -24,11 +25,9 @@ g, dg = T.gaussian_taps(0.5)
 k, _ = T.gaussian_taps(2.0)
 dev = torch.device("cuda:0")
 vp = lambda t: ctypes.c_void_p(t.data_ptr())
-GRAY = (lambda t: vp(t)) if os.environ.get("SRST_ST_SAVE_GRAY", "0") == "1" else (lambda t: None)
 HBM = 6539.9
-FWD_CFGS = [int(x) for x in os.environ.get('SWEEP_FWD', '0,1,2,3,4').split(',')]
-BWD_MAX = int(os.environ.get('SWEEP_BWD_MAX', '2'))
-BWD_CFGS = [int(x) for x in os.environ['SWEEP_BWD'].split(',')] if os.environ.get('SWEEP_BWD') else None
+FWD_CFGS = [int(x) for x in os.environ['SWEEP_FWD'].split(',')] if os.environ.get('SWEEP_FWD') else list(range(lib.srst_st_num_cfgs(0)))
+BWD_CFGS = [int(x) for x in os.environ['SWEEP_BWD'].split(',')] if os.environ.get('SWEEP_BWD') else list(range(lib.srst_st_num_cfgs(1)))
 
 
 def run(B, H, W, iters=40):
@@ -37,7 +36,7 @@ def run(B, H, W, iters=40):
     pool = [(torch.rand(B, 3, H, W, device=dev), torch.rand(B, 3, H, W, device=dev)) for _ in range(pool_n)]
     ds = torch.empty(B, 3, H, W, device=dev)
     d_sr = torch.empty(B, 3, H, W, device=dev)
-    gray = torch.empty(B, H, W, device=dev)
+    ixy = torch.empty(lib.srst_st_ixy_floats(B, H, W), device=dev)
     loss = torch.zeros((), device=dev)
     go = torch.ones((), device=dev)
     ws = torch.zeros(max(lib.srst_st_workspace_bytes(B, H, W), 4096), dtype=torch.uint8, device=dev)
@@ -47,11 +46,10 @@ def run(B, H, W, iters=40):
     def fwd(i):
         sr, hr = pool[i % pool_n]
         _cabi.check(lib.srst_st_forward(vp(sr), vp(hr), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8, 1, 1e-12,
-                                        vp(loss), vp(ds), None, GRAY(gray), None, vp(ws), ws.numel(), sp), "fwd")
+                                        vp(loss), vp(ds), None, vp(ixy), None, vp(ws), ws.numel(), sp), "fwd")
 
     def bwd(i):
-        sr, _ = pool[i % pool_n]
-        _cabi.check(lib.srst_st_backward(vp(sr), GRAY(gray), vp(ds), vp(go), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8,
+        _cabi.check(lib.srst_st_backward(vp(ixy), vp(ds), vp(go), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8,
                                          vp(d_sr), sp), "bwd")
 
     def timeit(fn):
@@ -83,26 +81,22 @@ def run(B, H, W, iters=40):
     torch.cuda.synchronize()
     px = B * H * W
     for cfg in FWD_CFGS:
-        os.environ["SRST_ST_FWD_CFG"] = str(cfg)
-        os.environ["SRST_ST_BWD_CFG"] = str(cfg % (BWD_MAX + 1))
-        tf, tb = timeit(fwd), timeit(bwd)
-        print(f"B={B:3d} {H}x{W} cfg={cfg}: fwd {tf*1e3:8.1f} us ({24*px/tf/1e6/HBM*100:5.1f}% HBM)  "
-              f"bwd {tb*1e3:8.1f} us ({36*px/tb/1e6/HBM*100:5.1f}% HBM)  pair {60*px/(tf+tb)/1e6/HBM*100:5.1f}%  "
-              f"{B/((tf+tb)*1e-3):.0f} img/s", flush=True)
-    if BWD_CFGS:
-        for cfg in BWD_CFGS:
-            os.environ["SRST_ST_BWD_CFG"] = str(cfg)
-            tb = timeit(bwd)
-            print(f"B={B:3d} {H}x{W} bwd cfg={cfg}: {tb*1e3:8.1f} us ({36*px/tb/1e6/HBM*100:5.1f}% HBM)", flush=True)
-    os.environ.pop("SRST_ST_FWD_CFG", None); os.environ.pop("SRST_ST_BWD_CFG", None)
-    if os.environ.get("SWEEP_STREAM", "1") == "1":
-        os.environ["SRST_ST_STREAM"] = "1"
+        lib.srst_st_force_cfg(cfg, -1)
         tf = timeit(fwd)
-        os.environ["SRST_ST_STREAM"] = "0"
-        print(f"B={B:3d} {H}x{W} STREAM: fwd {tf*1e3:8.1f} us ({24*px/tf/1e6/HBM*100:5.1f}% HBM)", flush=True)
+        print(f"B={B:3d} {H}x{W} fwd cfg={cfg}: {tf*1e3:8.1f} us ({24*px/tf/1e6/HBM*100:5.1f}% HBM)", flush=True)
+    for cfg in BWD_CFGS:
+        lib.srst_st_force_cfg(-1, cfg)
+        tb = timeit(bwd)
+        print(f"B={B:3d} {H}x{W} bwd cfg={cfg}: {tb*1e3:8.1f} us ({36*px/tb/1e6/HBM*100:5.1f}% HBM)", flush=True)
+    lib.srst_st_force_cfg(-1, -1)
+    tf, tb = timeit(fwd), timeit(bwd)
+    print(f"B={B:3d} {H}x{W} default: fwd {tf*1e3:8.1f} us ({24*px/tf/1e6/HBM*100:5.1f}% HBM)  "
+          f"bwd {tb*1e3:8.1f} us ({36*px/tb/1e6/HBM*100:5.1f}% HBM)  pair {60*px/(tf+tb)/1e6/HBM*100:5.1f}%  "
+          f"{B/((tf+tb)*1e-3):.0f} img/s", flush=True)
 
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    for shape in [(16, 96, 96), (64, 96, 96), (256, 96, 96), (1, 1356, 2040), (4, 1356, 2040)]:
+    shapes = [tuple(int(v) for v in t.split('x')) for t in os.environ['SWEEP_SHAPES'].split(',')] if os.environ.get('SWEEP_SHAPES') else [(16, 96, 96), (64, 96, 96), (1024, 96, 96), (1, 1356, 2040)]
+    for shape in shapes:
         run(*shape)
