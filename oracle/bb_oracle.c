@@ -172,11 +172,12 @@ int bb_oracle_forward_mode(const float* sr, const float* gt, const float* gt2, c
       for (int j = 0; j < M; ++j) {
         float d1 = fmaf(-2.0f, dotd(q1 + (size_t)i * Dd, y + (size_t)j * Dd, Dd), xn[i] + yn[j]);
         float d2 = fmaf(-2.0f, dotd(q2 + (size_t)i * Dd, y + (size_t)j * Dd, Dd), gn[i] + yn[j]);
-        d1 = d1 > 0.f ? d1 : 0.f;
-        d2 = d2 > 0.f ? d2 : 0.f;
+        d1 = d1 < 0.f ? 0.f : d1; /* torch.clamp(min=0) keeps NaN (utils.py:187) */
+        d2 = d2 < 0.f ? 0.f : d2;
         const float a = alpha * d1, bb = beta * d2;
         const float s = a + bb;
-        if (s < best) { second = best; best = s; bi = j; }
+        /* torch.min (loss.py:135): first minimum; a NaN beats every number and the first NaN wins */
+        if (s < best || (s != s && best == best)) { second = best; best = s; bi = j; }
         else if (s < second) second = s;
       }
       idx[(size_t)b * N + i] = bi;

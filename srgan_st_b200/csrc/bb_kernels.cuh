@@ -341,13 +341,20 @@ SRST_DEV float bb_score(float xn, float gn, float yn, float dot1, float dot2, fl
   // loss.py:132-133: alpha*d1 + beta*d2 (separate multiply and add roundings).
   float d1 = fmaf(-2.0f, dot1, __fadd_rn(xn, yn));
   float d2 = fmaf(-2.0f, dot2, __fadd_rn(gn, yn));
-  d1 = fmaxf(d1, 0.0f);
-  d2 = fmaxf(d2, 0.0f);
+  d1 = (d1 < 0.0f) ? 0.0f : d1;  // torch.clamp(min=0) keeps NaN (fmaxf would drop it)
+  d2 = (d2 < 0.0f) ? 0.0f : d2;
   return __fadd_rn(__fmul_rn(alpha, d1), __fmul_rn(beta, d2));
 }
 
+// torch.min order (loss.py:135): a NaN score is "smaller" than every number, the first NaN wins, ties go to the
+// lowest index.  (score, index) pairs merge lexicographically under that order.
+SRST_DEV bool bb_score_before(float so, int io, float s, int i) {
+  const bool nan_o = so != so, nan_s = s != s;
+  if (nan_o || nan_s) return nan_o && (!nan_s || io < i);
+  return so < s || (so == s && io < i);
+}
 SRST_DEV void bb_argmin_merge(float& s, int& i, float so, int io) {
-  if (so < s || (so == s && io < i)) { s = so; i = io; }
+  if (bb_score_before(so, io, s, i)) { s = so; i = io; }
 }
 
 // Search kernel: a cheap single-dot FILTER in front of the exact score.
@@ -447,7 +454,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     }
     if (tid < BB_CT) pfn = __ldg(P.yn + chunk + tid);
   };
-  auto commit = [&](int buf, [[maybe_unused]] int chunk) {
+  auto commit = [&](int buf, int chunk) {
 #pragma unroll
     for (int u = 0; u < NLD; ++u) {
       const int it = tid + u * BB_NT;
@@ -456,9 +463,10 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
         st4(&sY[buf][k][4 * c4], pf[u]);
       }
     }
-    // padded candidates carry |y|^2 = +inf: their lower bound is +inf (or NaN) and never passes
+    // padded candidates (|y|^2 = +inf in the workspace) get a lower bound of exactly +inf: it never passes the
+    // filter, not even against a NaN-poisoned comparison (inf - inf would be NaN, which now counts as a hit)
     if (tid < BB_CT) {
-      sYl[buf][tid] = (alpha + beta) * pfn - kBbKappa * ((aa + ab) * pfn);
+      sYl[buf][tid] = (chunk + tid < g.M) ? (alpha + beta) * pfn - kBbKappa * ((aa + ab) * pfn) : __int_as_float(0x7f800000);
       if constexpr (SHARE) {
         float m = (chunk + tid < g.M) ? (aa + ab) * pfn : 0.f;
 #pragma unroll
@@ -528,8 +536,9 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const float2 lo = __ffma2_rn(m2, acc[p][j], __fadd2_rn(cl[p], y2));
-          if (lo.x <= B[2 * p]) hit |= 1ull << (8 * j + 2 * p);
-          if (lo.y <= B[2 * p + 1]) hit |= 1ull << (8 * j + 2 * p + 1);
+          // !(lo > B): a NaN bound or a NaN candidate is a hit, so NaN inputs reach the exact path below
+          if (!(lo.x > B[2 * p])) hit |= 1ull << (8 * j + 2 * p);
+          if (!(lo.y > B[2 * p + 1])) hit |= 1ull << (8 * j + 2 * p + 1);
         }
       }
     } else {
@@ -565,8 +574,8 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
       for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          if (acc[p][j].x <= B[2 * p]) hit |= 1ull << (8 * j + 2 * p);
-          if (acc[p][j].y <= B[2 * p + 1]) hit |= 1ull << (8 * j + 2 * p + 1);
+          if (!(acc[p][j].x > B[2 * p])) hit |= 1ull << (8 * j + 2 * p);
+          if (!(acc[p][j].y > B[2 * p + 1])) hit |= 1ull << (8 * j + 2 * p + 1);
         }
     }
     if (hit) {  // rare: exact re-scoring, ascending candidate order per query
@@ -578,7 +587,8 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
           if ((hit >> (8 * j + i)) & 1ull) {
             const int qi = qbase + 4 * ty + (i & 3) + 64 * (i >> 2);
             const float s = bb_exact_score(P.q1, P.q2, P.y, P.xn, P.gn, P.yn, g.Npad, g.Mpad, D, qi, cj, alpha, beta);
-            if (s < best[i]) { best[i] = s; bidx[i] = cj; }  // ascending cj per thread: first minimum kept
+            // ascending cj per thread: first minimum kept; the first NaN beats every number (torch.min)
+            if (s < best[i] || (s != s && best[i] == best[i])) { best[i] = s; bidx[i] = cj; }
             B[i] = fminf(B[i], s);
           }
         }
@@ -598,7 +608,8 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
       bb_argmin_merge(best[i], bidx[i], so, io);
     }
     const int qi = qbase + 4 * ty + (i & 3) + 64 * (i >> 2);
-    if (tx == 0 && qi < g.N) idx_out[(size_t)b * g.N + qi] = (int64_t)bidx[i];
+    // no comparison ever passed (every score +inf): torch.min returns index 0; never emit an out-of-range index
+    if (tx == 0 && qi < g.N) idx_out[(size_t)b * g.N + qi] = (int64_t)(bidx[i] == 0x7fffffff ? 0 : bidx[i]);
   }
 }
 

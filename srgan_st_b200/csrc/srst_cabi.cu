@@ -36,14 +36,15 @@ static int forced_bwd() {
 
 // ---- compiled structure-tensor tile configurations (reference default radii: r_sigma 2, r_rho 8) ----
 //                       TH  TW  RS CSB RG RK MINB CHU
+//                                                 GPARK MINB without it
 using Fwd0 = StFwdCfg<48, 48, 12, 4, 2, 8, 2>;  // square quarter of a 96x96 crop, 288 threads
-using Fwd1 = StFwdCfg<32, 64, 16, 4, 2, 8, 2>;  // large images, 256 threads
+using Fwd1 = StFwdCfg<32, 64, 16, 4, 2, 8, 3, 1, true, 2>;  // large images, 256 threads, three CTAs per SM
 using Fwd2 = StFwdCfg<24, 96, 8, 4, 2, 8, 2>;   // full-width strip of a 96-wide crop (no horizontal halo), 288 threads
-using Fwd3 = StFwdCfg<32, 48, 16, 4, 2, 8, 3>;  // small footprint: three 192-thread CTAs per SM
-using Fwd4 = StFwdCfg<40, 64, 10, 4, 2, 8, 2>;  // taller tile, 320 threads
-using Fwd5 = StFwdCfg<24, 64, 12, 4, 2, 8, 3>;  // three 192-thread CTAs per SM
-using Fwd6 = StFwdCfg<48, 48, 12, 4, 2, 8, 2, 2>;  // Fwd0 with two chain iterations in flight
-using Fwd7 = StFwdCfg<32, 64, 16, 4, 2, 8, 2, 2>;  // Fwd1 with two chain iterations in flight
+using Fwd3 = StFwdCfg<24, 96, 8, 4, 2, 8, 3, 1, true, 2>;   // Fwd2, SR tensor parked in L2: three CTAs per SM
+using Fwd4 = StFwdCfg<40, 64, 10, 4, 2, 8, 2, 1, true, 2>;  // taller tile, 320 threads
+using Fwd5 = StFwdCfg<32, 64, 16, 4, 2, 8, 2>;  // Fwd1 with the SR tensor parked in shared memory (two CTAs per SM)
+using Fwd6 = StFwdCfg<48, 48, 12, 4, 2, 8, 2, 4>;  // Fwd0, per-pixel chain fully unrolled
+using Fwd7 = StFwdCfg<24, 96, 8, 4, 2, 8, 2, 4>;   // Fwd2, per-pixel chain fully unrolled
 constexpr int kNumFwdCfg = 8;
 //                       TH  TW  RS   NT RG RK MINB CSD
 using Bwd0 = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8>;  // large images: 16 row pairs per horizontal-pass column
@@ -139,6 +140,9 @@ template <class C, bool PX> struct BwdTag {};
 
 template <class C, bool PX = false>
 static int launch_st_forward(StFwdParams<C::RG, C::RK>& P, void* stream) {
+  if constexpr (C::GPARK) {  // the SR tensor is parked in ds_sr: without that buffer use the shared-memory twin
+    if (!P.ds_sr) return launch_st_forward<typename C::SmemPark, PX>(P, stream);
+  }
   P.tiles_x = (P.W + C::TW - 1) / C::TW;
   P.tiles_y = (P.H + C::TH - 1) / C::TH;
   const long long ntiles = (long long)P.B * P.tiles_x * P.tiles_y;

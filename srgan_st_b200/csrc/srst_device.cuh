@@ -75,6 +75,11 @@ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 SRST_DEV float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 SRST_DEV void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 SRST_DEV float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+#ifdef SRST_EMULATE
+SRST_DEV float4 ldcg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+#else
+SRST_DEV float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }  // L2 (data written by this kernel)
+#endif
 
 // torchvision rgb_to_grayscale weights (reference loss.py:400-401).
 constexpr float kGrayR = 0.2989f, kGrayG = 0.587f, kGrayB = 0.114f;

@@ -428,10 +428,17 @@ struct ItemMap {
 // ------------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------------
-template <int TH_, int TW_, int RS_, int CSB_, int RG_, int RK_, int MINB_, int CHU_ = 1>
+template <int TH_, int TW_, int RS_, int CSB_, int RG_, int RK_, int MINB_, int CHU_ = 1, bool GPARK_ = false,
+          int MINB_SMEM_ = MINB_>
 struct StFwdCfg {
   static constexpr int TH = TH_, TW = TW_, RS = RS_, CSB = CSB_, RG = RG_, RK = RK_, MINB = MINB_;
   static constexpr int CHU = CHU_;       // pixel pairs of the per-pixel chain in flight per thread (loop unroll)
+  // GPARK: the SR tensor waits in the ds_sr buffer (L2) instead of shared memory while the HR image is
+  // processed -- the thread later overwrites exactly those 24 floats with its ds values -- which frees
+  // 24 * NT floats of shared memory (one more CTA per SM on the large-image tile).  Needs ds_sr != NULL:
+  // without it the launcher falls back to the shared-memory twin `SmemPark`.
+  static constexpr bool GPARK = GPARK_;
+  using SmemPark = StFwdCfg<TH_, TW_, RS_, CSB_, RG_, RK_, MINB_SMEM_, CHU_, false, MINB_SMEM_>;
   static constexpr int LDEPTH = 2;       // gray-tile items (6 x LDG.128 each) in flight per thread
   static constexpr int HXD = round_up4(RK);  // x halo of the gradient (D) and V regions
   static constexpr int OFF = round_up4(RG);
@@ -450,9 +457,12 @@ struct StFwdCfg {
   // smem: D (Ix, Iy) | V (3 planes; the gray tile aliases it: dead once the gradient phase is done) | SP1.
   // The HR tensor is parked over D (SP2): dead once the vertical pass is done.
   static constexpr int VG_FLOATS = cmax(3 * V_FLOATS, G_FLOATS);
-  static constexpr int SP_OFF = 2 * D_FLOATS + VG_FLOATS;
-  static constexpr int SP2_OFF = (SP_FLOATS <= 2 * D_FLOATS) ? 0 : SP_OFF + SP_FLOATS;  // small radii: D is too small
-  static constexpr int SMEM_FLOATS = SP_OFF + SP_FLOATS + (SP2_OFF ? SP_FLOATS : 0);
+  static constexpr bool SP1_OVER_V = GPARK && SP_FLOATS <= VG_FLOATS;   // GPARK: re-loaded over the (dead) V region
+  static constexpr bool SP2_OVER_D = SP_FLOATS <= 2 * D_FLOATS;        // small radii: D is too small
+  static constexpr int SP_OFF = SP1_OVER_V ? 2 * D_FLOATS : 2 * D_FLOATS + VG_FLOATS;
+  static constexpr int SP1_END = 2 * D_FLOATS + VG_FLOATS + (SP1_OVER_V ? 0 : SP_FLOATS);
+  static constexpr int SP2_OFF = SP2_OVER_D ? 0 : SP1_END;
+  static constexpr int SMEM_FLOATS = SP1_END + (SP2_OVER_D ? 0 : SP_FLOATS);
   static constexpr size_t SMEM_BYTES = sizeof(float) * SMEM_FLOATS;
   static_assert((CSB == 4 || CSB == 8) && DW % CSB == 0, "bad gradient segment width");
   static_assert(TH % RS == 0 && RS % 2 == 0 && TH % 2 == 0 && TW % 4 == 0 && RG % 2 == 0 && RK % 2 == 0,
@@ -624,11 +634,64 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
     st_unit_tensor<C, PX>(smem, base, ixy, b, vec4, H, W, y0, x0, P.taps, tid, dvalid, q, seg, S,
                           (PX && img) ? P.sr + img_off : nullptr, &pxsum);
     if (dvalid) {
-      float* sp = img ? sp2 : sp1;
+      if (C::GPARK && img == 0) {
+        // park the SR tensor where this thread's ds values will go (same 6 x 16 bytes, same layout)
+        const int gy = y0 + 2 * q, gx = x0 + 4 * seg;
+        if (gx < W) {
+          const size_t plane = (size_t)H * W;
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
+          for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) st2(sp + 2 * C::NT * (c * 4 + j), S[c][j]);
+            for (int hf = 0; hf < 2; ++hf) {
+              if (gy + hf >= H) continue;
+              float* o = P.ds_sr + img_off + c * plane + (size_t)(gy + hf) * W + gx;
+              if (vec4) {
+                st4(o, hf ? make_float4(S[c][0].y, S[c][1].y, S[c][2].y, S[c][3].y)
+                          : make_float4(S[c][0].x, S[c][1].x, S[c][2].x, S[c][3].x));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (gx + j < W) o[j] = hf ? S[c][j].y : S[c][j].x;
+              }
+            }
+        }
+      } else {
+        float* sp = img ? sp2 : sp1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st2(sp + 2 * C::NT * (c * 4 + j), S[c][j]);
+      }
+    }
+  }
+  if constexpr (C::GPARK) {
+    if (C::SP1_OVER_V) __syncthreads();  // every thread is done with V (HR horizontal pass): SP1 may overwrite it
+    if (dvalid) {
+      const int gy = y0 + 2 * q, gx = x0 + 4 * seg;
+      const size_t plane = (size_t)H * W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float4 r[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          r[hf] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gx < W && gy + hf < H) {
+            const float* o = P.ds_sr + img_off + c * plane + (size_t)(gy + hf) * W + gx;
+            if (vec4) {
+              r[hf] = ldcg4(o);
+            } else {
+              r[hf].x = __ldcg(o);
+              if (gx + 1 < W) r[hf].y = __ldcg(o + 1);
+              if (gx + 2 < W) r[hf].z = __ldcg(o + 2);
+              if (gx + 3 < W) r[hf].w = __ldcg(o + 3);
+            }
+          }
+        }
+        st2(sp1 + 2 * C::NT * (c * 4 + 0), make_float2(r[0].x, r[1].x));
+        st2(sp1 + 2 * C::NT * (c * 4 + 1), make_float2(r[0].y, r[1].y));
+        st2(sp1 + 2 * C::NT * (c * 4 + 2), make_float2(r[0].z, r[1].z));
+        st2(sp1 + 2 * C::NT * (c * 4 + 3), make_float2(r[0].w, r[1].w));
+      }
     }
   }
 

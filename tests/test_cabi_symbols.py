@@ -49,3 +49,20 @@ def test_no_compute_entry_points_that_need_no_gpu():
     assert lib.srst_st_forward(None, None, 1, 8, 8, None, None, 2, None, 8, 1, 1e-12, None, None, None,
                                None, None, None, 0, None) == -1
     assert lib.srst_st_backward(None, None, None, 1, 8, 8, None, None, 2, None, 8, None, None) == -1
+
+
+def test_integration_md_binding_snippet_matches_the_abi():
+    """INTEGRATION.md section 2 shows a maintainer the ctypes stub; its argtypes lists must be the ones the
+    package binds (round 1 shipped a stale 18-argument srst_st_forward there: copying it corrupted the call)."""
+    from srgan_st_b200 import _cabi
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    env = {"ctypes": ctypes, "vp": ctypes.c_void_p, "fp": ctypes.POINTER(ctypes.c_float)}
+    found = 0
+    for name, body in re.findall(r"lib\.(srst_\w+)\.argtypes = (\[.*?\])\s*(?:#[^\n]*)?\n(?=\S)", md, flags=re.S):
+        body = re.sub(r"#[^\n]*", "", body)
+        argtypes = eval(body, env)  # noqa: S307 - a literal list of ctypes names from our own document
+        assert argtypes == _cabi.SIGNATURES[name][1], f"INTEGRATION.md: {name} argtypes differ from _cabi.SIGNATURES"
+        found += 1
+    assert found >= 2
+    m = re.search(r"srst_version\(\) // 100 == (\d+)", md)
+    assert m and int(m.group(1)) == _cabi.ABI_MAJOR

@@ -76,3 +76,28 @@ def test_bucket_grads_are_views():
     g(torch.rand(1, 3, 8, 8)).sum().backward()
     assert b.flat[:-1].abs().sum() > 0          # backward wrote through the views
     assert all(p.grad.data_ptr() >= b.flat.data_ptr() for p in g.parameters())
+
+
+def test_bucket_survives_zero_grad_set_to_none():
+    """optimizer.zero_grad() / module.zero_grad() (set_to_none=True by default) drop the views; the bucket must
+    notice and re-attach, otherwise the collective reduces stale zeros and ranks silently diverge."""
+    from srgan_st_b200.dist import FlatGradBucket
+    g = _model()
+    b = FlatGradBucket(g.parameters())
+    opt = torch.optim.SGD(g.parameters(), lr=0.1)
+    x = torch.rand(2, 3, 8, 8)
+    g(x).sum().backward()
+    want = torch.cat([p.grad.reshape(-1) for p in g.parameters()]).clone()
+    opt.zero_grad()                                   # set_to_none=True: every p.grad is None now
+    assert all(p.grad is None for p in g.parameters())
+    g(x).sum().backward()                             # fresh grad tensors OUTSIDE the bucket
+    assert any(p.grad.data_ptr() < b.flat.data_ptr() or p.grad.data_ptr() >= b.flat.data_ptr() + b.nbytes
+               for p in g.parameters())
+    b.all_reduce_mean()                               # world size 1: no collective, but the repair runs
+    assert torch.allclose(b.flat[:-1], want)          # the stray gradients were copied in
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(b.params, b._views))
+    g.zero_grad()                                     # again dropped ...
+    b.zero()                                          # ... and re-attached, zeroed
+    assert all(p.grad is not None and p.grad.abs().sum() == 0 for p in g.parameters())
+    g(x).sum().backward()
+    assert torch.allclose(b.flat[:-1], want)

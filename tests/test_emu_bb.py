@@ -82,3 +82,33 @@ def test_emulated_search_many_near_ties(lib):
     out = emu_bb(lib, sr, gt)
     orc = O.bb_forward_c(sr, gt)
     assert np.array_equal(out["idx"], orc["idx"])
+
+
+@pytest.mark.parametrize("mode", ["patch", "gram", "pst"])
+@pytest.mark.parametrize("where", ["sr", "gt"])
+def test_emulated_nan_input_gives_nan_loss_and_in_range_indices(lib, mode, where):
+    """A NaN pixel must propagate like in the reference (torch.clamp keeps NaN, torch.min returns the
+    first NaN: utils.py:187, loss.py:135) -- a NaN loss, every index inside [0, M), no out-of-bounds read
+    in the loss / backward kernels that consume the indices (the search used to emit 0x7fffffff)."""
+    rng = np.random.default_rng(5)
+    gt = rng.random((1, 3, 24, 24), dtype=np.float32)
+    sr = np.clip(gt + 0.05 * rng.standard_normal(gt.shape).astype(np.float32), 0, 1)
+    (sr if where == "sr" else gt)[0, 1, 7, 8] = np.nan
+    taps = None
+    if mode == "pst":
+        from oracle import st_oracle as S
+        taps = (*S.gaussian_taps(0.5, True), S.gaussian_taps(2.0))
+    out = emu_bb(lib, sr, gt, mode=mode, taps=taps)
+    N = 8 * 8
+    M = N + 4 * 4 + 2 * 2
+    assert out["idx"].min() >= 0 and out["idx"].max() < M
+    assert np.isnan(out["loss"])
+    if mode == "patch":
+        orc = O.bb_forward_c(sr, gt)
+        assert np.array_equal(out["idx"], orc["idx"]), "same torch.min NaN order as the oracle"
+        if where == "sr":
+            assert out["idx"][0, 2 * 8 + 2] == 0          # the query holding the NaN: every score NaN -> index 0
+        else:
+            want = np.full(N, 2 * 8 + 2)                  # the level-0 candidate holding the NaN wins every row ...
+            want[2 * 8 + 2] = 0                           # ... except its own query (g_i is NaN: every score NaN)
+            assert np.array_equal(out["idx"][0], want)

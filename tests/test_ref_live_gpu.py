@@ -1,0 +1,203 @@
+"""GPU: the CUDA path against the UNMODIFIED reference modules running on the same B200 (oracle/_ref,
+staged by oracle/make_ref.py) at the BASELINE.json sizes -- configs[1] (64 x 96x96), configs[4] (one
+1356x2040 image), configs[3]-shaped patch losses (4 x 192x192: the reference needs ~1.4 GB of [B,N,M]
+score matrices per image batch of 4; batch 64 does not fit its own memory appetite).
+
+The reference on a GPU runs its ten 1-channel convolutions per image through cuDNN, which by default may
+use TF32 (torch.backends.cudnn.allow_tf32 = True, ~1e-3 accuracy); BASELINE.json asks for fp32 parity,
+so TF32 is switched off for the reference here -- that is the only setting touched.
+
+Tolerances (north_star): loss rel 1e-5, input gradients 1e-4 (max-norm relative).  Every measured error
+is appended to gpurun_out/r02_parity.json (copied to profiles/ by hand after a run).
+Gradient conditioning: where SR and HR tensors nearly coincide 1/(2 sqrt(disc)) amplifies fp32 rounding
+and the reference's own gradient wanders from the fp64 truth (measured: 4.2e-4 on uniform-noise inputs,
+<= 3.4e-5 on SR-like inputs); the assertion is therefore  |ours - ref| <= 1e-4 + |ref - fp64 oracle|  and,
+independently,  |ours - fp64 oracle| <= 1e-4.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import make_ref as R
+from oracle import st_oracle as O
+from tests.helpers import ROOT, maxnorm_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+PARITY_LOG = os.path.join(ROOT, "gpurun_out", "r02_parity.json")
+
+
+def _record(key, **vals):
+    os.makedirs(os.path.dirname(PARITY_LOG), exist_ok=True)
+    try:
+        data = json.load(open(PARITY_LOG))
+    except Exception:
+        data = {}
+    data[key] = {k: (float(v) if not isinstance(v, (int, str)) else v) for k, v in vals.items()}
+    json.dump(data, open(PARITY_LOG, "w"), indent=1, sort_keys=True)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not R.available():
+        pytest.skip("oracle/_ref is not staged (run `python oracle/make_ref.py` in the build container)")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return R.load()
+
+
+def _pair(kind, B, H, W, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    if kind == "rand":
+        return (torch.rand(B, 3, H, W, device="cuda", generator=g), torch.rand(B, 3, H, W, device="cuda", generator=g))
+    hr = torch.randint(0, 256, (B, 3, H, W), device="cuda", generator=g).float()
+    hr = (F.avg_pool2d(hr, 3, 1, 1, count_include_pad=False).round() / 255).contiguous()
+    lo = F.interpolate(hr, size=(max(H // 4, 1), max(W // 4, 1)), mode="bicubic", align_corners=False)
+    sr = F.interpolate(lo, size=(H, W), mode="bicubic", align_corners=False)
+    sr = (sr + 0.02 * torch.randn(B, 3, H, W, device="cuda", generator=g)).clamp_(0, 1).contiguous()
+    return sr, hr
+
+
+@pytest.mark.parametrize("kind,B,H,W", [("srlike", 64, 96, 96), ("rand", 64, 96, 96), ("srlike", 1, 1356, 2040),
+                                         ("rand", 2, 333, 517)])
+def test_st_loss_and_gradients_match_the_live_reference(ref, kind, B, H, W):
+    from srgan_st_b200 import StructureTensorLoss
+    sr, hr = _pair(kind, B, H, W, 7 * B + H)
+    x = sr.clone().requires_grad_(True)
+    y = hr.clone().requires_grad_(True)
+    ours = StructureTensorLoss()(x, y)
+    ours.backward()
+    xr = sr.clone().requires_grad_(True)
+    yr = hr.clone().requires_grad_(True)
+    theirs = ref.loss.StructureTensorLoss()(xr, yr)          # reference loss.py:380-413, its own ATen path
+    theirs.backward()
+    torch.cuda.synchronize()
+    o64 = O.st_loss(sr.cpu().numpy(), hr.cpu().numpy(), want_hr_grad=True)   # fp64 referee
+    e = dict(loss_vs_ref=rel_err(ours.item(), theirs.item()), loss_vs_fp64=rel_err(ours.item(), o64["loss"]),
+             ref_loss_vs_fp64=rel_err(theirs.item(), o64["loss"]))
+    for nm, g_ours, g_ref, g64 in (("dsr", x.grad, xr.grad, o64["d_sr"]), ("dhr", y.grad, yr.grad, o64["d_hr"])):
+        a, b = g_ours.cpu().numpy(), g_ref.cpu().numpy()
+        e[nm + "_vs_ref"] = maxnorm_err(a, b)
+        e[nm + "_vs_fp64"] = maxnorm_err(a, g64)
+        e[nm + "_ref_vs_fp64"] = maxnorm_err(b, g64)
+    _record(f"st_{kind}_{B}x{H}x{W}", **e)
+    assert e["loss_vs_ref"] < 1e-5 and e["loss_vs_fp64"] < 1e-5
+    for nm in ("dsr", "dhr"):
+        assert e[nm + "_vs_fp64"] < 1e-4
+        assert e[nm + "_vs_ref"] < 1e-4 + e[nm + "_ref_vs_fp64"]
+    if kind == "srlike":   # well-conditioned inputs: strict 1e-4 against the reference itself
+        assert e["dsr_vs_ref"] < 1e-4 and e["dhr_vs_ref"] < 1e-4
+
+
+def _ref_indices(ref, m_ref, sr, hr, alpha, beta, patches):
+    """The reference's own argmin (loss.py:132-135) re-derived with its helpers, plus the top-2 gap."""
+    with torch.no_grad():
+        p1, p2 = patches(sr), patches(hr)
+        hr2 = F.interpolate(hr, scale_factor=0.5, mode="bicubic", align_corners=False)
+        hr4 = F.interpolate(hr, scale_factor=0.25, mode="bicubic", align_corners=False)
+        cat = torch.cat([p2, patches(hr2), patches(hr4)], 1)
+        score = alpha * ref.utils.batch_pairwise_distance(p1, cat, "l2") \
+            + beta * ref.utils.batch_pairwise_distance(p2, cat, "l2")
+        _, ind = torch.min(score, dim=2)
+        top2 = torch.topk(score, 2, dim=2, largest=False).values
+    return ind, top2, score
+
+
+@pytest.mark.parametrize("which", ["bb", "gram", "pst"])
+@pytest.mark.parametrize("kind", ["rand", "srlike"])
+def test_patch_losses_match_the_live_reference(ref, which, kind):
+    import srgan_st_b200 as pkg
+    B, H, W = 4, 192, 192
+    sr, hr = _pair(kind, B, H, W, 11 + len(which))
+    if kind == "srlike":
+        sr = (hr + 0.1 * torch.randn_like(hr)).clamp(0, 1)   # noisier SR: real competition between candidates
+    unf = lambda t: F.unfold(t, kernel_size=3, padding=0, stride=3).permute(0, 2, 1).contiguous()
+    if which == "bb":
+        ours_m, ref_m, patches = pkg.BestBuddyLoss(), ref.loss.BestBuddyLoss(), unf
+    elif which == "gram":
+        ours_m, ref_m = pkg.GramLoss(), ref.loss.GramLoss()
+        patches = ref_m.compute_patches
+    else:
+        ours_m, ref_m = pkg.PatchwiseStructureTensorLoss(), ref.loss.PatchwiseStructureTensorLoss()
+        patches = ref_m.compute_patches
+    x = sr.clone().requires_grad_(True)
+    lo = ours_m(x, hr)
+    lo.backward()
+    xr = sr.clone().requires_grad_(True)
+    lr_ = ref_m(xr, hr)
+    lr_.backward()
+    ind_ref, top2, score = _ref_indices(ref, ref_m, sr, hr, 1.0, 1.0, patches)
+    ours_idx = ours_m.last_indices
+    gap = top2[..., 1] - top2[..., 0]
+    noise = 4e-6 * top2[..., 1].clamp_min(1e-6) + 1e-6      # fp32 rounding of a ~|x|^2+|y|^2 sized sum (bmm order unknown)
+    differ = ours_idx != ind_ref
+    clear = gap > noise
+    n_diff = int(differ.sum().item())
+    co_min = True
+    if n_diff:
+        s_ours = torch.gather(score, 2, ours_idx.unsqueeze(-1)).squeeze(-1)
+        co_min = bool(((s_ours - top2[..., 0])[differ] <= noise[differ]).all().item())
+    e = dict(loss_vs_ref=rel_err(lo.item(), lr_.item()), rows=int(differ.numel()), rows_differ=n_diff,
+             rows_differ_clear=int((differ & clear).sum().item()), differ_are_cominimal=int(co_min),
+             dsr_vs_ref=maxnorm_err(x.grad.cpu().numpy(), xr.grad.cpu().numpy()))
+    _record(f"{which}_{kind}_{B}x{H}x{W}", **e)
+    assert e["rows_differ_clear"] == 0, "a clearly separated row picked a different candidate than the reference"
+    assert co_min, "a row inside the rounding band picked a candidate that is not co-minimal in the reference's scores"
+    assert n_diff <= 1e-3 * differ.numel()
+    assert e["loss_vs_ref"] < 1e-4 if n_diff else e["loss_vs_ref"] < 1e-5
+    if n_diff == 0:
+        assert e["dsr_vs_ref"] < 1e-4
+
+
+def test_reference_warmup_loop_with_our_criteria(ref):
+    """The reference's OWN registry and loop body (config.py:122-125 add_g_criterion, warmup.py:86-96) driven on
+    synthetic tensors with model.Generator: our modules register and train exactly where the reference's do, and
+    one step gives the same loss values and the same generator gradients as the reference's criteria."""
+    import copy
+    import srgan_st_b200 as pkg
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+
+    def make_config(st_module):
+        cfg = ref.config.Config()
+        cfg.DEVICE = "cuda:0"
+        cfg.MODEL.G_LOSS.WARMUP_CRITERIONS = {"Pixel": torch.nn.MSELoss()}
+        cfg.MODEL.G_LOSS.WARMUP_WEIGHTS = {"Pixel": 1.0}
+        cfg.MODEL.G_LOSS.WARMUP_CRITERIONS["ST"] = st_module.to(dev)      # "ST + MSE" of BASELINE configs[1]
+        cfg.MODEL.G_LOSS.WARMUP_WEIGHTS["ST"] = 1.0 / 3.0                 # config.py:80
+        cfg.add_g_criterion("ST", st_module, 1.0 / 3.0)                   # config.py:122-125 (the GAN-phase registry)
+        return cfg
+
+    gen0 = ref.model.Generator(ref.config.Config()).to(dev)
+    gt, _ = _pair("srlike", 16, 96, 96, 3)
+    lr = F.interpolate(gt, scale_factor=0.25, mode="bicubic", align_corners=False).clamp(0, 1)
+    results = []
+    for st_module in (pkg.StructureTensorLoss(), ref.loss.StructureTensorLoss()):
+        config = make_config(st_module)
+        generator = copy.deepcopy(gen0)
+        optimizer = torch.optim.Adam(generator.parameters(), lr=1e-4)
+        # ---- warmup.py:83-96, verbatim control flow ----
+        loss_values = {}
+        generator.zero_grad()
+        sr = generator(lr)
+        loss = torch.tensor(0.0, device=config.DEVICE)
+        for name, criterion in config.MODEL.G_LOSS.WARMUP_CRITERIONS.items():
+            weight = config.MODEL.G_LOSS.WARMUP_WEIGHTS[name]
+            l = criterion(sr, gt)
+            loss = loss + (l * weight)
+            loss_values[name] = (l * weight).item()
+        loss.backward()
+        grads = torch.cat([p.grad.flatten() for p in generator.parameters()])
+        optimizer.step()
+        results.append((loss_values, grads, loss.item()))
+        assert "ST" in config.MODEL.G_LOSS.CRITERIONS and config.MODEL.G_LOSS.CRITERION_WEIGHTS["ST"] == 1.0 / 3.0
+    (lv_o, g_o, l_o), (lv_r, g_r, l_r) = results
+    assert rel_err(lv_o["ST"], lv_r["ST"]) < 1e-5 and rel_err(lv_o["Pixel"], lv_r["Pixel"]) < 1e-6
+    gerr = maxnorm_err(g_o.cpu().numpy(), g_r.cpu().numpy())
+    _record("warmup_step_16x96x96", st_loss_vs_ref=rel_err(lv_o["ST"], lv_r["ST"]), total_vs_ref=rel_err(l_o, l_r),
+            generator_grad_vs_ref=gerr)
+    assert gerr < 1e-3   # generator weights' gradients: the loss gradient (1e-4) pushed through 37 conv layers of cuDNN

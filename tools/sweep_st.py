@@ -26,6 +26,7 @@ k, _ = T.gaussian_taps(2.0)
 dev = torch.device("cuda:0")
 vp = lambda t: ctypes.c_void_p(t.data_ptr())
 HBM = 6539.9
+NOIXY = os.environ.get('SWEEP_NOIXY', '0') == '1'   # forward without the saved-gradient stores (timing experiment only)
 FWD_CFGS = [int(x) for x in os.environ['SWEEP_FWD'].split(',')] if os.environ.get('SWEEP_FWD') else list(range(lib.srst_st_num_cfgs(0)))
 BWD_CFGS = [int(x) for x in os.environ['SWEEP_BWD'].split(',')] if os.environ.get('SWEEP_BWD') else list(range(lib.srst_st_num_cfgs(1)))
 
@@ -46,7 +47,7 @@ def run(B, H, W, iters=40):
     def fwd(i):
         sr, hr = pool[i % pool_n]
         _cabi.check(lib.srst_st_forward(vp(sr), vp(hr), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8, 1, 1e-12,
-                                        vp(loss), vp(ds), None, vp(ixy), None, vp(ws), ws.numel(), sp), "fwd")
+                                        vp(loss), vp(ds), None, (None if NOIXY else vp(ixy)), None, vp(ws), ws.numel(), sp), "fwd")
 
     def bwd(i):
         _cabi.check(lib.srst_st_backward(vp(ixy), vp(ds), vp(go), B, H, W, T.as_c(g), T.as_c(dg), 2, T.as_c(k), 8,
