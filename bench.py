@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- structure-tensor loss fwd+bwd throughput on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c5|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c2x|c5|c1] [--impl reference]
 
 One "step" = one forward + backward pass of the fused ST loss over one batch of synthetic
 SR/HR images (the hot path of SURVEY.md section 8).  Printed: ONE JSON line.
@@ -11,15 +11,21 @@ SR/HR images (the hot path of SURVEY.md section 8).  Printed: ONE JSON line.
              events on that stream, max over ranks.  Every step reads a different batch from a pool
              larger than the 126 MB L2, so no step sees L2-warm inputs.
   e2e        the same metric through the public API (StructureTensorLoss()(sr, gt); backward();
-             loss.item()) with each step's inputs copied host->device from pinned memory and the
-             loss read back, as the reference's train.py:119-144 does.
+             read the loss on the host) with each step's inputs copied host->device from pinned memory,
+             as the reference's train.py:119-144 does.  At N > 1 the step also all-reduces a
+             generator-sized gradient bucket (+ the loss in its tail).  `e2e.variants` separates the
+             costs: strict (collective and .item() inside the step, round 1's definition), pipelined
+             (collective on a side stream, the previous step's loss read while this step runs: the
+             headline), h2d_only, collective_only (device-resident inputs).
   roofline   forward kernel (dominant) against the measured HBM copy bandwidth of
              MEASURED_PEAKS.json; algorithmic bytes = 24 B/pixel forward, 36 B/pixel backward
              (SURVEY.md section 8d).  The fwd+bwd pair is reported beside it.
-  cpu_baseline  the oracle port (numpy fp32, one process per host core) on a bounded sample.
+  cpu_baseline  the reference's OWN modules (oracle/_ref, staged from /root/reference by
+             oracle/make_ref.py: loss.py:380-413 on ATen/MKL-DNN, fp32) on the host cores, one process
+             per core, on a bounded sample; `port` = the numpy restatement (oracle/st_oracle.py) beside it.
 
-`--impl reference` times that CPU port alone (the reference is pure Python/ATen; /root/reference
-does not exist on the GPU box, so the timed CPU arm is the oracle's restatement of it).
+`--impl reference` times that CPU arm alone (and, when a GPU is visible, adds the reference modules'
+own unfused ATen path on the B200 and the configs[1] warm-up step for context).
 """
 from __future__ import annotations
 
@@ -46,13 +52,15 @@ WORKLOADS = {
     "c5": dict(B=1, H=1356, W=2040, desc="ST loss fwd+bwd, 1 x 3x1356x2040 per GPU (configs[4])"),
     # configs[0]/[2]: batch 16 of 96x96 per GPU
     "c1": dict(B=16, H=96, W=96, desc="ST loss fwd+bwd, batch 16 x 3x96x96 per GPU (configs[0]/[2])"),
+    # steady state of the training shape: 1024 crops = 9.4 Mpx, 4096+ tiles, many waves
+    "c2x": dict(B=1024, H=96, W=96, desc="ST loss fwd+bwd, batch 1024 x 3x96x96 per GPU (steady state of the configs[1] shape)"),
 }
 BYTES_FWD, BYTES_BWD = 24, 36  # algorithmic bytes per pixel
 
 
 def _traffic(workload, kernel):
-    """dram bytes per launch from the committed ncu --set full capture (profiles/r01_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """dram bytes per launch from the committed ncu --set full capture (profiles/r02_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         return int(json.load(open(p))[workload][kernel])
     except Exception:
@@ -86,8 +94,16 @@ def _peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: oracle port, one process per core
+# CPU arm: the reference's own modules (oracle/_ref) on the host cores, one process per core;
+#          the numpy port (oracle/st_oracle.py) beside it
 # ------------------------------------------------------------------------------------------------
+def _avail_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def _cpu_worker(args):
     import numpy as np
     from oracle import st_oracle as O
@@ -108,11 +124,7 @@ def cpu_port_images_per_sec(H, W, n_images, cores=None):
     """Times oracle/st_oracle.py (fp32 port of the reference's algorithm, fwd + bwd) on
     `n_images` synthetic images split over `cores` processes.  Returns (images/s, cores)."""
     import multiprocessing as mp
-    try:
-        avail = len(os.sched_getaffinity(0))
-    except Exception:
-        avail = os.cpu_count() or 1
-    cores = max(1, min(cores or avail, n_images))
+    cores = max(1, min(cores or _avail_cores(), n_images))
     per = [n_images // cores + (1 if i < n_images % cores else 0) for i in range(cores)]
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     ctx = mp.get_context("fork")
@@ -124,38 +136,213 @@ def cpu_port_images_per_sec(H, W, n_images, cores=None):
     return n_images / dt, cores
 
 
+_REF_CRIT = None
+
+
+def _ref_worker(args):
+    """One process = one host core running the UNMODIFIED reference StructureTensorLoss (loss.py:380-413) forward +
+    backward on its share of the images, in sub-batches of `b` (the reference vmaps over the batch)."""
+    global _REF_CRIT
+    import torch
+    seed, n, b, H, W = args
+    torch.set_num_threads(1)
+    from oracle import make_ref as R
+    if _REF_CRIT is None:
+        _REF_CRIT = R.load().loss.StructureTensorLoss()
+    g = torch.Generator().manual_seed(seed)
+    t = 0.0
+    with R.on_cpu():  # utils.py:206,208 hard-code .cuda() on the taps
+        done = 0
+        while done < n:
+            bb = min(b, n - done)
+            x = torch.rand(bb, 3, H, W, generator=g).requires_grad_(True)
+            y = torch.rand(bb, 3, H, W, generator=g)
+            t0 = time.perf_counter()
+            _REF_CRIT(x, y).backward()
+            t += time.perf_counter() - t0
+            done += bb
+    return t
+
+
+class RefCpuPool:
+    """Spawned (not forked: the parent may hold a CUDA context and OpenMP threads) worker processes, kept alive across
+    steps -- importing torch + torchvision + cv2 in a fresh interpreter costs seconds."""
+
+    def __init__(self, cores=None):
+        import multiprocessing as mp
+        self.cores = max(1, cores or _avail_cores())
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        os.environ.setdefault("MKL_NUM_THREADS", "1")
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+        self.pool.map(_ref_worker, [(i, 1, 1, 16, 16) for i in range(self.cores)])  # imports + first-call set-up
+
+    def images_per_sec(self, H, W, n_images, sub_batch):
+        use = max(1, min(self.cores, n_images))
+        per = [n_images // use + (1 if i < n_images % use else 0) for i in range(use)]
+        t0 = time.perf_counter()
+        self.pool.map(_ref_worker, [(1000 + i, per[i], sub_batch, H, W) for i in range(use)], chunksize=1)
+        return n_images / (time.perf_counter() - t0), use
+
+    def close(self):
+        self.pool.terminate()
+        self.pool.join()
+
+
+def ref_available():
+    from oracle import make_ref as R
+    return R.available()
+
+
+def ref_inproc_images_per_sec(B, H, W, reps=3):
+    """The reference module as a user would call it on the host: one process, all intra-op threads."""
+    import torch
+    from oracle import make_ref as R
+    crit = R.load().loss.StructureTensorLoss()
+    torch.set_num_threads(_avail_cores())
+    x = torch.rand(B, 3, H, W).requires_grad_(True)
+    y = torch.rand(B, 3, H, W)
+    with R.on_cpu():
+        crit(x, y).backward()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            crit(x, y).backward()
+        dt = (time.perf_counter() - t0) / reps
+    return B / dt, torch.get_num_threads()
+
+
+def _ref_gpu_context(wl):
+    """Reference-arm context on a visible GPU (no kernel of ours involved): the reference modules' own unfused ATen path
+    on the B200 (BASELINE.md's "same hardware" figure), and the configs[1] warm-up step (warmup.py:83-96) with the
+    reference's Generator, Adam and its two criteria (Pixel + ST)."""
+    import torch
+    from oracle import make_ref as R
+    if not torch.cuda.is_available():
+        return None
+    ns = R.load()
+    dev = torch.device("cuda:0")
+    out = {}
+
+    def timed(fn, n=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    B, H, W = wl["B"], wl["H"], wl["W"]
+    B = min(B, 64)
+    g = torch.Generator(device=dev).manual_seed(5)
+    y = torch.rand(B, 3, H, W, device=dev, generator=g)
+    x = (y + 0.05 * torch.randn(B, 3, H, W, device=dev, generator=g)).clamp(0, 1).requires_grad_(True)
+    crit = ns.loss.StructureTensorLoss()
+
+    def st_step():
+        x.grad = None
+        crit(x, y).backward()
+
+    for tf32 in (True, False):
+        torch.backends.cudnn.allow_tf32 = tf32
+        ms = timed(st_step)
+        out["st_fwd_bwd_tf32_conv" if tf32 else "st_fwd_bwd_fp32"] = {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3)}
+    torch.backends.cudnn.allow_tf32 = True
+    out["note"] = (f"reference loss.py:380-413 fwd+bwd on cuda:0, batch {B} x 3x{H}x{W}, eager ATen/cuDNN (about 100 launches "
+                   "forward, 300 backward); cuDNN's default allows TF32 convolutions, the fp32 line switches that off")
+    if H == 96 and W == 96:
+        cfg = ns.config.Config()
+        gen = ns.model.Generator(cfg).to(dev)
+        opt = torch.optim.Adam(gen.parameters(), lr=1e-4)
+        lr_in = torch.nn.functional.interpolate(y, scale_factor=0.25, mode="bicubic", align_corners=False).clamp(0, 1)
+        crits = {"Pixel": (torch.nn.MSELoss(), 1.0), "ST": (ns.loss.StructureTensorLoss(), 1.0 / 3.0)}
+
+        def warm_step():
+            gen.zero_grad()
+            sr = gen(lr_in)
+            loss = torch.tensor(0.0, device=dev)
+            vals = {}
+            for name, (c, w) in crits.items():
+                l = c(sr, y)
+                loss = loss + l * w
+                vals[name] = (l * w).item()          # the per-criterion sync of warmup.py:93
+            loss.backward()
+            opt.step()
+
+        ms = timed(warm_step, n=10, warm=3)
+        out["warmup_step_reference"] = {"ms_per_step": ms, "images_per_s": B / (ms * 1e-3),
+                                        "what": f"warmup.py:83-96 loop body, reference Generator (1 547 350 params) + Adam + Pixel "
+                                                f"+ reference ST criterion, batch {B} x 96x96 HR, eager, default cuDNN settings"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     wl = WORKLOADS[args.workload]
     H, W = wl["H"], wl["W"]
-    # bounded sample per step: ~1.5 s of CPU work on one core per step and core
-    probe, cores = cpu_port_images_per_sec(H, W, 4 if H * W > 1e6 else 64)
-    budget_s = min(1.5, 150.0 / max(args.steps + args.warmup, 1))  # whole run stays within minutes
-    n_step = max(cores, int(probe * budget_s)) if H * W <= 1e6 else max(2, min(cores, 16))
-    for _ in range(args.warmup):
-        cpu_port_images_per_sec(H, W, max(1, n_step // 4))
+    big = H * W > 1e6
+    sub = 1 if big else 4
+    use_ref = ref_available()
+    if use_ref:
+        pool = RefCpuPool()
+        measure = lambda n: pool.images_per_sec(H, W, n, sub)
+        kind, how = "reference", "oracle/_ref loss.py StructureTensorLoss (unmodified reference, ATen/MKL-DNN fp32) fwd+bwd"
+    else:  # not staged: the numpy port stands in (and says so)
+        measure = lambda n: cpu_port_images_per_sec(H, W, n)
+        kind, how = "port", "oracle/st_oracle.py fp32 fwd+bwd (oracle/_ref not staged on this box)"
+    probe, cores = measure(max(2, _avail_cores()) if big else 4 * _avail_cores())
+    budget_s = min(1.5, 150.0 / max(args.steps + args.warmup, 1))   # the whole run stays within a few minutes
+    n_step = max(cores, int(probe * budget_s)) if not big else max(2, min(cores, 16))
+    for _ in range(min(args.warmup, 3)):
+        measure(max(1, n_step // 4))
     rates = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r, cores = cpu_port_images_per_sec(H, W, n_step)
+        r, cores = measure(n_step)
         rates.append(r)
     total = time.perf_counter() - t0
     value = statistics.median(rates)
+    extra = {}
+    if use_ref:
+        pool.close()
+        try:
+            v, thr = ref_inproc_images_per_sec(min(wl["B"], 64), H, W)
+            extra["inproc_all_threads"] = {"value": v, "unit": UNIT, "threads": thr,
+                                           "what": "one process, torch intra-op threads = all cores (how a user would call it)"}
+        except Exception as e:  # context only
+            extra["inproc_all_threads"] = {"error": repr(e)}
+        try:
+            ctx = _ref_gpu_context(wl)
+            if ctx:
+                extra["reference_gpu_unfused"] = ctx
+        except Exception as e:
+            extra["reference_gpu_unfused"] = {"error": repr(e)}
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "sample_images_per_step": n_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_step} images of 3x{H}x{W} per step, oracle/st_oracle.py fp32 fwd+bwd, "
-                                   f"one process per core"},
+        "config": _config_dict(wl, args.gpus, extra={"sample_images_per_step": n_step}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{n_step} images of 3x{H}x{W} per step, {how}, one process per core "
+                                   f"(sub-batches of {sub})", **extra},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(out)
     return 0
+
+
+def _config_dict(wl, world, extra=None):
+    """The same keys on both arms (the driver compares the two `config` objects)."""
+    c = {"workload": wl["desc"], "per_gpu_batch": wl["B"], "height": wl["H"], "width": wl["W"],
+         "sigma": 0.5, "rho": 2.0, "parallelism": f"batch-sharded x{world}, no data-path collective"}
+    if extra:
+        c.update(extra)
+    return c
 
 
 # ------------------------------------------------------------------------------------------------
@@ -363,32 +550,86 @@ def run_gpu(args):
             # copy is issued and completed inside the timed region
             slots = [torch.empty(2, B, 3, H, W, device=dev) for _ in range(2)]
             copy_stream = torch.cuda.Stream(device=dev)
-            copied = [torch.cuda.Event(), torch.cuda.Event()]
-            consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-            def issue_copy(i):
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(consumed[i % 2])     # slot free (previous user finished)
-                    slots[i % 2].copy_(host[i % n_host], non_blocking=True)
-                    copied[i % 2].record(copy_stream)
+            def run_e2e(h2d, collective, pipelined, Ksteps):
+                """K steps through the public module.  h2d: copy each step's inputs from pinned host memory (else the
+                slots keep their contents); collective: all-reduce the gradient bucket every step (N > 1);
+                pipelined: the collective runs on a side stream and the host reads the PREVIOUS step's loss while this
+                step runs (one read per step, one step late) instead of stalling on its own loss."""
+                copied = [torch.cuda.Event(), torch.cuda.Event()]
+                consumed = [torch.cuda.Event(), torch.cuda.Event()]
+                use_bucket = bucket is not None and collective
+                loss_ring = [torch.zeros((), device=dev) for _ in range(2)]
+                host_loss = [torch.zeros((), pin_memory=True) for _ in range(2)]
+                read_done = [torch.cuda.Event(), torch.cuda.Event()]
 
-            def step(i, last):
-                sr_d, hr_d = slots[i % 2][0], slots[i % 2][1]
-                cur = torch.cuda.current_stream()
-                cur.wait_event(copied[i % 2])
-                if not last:
-                    issue_copy(i + 1)
-                x = sr_d.detach().requires_grad_(True)
-                l = crit(x, hr_d)
-                l.backward()
-                consumed[i % 2].record(cur)
-                if bucket is not None:
-                    bucket.set_loss(l)
-                    l = bucket.all_reduce_mean()
-                return l.item()  # device->host read of the step's result, as train.py:141
+                def issue_copy(i):
+                    if not h2d:
+                        return
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(consumed[i % 2])     # slot free (previous user finished)
+                        slots[i % 2].copy_(host[i % n_host], non_blocking=True)
+                        copied[i % 2].record(copy_stream)
 
-            for ev in consumed:
-                ev.record()
+                def step(i, last):
+                    sr_d, hr_d = slots[i % 2][0], slots[i % 2][1]
+                    cur = torch.cuda.current_stream()
+                    if h2d:
+                        cur.wait_event(copied[i % 2])
+                        if not last:
+                            issue_copy(i + 1)
+                    x = sr_d.detach().requires_grad_(True)
+                    l = crit(x, hr_d)
+                    l.backward()
+                    consumed[i % 2].record(cur)
+                    if not pipelined:
+                        if use_bucket:
+                            bucket.set_loss(l)
+                            l = bucket.all_reduce_mean()
+                        return l.item()  # device->host read of the step's result, as train.py:141
+                    # pipelined: previous step's collective must be done before the bucket is reused
+                    if use_bucket:
+                        bucket.wait()
+                        bucket.set_loss(l)
+                        bucket.all_reduce_mean_async()
+                        src = bucket.loss_slot[0]
+                        with torch.cuda.stream(bucket._comm_stream):
+                            host_loss[i % 2].copy_(src, non_blocking=True)
+                            read_done[i % 2].record(bucket._comm_stream)
+                    else:
+                        host_loss[i % 2].copy_(l.detach(), non_blocking=True)
+                        read_done[i % 2].record(cur)
+                    if i > 0:
+                        read_done[(i - 1) % 2].synchronize()   # the host now holds step i-1's loss
+                        return float(host_loss[(i - 1) % 2])
+                    return None
+
+                def drain(n):
+                    if pipelined and n > 0:
+                        read_done[(n - 1) % 2].synchronize()
+                        _ = float(host_loss[(n - 1) % 2])
+                        if use_bucket:
+                            bucket.wait()
+
+                for ev in consumed:
+                    ev.record()
+                nw = max(Wm, 3)
+                issue_copy(0)
+                for i in range(nw):
+                    step(i, i == nw - 1)
+                drain(nw)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                issue_copy(0)
+                for i in range(Ksteps):
+                    step(i, i == Ksteps - 1)
+                drain(Ksteps)
+                e1.record()
+                barrier()
+                ms = max_over_ranks(e0.elapsed_time(e1))
+                return {"value": world * B * Ksteps / (ms * 1e-3), "ms_per_step": ms / Ksteps}
+
             # PCIe links idle down between phases of this script (the CPU arm runs for seconds before this leg on a
             # fresh box): bring the H2D path to its steady state with an untimed burst of copies first, otherwise
             # the short timed region (K steps of ~0.3 ms) measures the link's ramp-up (observed: 28 vs 52 GB/s)
@@ -397,22 +638,22 @@ def run_gpu(args):
                 for j in range(8):
                     slots[j % 2].copy_(host[j % n_host], non_blocking=True)
                 torch.cuda.synchronize()
-            nw = max(Wm, 3)
-            issue_copy(0)
-            for i in range(nw):
-                step(i, i == nw - 1)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            issue_copy(0)
-            for i in range(K):
-                step(i, i == K - 1)
-            e1.record()
-            barrier()
-            ms = max_over_ranks(e0.elapsed_time(e1))
-            res["e2e"] = {"value": world * B * K / (ms * 1e-3), "unit": UNIT,
+            variants = {}
+            variants["strict"] = run_e2e(True, True, False, K)
+            variants["pipelined"] = run_e2e(True, True, True, K)
+            if world > 1:
+                variants["h2d_only"] = run_e2e(True, False, True, K)
+                variants["collective_only"] = run_e2e(False, True, True, K)
+            variants["device_resident_module"] = run_e2e(False, False, True, K)
+            head = variants["pipelined"]
+            res["e2e"] = {"value": head["value"], "unit": UNIT,
                           "h2d_bytes_per_step": bytes_pair, "d2h_bytes_per_step": 4,
-                          "ms_per_step": ms / K,
+                          "ms_per_step": head["ms_per_step"],
+                          "h2d_gbs_per_gpu": bytes_pair / (head["ms_per_step"] * 1e-3) / 1e9,
+                          "definition": "pipelined: every step copies its inputs H2D from pinned memory and the host reads one loss "
+                                        "per step (the previous step's, so the read never stalls the enqueue); at N > 1 the gradient "
+                                        "bucket all-reduce runs on a side stream",
+                          "variants": variants,
                           "host_affinity": numa_note,
                           "collective": (f"one NCCL all-reduce of {bucket.nbytes} B (generator-grad bucket + loss) per step"
                                          if bucket is not None else "none (1 GPU)")}
@@ -427,7 +668,7 @@ def run_gpu(args):
     if not args.no_extra:
         for name in WORKLOADS:
             if name != args.workload:
-                r = measure(name, max(20, min(K, 200)), Wm, with_e2e=False)
+                r = measure(name, 40 if name == "c2x" else max(20, min(K, 200)), Wm, with_e2e=False)
                 others[name] = {"workload": r["wl"]["desc"], "images_per_s": r["images_per_s"],
                                 "ms_per_step": r["ms_step"], "ms_fwd": r["ms_fwd"], "ms_bwd": r["ms_bwd"],
                                 "hbm_frac_fwd": r["roofline_fwd"] / hbm_peak, "hbm_frac_bwd": r["roofline_bwd"] / hbm_peak,
@@ -463,15 +704,110 @@ def run_gpu(args):
                                    "filtered dot product per pair and re-scores survivors exactly (bit-identical indices)"}
         del gtb, xb
 
+    if not args.no_extra:
+        # BASELINE.json configs[1]: "SRResNet warmup.py step with ST + MSE loss, batch 64, 96x96 patches": the loop body of
+        # warmup.py:83-96 (generator forward, the registered criteria with .item() after each, backward, Adam) on an
+        # SRResNet-shaped generator built from stock torch layers (the generator is ballast here, not part of the hot
+        # path: 16 residual blocks, 64 channels, two PixelShuffle stages -- 1 547 350 parameters like model.py:193).
+        nn = torch.nn
+
+        class _Res(nn.Module):
+            def __init__(self, c):
+                super().__init__()
+                self.f = nn.Sequential(nn.Conv2d(c, c, 3, 1, 1, bias=False), nn.BatchNorm2d(c), nn.PReLU(),
+                                       nn.Conv2d(c, c, 3, 1, 1, bias=False), nn.BatchNorm2d(c))
+
+            def forward(self, x):
+                return x + self.f(x)
+
+        class _SRResNet(nn.Module):
+            def __init__(self, c=64, nb=16):
+                super().__init__()
+                self.head = nn.Sequential(nn.Conv2d(3, c, 9, 1, 4), nn.PReLU())
+                self.body = nn.Sequential(*[_Res(c) for _ in range(nb)])
+                self.fuse = nn.Sequential(nn.Conv2d(c, c, 3, 1, 1, bias=False), nn.BatchNorm2d(c))
+                self.up = nn.Sequential(*[nn.Sequential(nn.Conv2d(c, 4 * c, 3, 1, 1), nn.PixelShuffle(2), nn.PReLU())
+                                          for _ in range(2)])
+                self.tail = nn.Conv2d(c, 3, 9, 1, 4)
+
+            def forward(self, x):
+                h = self.head(x)
+                return self.tail(self.up(h + self.fuse(self.body(h)))).clamp(0.0, 1.0)
+
+        from srgan_st_b200 import StructureTensorPixelLoss
+        torch.manual_seed(7 + rank)
+        gen = _SRResNet().to(dev)
+        n_par = sum(p.numel() for p in gen.parameters())
+        Bw = 64
+        gtw = torch.rand(Bw, 3, 96, 96, device=dev)
+        lrw = torch.nn.functional.interpolate(gtw, scale_factor=0.25, mode="bicubic", align_corners=False).clamp(0, 1)
+        opt = torch.optim.Adam(gen.parameters(), lr=1e-4)
+
+        def loop_body(crits):
+            gen.zero_grad()
+            sr = gen(lrw)
+            loss = torch.tensor(0.0, device=dev)
+            vals = {}
+            for name, (c, w) in crits.items():
+                l = c(sr, gtw)
+                loss = loss + l * w
+                vals[name] = (l * w).item()            # warmup.py:93
+            loss.backward()
+            opt.step()
+
+        def timed(fn, n=20, warm=5):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        two = {"Pixel": (nn.MSELoss(), 1.0), "ST": (StructureTensorLoss(), 1.0 / 3.0)}
+        one = {"ST+Pixel": (StructureTensorPixelLoss(st_weight=1.0 / 3.0, pixel_weight=1.0), 1.0)}
+        only_px = {"Pixel": (nn.MSELoss(), 1.0)}
+        ms_two, ms_one, ms_px = timed(lambda: loop_body(two)), timed(lambda: loop_body(one)), timed(lambda: loop_body(only_px))
+        others["warmup_step"] = {
+            "workload": f"warmup.py:83-96 loop body, SRResNet-shaped generator ({n_par} params, stock torch/cuDNN eager) + Adam, "
+                        f"batch {Bw} x 96x96 HR per GPU (BASELINE configs[1])",
+            "ms_per_step_pixel_plus_st": ms_two, "ms_per_step_fused_st_pixel": ms_one, "ms_per_step_pixel_only": ms_px,
+            "images_per_s_per_gpu": Bw / (ms_two * 1e-3),
+            "st_criterion_cost_ms": ms_two - ms_px,
+            "note": "the ST criterion's whole cost inside the step (module call, two kernels, .item()) is the difference to the "
+                    "Pixel-only step; the reference's own criteria on the same step are timed by `--impl reference` "
+                    "(reference_gpu_unfused.warmup_step_reference)"}
+        del gen, opt, gtw, lrw
+        torch.cuda.empty_cache()
+
     os.sched_setaffinity(0, all_cpus)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         wl = main["wl"]
-        probe, cores = cpu_port_images_per_sec(wl["H"], wl["W"], 4 if wl["H"] * wl["W"] > 1e6 else 128)
-        n = int(min(max(probe * 12, cores), 200000)) if wl["H"] * wl["W"] <= 1e6 else max(cores, 8)
+        big = wl["H"] * wl["W"] > 1e6
+        probe, cores = cpu_port_images_per_sec(wl["H"], wl["W"], 4 if big else 128)
+        n = int(min(max(probe * 6, cores), 200000)) if not big else max(cores, 8)
         v, cores = cpu_port_images_per_sec(wl["H"], wl["W"], n)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} synthetic images of 3x{wl['H']}x{wl['W']}, oracle/st_oracle.py fp32 fwd+bwd, one process per core"}
+        port = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{n} synthetic images of 3x{wl['H']}x{wl['W']}, oracle/st_oracle.py fp32 fwd+bwd, one process per core"}
+        cpu = port
+        if ref_available():
+            try:
+                rp = RefCpuPool()
+                sub = 1 if big else 4
+                probe, cores = rp.images_per_sec(wl["H"], wl["W"], max(2, cores) if big else 4 * cores, sub)
+                n = int(min(max(probe * 12, cores), 50000)) if not big else max(cores, 8)
+                v, cores = rp.images_per_sec(wl["H"], wl["W"], n, sub)
+                rp.close()
+                cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                       "sample": f"{n} synthetic images of 3x{wl['H']}x{wl['W']}, oracle/_ref loss.py StructureTensorLoss (the unmodified "
+                                 f"reference on ATen/MKL-DNN, fp32) fwd+bwd, one process per core, sub-batches of {sub}",
+                       "port": port}
+            except Exception as e:  # the reference could not run on this host: keep the port, say why
+                port["reference_error"] = repr(e)
 
     if rank == 0:
         wl = main["wl"]
@@ -479,17 +815,16 @@ def run_gpu(args):
             "metric": METRIC, "value": main["images_per_s"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": main["ms_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "per_gpu_batch": wl["B"], "height": wl["H"], "width": wl["W"],
-                       "sigma": 0.5, "rho": 2.0, "parallelism": f"batch-sharded x{world}, no data-path collective",
-                       "l2_policy": f"inputs cycle through a pool of {main['pool_n']} batches (> 2x L2) so every step is L2-cold",
-                       "timing": "CUDA graph of K (fwd,bwd) kernel pairs on one stream, CUDA events, max over ranks, best of 3"},
+            "config": _config_dict(wl, world, extra={
+                "l2_policy": f"inputs cycle through a pool of {main['pool_n']} batches (> 2x L2) so every step is L2-cold",
+                "timing": "CUDA graph of K (fwd,bwd) kernel pairs on one stream, CUDA events, max over ranks, best of 3"}),
             "clocks": main["clocks"],
             "e2e": main.get("e2e"),
             "gpu_launches": 2 * K,
             "roofline": {"bound": "hbm", "kernel": "st_forward_kernel", "achieved": main["roofline_fwd"], "peak": hbm_peak,
                          "unit": "GB/s", "frac": main["roofline_fwd"] / hbm_peak,
                          "traffic": _traffic(args.workload, "st_forward_kernel"),
-                         "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read+write per launch)",
+                         "traffic_source": "profiles/r02_traffic.json (ncu --set full, dram__bytes_read+write per launch)",
                          "peak_source": peak_src, "bytes_per_pixel": BYTES_FWD,
                          "backward": {"kernel": "st_backward_kernel", "achieved": main["roofline_bwd"],
                                       "frac": main["roofline_bwd"] / hbm_peak, "bytes_per_pixel": BYTES_BWD},

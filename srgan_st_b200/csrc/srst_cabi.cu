@@ -36,15 +36,14 @@ static int forced_bwd() {
 
 // ---- compiled structure-tensor tile configurations (reference default radii: r_sigma 2, r_rho 8) ----
 //                       TH  TW  RS CSB RG RK MINB CHU
-//                                                 GPARK MINB without it
-using Fwd0 = StFwdCfg<48, 48, 12, 4, 2, 8, 2>;  // square quarter of a 96x96 crop, 288 threads
-using Fwd1 = StFwdCfg<32, 64, 16, 4, 2, 8, 3, 1, true, 2>;  // large images, 256 threads, three CTAs per SM
-using Fwd2 = StFwdCfg<24, 96, 8, 4, 2, 8, 2>;   // full-width strip of a 96-wide crop (no horizontal halo), 288 threads
-using Fwd3 = StFwdCfg<24, 96, 8, 4, 2, 8, 3, 1, true, 2>;   // Fwd2, SR tensor parked in L2: three CTAs per SM
-using Fwd4 = StFwdCfg<40, 64, 10, 4, 2, 8, 2, 1, true, 2>;  // taller tile, 320 threads
-using Fwd5 = StFwdCfg<32, 64, 16, 4, 2, 8, 2>;  // Fwd1 with the SR tensor parked in shared memory (two CTAs per SM)
-using Fwd6 = StFwdCfg<48, 48, 12, 4, 2, 8, 2, 4>;  // Fwd0, per-pixel chain fully unrolled
-using Fwd7 = StFwdCfg<24, 96, 8, 4, 2, 8, 2, 4>;   // Fwd2, per-pixel chain fully unrolled
+using Fwd0 = StFwdCfg<48, 48, 12, 4, 2, 8, 2>;     // square quarter of a 96x96 crop, 288 threads, rolled
+using Fwd1 = StFwdCfg<32, 64, 16, 4, 2, 8, 3, 0, true>;  // large images, 256 threads, unrolled: three CTAs per SM; plane-split vertical items
+using Fwd2 = StFwdCfg<24, 96, 8, 4, 2, 8, 2>;      // full-width strip of a 96-wide crop (no horizontal halo), 288 threads, rolled
+using Fwd3 = StFwdCfg<24, 96, 8, 4, 2, 8, 2, 0>;   // Fwd2 unrolled
+using Fwd4 = StFwdCfg<48, 48, 12, 4, 2, 8, 2, 0>;  // Fwd0 unrolled (round 1's 96-wide default)
+using Fwd5 = StFwdCfg<32, 64, 16, 4, 2, 8, 3, 0>;  // Fwd1 with joint (segment, column) vertical items
+using Fwd6 = StFwdCfg<24, 96, 8, 4, 2, 8, 3, 0>;   // Fwd3 with three CTAs per SM (72 registers)
+using Fwd7 = StFwdCfg<40, 64, 10, 4, 2, 8, 2, 0>;  // taller unrolled tile, 320 threads
 constexpr int kNumFwdCfg = 8;
 //                       TH  TW  RS   NT RG RK MINB CSD
 using Bwd0 = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8>;  // large images: 16 row pairs per horizontal-pass column
@@ -53,7 +52,9 @@ using Bwd2 = StBwdCfg<12, 96, 8, 224, 2, 8, 2, 8>;   // shorter strips for small
 using Bwd3 = StBwdCfg<20, 56, 12, 192, 2, 8, 3, 8>;  // three CTAs per SM
 using Bwd4 = StBwdCfg<24, 64, 14, 256, 2, 8, 2, 8>;
 using Bwd5 = StBwdCfg<28, 96, 16, 384, 2, 8, 1, 8>;  // 96-wide crops, one large CTA per SM
-constexpr int kNumBwdCfg = 6;
+using Bwd6 = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8, true>;  // Bwd0, persistent with the next tile's boxes prefetched
+using Bwd7 = StBwdCfg<12, 96, 8, 224, 2, 8, 2, 8, true>;   // Bwd2, persistent with the next tile's boxes prefetched
+constexpr int kNumBwdCfg = 8;
 
 constexpr int kMinFwdTH = 24, kMinFwdTW = 48;  // finest compiled forward tiling (workspace sizing)
 
@@ -135,29 +136,6 @@ static const StTaps<RG, RK>& cached_taps(const float* g, const float* dg, int rs
   return e.taps;
 }
 
-template <class C, bool PX, bool HR> struct FwdTag {};  // once-flag tag per forward instantiation
-template <class C, bool PX> struct BwdTag {};
-
-template <class C, bool PX = false>
-static int launch_st_forward(StFwdParams<C::RG, C::RK>& P, void* stream) {
-  if constexpr (C::GPARK) {  // the SR tensor is parked in ds_sr: without that buffer use the shared-memory twin
-    if (!P.ds_sr) return launch_st_forward<typename C::SmemPark, PX>(P, stream);
-  }
-  P.tiles_x = (P.W + C::TW - 1) / C::TW;
-  P.tiles_y = (P.H + C::TH - 1) / C::TH;
-  const long long ntiles = (long long)P.B * P.tiles_x * P.tiles_y;
-  if (ntiles <= 0 || ntiles > 0x7fffffffLL) return SRST_E_SHAPE;
-  int e;
-  if (P.ds_hr) {
-    if ((e = ensure_smem<FwdTag<C, PX, true>>(st_forward_kernel<C, PX, true>, C::SMEM_BYTES)) != 0) return e;
-    SRST_LAUNCH_PDL((st_forward_kernel<C, PX, true>), dim3((unsigned)ntiles), dim3(C::NT), C::SMEM_BYTES, stream, P);
-  } else {
-    if ((e = ensure_smem<FwdTag<C, PX, false>>(st_forward_kernel<C, PX, false>, C::SMEM_BYTES)) != 0) return e;
-    SRST_LAUNCH_PDL((st_forward_kernel<C, PX, false>), dim3((unsigned)ntiles), dim3(C::NT), C::SMEM_BYTES, stream, P);
-  }
-  return (int)cudaGetLastError();
-}
-
 // Tensor map of an fp32 tensor viewed as [planes][rows][cols] with a [box_p][box_h][box_w] box (no
 // swizzle, zero OOB fill).  Returns false when TMA cannot be used (unaligned tensor, row pitch not a
 // multiple of 16 bytes, driver entry point missing): the kernel then stages with plain loads.
@@ -213,6 +191,26 @@ static bool make_plane_map(SrstTmap* map, const float* base, long long planes, i
 #endif
 }
 
+template <class C, bool PX, bool HR> struct FwdTag {};  // once-flag tag per forward instantiation
+template <class C, bool PX> struct BwdTag {};
+
+template <class C, bool PX = false>
+static int launch_st_forward(StFwdParams<C::RG, C::RK>& P, void* stream) {
+  P.tiles_x = (P.W + C::TW - 1) / C::TW;
+  P.tiles_y = (P.H + C::TH - 1) / C::TH;
+  const long long ntiles = (long long)P.B * P.tiles_x * P.tiles_y;
+  if (ntiles <= 0 || ntiles > 0x7fffffffLL) return SRST_E_SHAPE;
+  int e;
+  if (P.ds_hr) {
+    if ((e = ensure_smem<FwdTag<C, PX, true>>(st_forward_kernel<C, PX, true>, C::SMEM_BYTES)) != 0) return e;
+    SRST_LAUNCH_PDL((st_forward_kernel<C, PX, true>), dim3((unsigned)ntiles), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  } else {
+    if ((e = ensure_smem<FwdTag<C, PX, false>>(st_forward_kernel<C, PX, false>, C::SMEM_BYTES)) != 0) return e;
+    SRST_LAUNCH_PDL((st_forward_kernel<C, PX, false>), dim3((unsigned)ntiles), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  }
+  return (int)cudaGetLastError();
+}
+
 template <class C, bool PX = false>
 static int launch_st_backward(StBwdParams<C::RG, C::RK>& P, void* stream) {
   static const bool tma_env = env_int_once("SRST_ST_BWD_TMA", 1) != 0;
@@ -226,22 +224,31 @@ static int launch_st_backward(StBwdParams<C::RG, C::RK>& P, void* stream) {
   if (nblk <= 0 || nblk > 0x7fffffffLL) return SRST_E_SHAPE;
   int e = ensure_smem<BwdTag<C, PX>>(st_backward_kernel<C, PX>, C::SMEM_BYTES);
   if (e) return e;
-  SRST_LAUNCH_PDL((st_backward_kernel<C, PX>), dim3((unsigned)nblk), dim3(C::NT), C::SMEM_BYTES, stream, P);
+  long long grid = nblk;
+  if (C::PIPE && P.use_tma) {  // persistent: one wave of resident CTAs, each looping over tiles
+    const long long slots = (long long)sm_count() * C::MINB;
+    if (grid > slots) grid = slots;
+  }
+  SRST_LAUNCH_PDL((st_backward_kernel<C, PX>), dim3((unsigned)grid), dim3(C::NT), C::SMEM_BYTES, stream, P);
   return (int)cudaGetLastError();
 }
 
-static int pick_fwd_cfg(int H, int W) {
+static int pick_fwd_cfg(int B, int H, int W) {
   const int forced = forced_fwd();
   if (forced >= 0 && forced < kNumFwdCfg) return forced;
-  (void)H;
-  if (W <= 96) return 0;
+  // measured on B200 (profiles/r02_tile_sweep.log): full-width 24x96 strips win on 96-wide crops -- the rolled kernel
+  // (two CTAs per SM) while the batch is a single wave, the unrolled 72-register variant (three CTAs per SM) once
+  // there are several waves of strips; the unrolled 32x64 tile with three CTAs per SM wins on large images
+  if (W <= 96) return ((long long)B * ((H + 23) / 24) >= 6LL * sm_count()) ? 6 : 2;
   return 1;
 }
 static int pick_bwd_cfg(int B, int H, int W) {
   const int forced = forced_bwd();
   if (forced >= 0 && forced < kNumBwdCfg) return forced;
-  if (W <= 96) return ((long long)B * ((H + 15) / 16) >= 2LL * sm_count()) ? 1 : 2;
-  return 0;
+  // measured on B200 (profiles/r02_tile_sweep.log): the persistent, prefetching kernels win everywhere -- full-width
+  // 12x96 strips on 96-wide crops, the 28x56 tile on large images
+  (void)B; (void)H;
+  return W <= 96 ? 7 : 6;
 }
 
 }  // namespace srst
@@ -329,9 +336,9 @@ static int st_forward_rr(const StCall& c) {
   P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
   P.taps = cached_taps<RG, RK>(c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
-    const int cfg = pick_fwd_cfg(c.H, c.W);
+    const int cfg = pick_fwd_cfg(c.B, c.H, c.W);
     if (c.px) {  // the fused Pixel term is compiled into the two default tile shapes only
-      if (cfg == 0 || (cfg != 1 && c.W <= 96)) return launch_st_forward<Fwd0, true>(P, c.stream);
+      if (cfg != 1 && c.W <= 96) return launch_st_forward<Fwd2, true>(P, c.stream);
       return launch_st_forward<Fwd1, true>(P, c.stream);
     }
     switch (cfg) {
@@ -345,7 +352,7 @@ static int st_forward_rr(const StCall& c) {
       default: return launch_st_forward<Fwd1>(P, c.stream);
     }
   } else {
-    using G = StFwdCfg<32, 64, 16, 4, RG, RK, (RK <= 8 ? 2 : 1)>;
+    using G = StFwdCfg<32, 64, 16, 4, RG, RK, (RK <= 8 ? 2 : 1), 0>;
     return c.px ? launch_st_forward<G, true>(P, c.stream) : launch_st_forward<G>(P, c.stream);
   }
 }
@@ -362,8 +369,8 @@ static int st_backward_rr(const StCall& c) {
   P.taps = cached_taps<RG, RK>(c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
     if (c.px_other) {  // the fused Pixel term is compiled into the two default tile shapes only
-      if (c.W <= 96) return launch_st_backward<Bwd1, true>(P, c.stream);
-      return launch_st_backward<Bwd0, true>(P, c.stream);
+      if (c.W <= 96) return launch_st_backward<Bwd7, true>(P, c.stream);
+      return launch_st_backward<Bwd6, true>(P, c.stream);
     }
     switch (pick_bwd_cfg(c.B, c.H, c.W)) {
       case 1: return launch_st_backward<Bwd1>(P, c.stream);
@@ -371,6 +378,8 @@ static int st_backward_rr(const StCall& c) {
       case 3: return launch_st_backward<Bwd3>(P, c.stream);
       case 4: return launch_st_backward<Bwd4>(P, c.stream);
       case 5: return launch_st_backward<Bwd5>(P, c.stream);
+      case 6: return launch_st_backward<Bwd6>(P, c.stream);
+      case 7: return launch_st_backward<Bwd7>(P, c.stream);
       default: return launch_st_backward<Bwd0>(P, c.stream);
     }
   } else {

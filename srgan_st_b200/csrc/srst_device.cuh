@@ -135,7 +135,8 @@ SRST_DEV void tma_load_3d(unsigned long long* mbar, float* dst, const SrstTmap* 
         dst[(p * bh + r) * bw + c] = ok ? m->base[((size_t)gp * m->H + gy) * m->W + gx] : 0.f;
       }
 }
-SRST_DEV void tma_wait(unsigned long long* mbar) { (void)mbar; }
+SRST_DEV void tma_wait(unsigned long long* mbar, unsigned parity = 0) { (void)mbar; (void)parity; }
+SRST_DEV void fence_async_smem() {}
 #else
 }  // namespace srst
 #include <cuda.h>
@@ -164,17 +165,20 @@ SRST_DEV void tma_load_3d(unsigned long long* mbar, float* dst, const SrstTmap* 
       ::"r"(sdst), "l"(reinterpret_cast<unsigned long long>(m)), "r"(x), "r"(y), "r"(z), "r"(bar)
       : "memory");
 }
-SRST_DEV void tma_wait(unsigned long long* mbar) {
+// Waits for the phase of `mbar` with the given parity (0 for the first use of a barrier, then alternating).
+SRST_DEV void tma_wait(unsigned long long* mbar, unsigned parity = 0) {
   const unsigned bar = (unsigned)__cvta_generic_to_shared(mbar);
   unsigned done = 0;
   while (!done) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar)
+        : "r"(bar), "r"(parity)
         : "memory");
   }
 }
+// Orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes.
+SRST_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
 // Named barriers for producer/consumer warp roles: `n` = number of participating threads.

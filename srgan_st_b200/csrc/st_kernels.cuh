@@ -399,6 +399,57 @@ SRST_DEV void smooth_h_rowpair_n(const float* row, const Taps& tp, float2 (&out)
     out[j] = s;
   }
 }
+// Chain + stores for one thread's 2 x 4 pixels; returns the sum of the valid distances.
+template <bool WANT_HR>
+SRST_DEV float st_chain_store(const float2 (&S1)[3][4], const float2 (&S2)[3][4], bool norm, float eps,
+                              float* __restrict__ ds_sr, float* __restrict__ ds_hr, size_t img_off, int H, int W,
+                              int gy0, int gx0, bool vec4) {
+  float lsum = 0.f;
+  float2 gs[3][4], gh[3][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    StPixelGrad2 G;
+    G.da = G.db = G.dc = G.de = G.df = G.dh = make_float2(0.f, 0.f);
+    const float2 d = st_pixel2<true, WANT_HR>(S1[0][j], S1[1][j], S1[2][j], S2[0][j], S2[1][j], S2[2][j], norm, eps, G);
+    const bool okx = gx0 + j < W;
+    lsum += (okx && gy0 < H) ? d.x : 0.f;
+    lsum += (okx && gy0 + 1 < H) ? d.y : 0.f;
+    gs[0][j] = G.da; gs[1][j] = G.db; gs[2][j] = G.dc;
+    if (WANT_HR) { gh[0][j] = G.de; gh[1][j] = G.df; gh[2][j] = G.dh; }
+  }
+  if (gx0 >= W) return lsum;
+  const size_t plane = (size_t)H * W;
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    if (gy0 + hf >= H) continue;
+    const size_t o = img_off + (size_t)(gy0 + hf) * W + gx0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v0 = hf ? gs[c][0].y : gs[c][0].x, v1 = hf ? gs[c][1].y : gs[c][1].x;
+      const float v2 = hf ? gs[c][2].y : gs[c][2].x, v3 = hf ? gs[c][3].y : gs[c][3].x;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+      if (WANT_HR) {
+        w0 = hf ? gh[c][0].y : gh[c][0].x; w1 = hf ? gh[c][1].y : gh[c][1].x;
+        w2 = hf ? gh[c][2].y : gh[c][2].x; w3 = hf ? gh[c][3].y : gh[c][3].x;
+      }
+      if (vec4) {
+        if (ds_sr) st4(ds_sr + o + c * plane, make_float4(v0, v1, v2, v3));
+        if (WANT_HR) st4(ds_hr + o + c * plane, make_float4(w0, w1, w2, w3));
+      } else {
+        const float vv[4] = {v0, v1, v2, v3}, ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (gx0 + j < W) {
+            if (ds_sr) ds_sr[o + c * plane + j] = vv[j];
+            if (WANT_HR) ds_hr[o + c * plane + j] = ww[j];
+          }
+        }
+      }
+    }
+  }
+  return lsum;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Lane -> item mapping of the register-blocked (row pair x CS columns) phases.  An item reads
 // LDS.128 windows at q*PITCH + 2*CS*seg + const with PITCH == 4 mod 8, i.e. 16-byte bank group
@@ -428,17 +479,20 @@ struct ItemMap {
 // ------------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------------
-template <int TH_, int TW_, int RS_, int CSB_, int RG_, int RK_, int MINB_, int CHU_ = 1, bool GPARK_ = false,
-          int MINB_SMEM_ = MINB_>
+template <int TH_, int TW_, int RS_, int CSB_, int RG_, int RK_, int MINB_, int CHU_ = 1, bool CSPLIT_ = false>
 struct StFwdCfg {
+  // CSPLIT: the vertical pass hands out (plane, row segment, column) items instead of (row segment, column): used
+  // when columns x segments alone leave a large part of the CTA idle (32x64 tile: 160 items for 256 threads).
+  static constexpr bool CSPLIT = CSPLIT_;
   static constexpr int TH = TH_, TW = TW_, RS = RS_, CSB = CSB_, RG = RG_, RK = RK_, MINB = MINB_;
-  static constexpr int CHU = CHU_;       // pixel pairs of the per-pixel chain in flight per thread (loop unroll)
-  // GPARK: the SR tensor waits in the ds_sr buffer (L2) instead of shared memory while the HR image is
-  // processed -- the thread later overwrites exactly those 24 floats with its ds values -- which frees
-  // 24 * NT floats of shared memory (one more CTA per SM on the large-image tile).  Needs ds_sr != NULL:
-  // without it the launcher falls back to the shared-memory twin `SmemPark`.
-  static constexpr bool GPARK = GPARK_;
-  using SmemPark = StFwdCfg<TH_, TW_, RS_, CSB_, RG_, RK_, MINB_SMEM_, CHU_, false, MINB_SMEM_>;
+  // CHU > 0: ROLLED kernel -- SR and HR run through one copy of the filter code, both smoothed tensors are
+  //          parked in thread-private shared-memory slots and the per-pixel chain is a loop over the thread's four
+  //          pixel pairs, CHU of them in flight (half the code, no spills, 24 * NT floats of shared memory more).
+  // CHU == 0: UNROLLED kernel -- two inlined copies of the filter phases, the SR tensor waits in registers while
+  //          the HR image is processed, chain on all eight pixels at once (more registers, less shared memory:
+  //          what lets the large-image tile keep three CTAs per SM).
+  static constexpr int CHU = CHU_;
+  static constexpr bool ROLLED = CHU_ > 0;
   static constexpr int LDEPTH = 2;       // gray-tile items (6 x LDG.128 each) in flight per thread
   static constexpr int HXD = round_up4(RK);  // x halo of the gradient (D) and V regions
   static constexpr int OFF = round_up4(RG);
@@ -457,18 +511,16 @@ struct StFwdCfg {
   // smem: D (Ix, Iy) | V (3 planes; the gray tile aliases it: dead once the gradient phase is done) | SP1.
   // The HR tensor is parked over D (SP2): dead once the vertical pass is done.
   static constexpr int VG_FLOATS = cmax(3 * V_FLOATS, G_FLOATS);
-  static constexpr bool SP1_OVER_V = GPARK && SP_FLOATS <= VG_FLOATS;   // GPARK: re-loaded over the (dead) V region
   static constexpr bool SP2_OVER_D = SP_FLOATS <= 2 * D_FLOATS;        // small radii: D is too small
-  static constexpr int SP_OFF = SP1_OVER_V ? 2 * D_FLOATS : 2 * D_FLOATS + VG_FLOATS;
-  static constexpr int SP1_END = 2 * D_FLOATS + VG_FLOATS + (SP1_OVER_V ? 0 : SP_FLOATS);
-  static constexpr int SP2_OFF = SP2_OVER_D ? 0 : SP1_END;
-  static constexpr int SMEM_FLOATS = SP1_END + (SP2_OVER_D ? 0 : SP_FLOATS);
+  static constexpr int SP_OFF = 2 * D_FLOATS + VG_FLOATS;
+  static constexpr int SP2_OFF = SP2_OVER_D ? 0 : SP_OFF + SP_FLOATS;
+  static constexpr int SMEM_FLOATS = ROLLED ? SP_OFF + SP_FLOATS + (SP2_OVER_D ? 0 : SP_FLOATS) : SP_OFF;
   static constexpr size_t SMEM_BYTES = sizeof(float) * SMEM_FLOATS;
   static_assert((CSB == 4 || CSB == 8) && DW % CSB == 0, "bad gradient segment width");
   static_assert(TH % RS == 0 && RS % 2 == 0 && TH % 2 == 0 && TW % 4 == 0 && RG % 2 == 0 && RK % 2 == 0,
                 "bad forward tile");
   static_assert(NT % 32 == 0 && NT <= 1024, "bad forward block size");
-  static_assert(CHU == 1 || CHU == 2 || CHU == 4, "chain unroll");
+  static_assert(CHU == 0 || CHU == 1 || CHU == 2 || CHU == 4, "chain unroll");
 };
 
 // Phases A-D for one image of the tile: leaves the smoothed tensor (Jxx,Jyy,Jxy) of this thread's
@@ -500,14 +552,16 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float*
     if (gy + 1 >= 0 && gy < H && gx0 + C::CSB - 1 >= 0 && gx0 < W) {
       const float* p = sG + q * C::PG + 2 * (dx0 + C::BW_LO);
       grad_rowpair<C::RG, C::CSB, C::BWIN, C::OFF - C::BW_LO, C::PG, true>(p, p, tp, Ix, Iy);
-      const bool r0 = gy >= 0, r1 = gy + 1 < H;  // gy < H and gy + 1 >= 0 hold here
+      if (!(gy >= 0 && gy + 1 < H && gx0 >= 0 && gx0 + C::CSB <= W)) {  // straddles the image border: mask
+        const bool r0 = gy >= 0, r1 = gy + 1 < H;  // gy < H and gy + 1 >= 0 hold here
 #pragma unroll
-      for (int j = 0; j < C::CSB; ++j) {
-        const bool ok = (gx0 + j >= 0) && (gx0 + j < W);
-        Ix[j].x = (ok && r0) ? Ix[j].x : 0.f;
-        Ix[j].y = (ok && r1) ? Ix[j].y : 0.f;
-        Iy[j].x = (ok && r0) ? Iy[j].x : 0.f;
-        Iy[j].y = (ok && r1) ? Iy[j].y : 0.f;
+        for (int j = 0; j < C::CSB; ++j) {
+          const bool ok = (gx0 + j >= 0) && (gx0 + j < W);
+          Ix[j].x = (ok && r0) ? Ix[j].x : 0.f;
+          Ix[j].y = (ok && r1) ? Ix[j].y : 0.f;
+          Iy[j].x = (ok && r0) ? Iy[j].x : 0.f;
+          Iy[j].y = (ok && r1) ? Iy[j].y : 0.f;
+        }
       }
       if (ixy && gy >= y0 && gy < y0 + C::TH && gx0 >= x0 && gx0 < x0 + C::TW) {  // tile interior, inside the image
         float* ox = ixy + ixy_offset(b, 0, Hp, W, gy >> 1, gx0);
@@ -544,45 +598,76 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float*
     const int c_lo = max(0, C::HXD - x0), c_hi = min(C::DW, W + C::HXD - x0);  // valid D columns
     const int ncol = c_hi - c_lo;
     const int nclr = C::DW - ncol;
-    for (int it = tid; it < nclr * (C::TH / 2); it += C::NT) {
-      const int q = it / nclr, u = it - q * nclr;
-      const int dx = (u < c_lo) ? u : (c_hi + (u - c_lo));
+    // it / ncol and it / nclr by multiplication: exact for it < 4096, divisor <= 256 (item counts stay below that)
+    const unsigned mg_col = (1048576u + (unsigned)ncol - 1u) / (unsigned)ncol;
+    if (nclr > 0) {
+      const unsigned mg_clr = (1048576u + (unsigned)nclr - 1u) / (unsigned)nclr;
+      for (int it = tid; it < nclr * (C::TH / 2); it += C::NT) {
+        const int q = (int)(((unsigned)it * mg_clr) >> 20), u = it - q * nclr;
+        const int dx = (u < c_lo) ? u : (c_hi + (u - c_lo));
 #pragma unroll
-      for (int c = 0; c < 3; ++c) st2(sV + c * C::V_FLOATS + q * C::PV + 2 * dx, make_float2(0.f, 0.f));
-    }
-    for (int it = tid; it < ncol * C::NSEG; it += C::NT) {
-      const int seg = it / ncol, dx = c_lo + (it - seg * ncol);
-      float2 acc[3][C::RS / 2];
-#pragma unroll
-      for (int j = 0; j < C::RS / 2; ++j) {
-        acc[0][j] = make_float2(0.f, 0.f); acc[1][j] = make_float2(0.f, 0.f); acc[2][j] = make_float2(0.f, 0.f);
+        for (int c = 0; c < 3; ++c) st2(sV + c * C::V_FLOATS + q * C::PV + 2 * dx, make_float2(0.f, 0.f));
       }
-      const float* p0 = sD0 + (seg * (C::RS / 2)) * C::PD + 2 * dx;
-      const float* p1 = sD1 + (seg * (C::RS / 2)) * C::PD + 2 * dx;
+    }
+    if constexpr (!C::CSPLIT) {
+      for (int it = tid; it < ncol * C::NSEG; it += C::NT) {
+        const int seg = (int)(((unsigned)it * mg_col) >> 20), dx = c_lo + (it - seg * ncol);
+        float2 acc[3][C::RS / 2];
 #pragma unroll
-      for (int rq = 0; rq < C::RS / 2 + C::RK; ++rq) {
-        const float2 ix = ld2(p0 + rq * C::PD), iy = ld2(p1 + rq * C::PD);
-        const float2 pxx = mul2(ix, ix), pyy = mul2(iy, iy), pxy = mul2(ix, iy);  // packed FMUL2
+        for (int j = 0; j < C::RS / 2; ++j) {
+          acc[0][j] = make_float2(0.f, 0.f); acc[1][j] = make_float2(0.f, 0.f); acc[2][j] = make_float2(0.f, 0.f);
+        }
+        const float* p0 = sD0 + (seg * (C::RS / 2)) * C::PD + 2 * dx;
+        const float* p1 = sD1 + (seg * (C::RS / 2)) * C::PD + 2 * dx;
 #pragma unroll
-        for (int jp = 0; jp < C::RS / 2; ++jp) {
-          const int u0 = 2 * rq - 2 * jp;  // tap-pair index of input row 2rq for output pair jp
-          if (u0 >= 0 && u0 <= 2 * C::RK + 1) {
-            acc[0][jp] = ffma2(bcast2(pxx.x), tp.kp[u0], acc[0][jp]);
-            acc[1][jp] = ffma2(bcast2(pyy.x), tp.kp[u0], acc[1][jp]);
-            acc[2][jp] = ffma2(bcast2(pxy.x), tp.kp[u0], acc[2][jp]);
-          }
-          if (u0 + 1 >= 0 && u0 + 1 <= 2 * C::RK + 1) {
-            acc[0][jp] = ffma2(bcast2(pxx.y), tp.kp[u0 + 1], acc[0][jp]);
-            acc[1][jp] = ffma2(bcast2(pyy.y), tp.kp[u0 + 1], acc[1][jp]);
-            acc[2][jp] = ffma2(bcast2(pxy.y), tp.kp[u0 + 1], acc[2][jp]);
+        for (int rq = 0; rq < C::RS / 2 + C::RK; ++rq) {
+          const float2 ix = ld2(p0 + rq * C::PD), iy = ld2(p1 + rq * C::PD);
+          const float2 pxx = mul2(ix, ix), pyy = mul2(iy, iy), pxy = mul2(ix, iy);  // packed FMUL2
+#pragma unroll
+          for (int jp = 0; jp < C::RS / 2; ++jp) {
+            const int u0 = 2 * rq - 2 * jp;  // tap-pair index of input row 2rq for output pair jp
+            if (u0 >= 0 && u0 <= 2 * C::RK + 1) {
+              acc[0][jp] = ffma2(bcast2(pxx.x), tp.kp[u0], acc[0][jp]);
+              acc[1][jp] = ffma2(bcast2(pyy.x), tp.kp[u0], acc[1][jp]);
+              acc[2][jp] = ffma2(bcast2(pxy.x), tp.kp[u0], acc[2][jp]);
+            }
+            if (u0 + 1 >= 0 && u0 + 1 <= 2 * C::RK + 1) {
+              acc[0][jp] = ffma2(bcast2(pxx.y), tp.kp[u0 + 1], acc[0][jp]);
+              acc[1][jp] = ffma2(bcast2(pyy.y), tp.kp[u0 + 1], acc[1][jp]);
+              acc[2][jp] = ffma2(bcast2(pxy.y), tp.kp[u0 + 1], acc[2][jp]);
+            }
           }
         }
-      }
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < 3; ++c) {
+          float* o = sV + c * C::V_FLOATS + (seg * (C::RS / 2)) * C::PV + 2 * dx;
+#pragma unroll
+          for (int jp = 0; jp < C::RS / 2; ++jp) st2(o + jp * C::PV, acc[c][jp]);
+        }
+      }
+    } else {
+      // one item = (plane, row segment, column): plane 0 = Ix^2, 1 = Iy^2, 2 = Ix*Iy
+      for (int it = tid; it < 3 * ncol * C::NSEG; it += C::NT) {
+        const int cs = (int)(((unsigned)it * mg_col) >> 20), dx = c_lo + (it - cs * ncol);
+        const int c = cs / C::NSEG, seg = cs - c * C::NSEG;
+        float2 acc[C::RS / 2];
+#pragma unroll
+        for (int j = 0; j < C::RS / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+        const float* pa = (c == 1 ? sD1 : sD0) + (seg * (C::RS / 2)) * C::PD + 2 * dx;
+        const float* pb = (c == 0 ? sD0 : sD1) + (seg * (C::RS / 2)) * C::PD + 2 * dx;
+#pragma unroll
+        for (int rq = 0; rq < C::RS / 2 + C::RK; ++rq) {
+          const float2 pr = mul2(ld2(pa + rq * C::PD), ld2(pb + rq * C::PD));
+#pragma unroll
+          for (int jp = 0; jp < C::RS / 2; ++jp) {
+            const int u0 = 2 * rq - 2 * jp;
+            if (u0 >= 0 && u0 <= 2 * C::RK + 1) acc[jp] = ffma2(bcast2(pr.x), tp.kp[u0], acc[jp]);
+            if (u0 + 1 >= 0 && u0 + 1 <= 2 * C::RK + 1) acc[jp] = ffma2(bcast2(pr.y), tp.kp[u0 + 1], acc[jp]);
+          }
+        }
         float* o = sV + c * C::V_FLOATS + (seg * (C::RS / 2)) * C::PV + 2 * dx;
 #pragma unroll
-        for (int jp = 0; jp < C::RS / 2; ++jp) st2(o + jp * C::PV, acc[c][jp]);
+        for (int jp = 0; jp < C::RS / 2; ++jp) st2(o + jp * C::PV, acc[jp]);
       }
     }
   }
@@ -625,121 +710,80 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
   float* sp2 = smem + C::SP2_OFF + 2 * tid;  // HR tensor, parked over the (dead) D region when it fits there
   [[maybe_unused]] float pxsum = 0.f;
 
-  // SR, then HR, through one copy of the filter code
-#pragma unroll 1
-  for (int img = 0; img < 2; ++img) {
-    float2 S[3][4];
-    const float* base = (img ? P.hr : P.sr) + img_off;
-    float* ixy = img ? P.ixy_hr : P.ixy_sr;
-    st_unit_tensor<C, PX>(smem, base, ixy, b, vec4, H, W, y0, x0, P.taps, tid, dvalid, q, seg, S,
-                          (PX && img) ? P.sr + img_off : nullptr, &pxsum);
-    if (dvalid) {
-      if (C::GPARK && img == 0) {
-        // park the SR tensor where this thread's ds values will go (same 6 x 16 bytes, same layout)
-        const int gy = y0 + 2 * q, gx = x0 + 4 * seg;
-        if (gx < W) {
-          const size_t plane = (size_t)H * W;
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              if (gy + hf >= H) continue;
-              float* o = P.ds_sr + img_off + c * plane + (size_t)(gy + hf) * W + gx;
-              if (vec4) {
-                st4(o, hf ? make_float4(S[c][0].y, S[c][1].y, S[c][2].y, S[c][3].y)
-                          : make_float4(S[c][0].x, S[c][1].x, S[c][2].x, S[c][3].x));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (gx + j < W) o[j] = hf ? S[c][j].y : S[c][j].x;
-              }
-            }
-        }
-      } else {
-        float* sp = img ? sp2 : sp1;
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) st2(sp + 2 * C::NT * (c * 4 + j), S[c][j]);
-      }
-    }
-  }
-  if constexpr (C::GPARK) {
-    if (C::SP1_OVER_V) __syncthreads();  // every thread is done with V (HR horizontal pass): SP1 may overwrite it
-    if (dvalid) {
-      const int gy = y0 + 2 * q, gx = x0 + 4 * seg;
-      const size_t plane = (size_t)H * W;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float4 r[2];
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          r[hf] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gx < W && gy + hf < H) {
-            const float* o = P.ds_sr + img_off + c * plane + (size_t)(gy + hf) * W + gx;
-            if (vec4) {
-              r[hf] = ldcg4(o);
-            } else {
-              r[hf].x = __ldcg(o);
-              if (gx + 1 < W) r[hf].y = __ldcg(o + 1);
-              if (gx + 2 < W) r[hf].z = __ldcg(o + 2);
-              if (gx + 3 < W) r[hf].w = __ldcg(o + 3);
-            }
-          }
-        }
-        st2(sp1 + 2 * C::NT * (c * 4 + 0), make_float2(r[0].x, r[1].x));
-        st2(sp1 + 2 * C::NT * (c * 4 + 1), make_float2(r[0].y, r[1].y));
-        st2(sp1 + 2 * C::NT * (c * 4 + 2), make_float2(r[0].z, r[1].z));
-        st2(sp1 + 2 * C::NT * (c * 4 + 3), make_float2(r[0].w, r[1].w));
-      }
-    }
-  }
-
-  // Per-pixel chain on this thread's 2 x 4 pixels, one pixel pair (two rows of one column) per
-  // iteration; operands come from the thread's parked slots and the results go back into them.
   float lsum = 0.f;
   const int gy0 = y0 + 2 * q, gx0 = x0 + 4 * seg;
-  if (dvalid) {
-#pragma unroll C::CHU
-    for (int j = 0; j < 4; ++j) {
-      float* a1 = sp1 + 2 * C::NT * j;
-      float* a2 = sp2 + 2 * C::NT * j;
-      StPixelGrad2 G;
-      G.da = G.db = G.dc = G.de = G.df = G.dh = make_float2(0.f, 0.f);
-      const float2 d = st_pixel2<true, WANT_HR>(ld2(a1), ld2(a1 + 8 * C::NT), ld2(a1 + 16 * C::NT), ld2(a2),
-                                                ld2(a2 + 8 * C::NT), ld2(a2 + 16 * C::NT), norm, P.eps, G);
-      const bool okx = gx0 + j < W;
-      lsum += (okx && gy0 < H) ? d.x : 0.f;
-      lsum += (okx && gy0 + 1 < H) ? d.y : 0.f;
-      st2(a1, G.da); st2(a1 + 8 * C::NT, G.db); st2(a1 + 16 * C::NT, G.dc);
-      if (WANT_HR) { st2(a2, G.de); st2(a2 + 8 * C::NT, G.df); st2(a2 + 16 * C::NT, G.dh); }
-    }
-    // ds stores: rows of 4 consecutive columns per channel (STG.128)
-    if (gx0 < W && (P.ds_sr || WANT_HR)) {
-      const size_t plane = (size_t)H * W;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float2 v[4], w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[j] = ld2(sp1 + 2 * C::NT * (c * 4 + j));
-          if (WANT_HR) w[j] = ld2(sp2 + 2 * C::NT * (c * 4 + j));
+  if constexpr (!C::ROLLED) {
+    // UNROLLED: two inlined copies of the filter phases; S1 waits in registers while HR is processed
+    float2 S1[3][4], S2[3][4];
+    st_unit_tensor<C, false>(smem, P.sr + img_off, P.ixy_sr, b, vec4, H, W, y0, x0, P.taps, tid, dvalid, q, seg, S1,
+                             nullptr, nullptr);
+    st_unit_tensor<C, PX>(smem, P.hr + img_off, P.ixy_hr, b, vec4, H, W, y0, x0, P.taps, tid, dvalid, q, seg, S2,
+                          PX ? P.sr + img_off : nullptr, &pxsum);
+    if (dvalid)
+      lsum = st_chain_store<WANT_HR>(S1, S2, norm, P.eps, P.ds_sr, P.ds_hr, img_off, H, W, gy0, gx0, vec4);
+  } else {
+    // SR, then HR, through one copy of the filter code
+  #pragma unroll 1
+    for (int img = 0; img < 2; ++img) {
+      float2 S[3][4];
+      const float* base = (img ? P.hr : P.sr) + img_off;
+      float* ixy = img ? P.ixy_hr : P.ixy_sr;
+      st_unit_tensor<C, PX>(smem, base, ixy, b, vec4, H, W, y0, x0, P.taps, tid, dvalid, q, seg, S,
+                            (PX && img) ? P.sr + img_off : nullptr, &pxsum);
+      if (dvalid) {
+        {
+          float* sp = img ? sp2 : sp1;
+  #pragma unroll
+          for (int c = 0; c < 3; ++c)
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) st2(sp + 2 * C::NT * (c * 4 + j), S[c][j]);
         }
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          if (gy0 + hf >= H) continue;
-          const size_t o = img_off + c * plane + (size_t)(gy0 + hf) * W + gx0;
-          if (vec4) {
-            if (P.ds_sr) st4(P.ds_sr + o, hf ? make_float4(v[0].y, v[1].y, v[2].y, v[3].y)
-                                           : make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
-            if (WANT_HR) st4(P.ds_hr + o, hf ? make_float4(w[0].y, w[1].y, w[2].y, w[3].y)
-                                             : make_float4(w[0].x, w[1].x, w[2].x, w[3].x));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (gx0 + j < W) {
-                if (P.ds_sr) P.ds_sr[o + j] = hf ? v[j].y : v[j].x;
-                if (WANT_HR) P.ds_hr[o + j] = hf ? w[j].y : w[j].x;
+      }
+    }
+    // Per-pixel chain on this thread's 2 x 4 pixels, one pixel pair (two rows of one column) per
+    // iteration; operands come from the thread's parked slots and the results go back into them.
+    if (dvalid) {
+  #pragma unroll C::CHU
+      for (int j = 0; j < 4; ++j) {
+        float* a1 = sp1 + 2 * C::NT * j;
+        float* a2 = sp2 + 2 * C::NT * j;
+        StPixelGrad2 G;
+        G.da = G.db = G.dc = G.de = G.df = G.dh = make_float2(0.f, 0.f);
+        const float2 d = st_pixel2<true, WANT_HR>(ld2(a1), ld2(a1 + 8 * C::NT), ld2(a1 + 16 * C::NT), ld2(a2),
+                                                  ld2(a2 + 8 * C::NT), ld2(a2 + 16 * C::NT), norm, P.eps, G);
+        const bool okx = gx0 + j < W;
+        lsum += (okx && gy0 < H) ? d.x : 0.f;
+        lsum += (okx && gy0 + 1 < H) ? d.y : 0.f;
+        st2(a1, G.da); st2(a1 + 8 * C::NT, G.db); st2(a1 + 16 * C::NT, G.dc);
+        if (WANT_HR) { st2(a2, G.de); st2(a2 + 8 * C::NT, G.df); st2(a2 + 16 * C::NT, G.dh); }
+      }
+      // ds stores: rows of 4 consecutive columns per channel (STG.128)
+      if (gx0 < W && (P.ds_sr || WANT_HR)) {
+        const size_t plane = (size_t)H * W;
+  #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float2 v[4], w[4];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[j] = ld2(sp1 + 2 * C::NT * (c * 4 + j));
+            if (WANT_HR) w[j] = ld2(sp2 + 2 * C::NT * (c * 4 + j));
+          }
+  #pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            if (gy0 + hf >= H) continue;
+            const size_t o = img_off + c * plane + (size_t)(gy0 + hf) * W + gx0;
+            if (vec4) {
+              if (P.ds_sr) st4(P.ds_sr + o, hf ? make_float4(v[0].y, v[1].y, v[2].y, v[3].y)
+                                             : make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
+              if (WANT_HR) st4(P.ds_hr + o, hf ? make_float4(w[0].y, w[1].y, w[2].y, w[3].y)
+                                               : make_float4(w[0].x, w[1].x, w[2].x, w[3].x));
+            } else {
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (gx0 + j < W) {
+                  if (P.ds_sr) P.ds_sr[o + j] = hf ? v[j].y : v[j].x;
+                  if (WANT_HR) P.ds_hr[o + j] = hf ? w[j].y : w[j].x;
+                }
               }
             }
           }
@@ -801,9 +845,14 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
 // ------------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------------
-template <int TH_, int TW_, int RS_, int NT_, int RG_, int RK_, int MINB_, int CSD_ = 8>
+template <int TH_, int TW_, int RS_, int NT_, int RG_, int RK_, int MINB_, int CSD_ = 8, bool PIPE_ = false>
 struct StBwdCfg {
   static constexpr int TH = TH_, TW = TW_, RS = RS_, NT = NT_, RG = RG_, RK = RK_, MINB = MINB_;
+  // PIPE: persistent CTAs that loop over tiles and fetch the NEXT tile's ds box as soon as the vertical pass has
+  // consumed this one (and its Ix, Iy box as soon as the product rule has), so that the TMA round trip -- a third
+  // of the warp time when every CTA waits for its own tile first -- hides behind the rest of the current tile.
+  // dIx|dIy then need their own region instead of re-using the ds staging.
+  static constexpr bool PIPE = PIPE_;
   static constexpr int CSD = CSD_;  // output columns per phase-D' item: 8 reads a 24-column window per 8 outputs
                                     // (3x shared-memory amplification) instead of 20 per 4 (5x)
   static constexpr int HXE = round_up4(RG);  // x halo of the E region (where dIx, dIy are needed)
@@ -823,10 +872,11 @@ struct StBwdCfg {
   // dead once the vertical pass has consumed it) | I: saved Ix, Iy [2][EH/2][PI] (TMA destination) | V (3 planes)
   static constexpr int V_FLOATS = (EH / 2) * PV, I_FLOATS = (EH / 2) * PI, DI_FLOATS = (EH / 2) * PE;
   static constexpr int S_FLOATS = SH * VW;
-  static constexpr int X_FLOATS = cmax(2 * DI_FLOATS, 3 * S_FLOATS);
+  static constexpr int X_FLOATS = PIPE ? 3 * S_FLOATS : cmax(2 * DI_FLOATS, 3 * S_FLOATS);
   static constexpr int I_OFF = (X_FLOATS + 31) / 32 * 32;               // 128-byte aligned (TMA destination)
   static constexpr int V_OFF = (I_OFF + 2 * I_FLOATS + 31) / 32 * 32;
-  static constexpr int SMEM_FLOATS = V_OFF + 3 * V_FLOATS;
+  static constexpr int DI_OFF = PIPE ? V_OFF + 3 * V_FLOATS : 0;
+  static constexpr int SMEM_FLOATS = V_OFF + 3 * V_FLOATS + (PIPE ? 2 * DI_FLOATS : 0);
   static constexpr size_t SMEM_BYTES = sizeof(float) * SMEM_FLOATS;
   static_assert(PI % 8 == 4 && PE % 8 == 4 && PV % 8 == 4, "row-pair pitches must be == 4 mod 8");
   static_assert(EH % RS == 0 && RS % 2 == 0 && TH % 2 == 0 && TW % 4 == 0 && RG % 2 == 0 && RK % 2 == 0,
@@ -840,44 +890,62 @@ __global__ void __launch_bounds__(C::NT, C::MINB)
 st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
   SRST_DYN_SMEM(float, smem);
   float* sS = smem;                     // staged ds [3][SH][VW]
-  float* sdI0 = smem;                   // later: dIx [EH/2][PE]
-  float* sdI1 = smem + C::DI_FLOATS;    //        dIy
+  float* sdI0 = smem + C::DI_OFF;       // dIx [EH/2][PE]: over the (dead) staging, or its own region when pipelined
+  float* sdI1 = sdI0 + C::DI_FLOATS;    // dIy
   float* sI0 = smem + C::I_OFF;         // saved Ix [EH/2][PI]
   float* sI1 = sI0 + C::I_FLOATS;       // saved Iy
   float* sV = smem + C::V_OFF;          // [3][EH/2][PV]  vertical rho-pass of ds
-  __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ __align__(8) unsigned long long s_mbar;    // ds box (and the Ix, Iy box when not pipelined)
+  __shared__ __align__(8) unsigned long long s_mbar_i;  // Ix, Iy box (pipelined kernel)
 
   const int tid = threadIdx.x;
-  int tile = blockIdx.x;
-  const int tx = tile % P.tiles_x;
-  tile /= P.tiles_x;
-  const int ty = tile % P.tiles_y;
-  const int b = tile / P.tiles_y;
-  const int y0 = ty * C::TH, x0 = tx * C::TW;
   const int H = P.H, W = P.W;
   const size_t plane = (size_t)H * W;
-  const size_t img_off = (size_t)b * 3 * plane;
   const auto& tp = P.taps;
+  const int ntiles = P.B * P.tiles_y * P.tiles_x;
+  constexpr unsigned kBytesS = (unsigned)(3 * C::S_FLOATS * sizeof(float)), kBytesI = (unsigned)(2 * C::I_FLOATS * sizeof(float));
+  const bool pipe = C::PIPE && P.use_tma;
+  // tile -> coordinates of its staged boxes
+  auto issue_s = [&](int t) {
+    const int tx_ = t % P.tiles_x, r_ = t / P.tiles_x;
+    const int ty_ = r_ % P.tiles_y, b_ = r_ / P.tiles_y;
+    tma_expect(&s_mbar, pipe ? kBytesS : kBytesS + kBytesI);
+    tma_load_3d(&s_mbar, sS, &P.ds_map, tx_ * C::TW - C::HXE - C::HXK, ty_ * C::TH - C::RG - C::RK, b_ * 3, C::VW, C::SH, 3);
+  };
+  auto issue_i = [&](int t) {
+    const int tx_ = t % P.tiles_x, r_ = t / P.tiles_x;
+    const int ty_ = r_ % P.tiles_y, b_ = r_ / P.tiles_y;
+    if (pipe) tma_expect(&s_mbar_i, kBytesI);
+    tma_load_3d(pipe ? &s_mbar_i : &s_mbar, sI0, &P.ixy_map, 2 * (tx_ * C::TW - C::HXE), (ty_ * C::TH - C::RG) / 2, b_ * 2,
+                C::PI, C::EH / 2, 2);
+  };
+
+  if (P.use_tma && tid == 0) { tma_barrier_init(&s_mbar); tma_barrier_init(&s_mbar_i); }
+  pdl_wait();  // ds and ixy come from the forward kernel, grad_out from the autograd op before this launch
+  pdl_trigger();
+  if (P.use_tma && tid == 0 && (int)blockIdx.x < ntiles) { issue_s(blockIdx.x); issue_i(blockIdx.x); }
+  if (P.use_tma) __syncthreads();  // the barriers are initialised before anyone polls them
+
+  unsigned parity = 0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1u) {
+  const int next = tile + (int)gridDim.x;
+  const int tx = tile % P.tiles_x;
+  const int trow = tile / P.tiles_x;
+  const int ty = trow % P.tiles_y;
+  const int b = trow / P.tiles_y;
+  const int y0 = ty * C::TH, x0 = tx * C::TW;
+  const size_t img_off = (size_t)b * 3 * plane;
   const int xv0 = x0 - C::HXE - C::HXK;  // first staged / V column
   const int yv0 = y0 - C::RG - C::RK;    // first staged row
   const int xe0 = x0 - C::HXE;           // first E-region column
   const int qe0 = (y0 - C::RG) / 2;      // first E-region row pair (y0 - RG is even; may be -RG/2)
 
-  if (P.use_tma && tid == 0) tma_barrier_init(&s_mbar);
-  pdl_wait();  // ds and ixy come from the forward kernel, grad_out from the autograd op before this launch
-  pdl_trigger();
-
   // Stage the three ds planes (+halo) and the saved Ix, Iy tile.  Preferred path: two TMA box copies
   // issued by one thread (elements outside the tensors are zero-filled by the hardware = the zero padding
   // of the adjoint smoothing, and Ix = Iy = 0 outside the image); otherwise plain loads.
   if (P.use_tma) {
-    if (tid == 0) {
-      tma_expect(&s_mbar, (unsigned)((3 * C::S_FLOATS + 2 * C::I_FLOATS) * sizeof(float)));
-      tma_load_3d(&s_mbar, sS, &P.ds_map, xv0, yv0, b * 3, C::VW, C::SH, 3);
-      tma_load_3d(&s_mbar, sI0, &P.ixy_map, 2 * xe0, qe0, b * 2, C::PI, C::EH / 2, 2);
-    }
-    __syncthreads();  // the barrier is initialised before anyone polls it
-    tma_wait(&s_mbar);
+    tma_wait(&s_mbar, parity);
   } else {
     const float* dsb = P.ds + img_off;
     for (int it = tid; it < 3 * C::SH * C::VW; it += C::NT) {
@@ -931,7 +999,11 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
       for (int jp = 0; jp < C::RS / 2; ++jp) st2(o + jp * C::PV, acc[jp]);
     }
   }
-  __syncthreads();  // the staging is dead from here on: sdI may overwrite it
+  __syncthreads();  // the staging is dead from here on: sdI may overwrite it / the next tile's ds box may land in it
+  if (pipe) {
+    if (tid == 0 && next < ntiles) { fence_async_smem(); issue_s(next); }
+    tma_wait(&s_mbar_i, parity);
+  }
 
   // Phase D': horizontal rho-pass -> E = K*ds at the E-region pixels, then the product rule
   //   dIx = 2 Ix Exx + Iy Exy ,  dIy = 2 Iy Eyy + Ix Exy      (adjoint of utils.py:225-229)
@@ -964,6 +1036,7 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
     }
   }
   __syncthreads();
+  if (pipe && tid == 0 && next < ntiles) { fence_async_smem(); issue_i(next); }  // Ix, Iy of this tile are consumed
 
   // Phase E': adjoint of the derivative filters.  The adjoint of a zero-padded correlation is the
   // correlation with flipped taps; g is symmetric and dg antisymmetric, so
@@ -1014,6 +1087,11 @@ st_backward_kernel(const __grid_constant__ StBwdParams<C::RG, C::RK> P) {
       }
     }
   }
+    if (!pipe) {
+      __syncthreads();  // every thread is done with dIx|dIy (over the staging) and Ix, Iy: the next tile may be staged
+      if (P.use_tma && tid == 0 && next < ntiles) { fence_async_smem(); issue_s(next); issue_i(next); }
+    }
+  }  // tile loop
 }
 
 }  // namespace srst

@@ -31,10 +31,10 @@ def _run(sr, hr, normalize=True, want_hr=True, sigma=0.5, rho=2.0):
     return loss.item(), x.grad.cpu().numpy(), (y.grad.cpu().numpy() if want_hr else None)
 
 
-N_CFG = 6   # compiled tile shapes exercised per direction (srst_st_num_cfgs() >= this)
+N_CFG = 8   # compiled tile shapes exercised per direction (srst_st_num_cfgs() >= this)
 
 
-@pytest.fixture(params=[-1, 0, 1, 2, 3, 4, 5])
+@pytest.fixture(params=[-1, 0, 1, 2, 3, 4, 5, 6, 7])
 def tile_cfg(request):
     """-1 = the library's own choice; 0.. force a compiled forward / backward tile shape (srst_st_force_cfg)."""
     from srgan_st_b200 import _cabi
