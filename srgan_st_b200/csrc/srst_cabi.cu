@@ -40,11 +40,9 @@ using Fwd0 = StFwdCfg<48, 48, 12, 4, 2, 8, 2>;     // square quarter of a 96x96 
 using Fwd1 = StFwdCfg<32, 64, 16, 4, 2, 8, 3, 0, true>;  // large images, 256 threads, unrolled: three CTAs per SM; plane-split vertical items
 using Fwd2 = StFwdCfg<24, 96, 8, 4, 2, 8, 2>;      // full-width strip of a 96-wide crop (no horizontal halo), 288 threads, rolled
 using Fwd3 = StFwdCfg<24, 96, 8, 4, 2, 8, 2, 0>;   // Fwd2 unrolled
-using Fwd4 = StFwdCfg<48, 48, 12, 4, 2, 8, 2, 0>;  // Fwd0 unrolled (round 1's 96-wide default)
-using Fwd5 = StFwdCfg<32, 64, 16, 4, 2, 8, 3, 0>;  // Fwd1 with joint (segment, column) vertical items
-using Fwd6 = StFwdCfg<24, 96, 8, 4, 2, 8, 3, 0>;   // Fwd3 with three CTAs per SM (72 registers)
-using Fwd7 = StFwdCfg<40, 64, 10, 4, 2, 8, 2, 0>;  // taller unrolled tile, 320 threads
-constexpr int kNumFwdCfg = 8;
+using Fwd4 = StFwdCfg<24, 96, 8, 4, 2, 8, 3, 0>;   // Fwd3 with three CTAs per SM (72 registers): multi-wave batches of 96-wide crops
+using Fwd5 = StFwdCfg<40, 64, 10, 4, 2, 8, 2, 0>;  // taller unrolled tile, 320 threads, two CTAs per SM
+constexpr int kNumFwdCfg = 6;
 //                       TH  TW  RS   NT RG RK MINB CSD
 using Bwd0 = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8>;  // large images: 16 row pairs per horizontal-pass column
 using Bwd1 = StBwdCfg<16, 96, 10, 288, 2, 8, 2, 8>;  // full-width strips of 96-wide crops
@@ -236,10 +234,10 @@ static int launch_st_backward(StBwdParams<C::RG, C::RK>& P, void* stream) {
 static int pick_fwd_cfg(int B, int H, int W) {
   const int forced = forced_fwd();
   if (forced >= 0 && forced < kNumFwdCfg) return forced;
-  // measured on B200 (profiles/r02_tile_sweep.log): full-width 24x96 strips win on 96-wide crops -- the rolled kernel
-  // (two CTAs per SM) while the batch is a single wave, the unrolled 72-register variant (three CTAs per SM) once
-  // there are several waves of strips; the unrolled 32x64 tile with three CTAs per SM wins on large images
-  if (W <= 96) return ((long long)B * ((H + 23) / 24) >= 6LL * sm_count()) ? 6 : 2;
+  // measured on B200 (profiles/r02_tile_sweep.log): full-width 24x96 strips win on 96-wide crops -- two CTAs per SM
+  // while the batch is a single wave, the 72-register variant (three CTAs per SM) once there are several waves of
+  // strips; the 32x64 tile with three CTAs per SM wins on large images (all unrolled kernels)
+  if (W <= 96) return ((long long)B * ((H + 23) / 24) >= 6LL * sm_count()) ? 4 : 3;
   return 1;
 }
 static int pick_bwd_cfg(int B, int H, int W) {
@@ -278,6 +276,13 @@ const char* srst_error_string(int code) {
 // (2, 8) -- the reference default sigma=0.5, rho=2.0 -- has the tuned tile shapes; the other
 // classes use one generic shape each.
 int srst_st_supported(int r_sigma, int r_rho) { return (r_sigma >= 1 && r_sigma <= 4 && r_rho >= 1 && r_rho <= 12) ? 1 : 0; }
+
+#if defined(SRST_TIMING) && !defined(SRST_EMULATE)
+// tools-only build: where the kernels write their phase time stamps (32 slots per CTA); NULL turns them off
+int srst_debug_set_timing(long long* device_buffer) {
+  return (int)cudaMemcpyToSymbol(g_srst_timing, &device_buffer, sizeof(device_buffer));
+}
+#endif
 
 int srst_st_num_cfgs(int backward) { return backward ? kNumBwdCfg : kNumFwdCfg; }
 
@@ -338,7 +343,7 @@ static int st_forward_rr(const StCall& c) {
   if constexpr (RG == 2 && RK == 8) {
     const int cfg = pick_fwd_cfg(c.B, c.H, c.W);
     if (c.px) {  // the fused Pixel term is compiled into the two default tile shapes only
-      if (cfg != 1 && c.W <= 96) return launch_st_forward<Fwd2, true>(P, c.stream);
+      if (cfg != 1 && c.W <= 96) return launch_st_forward<Fwd3, true>(P, c.stream);
       return launch_st_forward<Fwd1, true>(P, c.stream);
     }
     switch (cfg) {
@@ -347,8 +352,6 @@ static int st_forward_rr(const StCall& c) {
       case 3: return launch_st_forward<Fwd3>(P, c.stream);
       case 4: return launch_st_forward<Fwd4>(P, c.stream);
       case 5: return launch_st_forward<Fwd5>(P, c.stream);
-      case 6: return launch_st_forward<Fwd6>(P, c.stream);
-      case 7: return launch_st_forward<Fwd7>(P, c.stream);
       default: return launch_st_forward<Fwd1>(P, c.stream);
     }
   } else {

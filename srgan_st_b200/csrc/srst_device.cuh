@@ -190,6 +190,22 @@ SRST_DEV void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id
 SRST_DEV void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 #endif
 
+// Optional phase time stamps (tools/phase_timing.py; compiled in only with -DSRST_TIMING, never in the product
+// library): thread 0 of every CTA records %globaltimer at the phase boundaries of its first tile.
+#if defined(SRST_TIMING) && !defined(SRST_EMULATE)
+__device__ long long* g_srst_timing = nullptr;
+SRST_DEV void srst_stamp(int slot) {
+  if (g_srst_timing && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_srst_timing[(size_t)blockIdx.x * 32 + slot] = t;
+  }
+}
+#define SRST_STAMP(slot) srst_stamp(slot)
+#else
+#define SRST_STAMP(slot) ((void)0)
+#endif
+
 SRST_DEV float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

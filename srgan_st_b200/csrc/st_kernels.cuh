@@ -479,7 +479,7 @@ struct ItemMap {
 // ------------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------------
-template <int TH_, int TW_, int RS_, int CSB_, int RG_, int RK_, int MINB_, int CHU_ = 1, bool CSPLIT_ = false>
+template <int TH_, int TW_, int RS_, int CSB_, int RG_, int RK_, int MINB_, int CHU_ = 1, bool CSPLIT_ = false, int LDEPTH_ = 2>
 struct StFwdCfg {
   // CSPLIT: the vertical pass hands out (plane, row segment, column) items instead of (row segment, column): used
   // when columns x segments alone leave a large part of the CTA idle (32x64 tile: 160 items for 256 threads).
@@ -493,7 +493,7 @@ struct StFwdCfg {
   //          what lets the large-image tile keep three CTAs per SM).
   static constexpr int CHU = CHU_;
   static constexpr bool ROLLED = CHU_ > 0;
-  static constexpr int LDEPTH = 2;       // gray-tile items (6 x LDG.128 each) in flight per thread
+  static constexpr int LDEPTH = LDEPTH_;  // gray-tile items (6 x LDG.128 each) in flight per thread
   static constexpr int HXD = round_up4(RK);  // x halo of the gradient (D) and V regions
   static constexpr int OFF = round_up4(RG);
   static constexpr int HXG = HXD + OFF;      // x halo of the gray (G) region
@@ -505,7 +505,7 @@ struct StFwdCfg {
   static constexpr int DW_LO = (HXD - RK) / 2 * 2, DW_HI = (HXD + 4 + RK + 1) / 2 * 2, DWIN = DW_HI - DW_LO;
   using MapB = ItemMap<DH / 2, DW / CSB, CSB>;  // gradient items
   using MapD = ItemMap<TH / 2, TW / 4, 4>;      // horizontal-pass items == the thread's 2 x 4 output pixels
-  static constexpr int NT = MapD::SLOTS;         // one horizontal-pass item per thread
+  static constexpr int NT = (MapD::SLOTS + 31) / 32 * 32;  // one horizontal-pass item per thread (idle tail lanes when not a warp multiple)
   static constexpr int D_FLOATS = (DH / 2) * PD, V_FLOATS = (TH / 2) * PV, G_FLOATS = (GH / 2) * PG;
   static constexpr int SP_FLOATS = 24 * NT;  // a parked tensor: 3 channels x 4 columns x float2 per thread
   // smem: D (Ix, Iy) | V (3 planes; the gray tile aliases it: dead once the gradient phase is done) | SP1.
@@ -528,16 +528,19 @@ struct StFwdCfg {
 template <class C, bool PX, class Taps>
 SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float* __restrict__ ixy, int b, bool vec4,
                              int H, int W, int y0, int x0, const Taps& tp, int tid, bool dvalid, int dq, int dseg,
-                             float2 (&S)[3][4], const float* __restrict__ px_other, float* px_acc) {
+                             float2 (&S)[3][4], const float* __restrict__ px_other, float* px_acc,
+                             [[maybe_unused]] int stamp0 = 0) {
   float* sD0 = smem;
   float* sD1 = sD0 + C::D_FLOATS;
   float* sV = sD1 + C::D_FLOATS;
   float* sG = sV;
 
   __syncthreads();  // every thread is done with sV / sD (SP2) of the previous unit
+  SRST_STAMP(stamp0 + 0);
   load_gray_tile<C::GH, C::GW, C::PG, C::NT, C::LDEPTH, PX>(sG, base, H, W, y0 - (C::RG + C::RK), x0 - C::HXG, vec4,
                                                             tid, y0, y0 + C::TH, x0, x0 + C::TW, px_other, px_acc);
   __syncthreads();
+  SRST_STAMP(stamp0 + 1);
 
   // Phase B: Ix, Iy on the D region; forced to zero outside the image because the reference
   // zero-pads the *products* for the rho-smoothing (utils.py:225-230).  Tile-interior items also
@@ -591,6 +594,7 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float*
     }
   }
   __syncthreads();
+  SRST_STAMP(stamp0 + 2);
 
   // Phase C: vertical rho-pass of the three products; a lane owns one column and RS output rows
   // (RS/2 row pairs).  Columns outside the image hold zeros and are only cleared.
@@ -672,6 +676,7 @@ SRST_DEV void st_unit_tensor(float* smem, const float* __restrict__ base, float*
     }
   }
   __syncthreads();
+  SRST_STAMP(stamp0 + 3);
 
   // Phase D: horizontal rho-pass; a lane owns 4 consecutive columns of one row pair.
   if (dvalid) {
@@ -691,6 +696,7 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
   __shared__ unsigned int s_last;
   [[maybe_unused]] __shared__ float s_red_px[PX ? 32 : 1];
   const int tid = threadIdx.x;
+  SRST_STAMP(15);
   pdl_wait();     // previous kernel of the stream is complete (it may have produced sr or used the workspace)
   pdl_trigger();  // the next PDL-launched kernel may start launching; it waits for this grid itself
 
@@ -716,9 +722,10 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
     // UNROLLED: two inlined copies of the filter phases; S1 waits in registers while HR is processed
     float2 S1[3][4], S2[3][4];
     st_unit_tensor<C, false>(smem, P.sr + img_off, P.ixy_sr, b, vec4, H, W, y0, x0, P.taps, tid, dvalid, q, seg, S1,
-                             nullptr, nullptr);
+                             nullptr, nullptr, 0);
     st_unit_tensor<C, PX>(smem, P.hr + img_off, P.ixy_hr, b, vec4, H, W, y0, x0, P.taps, tid, dvalid, q, seg, S2,
-                          PX ? P.sr + img_off : nullptr, &pxsum);
+                          PX ? P.sr + img_off : nullptr, &pxsum, 4);
+    SRST_STAMP(8);
     if (dvalid)
       lsum = st_chain_store<WANT_HR>(S1, S2, norm, P.eps, P.ds_sr, P.ds_hr, img_off, H, W, gy0, gx0, vec4);
   } else {
@@ -729,7 +736,8 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
       const float* base = (img ? P.hr : P.sr) + img_off;
       float* ixy = img ? P.ixy_hr : P.ixy_sr;
       st_unit_tensor<C, PX>(smem, base, ixy, b, vec4, H, W, y0, x0, P.taps, tid, dvalid, q, seg, S,
-                            (PX && img) ? P.sr + img_off : nullptr, &pxsum);
+                            (PX && img) ? P.sr + img_off : nullptr, &pxsum, 4 * img);
+      if (img) SRST_STAMP(8);
       if (dvalid) {
         {
           float* sp = img ? sp2 : sp1;
@@ -794,6 +802,7 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
 
   // Deterministic loss reduction: block partial -> workspace; the last block to finish sums all
   // partials in a fixed order (double) and re-zeroes the workspace for the next call.
+  SRST_STAMP(9);   // thread 0 is done with its chain + stores
   lsum = warp_sum(lsum);
   if constexpr (PX) pxsum = warp_sum(pxsum);
   if ((tid & 31) == 0) {
@@ -815,6 +824,7 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
     s_last = (tk == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
+  SRST_STAMP(10);  // every warp of the CTA is done
   if (s_last) {
     __threadfence();
     if (tid < 32) {

@@ -64,6 +64,26 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+def _raw_stream(device: torch.device) -> int:
+    """cudaStream_t of torch's current stream on `device` as an integer.  torch.cuda.current_stream() builds a
+    Stream object (~5 us); the raw getter behind it is a plain C call."""
+    return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
+
+
+_SIZES: Dict[Tuple[int, int, int], Tuple[int, int, int]] = {}
+
+
+def _st_sizes(B: int, H: int, W: int) -> Tuple[int, int, int]:
+    """(ds floats padded to 16 bytes, ixy floats, workspace bytes) of a [B,3,H,W] problem, cached per shape."""
+    key = (B, H, W)
+    v = _SIZES.get(key)
+    if v is None:
+        lib = _cabi.lib()
+        v = ((B * 3 * H * W + 3) // 4 * 4, lib.srst_st_ixy_floats(B, H, W), lib.srst_st_workspace_bytes(B, H, W))
+        _SIZES[key] = v
+    return v
+
+
 class _on_device:
     """`with torch.cuda.device(d)` costs ~10 us per call even when d is already current (the normal case in a
     training loop); this enters the context only when the tensor lives on another device."""
@@ -114,16 +134,15 @@ class _StructureTensorLossFn(torch.autograd.Function):
         hr = hr.contiguous()
         B, _, H, W = sr.shape
         tp = _st_taps(sigma, rho, "StructureTensorLoss")
-        need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-        n_ds = (B * 3 * H * W + 3) // 4 * 4          # keeps the ixy part 16-byte aligned
-        n_ixy = lib.srst_st_ixy_floats(B, H, W) if (need[0] or need[1]) else 0
+        need = ctx.needs_input_grad
+        n_ds, n_ixy, ws_bytes = _st_sizes(B, H, W)   # n_ds is padded: the ixy part stays 16-byte aligned
         with _on_device(sr.device):
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = _raw_stream(sr.device)
             loss = torch.empty((), dtype=torch.float32, device=sr.device)
-            saved = [torch.empty(n_ds + n_ixy, dtype=torch.float32, device=sr.device) if n else None for n in need]
+            saved = [torch.empty(n_ds + n_ixy, dtype=torch.float32, device=sr.device) if n else None for n in need[:2]]
             ds = [t.data_ptr() if t is not None else None for t in saved]
-            ixy = [t.data_ptr() + 4 * n_ds if t is not None else None for t in saved]
-            ws = _workspace("st", sr.device, stream, lib.srst_st_workspace_bytes(B, H, W))
+            ixy = [p + 4 * n_ds if p is not None else None for p in ds]
+            ws = _workspace("st", sr.device, stream, ws_bytes)
             rc = lib.srst_st_forward(sr.data_ptr(), hr.data_ptr(), B, H, W, tp[0], tp[1], tp[2], tp[3], tp[4],
                                      int(bool(normalize)), 1e-12, loss.data_ptr(), ds[0], ds[1], ixy[0], ixy[1],
                                      ws.data_ptr(), ws.numel(), stream)
@@ -143,7 +162,7 @@ class _StructureTensorLossFn(torch.autograd.Function):
         outs = [None, None]
         dev = grad_out.device
         with _on_device(dev):
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = _raw_stream(dev)
             for i, saved in enumerate(ctx.saved_tensors):
                 if saved is None or not ctx.needs_input_grad[i]:
                     continue
@@ -184,7 +203,7 @@ class StructureTensorLoss(nn.Module):
 
 class _StructureTensorPixelLossFn(torch.autograd.Function):
     """ST loss and the "Pixel" MSE criterion from ONE pass over (sr, gt) per direction.
-    Returns the two unweighted terms; gt carries no gradient."""
+    Returns the two unweighted terms as one 2-vector [st, mse]; gt carries no gradient."""
 
     @staticmethod
     def forward(ctx, sr, hr, sigma, rho, normalize):
@@ -194,27 +213,25 @@ class _StructureTensorPixelLossFn(torch.autograd.Function):
         B, _, H, W = sr.shape
         tp = _st_taps(sigma, rho, "StructureTensorPixelLoss")
         need_sr = ctx.needs_input_grad[0]
-        n_ds = (B * 3 * H * W + 3) // 4 * 4
-        n_ixy = lib.srst_st_ixy_floats(B, H, W)
+        n_ds, n_ixy, ws_bytes = _st_sizes(B, H, W)
         with _on_device(sr.device):
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = _raw_stream(sr.device)
             both = torch.empty(2, dtype=torch.float32, device=sr.device)
             saved = torch.empty(n_ds + n_ixy, dtype=torch.float32, device=sr.device) if need_sr else None
-            ws = _workspace("st", sr.device, stream, lib.srst_st_workspace_bytes(B, H, W))
+            p = saved.data_ptr() if need_sr else None
+            ws = _workspace("st", sr.device, stream, ws_bytes)
             rc = lib.srst_stpx_forward(sr.data_ptr(), hr.data_ptr(), B, H, W, tp[0], tp[1], tp[2], tp[3], tp[4],
-                                       int(bool(normalize)), 1e-12, both.data_ptr(),
-                                       saved.data_ptr() if need_sr else None,
-                                       saved.data_ptr() + 4 * n_ds if need_sr else None,
-                                       ws.data_ptr(), ws.numel(), stream)
+                                       int(bool(normalize)), 1e-12, both.data_ptr(), p,
+                                       p + 4 * n_ds if need_sr else None, ws.data_ptr(), ws.numel(), stream)
         if rc:
             _cabi.check(rc, "srst_stpx_forward")
         ctx.save_for_backward(sr, hr, saved)
         ctx.meta = (tp, n_ds)
-        return both[0], both[1]
+        return both
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, grad_st, grad_px):
+    def backward(ctx, grad_both):
         lib = _cabi.lib()
         sr, hr, saved = ctx.saved_tensors
         tp, n_ds = ctx.meta
@@ -222,13 +239,13 @@ class _StructureTensorPixelLossFn(torch.autograd.Function):
             return None, None, None, None, None
         B, _, H, W = sr.shape
         with _on_device(sr.device):
-            stream = torch.cuda.current_stream().cuda_stream
-            grad_st = grad_st.to(torch.float32).contiguous()
-            grad_px = grad_px.to(torch.float32).contiguous()
+            stream = _raw_stream(sr.device)
+            if grad_both.dtype != torch.float32 or not grad_both.is_contiguous():
+                grad_both = grad_both.to(torch.float32).contiguous()
             d_sr = torch.empty_like(sr)
+            g = grad_both.data_ptr()                       # [d/d st, d/d mse]: two adjacent device scalars
             rc = lib.srst_stpx_backward(sr.data_ptr(), hr.data_ptr(), saved.data_ptr() + 4 * n_ds, saved.data_ptr(),
-                                        grad_st.data_ptr(), grad_px.data_ptr(), B, H, W, tp[0], tp[1], tp[2], tp[3],
-                                        tp[4], d_sr.data_ptr(), stream)
+                                        g, g + 4, B, H, W, tp[0], tp[1], tp[2], tp[3], tp[4], d_sr.data_ptr(), stream)
         if rc:
             _cabi.check(rc, "srst_stpx_backward")
         return d_sr, None, None, None, None
@@ -252,15 +269,26 @@ class StructureTensorPixelLoss(nn.Module):
         self.normalize = normalize
         self.st_weight = st_weight
         self.pixel_weight = pixel_weight
-        self.last_terms = None
+        self._last = None
+        self._w = None   # (device, st_weight, pixel_weight, tensor): the weights as a device 2-vector
         _cabi.lib()
+
+    @property
+    def last_terms(self):
+        """(st, mse) of the most recent call as two 0-dim device tensors (detached), or None."""
+        return None if self._last is None else (self._last[0], self._last[1])
 
     def forward(self, x, gt):
         _check_pair(x, gt, "StructureTensorPixelLoss")
         _no_gt_grad(gt, "StructureTensorPixelLoss")
-        st, px = _StructureTensorPixelLossFn.apply(x, gt, self.sigma, self.rho, self.normalize)
-        self.last_terms = (st.detach(), px.detach())
-        return self.st_weight * st + self.pixel_weight * px
+        both = _StructureTensorPixelLossFn.apply(x, gt, self.sigma, self.rho, self.normalize)
+        self._last = both.detach()
+        w = self._w
+        if w is None or w[0] != x.device or w[1] != self.st_weight or w[2] != self.pixel_weight:
+            w = (x.device, self.st_weight, self.pixel_weight,
+                 torch.tensor([self.st_weight, self.pixel_weight], dtype=torch.float32, device=x.device))
+            self._w = w
+        return torch.dot(both, w[3])
 
     def extra_repr(self) -> str:
         return (f"sigma={self.sigma}, rho={self.rho}, normalize={self.normalize}, st_weight={self.st_weight}, "
@@ -281,7 +309,7 @@ class _BestBuddyLossFn(torch.autograd.Function):
         if H < 12 or W < 12:
             raise ValueError(f"BestBuddyLoss: images must be at least 12x12 (got {H}x{W})")
         with _on_device(sr.device):
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = _raw_stream(sr.device)
             if pyramid == "aten":
                 # the reference's own op for the HR pyramid (loss.py:123,127)
                 with torch.no_grad():
@@ -317,7 +345,7 @@ class _BestBuddyLossFn(torch.autograd.Function):
             return None, None, None, None, None, None, None
         grad_out = grad_out.to(torch.float32).contiguous()
         with _on_device(sr.device):
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = _raw_stream(sr.device)
             d_sr = torch.empty_like(sr)
             nbytes = lib.srst_bb_workspace_bytes(B, H, W)
             ws = _workspace("bb", sr.device, stream, nbytes)
@@ -431,7 +459,7 @@ class _PatchwiseStLossFn(torch.autograd.Function):
         g, dg = _taps.gaussian_taps(float(sigma))
         k, _ = _taps.gaussian_taps(float(rho))
         with _on_device(sr.device):
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = _raw_stream(sr.device)
             if pyramid == "aten":
                 with torch.no_grad():  # the reference's own op for the HR pyramid (loss.py:353,356)
                     gt2 = torch.nn.functional.interpolate(gt, scale_factor=0.5, mode="bicubic",
@@ -466,7 +494,7 @@ class _PatchwiseStLossFn(torch.autograd.Function):
             return (None,) * 8
         grad_out = grad_out.to(torch.float32).contiguous()
         with _on_device(sr.device):
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = _raw_stream(sr.device)
             d_sr = torch.empty_like(sr)
             ws = _workspace("bb", sr.device, stream, lib.srst_bb_workspace_bytes(B, H, W))
             rc = lib.srst_pst_backward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,

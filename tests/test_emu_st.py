@@ -15,11 +15,11 @@ def lib():
     return emu_lib()
 
 
-@pytest.fixture(params=[0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.fixture(params=[0, 1, 2, 3, 4, 5, 6, 7])  # backward shape = param; forward shape = param % 6
 def tile_cfg(request, lib):
     """Every compiled forward tile shape, paired with a backward shape (srst_st_force_cfg)."""
-    assert lib.srst_st_num_cfgs(0) >= 8 and lib.srst_st_num_cfgs(1) >= 8
-    assert lib.srst_st_force_cfg(request.param, request.param) == 0
+    assert lib.srst_st_num_cfgs(0) >= 6 and lib.srst_st_num_cfgs(1) >= 8
+    assert lib.srst_st_force_cfg(request.param % 6 if request.param >= 0 else -1, request.param) == 0
     yield request.param
     lib.srst_st_force_cfg(-1, -1)
 
