@@ -554,8 +554,8 @@ def run_gpu(args):
             def run_e2e(h2d, collective, pipelined, Ksteps):
                 """K steps through the public module.  h2d: copy each step's inputs from pinned host memory (else the
                 slots keep their contents); collective: all-reduce the gradient bucket every step (N > 1);
-                pipelined: the collective runs on a side stream and the host reads the PREVIOUS step's loss while this
-                step runs (one read per step, one step late) instead of stalling on its own loss."""
+                pipelined: the host reads the PREVIOUS step's loss (one read per step, one step late) instead of
+                stalling on its own loss, so enqueueing step i+1 overlaps the execution of step i."""
                 copied = [torch.cuda.Event(), torch.cuda.Event()]
                 consumed = [torch.cuda.Event(), torch.cuda.Event()]
                 use_bucket = bucket is not None and collective
@@ -587,18 +587,16 @@ def run_gpu(args):
                             bucket.set_loss(l)
                             l = bucket.all_reduce_mean()
                         return l.item()  # device->host read of the step's result, as train.py:141
-                    # pipelined: previous step's collective must be done before the bucket is reused
+                    # pipelined: nothing blocks the host inside the step.  The collective stays on the compute stream (it
+                    # overlaps the NEXT step's H2D copy, which runs on the copy stream; the kernels are ~30 us of a
+                    # ~260 us step) and the host reads the PREVIOUS step's loss from a pinned slot.
                     if use_bucket:
-                        bucket.wait()
                         bucket.set_loss(l)
-                        bucket.all_reduce_mean_async()
-                        src = bucket.loss_slot[0]
-                        with torch.cuda.stream(bucket._comm_stream):
-                            host_loss[i % 2].copy_(src, non_blocking=True)
-                            read_done[i % 2].record(bucket._comm_stream)
+                        src = bucket.all_reduce_mean()
                     else:
-                        host_loss[i % 2].copy_(l.detach(), non_blocking=True)
-                        read_done[i % 2].record(cur)
+                        src = l.detach()
+                    host_loss[i % 2].copy_(src, non_blocking=True)
+                    read_done[i % 2].record(cur)
                     if i > 0:
                         read_done[(i - 1) % 2].synchronize()   # the host now holds step i-1's loss
                         return float(host_loss[(i - 1) % 2])
@@ -608,8 +606,6 @@ def run_gpu(args):
                     if pipelined and n > 0:
                         read_done[(n - 1) % 2].synchronize()
                         _ = float(host_loss[(n - 1) % 2])
-                        if use_bucket:
-                            bucket.wait()
 
                 for ev in consumed:
                     ev.record()
@@ -656,7 +652,8 @@ def run_gpu(args):
                           "h2d_gbs_per_gpu": bytes_pair / (head["ms_per_step"] * 1e-3) / 1e9,
                           "definition": "strict: every step copies its inputs H2D from pinned memory (next batch prefetched on a copy "
                                         "stream), runs fwd+bwd (+ the bucket all-reduce at N > 1) and reads its own loss with .item(); "
-                                        "pipelined: same copies, the all-reduce on a side stream, the host reads the previous step's loss",
+                                        "pipelined: same copies and collective, but the host reads the previous step's loss, so it never "
+                                        "stalls inside a step",
                           "variants": variants,
                           "host_affinity": numa_note,
                           "collective": (f"one NCCL all-reduce of {bucket.nbytes} B (generator-grad bucket + loss) per step"

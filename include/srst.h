@@ -99,6 +99,21 @@ int srst_st_backward(const float* ixy, const float* ds, const float* grad_out,
                      const float* k, int r_rho,
                      float* d_img, void* stream);
 
+/* Structure-tensor FEATURES of one image tensor (diagnostic output; BASELINE.json north_star: "closed-form 2x2
+ * eigendecomposition giving orientation, coherence and eigenvalues").  The reference computes these only in an
+ * exploration notebook through the third-party `structure_tensor` package (data-exploration/structure_tensor.ipynb,
+ * cells 12-18: eig_special_2d, arctan2 of the eigenvector, 1 - val[0]/val[1]), which is not part of its checkout:
+ * the definitions below are this library's own (parity unpinned).
+ *   J_out      [B,3,H,W]  Jxx, Jyy, Jxy: the smoothed tensor of utils.structure_tensor (utils.py:212-233)
+ *   eig_out    [B,2,H,W]  lambda_small, lambda_large = (Jxx+Jyy)/2 -/+ sqrt(((Jxx-Jyy)/2)^2 + Jxy^2)
+ *   orient_out [B,H,W]    1/2 atan2(2 Jxy, Jxx - Jyy): angle of the dominant-gradient eigenvector against the H axis
+ *   coher_out  [B,H,W]    1 - lambda_small / lambda_large (0 where lambda_large == 0)
+ * Any output may be NULL (at least one must be given).  No gradient. */
+int srst_st_features(const float* img, int B, int H, int W,
+                     const float* g, const float* dg, int r_sigma,
+                     const float* k, int r_rho,
+                     float* J_out, float* eig_out, float* orient_out, float* coher_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Structure-tensor loss with the "Pixel" MSE criterion fused in.  The warm-up
  * and training loops evaluate MSELoss(sr, gt) and StructureTensorLoss(sr, gt) on the same two

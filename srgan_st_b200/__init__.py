@@ -6,8 +6,8 @@ Importing this package needs ``libsrst.so`` (build: ``python -m srgan_st_b200.bu
 no CPU or PyTorch fallback.
 """
 from .loss import (BestBuddyLoss, GramLoss, PatchwiseStructureTensorLoss, StructureTensorLoss,  # noqa: F401
-                   StructureTensorPixelLoss)
+                   StructureTensorPixelLoss, structure_tensor_features)
 
 __all__ = ["StructureTensorLoss", "BestBuddyLoss", "GramLoss", "PatchwiseStructureTensorLoss",
-           "StructureTensorPixelLoss"]
+           "StructureTensorPixelLoss", "structure_tensor_features"]
 __version__ = "0.1.0"

@@ -33,6 +33,8 @@ SIGNATURES = {
     "srst_st_backward": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
                                         vp, vp]),
+    "srst_st_features": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, vp, vp, vp, vp, vp]),
     "srst_stpx_forward": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_float, vp, vp, vp, vp, ctypes.c_size_t, vp]),

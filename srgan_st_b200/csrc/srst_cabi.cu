@@ -467,6 +467,45 @@ int srst_stpx_backward(const float* sr, const float* hr, const float* ixy, const
 
 }  // extern "C"
 
+namespace srst {
+template <int RG, int RK>
+static int st_features_rr(const float* img, int B, int H, int W, const float* g, const float* dg, int rs, const float* k, int rk,
+                          float* J, float* eig, float* orient, float* coher, int vec4, void* stream) {
+  using C = StFwdCfg<32, 64, 16, 4, RG, RK, (RK <= 8 ? 2 : 1), 0>;
+  static thread_local StFeatParams<RG, RK> P;
+  P.img = img; P.J = J; P.eig = eig; P.orient = orient; P.coher = coher;
+  P.B = B; P.H = H; P.W = W; P.vec4 = vec4;
+  P.tiles_x = (W + C::TW - 1) / C::TW;
+  P.tiles_y = (H + C::TH - 1) / C::TH;
+  const long long ntiles = (long long)B * P.tiles_x * P.tiles_y;
+  if (ntiles <= 0 || ntiles > 0x7fffffffLL) return SRST_E_SHAPE;
+  P.taps = cached_taps<RG, RK>(g, dg, rs, k, rk);
+  struct FeatTag {};
+  int e = ensure_smem<FeatTag>(st_features_kernel<C>, C::SMEM_BYTES);
+  if (e) return e;
+  const StFeatParams<RG, RK>& Pr = P;  // (the emulation runs kernel bodies on other OS threads: never name a thread_local there)
+  SRST_LAUNCH(st_features_kernel<C>, dim3((unsigned)ntiles), dim3(C::NT), C::SMEM_BYTES, stream, Pr);
+  return (int)cudaGetLastError();
+}
+}  // namespace srst
+
+extern "C" int srst_st_features(const float* img, int B, int H, int W, const float* g, const float* dg, int r_sigma,
+                                const float* k, int r_rho, float* J_out, float* eig_out, float* orient_out,
+                                float* coher_out, void* stream) {
+  if (!img || !g || !dg || !k || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
+  if (!J_out && !eig_out && !orient_out && !coher_out) return SRST_E_INVALID;
+  if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
+  const int vec4 = (W % 4 == 0 && aligned16(img)) ? 1 : 0;
+  const int rg = r_sigma <= 2 ? 2 : 4;
+  const int rk = r_rho <= 4 ? 4 : (r_rho <= 8 ? 8 : 12);
+#define SRST_FT(RG_, RK_) \
+  if (rg == RG_ && rk == RK_) \
+    return st_features_rr<RG_, RK_>(img, B, H, W, g, dg, r_sigma, k, r_rho, J_out, eig_out, orient_out, coher_out, vec4, stream);
+  SRST_FT(2, 8) SRST_FT(2, 4) SRST_FT(2, 12) SRST_FT(4, 4) SRST_FT(4, 8) SRST_FT(4, 12)
+#undef SRST_FT
+  return SRST_E_UNSUPPORTED;
+}
+
 // ---- Best-Buddy entry points ---------------------------------------------------------------
 extern "C" {
 

@@ -853,6 +853,76 @@ st_forward_kernel(const __grid_constant__ StFwdParams<C::RG, C::RK> P) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Structure-tensor features of ONE image tensor: the smoothed tensor itself and its closed-form 2x2
+// eigen-decomposition (BASELINE.json north_star: "closed-form 2x2 eigendecomposition giving orientation,
+// coherence and eigenvalues").  The reference computes these only in an exploration notebook, with the
+// third-party `structure_tensor` package (data-exploration/structure_tensor.ipynb: eig_special_2d, then
+// arctan2 of the eigenvector and 1 - val[0]/val[1]); that package is not part of the reference checkout, so
+// this output is a diagnostic with its own definition (parity unpinned):
+//   S = [[Jxx, Jxy], [Jxy, Jyy]]  (Jxx: derivative along H, as utils.py:219-229 names them)
+//   lambda_small/large = (Jxx + Jyy)/2 -/+ sqrt(((Jxx - Jyy)/2)^2 + Jxy^2)
+//   orientation = 1/2 atan2(2 Jxy, Jxx - Jyy)   angle of the dominant-gradient eigenvector against the H axis,
+//                                               in (-pi/2, pi/2]; the coherent structure runs perpendicular to it
+//   coherence   = 1 - lambda_small / lambda_large  (0 where lambda_large == 0)
+// Same tile phases as the forward kernel (st_unit_tensor); precise math functions: this is not a hot path.
+// ------------------------------------------------------------------------------------------------
+template <int RG, int RK>
+struct StFeatParams {
+  const float* img;
+  float* J;       // [B,3,H,W] (Jxx, Jyy, Jxy) or null
+  float* eig;     // [B,2,H,W] (small, large) or null
+  float* orient;  // [B,H,W] or null
+  float* coher;   // [B,H,W] or null
+  int B, H, W, tiles_x, tiles_y, vec4;
+  StTaps<RG, RK> taps;
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::MINB)
+st_features_kernel(const __grid_constant__ StFeatParams<C::RG, C::RK> P) {
+  SRST_DYN_SMEM(float, smem);
+  const int tid = threadIdx.x;
+  int t = blockIdx.x;
+  const int tx = t % P.tiles_x;
+  t /= P.tiles_x;
+  const int ty = t % P.tiles_y;
+  const int b = t / P.tiles_y;
+  const int y0 = ty * C::TH, x0 = tx * C::TW;
+  const int H = P.H, W = P.W;
+  int q, seg;
+  const bool dvalid = C::MapD::decode(tid, q, seg);
+  float2 S[3][4];
+  st_unit_tensor<C, false>(smem, P.img + (size_t)b * 3 * H * W, nullptr, b, P.vec4 != 0, H, W, y0, x0, P.taps, tid, dvalid, q,
+                           seg, S, nullptr, nullptr);
+  if (!dvalid) return;
+  const size_t plane = (size_t)H * W;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int gy = y0 + 2 * q + hf, gx = x0 + 4 * seg + j;
+      if (gy >= H || gx >= W) continue;
+      const float a = hf ? S[0][j].y : S[0][j].x, bb = hf ? S[1][j].y : S[1][j].x, c = hf ? S[2][j].y : S[2][j].x;
+      const size_t o = (size_t)gy * W + gx;
+      if (P.J) {
+        P.J[((size_t)b * 3 + 0) * plane + o] = a;
+        P.J[((size_t)b * 3 + 1) * plane + o] = bb;
+        P.J[((size_t)b * 3 + 2) * plane + o] = c;
+      }
+      const float hd = 0.5f * (a - bb), mean = 0.5f * (a + bb);
+      const float r = sqrtf(fmaf(hd, hd, c * c));
+      const float l_small = mean - r, l_large = mean + r;
+      if (P.eig) {
+        P.eig[((size_t)b * 2 + 0) * plane + o] = l_small;
+        P.eig[((size_t)b * 2 + 1) * plane + o] = l_large;
+      }
+      if (P.orient) P.orient[(size_t)b * plane + o] = 0.5f * atan2f(2.0f * c, a - bb);
+      if (P.coher) P.coher[(size_t)b * plane + o] = l_large > 0.f ? 1.0f - l_small / l_large : 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------------
 template <int TH_, int TW_, int RS_, int NT_, int RG_, int RK_, int MINB_, int CSD_ = 8, bool PIPE_ = false>

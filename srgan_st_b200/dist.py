@@ -82,8 +82,11 @@ class FlatGradBucket:
         """Sum over ranks, divide by the world size; returns the mean loss (a view, no sync)."""
         self.reattach()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.div_(dist.get_world_size(group))
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)   # mean inside NCCL: no extra kernel
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(dist.get_world_size(group))
         return self.loss_slot[0]
 
     def all_reduce_mean_async(self, group=None) -> None:
@@ -100,8 +103,7 @@ class FlatGradBucket:
         cur = torch.cuda.current_stream(self.flat.device)
         self._comm_stream.wait_stream(cur)
         with torch.cuda.stream(self._comm_stream):
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.div_(dist.get_world_size(group))
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
             self._done.record(self._comm_stream)
         self.flat.record_stream(self._comm_stream)
 

@@ -201,6 +201,33 @@ class StructureTensorLoss(nn.Module):
         return f"sigma={self.sigma}, rho={self.rho}, normalize={self.normalize}"
 
 
+def structure_tensor_features(img: torch.Tensor, sigma: float = 0.5, rho: float = 2.0):
+    """Diagnostic structure-tensor features of ``img`` ``[B,3,H,W]`` (fp32 CUDA), no gradient: a dict with
+    ``J`` ``[B,3,H,W]`` (Jxx, Jyy, Jxy as reference utils.py:212-233 names them), ``eigenvalues`` ``[B,2,H,W]`` (small,
+    large), ``orientation`` ``[B,H,W]`` (angle of the dominant-gradient eigenvector against the H axis, radians in
+    (-pi/2, pi/2]; the coherent structure runs perpendicular to it) and ``coherence`` ``[B,H,W]``
+    (``1 - lambda_small / lambda_large``).  The reference derives orientation / anisotropy only in an exploration
+    notebook via the third-party ``structure_tensor`` package; see ``include/srst.h`` (srst_st_features)."""
+    if not (isinstance(img, torch.Tensor) and img.is_cuda and img.dtype == torch.float32 and img.dim() == 4
+            and img.shape[1] == 3):
+        raise TypeError("structure_tensor_features: expected a float32 CUDA tensor [B,3,H,W] (no CPU fallback)")
+    lib = _cabi.lib()
+    img = img.detach().contiguous()
+    B, _, H, W = img.shape
+    tp = _st_taps(sigma, rho, "structure_tensor_features")
+    with _on_device(img.device):
+        stream = _raw_stream(img.device)
+        J = torch.empty((B, 3, H, W), dtype=torch.float32, device=img.device)
+        eig = torch.empty((B, 2, H, W), dtype=torch.float32, device=img.device)
+        orient = torch.empty((B, H, W), dtype=torch.float32, device=img.device)
+        coher = torch.empty((B, H, W), dtype=torch.float32, device=img.device)
+        rc = lib.srst_st_features(img.data_ptr(), B, H, W, tp[0], tp[1], tp[2], tp[3], tp[4], J.data_ptr(), eig.data_ptr(),
+                                  orient.data_ptr(), coher.data_ptr(), stream)
+    if rc:
+        _cabi.check(rc, "srst_st_features")
+    return {"J": J, "eigenvalues": eig, "orientation": orient, "coherence": coher}
+
+
 class _StructureTensorPixelLossFn(torch.autograd.Function):
     """ST loss and the "Pixel" MSE criterion from ONE pass over (sr, gt) per direction.
     Returns the two unweighted terms as one 2-vector [st, mse]; gt carries no gradient."""

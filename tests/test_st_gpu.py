@@ -31,7 +31,7 @@ def _run(sr, hr, normalize=True, want_hr=True, sigma=0.5, rho=2.0):
     return loss.item(), x.grad.cpu().numpy(), (y.grad.cpu().numpy() if want_hr else None)
 
 
-N_CFG = 8   # compiled tile shapes exercised per direction (srst_st_num_cfgs() >= this)
+N_FWD, N_BWD = 6, 8   # compiled tile shapes exercised per direction (srst_st_num_cfgs() >= these)
 
 
 @pytest.fixture(params=[-1, 0, 1, 2, 3, 4, 5, 6, 7])
@@ -39,8 +39,8 @@ def tile_cfg(request):
     """-1 = the library's own choice; 0.. force a compiled forward / backward tile shape (srst_st_force_cfg)."""
     from srgan_st_b200 import _cabi
     lib = _cabi.lib()
-    assert lib.srst_st_num_cfgs(0) >= N_CFG and lib.srst_st_num_cfgs(1) >= N_CFG
-    assert lib.srst_st_force_cfg(request.param % 6 if request.param >= 0 else -1, request.param) == 0
+    assert lib.srst_st_num_cfgs(0) >= N_FWD and lib.srst_st_num_cfgs(1) >= N_BWD
+    assert lib.srst_st_force_cfg(request.param % N_FWD if request.param >= 0 else -1, request.param) == 0
     yield request.param
     lib.srst_st_force_cfg(-1, -1)
 
