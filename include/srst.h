@@ -59,6 +59,10 @@ int srst_st_supported(int r_sigma, int r_rho);
  * (read once). */
 int srst_st_num_cfgs(int backward);
 int srst_st_force_cfg(int fwd_cfg, int bwd_cfg);
+/* Forward cfgs 6 and 7 are the row-marching kernel (96- / 128-column strips).  It cuts a strip into row chunks so
+ * that small batches fill the machine; `blocks` > 0 forces the chunk height to blocks*16 rows (tests), <= 0 hands
+ * the choice back to the library.  Process-wide; SRST_ST_CHUNK_BLOCKS sets the initial value. */
+int srst_st_force_chunk_blocks(int blocks);
 
 /* Scratch bytes srst_st_forward / srst_stpx_forward need for a [B,3,H,W] problem (per-CTA partial sums + ticket).
  * The workspace must be 16-byte aligned; its first 16 bytes (the ticket counter) must be ZERO before the

@@ -24,6 +24,7 @@ SIGNATURES = {
     "srst_st_supported": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "srst_st_num_cfgs": (ctypes.c_int, [ctypes.c_int]),
     "srst_st_force_cfg": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "srst_st_force_chunk_blocks": (ctypes.c_int, [ctypes.c_int]),
     "srst_st_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
     "srst_st_ixy_floats": (ctypes.c_size_t, [ctypes.c_int] * 3),
     "srst_st_forward": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -12,6 +12,7 @@
 #include <type_traits>
 
 #include "st_kernels.cuh"
+#include "st_march.cuh"
 #include "bb_kernels.cuh"
 
 namespace srst {
@@ -25,9 +26,14 @@ static int env_int_once(const char* name, int dflt) {
   return (s && *s) ? std::atoi(s) : dflt;
 }
 static int g_force_fwd = -2, g_force_bwd = -2;  // -2: not initialised, -1: library's own choice
+static int g_force_chunk = -2;                  // row blocks per chunk of the marching forward (0 / -1: own choice)
 static int forced_fwd() {
   if (g_force_fwd == -2) g_force_fwd = env_int_once("SRST_ST_FWD_CFG", -1);
   return g_force_fwd;
+}
+static int forced_chunk() {
+  if (g_force_chunk == -2) g_force_chunk = env_int_once("SRST_ST_CHUNK_BLOCKS", -1);
+  return g_force_chunk;
 }
 static int forced_bwd() {
   if (g_force_bwd == -2) g_force_bwd = env_int_once("SRST_ST_BWD_CFG", -1);
@@ -42,7 +48,11 @@ using Fwd2 = StFwdCfg<24, 96, 8, 4, 2, 8, 2>;      // full-width strip of a 96-w
 using Fwd3 = StFwdCfg<24, 96, 8, 4, 2, 8, 2, 0>;   // Fwd2 unrolled
 using Fwd4 = StFwdCfg<24, 96, 8, 4, 2, 8, 3, 0>;   // Fwd3 with three CTAs per SM (72 registers): multi-wave batches of 96-wide crops
 using Fwd5 = StFwdCfg<40, 64, 10, 4, 2, 8, 2, 0>;  // taller unrolled tile, 320 threads, two CTAs per SM
-constexpr int kNumFwdCfg = 6;
+// cfg 6, 7: the row-marching kernel (st_march.cuh), 96- and 112-column strips -- the default whenever TMA can
+// fetch the images; the tiled shapes above remain for unaligned tensors and as the fall-back
+using March96 = StMarchCfg<96, 2, 8>;
+using March112 = StMarchCfg<112, 2, 8>;
+constexpr int kNumFwdCfg = 8;
 //                       TH  TW  RS   NT RG RK MINB CSD
 using Bwd0 = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8>;  // large images: 16 row pairs per horizontal-pass column
 using Bwd1 = StBwdCfg<16, 96, 10, 288, 2, 8, 2, 8>;  // full-width strips of 96-wide crops
@@ -54,7 +64,7 @@ using Bwd6 = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8, true>;  // Bwd0, persistent w
 using Bwd7 = StBwdCfg<12, 96, 8, 224, 2, 8, 2, 8, true>;   // Bwd2, persistent with the next tile's boxes prefetched
 constexpr int kNumBwdCfg = 8;
 
-constexpr int kMinFwdTH = 24, kMinFwdTW = 48;  // finest compiled forward tiling (workspace sizing)
+constexpr int kMinFwdTH = 16, kMinFwdTW = 48;  // finest forward work split (workspace sizing): 16-row chunks, 48-wide tiles
 
 static int sm_count() {
 #ifdef SRST_EMULATE
@@ -209,6 +219,44 @@ static int launch_st_forward(StFwdParams<C::RG, C::RK>& P, void* stream) {
   return (int)cudaGetLastError();
 }
 
+// Row-marching forward.  Returns kMarchUnusable when the images cannot be fetched by TMA (the caller then uses a
+// tiled shape).  Chunking: whole strips when B * strips already fills the machine, otherwise each strip is cut
+// into as many row chunks as there are idle SMs (a chunk costs one extra 16-row block of gradient + horizontal work).
+constexpr int kMarchUnusable = -1000;
+template <class C, bool PX, bool HR> struct MarchTag {};
+template <class C, bool PX = false>
+static int launch_st_march(const StFwdParams<C::RG, C::RK>& F, void* stream) {
+  static thread_local StMarchParams<C::RG, C::RK> MP_tls;
+  auto& MP = MP_tls;  // a plain reference: the emulation's kernel threads must see THIS thread's instance
+  if (!F.vec4) return kMarchUnusable;
+  if (!make_plane_map(&MP.sr_map, F.sr, (long long)F.B * 3, F.H, F.W, C::GW, C::RS, 3) ||
+      !make_plane_map(&MP.hr_map, F.hr, (long long)F.B * 3, F.H, F.W, C::GW, C::RS, 3))
+    return kMarchUnusable;
+  MP.F = F;
+  const int nblk = (F.H + C::RS - 1) / C::RS;
+  MP.nstrips = (F.W + C::TW - 1) / C::TW;
+  const long long base = (long long)F.B * MP.nstrips;
+  long long nch = 1;
+  const int slots = sm_count();
+  if (base < slots) nch = slots / base;
+  if (nch > nblk) nch = nblk;
+  int cb = (int)((nblk + nch - 1) / nch);
+  if (forced_chunk() > 0) cb = forced_chunk() < nblk ? forced_chunk() : nblk;
+  MP.chunk_blocks = cb;
+  MP.nchunks = (nblk + cb - 1) / cb;
+  const long long grid = base * MP.nchunks;
+  if (grid <= 0 || grid > 0x7fffffffLL) return SRST_E_SHAPE;
+  int e;
+  if (F.ds_hr) {
+    if ((e = ensure_smem<MarchTag<C, PX, true>>(st_forward_march_kernel<C, PX, true>, C::SMEM_BYTES)) != 0) return e;
+    SRST_LAUNCH_PDL((st_forward_march_kernel<C, PX, true>), dim3((unsigned)grid), dim3(C::NT), C::SMEM_BYTES, stream, MP);
+  } else {
+    if ((e = ensure_smem<MarchTag<C, PX, false>>(st_forward_march_kernel<C, PX, false>, C::SMEM_BYTES)) != 0) return e;
+    SRST_LAUNCH_PDL((st_forward_march_kernel<C, PX, false>), dim3((unsigned)grid), dim3(C::NT), C::SMEM_BYTES, stream, MP);
+  }
+  return (int)cudaGetLastError();
+}
+
 template <class C, bool PX = false>
 static int launch_st_backward(StBwdParams<C::RG, C::RK>& P, void* stream) {
   static const bool tma_env = env_int_once("SRST_ST_BWD_TMA", 1) != 0;
@@ -239,6 +287,17 @@ static int pick_fwd_cfg(int B, int H, int W) {
   // strips; the 32x64 tile with three CTAs per SM wins on large images (all unrolled kernels)
   if (W <= 96) return ((long long)B * ((H + 23) / 24) >= 6LL * sm_count()) ? 4 : 3;
   return 1;
+}
+// Strip width of the marching kernel: the one that pads the image width least (cost = strips * (TW + 2 RK) columns
+// of gradient work); cfg 6 = 96 columns, cfg 7 = 112 (15 warps: four per scheduler, 128 registers).
+static int pick_march_cfg(int W) {
+  const int forced = forced_fwd();
+  if (forced == 6 || forced == 7) return forced;
+  if (forced >= 0) return -1;  // a tiled shape was asked for
+  static const bool off = env_int_once("SRST_ST_MARCH", 1) == 0;
+  if (off) return -1;
+  const long long c96 = (long long)((W + 95) / 96) * (96 + 16), c112 = (long long)((W + 111) / 112) * (112 + 16);
+  return c96 <= c112 ? 6 : 7;
 }
 static int pick_bwd_cfg(int B, int H, int W) {
   const int forced = forced_bwd();
@@ -285,6 +344,11 @@ int srst_debug_set_timing(long long* device_buffer) {
 #endif
 
 int srst_st_num_cfgs(int backward) { return backward ? kNumBwdCfg : kNumFwdCfg; }
+
+int srst_st_force_chunk_blocks(int blocks) {
+  g_force_chunk = blocks > 0 ? blocks : -1;
+  return 0;
+}
 
 int srst_st_force_cfg(int fwd_cfg, int bwd_cfg) {
   if (fwd_cfg < -1 || fwd_cfg >= kNumFwdCfg || bwd_cfg < -1 || bwd_cfg >= kNumBwdCfg) return SRST_E_INVALID;
@@ -341,7 +405,15 @@ static int st_forward_rr(const StCall& c) {
   P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
   P.taps = cached_taps<RG, RK>(c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
-    const int cfg = pick_fwd_cfg(c.B, c.H, c.W);
+    const int mcfg = pick_march_cfg(c.W);
+    if (mcfg >= 0) {
+      int e;
+      if (mcfg == 6) e = c.px ? launch_st_march<March96, true>(P, c.stream) : launch_st_march<March96>(P, c.stream);
+      else e = c.px ? launch_st_march<March112, true>(P, c.stream) : launch_st_march<March112>(P, c.stream);
+      if (e != kMarchUnusable) return e;
+    }
+    int cfg = pick_fwd_cfg(c.B, c.H, c.W);
+    if (cfg >= 6) cfg = (c.W <= 96) ? 3 : 1;  // a marching shape was forced but TMA cannot fetch these tensors
     if (c.px) {  // the fused Pixel term is compiled into the two default tile shapes only
       if (cfg != 1 && c.W <= 96) return launch_st_forward<Fwd3, true>(P, c.stream);
       return launch_st_forward<Fwd1, true>(P, c.stream);

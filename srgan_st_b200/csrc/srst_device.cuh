@@ -118,15 +118,20 @@ SRST_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "m
 // TMA (cp.async.bulk.tensor) staging of a 3-D box [bp planes][bh rows][bw cols] of an fp32 tensor
 // viewed as [P planes][H][W] into shared memory.  One thread issues ONE instruction for the whole
 // box; coordinates may start outside the tensor (negative or past the end) and the hardware fills
-// those elements with zeros -- the reference's zero padding.  Completion is signalled on an
-// mbarrier that every consumer thread polls.
+// those elements with zeros -- the reference's zero padding.  The first box column must be a multiple of
+// 4 floats (16 bytes) all the same: a box starting at x = -10 raises "illegal instruction" on B200 (measured,
+// round 2); the emulation aborts on it.  Completion is signalled on an mbarrier that every consumer thread polls.
 #ifdef SRST_EMULATE
 struct SrstTmap { const float* base; int W, H, P; };
-SRST_DEV void tma_barrier_init(unsigned long long* mbar) { (void)mbar; }
-SRST_DEV void tma_expect(unsigned long long* mbar, unsigned bytes) { (void)mbar; (void)bytes; }
+// The emulated mbarrier keeps (completed phases) in its low and (bytes still expected) in its high 32 bits, so that
+// tma_wait really waits for the issuing thread (OS threads run ahead of each other just like warps do).
+SRST_DEV void tma_barrier_init(unsigned long long* mbar) { __atomic_store_n(mbar, 0ull, __ATOMIC_SEQ_CST); }
+SRST_DEV void tma_expect(unsigned long long* mbar, unsigned bytes) {
+  __atomic_fetch_add(mbar, (unsigned long long)bytes << 32, __ATOMIC_SEQ_CST);
+}
 SRST_DEV void tma_load_3d(unsigned long long* mbar, float* dst, const SrstTmap* m, int x, int y, int z, int bw,
                           int bh, int bp) {
-  (void)mbar;
+  if ((x & 3) != 0 || (bw & 3) != 0) { std::fprintf(stderr, "emulated TMA: box column %d / width %d not a multiple of 4\n", x, bw); std::abort(); }
   for (int p = 0; p < bp; ++p)
     for (int r = 0; r < bh; ++r)
       for (int c = 0; c < bw; ++c) {
@@ -134,8 +139,13 @@ SRST_DEV void tma_load_3d(unsigned long long* mbar, float* dst, const SrstTmap* 
         const bool ok = gx >= 0 && gx < m->W && gy >= 0 && gy < m->H && gp >= 0 && gp < m->P;
         dst[(p * bh + r) * bw + c] = ok ? m->base[((size_t)gp * m->H + gy) * m->W + gx] : 0.f;
       }
+  const unsigned long long bytes = (unsigned long long)bp * bh * bw * sizeof(float);
+  const unsigned long long after = __atomic_sub_fetch(mbar, bytes << 32, __ATOMIC_SEQ_CST);
+  if ((after >> 32) == 0) __atomic_fetch_add(mbar, 1ull, __ATOMIC_SEQ_CST);  // the phase is complete
 }
-SRST_DEV void tma_wait(unsigned long long* mbar, unsigned parity = 0) { (void)mbar; (void)parity; }
+SRST_DEV void tma_wait(unsigned long long* mbar, unsigned parity = 0) {
+  while (((unsigned)__atomic_load_n(mbar, __ATOMIC_SEQ_CST) & 1u) == parity) std::this_thread::yield();
+}
 SRST_DEV void fence_async_smem() {}
 #else
 }  // namespace srst

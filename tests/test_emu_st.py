@@ -15,13 +15,35 @@ def lib():
     return emu_lib()
 
 
-@pytest.fixture(params=[0, 1, 2, 3, 4, 5, 6, 7])  # backward shape = param; forward shape = param % 6
+@pytest.fixture(params=[0, 1, 2, 3, 4, 5, 6, 7])  # forward shape = backward shape = param
 def tile_cfg(request, lib):
-    """Every compiled forward tile shape, paired with a backward shape (srst_st_force_cfg)."""
-    assert lib.srst_st_num_cfgs(0) >= 6 and lib.srst_st_num_cfgs(1) >= 8
-    assert lib.srst_st_force_cfg(request.param % 6 if request.param >= 0 else -1, request.param) == 0
+    """Every compiled forward shape (0-5 tiled, 6-7 row-marching), paired with a backward shape (srst_st_force_cfg)."""
+    assert lib.srst_st_num_cfgs(0) >= 8 and lib.srst_st_num_cfgs(1) >= 8
+    assert lib.srst_st_force_cfg(request.param, request.param) == 0
     yield request.param
     lib.srst_st_force_cfg(-1, -1)
+
+
+@pytest.mark.parametrize("cfg", [6, 7])
+@pytest.mark.parametrize("chunk_blocks", [1, 2, 3])
+@pytest.mark.parametrize("shape", [(1, 100, 152), (2, 96, 96), (1, 37, 52), (1, 52, 204)])
+def test_emulated_marching_forward_row_chunks(lib, cfg, chunk_blocks, shape):
+    """The row-marching forward cut into chunks of 16, 32, 48 rows: chunk seams, the warm-up block above a chunk, the
+    ragged last block and strips wider than the image must all reproduce the oracle (and the saved Ix, Iy planes)."""
+    assert lib.srst_st_force_cfg(cfg, -1) == 0 and lib.srst_st_force_chunk_blocks(chunk_blocks) == 0
+    try:
+        rng = np.random.default_rng(sum(shape) + chunk_blocks)
+        sr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+        hr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+        taps = (*O.gaussian_taps(0.5, True), O.gaussian_taps(2.0))
+        out = emu_st(lib, sr, hr, taps, want_hr=True)
+        ref = O.st_loss(sr, hr, taps=taps, want_hr_grad=True)
+        assert rel_err(out["loss"], ref["loss"]) < 1e-5
+        assert maxnorm_err(out["d_sr"], ref["d_sr"]) < 1e-4 and maxnorm_err(out["d_hr"], ref["d_hr"]) < 1e-4
+        assert not np.isnan(out["ixy_sr"]).any() and np.all(out["ws"] == 0)
+    finally:
+        lib.srst_st_force_cfg(-1, -1)
+        lib.srst_st_force_chunk_blocks(0)
 
 
 @pytest.mark.parametrize("name", ["st_rand_2x24x36", "st_srlike_2x40x52", "st_rand_ragged_1x37x53"])

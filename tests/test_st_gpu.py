@@ -31,7 +31,7 @@ def _run(sr, hr, normalize=True, want_hr=True, sigma=0.5, rho=2.0):
     return loss.item(), x.grad.cpu().numpy(), (y.grad.cpu().numpy() if want_hr else None)
 
 
-N_FWD, N_BWD = 6, 8   # compiled tile shapes exercised per direction (srst_st_num_cfgs() >= these)
+N_FWD, N_BWD = 8, 8   # compiled tile shapes exercised per direction (srst_st_num_cfgs() >= these)
 
 
 @pytest.fixture(params=[-1, 0, 1, 2, 3, 4, 5, 6, 7])
@@ -105,6 +105,27 @@ def test_matches_oracle_on_larger_shapes(shape):
     assert rel_err(loss, ref["loss"]) < 1e-5
     assert maxnorm_err(d_sr, ref["d_sr"]) < 1e-4
     assert maxnorm_err(d_hr, ref["d_hr"]) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", [6, 7])
+@pytest.mark.parametrize("chunk_blocks", [1, 2, 5])
+@pytest.mark.parametrize("shape", [(2, 96, 96), (1, 100, 152), (1, 333, 516)])
+def test_marching_forward_row_chunks(cfg, chunk_blocks, shape):
+    """Forward cfgs 6 / 7 (row-marching kernel) cut into chunks of 16, 32, 80 rows: seams, warm-up block, ragged tail."""
+    from srgan_st_b200 import _cabi
+    lib = _cabi.lib()
+    assert lib.srst_st_force_cfg(cfg, -1) == 0 and lib.srst_st_force_chunk_blocks(chunk_blocks) == 0
+    try:
+        rng = np.random.default_rng(shape[1] + chunk_blocks)
+        sr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+        hr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+        loss, d_sr, d_hr = _run(sr, hr)
+        ref = O.st_loss(sr, hr, taps=None, want_hr_grad=True)
+        assert rel_err(loss, ref["loss"]) < 1e-5
+        assert maxnorm_err(d_sr, ref["d_sr"]) < 1e-4 and maxnorm_err(d_hr, ref["d_hr"]) < 1e-4
+    finally:
+        lib.srst_st_force_cfg(-1, -1)
+        lib.srst_st_force_chunk_blocks(0)
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (1, 5, 7), (2, 17, 4), (1, 2, 130), (3, 9, 9)])
