@@ -237,7 +237,7 @@ static int launch_st_march(const StFwdParams<C::RG, C::RK>& F, void* stream) {
   MP.nstrips = (F.W + C::TW - 1) / C::TW;
   const long long base = (long long)F.B * MP.nstrips;
   long long nch = 1;
-  const int slots = sm_count();
+  const int slots = sm_count() * C::MINB;
   if (base < slots) nch = slots / base;
   if (nch > nblk) nch = nblk;
   int cb = (int)((nblk + nch - 1) / nch);

@@ -83,7 +83,9 @@ SRST_DEV float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const flo
 
 // torchvision rgb_to_grayscale weights (reference loss.py:400-401).
 constexpr float kGrayR = 0.2989f, kGrayG = 0.587f, kGrayB = 0.114f;
-SRST_DEV float gray_of(float r, float g, float b) { return (kGrayR * r + kGrayG * g) + kGrayB * b; }
+// One fixed contraction, so that every load path of every kernel rounds a pixel the same way (the compiler is
+// otherwise free to fuse either product into an FMA, and two code sites then differ in the last bit).
+SRST_DEV float gray_of(float r, float g, float b) { return __fmaf_rn(kGrayB, b, __fmaf_rn(kGrayR, r, __fmul_rn(kGrayG, g))); }
 
 // Raw SFU approximations (MUFU.RSQ / MUFU.LG2 / MUFU.RCP, <= 2 ulp) without the denormal/special
 // fix-up code that rsqrtf()/__logf()/__fdividef() add; callers guarantee normal-range inputs.
@@ -147,6 +149,7 @@ SRST_DEV void tma_wait(unsigned long long* mbar, unsigned parity = 0) {
   while (((unsigned)__atomic_load_n(mbar, __ATOMIC_SEQ_CST) & 1u) == parity) std::this_thread::yield();
 }
 SRST_DEV void fence_async_smem() {}
+SRST_DEV void tma_prefetch_3d(const SrstTmap* m, int x, int y, int z) { (void)m; (void)x; (void)y; (void)z; }
 #else
 }  // namespace srst
 #include <cuda.h>
@@ -174,6 +177,12 @@ SRST_DEV void tma_load_3d(unsigned long long* mbar, float* dst, const SrstTmap* 
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(sdst), "l"(reinterpret_cast<unsigned long long>(m)), "r"(x), "r"(y), "r"(z), "r"(bar)
       : "memory");
+}
+// L2 prefetch of a box (no shared-memory destination, no completion signal): a later tma_load_3d of the same box
+// then takes an L2 hit instead of a DRAM round trip.
+SRST_DEV void tma_prefetch_3d(const SrstTmap* m, int x, int y, int z) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<unsigned long long>(m)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 // Waits for the phase of `mbar` with the given parity (0 for the first use of a barrier, then alternating).
 SRST_DEV void tma_wait(unsigned long long* mbar, unsigned parity = 0) {

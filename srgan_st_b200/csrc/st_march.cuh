@@ -29,15 +29,12 @@
 
 namespace srst {
 
-#ifdef SRST_MARCH_DBG
-__device__ int g_march_dbg = 100;
-#define MARCH_DBG(n) do { if ((g_march_dbg & 255) <= (n)) return; } while (0)
-#define MARCH_DBG_ON(n) ((g_march_dbg & 255) > (n))
-#define MARCH_DBG_FLAG(bit) ((g_march_dbg >> (bit)) & 1)
+// tools/march_bench.cu only: run-time ablation mask (skip a phase) to measure what each phase costs
+#ifdef SRST_MARCH_ABL
+__device__ int g_march_abl = 0;
+#define MARCH_ON(bit) (((g_march_abl >> (bit)) & 1) == 0)
 #else
-#define MARCH_DBG(n) ((void)0)
-#define MARCH_DBG_ON(n) true
-#define MARCH_DBG_FLAG(bit) 0
+#define MARCH_ON(bit) true
 #endif
 
 template <int RG, int RK>
@@ -48,9 +45,10 @@ struct StMarchParams {
   int nstrips, nchunks, chunk_blocks;  // grid = B * nchunks * nstrips; a chunk = chunk_blocks * 16 rows
 };
 
-template <int TW_, int RG_, int RK_>
+template <int TW_, int RG_, int RK_, int CR_ = 8>
 struct StMarchCfg {
   static constexpr int TW = TW_, RG = RG_, RK = RK_;
+  static constexpr int CR = CR_, CQ = CR_ / 2;       // rows / row pairs of a block that one consumer thread owns (8 or 4 rows)
   static constexpr int RS = 16, NQ = 8;             // rows / row pairs per block
   static constexpr int GXH = round_up4(RK + RG);    // x halo of the gray rows; a multiple of 4: TMA wants the first box column 16-byte aligned
   static constexpr int GOFF = GXH - RK - RG;        // gray columns left of the first gradient window
@@ -62,22 +60,24 @@ struct StMarchCfg {
   static constexpr int PH = smem_pitch(2 * TW);
   static constexpr int BWIN = 8 + 2 * RG;           // gray window of a gradient item
   static constexpr int HWIN = 8 + 2 * RK;           // Ix, Iy window of a horizontal item
-  static constexpr int NIN = RK + 4;                // ring row pairs a consumer reads for its 4 output row pairs
+  static constexpr int NIN = RK + CQ;               // ring row pairs a consumer reads for its CQ output row pairs
   static constexpr int NP = 2 * NQ * NSEGB;         // producers: one gradient item each (2 images x 8 row pairs x segments)
   static constexpr int NH = 2 * NQ * NSEGH;         // horizontal items (the first NH producers)
-  static constexpr int NC = 2 * TW;                 // consumers: column x row half
+  static constexpr int NC = (RS / CR) * TW;         // consumers: column x row part of the block
   static constexpr int NT = NP + NC;
   static constexpr int RAW_IMG = 3 * RS * GW;       // one TMA box
   static constexpr int GRAY_IMG = GP * PG, D_PLANE = NQ * PD, H_PLANE = 2 * NQ * PH;
   static constexpr int GRAY_OFF = (2 * RAW_IMG + 31) / 32 * 32;
-  static constexpr int D_OFF = GRAY_OFF + 2 * GRAY_IMG;
+  static constexpr int D_OFF = GRAY_OFF + 4 * GRAY_IMG;   // two gray buffers (block parity) x two images
   static constexpr int H_OFF = D_OFF + 4 * D_PLANE;
   static constexpr int SMEM_FLOATS = H_OFF + 6 * H_PLANE;
   static constexpr size_t SMEM_BYTES = sizeof(float) * SMEM_FLOATS;
+  static constexpr int MINB = SMEM_BYTES <= 112 * 1024 ? 2 : 1;  // CTAs per SM
+  static_assert(CR == 8 || CR == 4, "march: consumer rows");
   static_assert(RG % 2 == 0 && RK == 8, "march: radii (two ring blocks cover 16 + 2 RK rows; 8-column items aligned to the strip)");
   static_assert(TW % 16 == 0 && NP % 32 == 0 && NC % 32 == 0 && NT <= 1024, "march: strip width");
   static_assert(GW % 4 == 0 && GW <= 256 && (RAW_IMG * 4) % 128 == 0 && GOFF % 2 == 0, "march: TMA box");
-  static_assert(NH <= NP, "march: horizontal items");
+  static_assert(NH <= NP && NP - NH == 32 && TW / 2 <= 64, "march: horizontal items; one copy warp, two float4 per lane and row pair");
 };
 
 // The per-pixel chain on RAW tensors: same mathematics as st_pixel2 with the normalisation folded in.  With
@@ -164,7 +164,7 @@ SRST_DEV float2 st_pixel2_raw(float2 a, float2 b, float2 c, float2 e, float2 f, 
 }
 
 template <class C, bool PX = false, bool WANT_HR = false>
-__global__ void __launch_bounds__(C::NT, 1)
+__global__ void __launch_bounds__(C::NT, C::MINB)
 st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) {
   SRST_DYN_SMEM(float, smem);
   __shared__ float s_red[32];
@@ -176,7 +176,7 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
   constexpr int RG = C::RG, RK = C::RK, NQ = C::NQ;
 
   float* sRaw = smem;                 // [2 images][3][16][GW]   TMA destination
-  float* sGray = smem + C::GRAY_OFF;  // [2][GP row pairs][PG]   row-pair interleaved
+  float* sGray = smem + C::GRAY_OFF;  // [block parity][2 images][GP row pairs][PG]   row-pair interleaved
   float* sD = smem + C::D_OFF;        // [2][Ix|Iy][8][PD]
   float* sH = smem + C::H_OFF;        // [2][3][16 ring row pairs][PH]
 
@@ -200,103 +200,148 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
   pdl_wait();     // previous kernel of the stream is complete (it may have produced sr or used the workspace)
   pdl_trigger();
   __syncthreads();  // the barrier is initialised before anyone polls it
-  MARCH_DBG(1);
 
   // first image row of H block k
   auto hb = [&](int k) { return y0 - RK + C::RS * k; };
-  // raw rows of block k = the 16 NEW gray rows its gradients need: hb(k) + RG ..
+  // raw rows of block k = the 16 NEW gray rows its gradients need: hb(k) + RG ..  (blocks 1.. only: block 0 is
+  // loaded directly while the first box is in flight)
   auto issue_raw = [&](int k) {
     tma_expect(&s_mbar, (unsigned)(2 * C::RAW_IMG * sizeof(float)));
     tma_load_3d(&s_mbar, sRaw, &MP.sr_map, x0 - C::GXH, hb(k) + RG, b * 3, C::GW, C::RS, 3);
     tma_load_3d(&s_mbar, sRaw + C::RAW_IMG, &MP.hr_map, x0 - C::GXH, hb(k) + RG, b * 3, C::GW, C::RS, 3);
   };
-  // raw box -> gray rows (pairs RG .. RG+7 of the gray buffer); item = image x row pair x 4 columns
-  auto convert = [&]() {
+  // L2 prefetch of the raw rows of block k: the boxes are requested one block ahead only (one raw buffer), which
+  // does not cover a DRAM round trip while the pipeline is filling; two more blocks ahead in L2 do
+  auto prefetch_raw = [&](int k) {
+    if (hb(k) + RG < H) {
+      tma_prefetch_3d(&MP.sr_map, x0 - C::GXH, hb(k) + RG, b * 3);
+      tma_prefetch_3d(&MP.hr_map, x0 - C::GXH, hb(k) + RG, b * 3);
+    }
+  };
+  [[maybe_unused]] float pxsum = 0.f;
+  // raw box of block k -> gray row pairs RG .. RG+7 of gray buffer k&1; item = image x row pair x 4 columns
+  auto convert = [&](int k) {
     constexpr int C4 = C::GW / 4;
+    float* gbuf = sGray + (k & 1) * 2 * C::GRAY_IMG;
     for (int it = tid; it < 2 * NQ * C4; it += C::NP) {
       const int c4 = it % C4, rr = it / C4;
       const int q = rr % NQ, img = rr / NQ;
       const float* r0 = sRaw + img * C::RAW_IMG + (2 * q) * C::GW + 4 * c4;
       const float4 R0 = ld4(r0), G0 = ld4(r0 + C::RS * C::GW), B0 = ld4(r0 + 2 * C::RS * C::GW);
       const float4 R1 = ld4(r0 + C::GW), G1 = ld4(r0 + C::GW + C::RS * C::GW), B1 = ld4(r0 + C::GW + 2 * C::RS * C::GW);
-      float* o = sGray + img * C::GRAY_IMG + (RG + q) * C::PG + 8 * c4;
+      float* o = gbuf + img * C::GRAY_IMG + (RG + q) * C::PG + 8 * c4;
       st4(o, make_float4(gray_of(R0.x, G0.x, B0.x), gray_of(R1.x, G1.x, B1.x), gray_of(R0.y, G0.y, B0.y),
                          gray_of(R1.y, G1.y, B1.y)));
       st4(o + 4, make_float4(gray_of(R0.z, G0.z, B0.z), gray_of(R1.z, G1.z, B1.z), gray_of(R0.w, G0.w, B0.w),
                              gray_of(R1.w, G1.w, B1.w)));
     }
-  };
-  [[maybe_unused]] float pxsum = 0.f;
-  // fused Pixel term: squared RGB difference over the rows of raw block k that belong to this chunk
-  [[maybe_unused]] auto pixel_term = [&](int k) {
-    constexpr int C2 = C::TW / 2;
-    const int ry0 = hb(k) + RG;
-    for (int it = tid; it < C::RS * C2; it += C::NP) {
-      const int c2 = it % C2, r = it / C2;
-      const int gy = ry0 + r, gx = x0 + 2 * c2;
-      if (gy < y0 || gy >= y1 || gx >= W) continue;
-      const float* ps = sRaw + r * C::GW + C::GXH + 2 * c2;
-      float acc = 0.f;
+    if constexpr (PX) {
+      // fused Pixel term: squared RGB difference over the rows of this raw block that belong to the chunk
+      constexpr int C2 = C::TW / 2;
+      const int ry0 = hb(k) + RG;
+      for (int it = tid; it < C::RS * C2; it += C::NP) {
+        const int c2 = it % C2, r = it / C2;
+        const int gy = ry0 + r, gx = x0 + 2 * c2;
+        if (gy < y0 || gy >= y1 || gx >= W) continue;
+        const float* ps = sRaw + r * C::GW + C::GXH + 2 * c2;
+        float acc = 0.f;
 #pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const float2 u = ld2(ps + ch * C::RS * C::GW), v = ld2(ps + C::RAW_IMG + ch * C::RS * C::GW);
-        const float d0 = u.x - v.x, d1 = u.y - v.y;
-        acc = fmaf(d0, d0, acc);
-        acc = fmaf(d1, d1, acc);
+        for (int ch = 0; ch < 3; ++ch) {
+          const float2 u = ld2(ps + ch * C::RS * C::GW), v = ld2(ps + C::RAW_IMG + ch * C::RS * C::GW);
+          const float d0 = u.x - v.x, d1 = u.y - v.y;
+          acc = fmaf(d0, d0, acc);
+          acc = fmaf(d1, d1, acc);
+        }
+        pxsum += acc;
       }
-      pxsum += acc;
     }
   };
 
-  if (producer && MARCH_DBG_ON(2)) {
-    if (tid == 0 && !MARCH_DBG_FLAG(9)) issue_raw(0);
-    if (!MARCH_DBG_FLAG(8))
-    // the RG carried row pairs of block 0 (image rows hb(0) - RG .. hb(0) + RG - 1) come straight from global memory
-    for (int it = tid; it < 2 * 2 * RG * C::GW; it += C::NP) {
-      const int g = it % C::GW, rr = it / C::GW;
-      const int r = rr % (2 * RG), img = rr / (2 * RG);
-      const int gy = hb(0) - RG + r, gx = x0 - C::GXH + g;
-      float v = 0.f;
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        const float* p = (img ? P.hr : P.sr) + img_off + (size_t)gy * W + gx;
-        v = gray_of(__ldg(p), __ldg(p + plane), __ldg(p + 2 * plane));
+  if (producer) {
+    if (tid == 0) {
+      issue_raw(1);  // H blocks 0..NB, NB >= 1: block 1 always exists
+      if (MARCH_ON(8)) { if (2 <= NB) prefetch_raw(2); if (3 <= NB) prefetch_raw(3); }
+    }
+    // Block 0 (its RG carried row pairs and its 8 new ones: image rows hb(0) - RG .. hb(0) + RG + 15) comes straight
+    // from global memory while the box of block 1 is in flight; item = row pair x 4 columns of BOTH images.
+    constexpr int C4 = C::GW / 4;
+    for (int it = tid; it < C::GP * C4; it += C::NP) {
+      const int c4 = it % C4, pr = it / C4;
+      const int gx = x0 - C::GXH + 4 * c4;
+      const bool xin = gx >= 0 && gx < W;  // x0 - GXH and W are multiples of 4: a float4 is all-in or all-out
+      float4 v[2][2][3];                   // [image][row of the pair][channel]
+      bool ok[2];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int gy = hb(0) - RG + 2 * pr + hf;
+        ok[hf] = xin && gy >= 0 && gy < H;
+        if (ok[hf]) {
+          const size_t o = img_off + (size_t)gy * W + gx;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) { v[0][hf][ch] = ldg4(P.sr + o + ch * plane); v[1][hf][ch] = ldg4(P.hr + o + ch * plane); }
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) { v[0][hf][ch] = make_float4(0.f, 0.f, 0.f, 0.f); v[1][hf][ch] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        }
       }
-      sGray[img * C::GRAY_IMG + (r >> 1) * C::PG + 2 * g + (r & 1)] = v;
-    }
-    if (!MARCH_DBG_FLAG(9)) tma_wait(&s_mbar, 0);
-    if (MARCH_DBG_ON(3)) {
-    convert();
-    if constexpr (PX) pixel_term(0);
-    bar_sync(1, C::NP);  // every producer is done with the raw box
-    }
-    if (MARCH_DBG_ON(4)) {
-    if (tid == 0) { fence_async_smem(); issue_raw(1); }
-    if (!MARCH_DBG_ON(8)) tma_wait(&s_mbar, 1);
+#pragma unroll
+      for (int img = 0; img < 2; ++img) {
+        const float4 *a0 = v[img][0], *a1 = v[img][1];
+        float* o = sGray + img * C::GRAY_IMG + pr * C::PG + 8 * c4;
+        st4(o, make_float4(gray_of(a0[0].x, a0[1].x, a0[2].x), gray_of(a1[0].x, a1[1].x, a1[2].x),
+                           gray_of(a0[0].y, a0[1].y, a0[2].y), gray_of(a1[0].y, a1[1].y, a1[2].y)));
+        st4(o + 4, make_float4(gray_of(a0[0].z, a0[1].z, a0[2].z), gray_of(a1[0].z, a1[1].z, a1[2].z),
+                               gray_of(a0[0].w, a0[1].w, a0[2].w), gray_of(a1[0].w, a1[1].w, a1[2].w)));
+        if (pr >= NQ) {  // the last RG row pairs of block 0 are the first RG of block 1 (the other gray buffer)
+          float* o1 = o + 2 * C::GRAY_IMG - NQ * C::PG;
+          st4(o1, ld4(o));
+          st4(o1 + 4, ld4(o + 4));
+        }
+      }
+      if constexpr (PX) {
+        if (gx >= x0 && gx < x0 + C::TW) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int gy = hb(0) - RG + 2 * pr + hf;
+            if (!ok[hf] || gy < y0 || gy >= y1) continue;
+            float acc = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              const float4 u = v[0][hf][ch], w = v[1][hf][ch];
+              const float d0 = u.x - w.x, d1 = u.y - w.y, d2 = u.z - w.z, d3 = u.w - w.w;
+              acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+            }
+            pxsum += acc;
+          }
+        }
+      }
     }
   }
   __syncthreads();
-  MARCH_DBG(5);
 
   // consumer state: the smoothed tensors of this thread's column, 4 row pairs, both images
   const int ct = tid - C::NP;
   const int chalf = producer ? 0 : ct / C::TW, ccol = producer ? 0 : ct % C::TW;
-  float2 S1[3][4], S2[3][4];
+  float2 S1[3][C::CQ], S2[3][C::CQ];
   float lsum = 0.f;
   const int Hp = (H + 1) >> 1;
 
+  // Named barriers (0 is __syncthreads): kBarP among the producers; kBarH "ring block complete" (producers arrive,
+  // consumers wait); kBarV "ring slot free" (consumers arrive, producers wait).  The two groups are coupled by these
+  // hand-shakes only, so the latency-bound chain of the consumers overlaps whatever the producers are doing.
+  constexpr int kBarP = 1, kBarH = 2, kBarV = 3;
+  if (producer) {
 #pragma unroll 1
-  for (int k = 0; k <= NB + 1; ++k) {
-    // ------------------------------------------------------------------ Y_k
-    if (producer) {
-      if (k <= NB && MARCH_DBG_ON(6)) {
+    for (int k = 0; k <= NB; ++k) {
+      {
         // gradients of block k: Ix, Iy on 8 row pairs x DW columns of both images; zero outside the image (the
         // reference zero-pads the PRODUCTS, utils.py:225-230); strip-interior items save them for the backward
         const int q = tid & 7, rest = tid >> 3;
         const int seg = rest % C::NSEGB, img = rest / C::NSEGB;
         const int gy = hb(k) + 2 * q, gx0 = x0 - RK + 8 * seg;
         float2 Ix[8], Iy[8];
-        if (gy + 1 >= 0 && gy < H && gx0 + 7 >= 0 && gx0 < W) {
-          const float* p = sGray + img * C::GRAY_IMG + q * C::PG + 2 * (8 * seg + C::GOFF);
+        if (gy + 1 >= 0 && gy < H && gx0 + 7 >= 0 && gx0 < W && MARCH_ON(3)) {
+          const float* p = sGray + ((k & 1) * 2 + img) * C::GRAY_IMG + q * C::PG + 2 * (8 * seg + C::GOFF);
           grad_rowpair<RG, 8, C::BWIN, RG, C::PG, true>(p, p, tp, Ix, Iy);
           if (!(gy >= 0 && gy + 1 < H && gx0 >= 0 && gx0 + 8 <= W)) {  // straddles the image border: mask
             const bool r0 = gy >= 0, r1 = gy + 1 < H;
@@ -307,18 +352,6 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
               Ix[j].y = (ok && r1) ? Ix[j].y : 0.f;
               Iy[j].x = (ok && r0) ? Iy[j].x : 0.f;
               Iy[j].y = (ok && r1) ? Iy[j].y : 0.f;
-            }
-          }
-          float* ixy = img ? P.ixy_hr : P.ixy_sr;
-          if (ixy && gy >= y0 && gy < y1 && seg >= RK / 8 && seg < RK / 8 + C::NSEGH) {
-            float* ox = ixy + ixy_offset(b, 0, Hp, W, gy >> 1, gx0);
-            float* oy = ixy + ixy_offset(b, 1, Hp, W, gy >> 1, gx0);
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              if (gx0 + j < W) {  // W % 4 == 0: column pairs are all-in or all-out
-                st4(ox + 2 * j, make_float4(Ix[j].x, Ix[j].y, Ix[j + 1].x, Ix[j + 1].y));
-                st4(oy + 2 * j, make_float4(Iy[j].x, Iy[j].y, Iy[j + 1].x, Iy[j + 1].y));
-              }
             }
           }
         } else {
@@ -332,62 +365,84 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
           st4(o0 + 2 * j, make_float4(Ix[j].x, Ix[j].y, Ix[j + 1].x, Ix[j + 1].y));
           st4(o1 + 2 * j, make_float4(Iy[j].x, Iy[j].y, Iy[j + 1].x, Iy[j + 1].y));
         }
-      }
-    } else if (k >= 2 && MARCH_DBG_ON(7)) {
-      // vertical rho-pass of output block j = k-2 from ring blocks j, j+1: this thread's column, output row
-      // pairs 4*chalf .. +3, input ring row pairs 4*chalf .. 4*chalf + NIN - 1 (relative to block j)
-      const int j = k - 2;
-      const int rp0 = 8 * (j & 1) + 4 * chalf;
-#pragma unroll
-      for (int img = 0; img < 2; ++img) {
-        float2 acc[3][4];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int o = 0; o < 4; ++o) acc[c][o] = make_float2(0.f, 0.f);
-        const float* base = sH + (img * 3) * C::H_PLANE + 2 * ccol;
-#pragma unroll
-        for (int i = 0; i < C::NIN; ++i) {
-          const float* p = base + ((rp0 + i) & 15) * C::PH;
-          const float2 v0 = ld2(p), v1 = ld2(p + C::H_PLANE), v2 = ld2(p + 2 * C::H_PLANE);
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            const int u0 = 2 * (i - o);  // tap-pair index of the even input row for output pair o
-            if (u0 >= 0 && u0 <= 2 * RK + 1) {
-              acc[0][o] = ffma2(bcast2(v0.x), tp.kp[u0], acc[0][o]);
-              acc[1][o] = ffma2(bcast2(v1.x), tp.kp[u0], acc[1][o]);
-              acc[2][o] = ffma2(bcast2(v2.x), tp.kp[u0], acc[2][o]);
-            }
-            if (u0 + 1 >= 0 && u0 + 1 <= 2 * RK + 1) {
-              acc[0][o] = ffma2(bcast2(v0.y), tp.kp[u0 + 1], acc[0][o]);
-              acc[1][o] = ffma2(bcast2(v1.y), tp.kp[u0 + 1], acc[1][o]);
-              acc[2][o] = ffma2(bcast2(v2.y), tp.kp[u0 + 1], acc[2][o]);
-            }
-          }
+        // gray rows of block k+1 into the other gray buffer (its box was requested one half-step ago)
+        if (k + 1 <= NB) {
+          if (MARCH_ON(7)) tma_wait(&s_mbar, (unsigned)(k & 1));  // box of block k+1 is the k-th use of the barrier
+          if (MARCH_ON(4)) convert(k + 1);
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            if (img == 0) S1[c][o] = acc[c][o];
-            else S2[c][o] = acc[c][o];
-          }
       }
-    }
-    __syncthreads();
-    // ------------------------------------------------------------------ X_k
-    if (producer) {
-      if (k <= NB && MARCH_DBG_ON(8)) {
-        // carry the last RG gray row pairs of block k to the top of the buffer (block k+1 needs them)
-        for (int it = tid; it < 2 * RG * (C::PG / 4); it += C::NP) {
-          const int e4 = it % (C::PG / 4), rr = it / (C::PG / 4);
-          const int r = rr % RG, img = rr / RG;
-          float* gb = sGray + img * C::GRAY_IMG;
-          st4(gb + r * C::PG + 4 * e4, ld4(gb + (NQ + r) * C::PG + 4 * e4));
+      bar_sync(kBarP, C::NP);  // Ix, Iy of block k and the gray rows of block k+1 are complete; the raw box is free
+      if (k >= 1) bar_sync(kBarV, C::NT);  // k == 1: the consumers have seen block 0; k >= 2: they are done with block k-2
+      {
+        if (tid >= C::NH) {
+          // The producers beyond the horizontal items (one warp: the x halo of the gradient items) do the copies.
+          // Every producer is done with the raw box (block k+1 was converted in Y_k): request block k+2.
+          const int lane = tid - C::NH;
+          constexpr int NL = C::NP - C::NH;
+          if (lane == 0 && k + 2 <= NB) {
+            fence_async_smem();
+            issue_raw(k + 2);
+            if (k + 4 <= NB && MARCH_ON(8)) prefetch_raw(k + 4);
+          }
+          // the last RG gray row pairs of block k+1 are the first RG of block k+2 (gray buffer k&1 again)
+          if (k + 2 <= NB) {
+            const float* src = sGray + ((k + 1) & 1) * 2 * C::GRAY_IMG + NQ * C::PG + 4 * lane;
+            float* dst = sGray + (k & 1) * 2 * C::GRAY_IMG + 4 * lane;
+            constexpr int N4 = RG * (C::PG / 4), NIT = (N4 + NL - 1) / NL;  // RG consecutive row pairs = one contiguous run
+            float4 v[2][NIT];
+#pragma unroll
+            for (int img = 0; img < 2; ++img)
+#pragma unroll
+              for (int i = 0; i < NIT; ++i)
+                if (lane + i * NL < N4) v[img][i] = ld4(src + img * C::GRAY_IMG + 4 * NL * i);
+#pragma unroll
+            for (int img = 0; img < 2; ++img)
+#pragma unroll
+              for (int i = 0; i < NIT; ++i)
+                if (lane + i * NL < N4) st4(dst + img * C::GRAY_IMG + 4 * NL * i, v[img][i]);
+          }
+          // save Ix, Iy of block k for the backward: the strip-interior columns of the D rows that belong to this
+          // chunk, copied out with fully coalesced 16-byte stores (a row pair of a plane is 2*TW contiguous floats);
+          // four row pairs are loaded before they are stored so that the copy is not one long LDS -> STG chain
+          if (MARCH_ON(6)) {
+            constexpr int E4 = C::TW / 2;  // float4 per row pair
+            const int n4 = min(E4, (W - x0) / 2);
+            const bool c0 = lane < n4, c1 = lane + NL < n4;
+            const size_t rstride = 2 * (size_t)W, pstride = (size_t)Hp * rstride;
+            const int gp0 = hb(k) >> 1;  // first row pair of the block (hb(k) is even; negative above the image)
+#pragma unroll
+            for (int img = 0; img < (WANT_HR ? 2 : 1); ++img) {
+              float* ixy = img ? P.ixy_hr : P.ixy_sr;
+              if (!ixy) continue;
+              float* g0 = ixy + (size_t)b * 2 * pstride + 2 * (size_t)x0 + 4 * lane;
+#pragma unroll
+              for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+                for (int qb = 0; qb < NQ; qb += 4) {
+                  float4 va[4], vb[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float* so = sD + (img * 2 + pl) * C::D_PLANE + (qb + u) * C::PD + 2 * RK + 4 * lane;
+                    va[u] = ld4(so);
+                    if (E4 > NL) vb[u] = c1 ? ld4(so + 4 * NL) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  }
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const int gy = hb(k) + 2 * (qb + u);
+                    if (gy >= y0 && gy < y1) {
+                      float* go = g0 + pl * pstride + (size_t)(gp0 + qb + u) * rstride;
+                      if (c0) st4(go, va[u]);
+                      if (E4 > NL && c1) st4(go + 4 * NL, vb[u]);
+                    }
+                  }
+                }
+              }
+            }
+          }
         }
         // products + horizontal rho-pass of block k -> ring row pairs 8*(k&1) ..; item = image x row pair x 8 columns.
         // Scatter form: window column j contributes k[j - o] to output column o, so Ix, Iy are read once.
-        if (tid < C::NH) {
+        if (tid < C::NH && MARCH_ON(2)) {
           const int q = tid & 7, rest = tid >> 3;
           const int seg = rest % C::NSEGH, img = rest / C::NSEGH;
           const float* pix = sD + (img * 2) * C::D_PLANE + q * C::PD + 2 * (8 * seg);
@@ -424,45 +479,94 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
             for (int jj = 0; jj < 8; jj += 2)
               st4(o + c * C::H_PLANE + 2 * jj, make_float4(acc[c][jj].x, acc[c][jj].y, acc[c][jj + 1].x, acc[c][jj + 1].y));
         }
-        bar_sync(1, C::NP);  // the carried rows are in place before the new rows below them are overwritten
-        if (k + 1 <= NB) {
-          tma_wait(&s_mbar, (unsigned)((k + 1) & 1));
-          convert();
-          if constexpr (PX) pixel_term(k + 1);
-          bar_sync(1, C::NP);
-          if (tid == 0 && k + 2 <= NB) { fence_async_smem(); issue_raw(k + 2); }
-        }
       }
-    } else if (k >= 2 && MARCH_DBG_ON(9)) {
+      __threadfence_block();
+      bar_arrive(kBarH, C::NT);  // ring block k is complete
+      bar_sync(kBarP, C::NP);    // every producer is done with Ix, Iy of block k; the carried gray rows are in place
+    }
+  } else {
+    bar_sync(kBarH, C::NT);    // ring block 0
+    bar_arrive(kBarV, C::NT);
+#pragma unroll 1
+    for (int jb = 0; jb < NB; ++jb) {
+      const int k = jb + 2;
+      bar_sync(kBarH, C::NT);  // ring block jb+1
+      if (MARCH_ON(1)) {
+      // vertical rho-pass of output block j = k-2 from ring blocks j, j+1: this thread's column, output row
+      // pairs 4*chalf .. +3, input ring row pairs 4*chalf .. 4*chalf + NIN - 1 (relative to block j)
+      const int j = k - 2;
+      const int rp0 = 8 * (j & 1) + C::CQ * chalf;
+#pragma unroll
+      for (int img = 0; img < 2; ++img) {
+        float2 acc[3][C::CQ];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int o = 0; o < C::CQ; ++o) acc[c][o] = make_float2(0.f, 0.f);
+        const float* base = sH + (img * 3) * C::H_PLANE + 2 * ccol;
+#pragma unroll
+        for (int i = 0; i < C::NIN; ++i) {
+          const float* p = base + ((rp0 + i) & 15) * C::PH;
+          const float2 v0 = ld2(p), v1 = ld2(p + C::H_PLANE), v2 = ld2(p + 2 * C::H_PLANE);
+#pragma unroll
+          for (int o = 0; o < C::CQ; ++o) {
+            const int u0 = 2 * (i - o);  // tap-pair index of the even input row for output pair o
+            if (u0 >= 0 && u0 <= 2 * RK + 1) {
+              acc[0][o] = ffma2(bcast2(v0.x), tp.kp[u0], acc[0][o]);
+              acc[1][o] = ffma2(bcast2(v1.x), tp.kp[u0], acc[1][o]);
+              acc[2][o] = ffma2(bcast2(v2.x), tp.kp[u0], acc[2][o]);
+            }
+            if (u0 + 1 >= 0 && u0 + 1 <= 2 * RK + 1) {
+              acc[0][o] = ffma2(bcast2(v0.y), tp.kp[u0 + 1], acc[0][o]);
+              acc[1][o] = ffma2(bcast2(v1.y), tp.kp[u0 + 1], acc[1][o]);
+              acc[2][o] = ffma2(bcast2(v2.y), tp.kp[u0 + 1], acc[2][o]);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int o = 0; o < C::CQ; ++o) {
+            if (img == 0) S1[c][o] = acc[c][o];
+            else S2[c][o] = acc[c][o];
+          }
+      }
+      }
+      if (jb + 2 <= NB) bar_arrive(kBarV, C::NT);  // ring slot jb&1 may be overwritten (block jb+2)
+      if (MARCH_ON(0)) {
       // per-pixel chain + stores of output block j: rows y0 + 16j + 8*chalf + 2o (+1), column x0 + ccol
       const int j = k - 2;
       const int gx = x0 + ccol;
-      const int ry = y0 + C::RS * j + 8 * chalf;
+      const int ry = y0 + C::RS * j + C::CR * chalf;
       if (gx < W) {
+        float* ps = P.ds_sr ? P.ds_sr + img_off + (size_t)ry * W + gx : nullptr;
+        [[maybe_unused]] float* ph = WANT_HR ? P.ds_hr + img_off + (size_t)ry * W + gx : nullptr;
+        // all four pixel pairs are evaluated unconditionally (rows past the chunk hold finite filler) so that the
+        // compiler can interleave their SFU / FMA dependency chains; only the loss and the stores are masked
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
+        for (int o = 0; o < C::CQ; ++o) {
           const int gy = ry + 2 * o;
-          if (gy >= y1) break;
           StPixelGrad2 G;
           G.da = G.db = G.dc = G.de = G.df = G.dh = make_float2(0.f, 0.f);
           const float2 d = st_pixel2_raw<true, WANT_HR>(S1[0][o], S1[1][o], S1[2][o], S2[0][o], S2[1][o], S2[2][o], norm,
                                                         P.eps, G);
-          const bool two = gy + 1 < y1;
-          lsum += d.x;
+          const bool one = gy < y1, two = gy + 1 < y1;
+          lsum += one ? d.x : 0.f;
           lsum += two ? d.y : 0.f;
-          const size_t o0 = img_off + (size_t)gy * W + gx;
-          if (P.ds_sr) {
-            P.ds_sr[o0] = G.da.x; P.ds_sr[o0 + plane] = G.db.x; P.ds_sr[o0 + 2 * plane] = G.dc.x;
-            if (two) { P.ds_sr[o0 + W] = G.da.y; P.ds_sr[o0 + plane + W] = G.db.y; P.ds_sr[o0 + 2 * plane + W] = G.dc.y; }
+          if (ps && MARCH_ON(5)) {
+            if (one) { ps[0] = G.da.x; ps[plane] = G.db.x; ps[2 * plane] = G.dc.x; }
+            if (two) { ps[W] = G.da.y; ps[plane + W] = G.db.y; ps[2 * plane + W] = G.dc.y; }
+            ps += 2 * W;
           }
-          if (WANT_HR) {
-            P.ds_hr[o0] = G.de.x; P.ds_hr[o0 + plane] = G.df.x; P.ds_hr[o0 + 2 * plane] = G.dh.x;
-            if (two) { P.ds_hr[o0 + W] = G.de.y; P.ds_hr[o0 + plane + W] = G.df.y; P.ds_hr[o0 + 2 * plane + W] = G.dh.y; }
+          if constexpr (WANT_HR) {
+            if (one) { ph[0] = G.de.x; ph[plane] = G.df.x; ph[2 * plane] = G.dh.x; }
+            if (two) { ph[W] = G.de.y; ph[plane + W] = G.df.y; ph[2 * plane + W] = G.dh.y; }
+            ph += 2 * W;
           }
         }
       }
+      }
     }
-    __syncthreads();
   }
 
   // Deterministic loss reduction: block partial -> workspace; the last block to finish sums all
