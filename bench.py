@@ -822,9 +822,9 @@ def run_gpu(args):
             "clocks": main["clocks"],
             "e2e": main.get("e2e"),
             "gpu_launches": 2 * K,
-            "roofline": {"bound": "hbm", "kernel": "st_forward_kernel", "achieved": main["roofline_fwd"], "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": "st_forward_march_kernel", "achieved": main["roofline_fwd"], "peak": hbm_peak,
                          "unit": "GB/s", "frac": main["roofline_fwd"] / hbm_peak,
-                         "traffic": _traffic(args.workload, "st_forward_kernel"),
+                         "traffic": _traffic(args.workload, "st_forward_march_kernel"),
                          "traffic_source": "profiles/r02_traffic.json (ncu --set full, dram__bytes_read+write per launch)",
                          "peak_source": peak_src, "bytes_per_pixel": BYTES_FWD,
                          "backward": {"kernel": "st_backward_kernel", "achieved": main["roofline_bwd"],

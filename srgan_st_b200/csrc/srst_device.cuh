@@ -149,7 +149,6 @@ SRST_DEV void tma_wait(unsigned long long* mbar, unsigned parity = 0) {
   while (((unsigned)__atomic_load_n(mbar, __ATOMIC_SEQ_CST) & 1u) == parity) std::this_thread::yield();
 }
 SRST_DEV void fence_async_smem() {}
-SRST_DEV void tma_prefetch_3d(const SrstTmap* m, int x, int y, int z) { (void)m; (void)x; (void)y; (void)z; }
 #else
 }  // namespace srst
 #include <cuda.h>
@@ -177,12 +176,6 @@ SRST_DEV void tma_load_3d(unsigned long long* mbar, float* dst, const SrstTmap* 
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(sdst), "l"(reinterpret_cast<unsigned long long>(m)), "r"(x), "r"(y), "r"(z), "r"(bar)
       : "memory");
-}
-// L2 prefetch of a box (no shared-memory destination, no completion signal): a later tma_load_3d of the same box
-// then takes an L2 hit instead of a DRAM round trip.
-SRST_DEV void tma_prefetch_3d(const SrstTmap* m, int x, int y, int z) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-               ::"l"(reinterpret_cast<unsigned long long>(m)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 // Waits for the phase of `mbar` with the given parity (0 for the first use of a barrier, then alternating).
 SRST_DEV void tma_wait(unsigned long long* mbar, unsigned parity = 0) {

@@ -33,7 +33,21 @@ namespace srst {
 #ifdef SRST_MARCH_ABL
 __device__ int g_march_abl = 0;
 #define MARCH_ON(bit) (((g_march_abl >> (bit)) & 1) == 0)
+#endif
+#ifdef SRST_MARCH_STAMPS
+__device__ long long* g_march_stamp = nullptr;  // [grid][128] %globaltimer stamps of producer thread 0 (slots 0..63) and consumer thread 0 (64..127)
+SRST_DEV void march_stamp(bool who, int slot) {
+  if (g_march_stamp && who && slot < 64) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_march_stamp[(size_t)blockIdx.x * 128 + slot + (threadIdx.x ? 64 : 0)] = t;
+  }
+}
+#define MSTAMP(who, slot) march_stamp(who, slot)
 #else
+#define MSTAMP(who, slot) ((void)0)
+#endif
+#ifndef SRST_MARCH_ABL
 #define MARCH_ON(bit) true
 #endif
 
@@ -196,6 +210,7 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
   const size_t img_off = (size_t)b * 3 * plane;
   const bool norm = P.normalize != 0;
 
+  MSTAMP(tid == 0, 0);
   if (tid == 0) tma_barrier_init(&s_mbar);
   pdl_wait();     // previous kernel of the stream is complete (it may have produced sr or used the workspace)
   pdl_trigger();
@@ -209,14 +224,6 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
     tma_expect(&s_mbar, (unsigned)(2 * C::RAW_IMG * sizeof(float)));
     tma_load_3d(&s_mbar, sRaw, &MP.sr_map, x0 - C::GXH, hb(k) + RG, b * 3, C::GW, C::RS, 3);
     tma_load_3d(&s_mbar, sRaw + C::RAW_IMG, &MP.hr_map, x0 - C::GXH, hb(k) + RG, b * 3, C::GW, C::RS, 3);
-  };
-  // L2 prefetch of the raw rows of block k: the boxes are requested one block ahead only (one raw buffer), which
-  // does not cover a DRAM round trip while the pipeline is filling; two more blocks ahead in L2 do
-  auto prefetch_raw = [&](int k) {
-    if (hb(k) + RG < H) {
-      tma_prefetch_3d(&MP.sr_map, x0 - C::GXH, hb(k) + RG, b * 3);
-      tma_prefetch_3d(&MP.hr_map, x0 - C::GXH, hb(k) + RG, b * 3);
-    }
   };
   [[maybe_unused]] float pxsum = 0.f;
   // raw box of block k -> gray row pairs RG .. RG+7 of gray buffer k&1; item = image x row pair x 4 columns
@@ -257,15 +264,15 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
     }
   };
 
-  if (producer) {
-    if (tid == 0) {
-      issue_raw(1);  // H blocks 0..NB, NB >= 1: block 1 always exists
-      if (MARCH_ON(8)) { if (2 <= NB) prefetch_raw(2); if (3 <= NB) prefetch_raw(3); }
-    }
+  if (tid == 0) {
+    issue_raw(1);  // H blocks 0..NB, NB >= 1: block 1 always exists
+  }
+  {
     // Block 0 (its RG carried row pairs and its 8 new ones: image rows hb(0) - RG .. hb(0) + RG + 15) comes straight
-    // from global memory while the box of block 1 is in flight; item = row pair x 4 columns of BOTH images.
+    // from global memory while the box of block 1 is in flight; item = row pair x 4 columns of BOTH images, spread
+    // over ALL threads of the CTA (the consumers have nothing else to do yet).
     constexpr int C4 = C::GW / 4;
-    for (int it = tid; it < C::GP * C4; it += C::NP) {
+    for (int it = tid; it < C::GP * C4; it += C::NT) {
       const int c4 = it % C4, pr = it / C4;
       const int gx = x0 - C::GXH + 4 * c4;
       const bool xin = gx >= 0 && gx < W;  // x0 - GXH and W are multiples of 4: a float4 is all-in or all-out
@@ -330,6 +337,8 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
   // consumers wait); kBarV "ring slot free" (consumers arrive, producers wait).  The two groups are coupled by these
   // hand-shakes only, so the latency-bound chain of the consumers overlaps whatever the producers are doing.
   constexpr int kBarP = 1, kBarH = 2, kBarV = 3;
+  MSTAMP(tid == 0, 1);        // prologue done
+  MSTAMP(tid == C::NP, 1);
   if (producer) {
 #pragma unroll 1
     for (int k = 0; k <= NB; ++k) {
@@ -365,14 +374,19 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
           st4(o0 + 2 * j, make_float4(Ix[j].x, Ix[j].y, Ix[j + 1].x, Ix[j + 1].y));
           st4(o1 + 2 * j, make_float4(Iy[j].x, Iy[j].y, Iy[j + 1].x, Iy[j + 1].y));
         }
+        MSTAMP(tid == 0, 2 + 6 * k);  // gradients done
         // gray rows of block k+1 into the other gray buffer (its box was requested one half-step ago)
         if (k + 1 <= NB) {
           if (MARCH_ON(7)) tma_wait(&s_mbar, (unsigned)(k & 1));  // box of block k+1 is the k-th use of the barrier
+          MSTAMP(tid == 0, 3 + 6 * k);  // box arrived
           if (MARCH_ON(4)) convert(k + 1);
+          MSTAMP(tid == 0, 4 + 6 * k);  // converted
         }
       }
       bar_sync(kBarP, C::NP);  // Ix, Iy of block k and the gray rows of block k+1 are complete; the raw box is free
+      MSTAMP(tid == 0, 5 + 6 * k);
       if (k >= 1) bar_sync(kBarV, C::NT);  // k == 1: the consumers have seen block 0; k >= 2: they are done with block k-2
+      MSTAMP(tid == 0, 6 + 6 * k);
       {
         if (tid >= C::NH) {
           // The producers beyond the horizontal items (one warp: the x halo of the gradient items) do the copies.
@@ -382,7 +396,6 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
           if (lane == 0 && k + 2 <= NB) {
             fence_async_smem();
             issue_raw(k + 2);
-            if (k + 4 <= NB && MARCH_ON(8)) prefetch_raw(k + 4);
           }
           // the last RG gray row pairs of block k+1 are the first RG of block k+2 (gray buffer k&1 again)
           if (k + 2 <= NB) {
@@ -452,6 +465,8 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
           for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int o = 0; o < 8; ++o) acc[c][o] = make_float2(0.f, 0.f);
+          const int gyh = hb(k) + 2 * q;
+          if (gyh + 1 >= 0 && gyh < H) {  // a row pair outside the image holds Ix = Iy = 0: its smoothed products are zeros
 #pragma unroll
           for (int m = 0; m < C::HWIN / 2; ++m) {
             const float4 xv = ld4(pix + 4 * m), yv = ld4(piy + 4 * m);
@@ -472,6 +487,7 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
               }
             }
           }
+          }
           float* o = sH + (img * 3) * C::H_PLANE + (8 * (k & 1) + q) * C::PH + 2 * (8 * seg);
 #pragma unroll
           for (int c = 0; c < 3; ++c)
@@ -480,6 +496,7 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
               st4(o + c * C::H_PLANE + 2 * jj, make_float4(acc[c][jj].x, acc[c][jj].y, acc[c][jj + 1].x, acc[c][jj + 1].y));
         }
       }
+      MSTAMP(tid == 0, 7 + 6 * k);  // horizontal pass done
       __threadfence_block();
       bar_arrive(kBarH, C::NT);  // ring block k is complete
       bar_sync(kBarP, C::NP);    // every producer is done with Ix, Iy of block k; the carried gray rows are in place
@@ -491,6 +508,7 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
     for (int jb = 0; jb < NB; ++jb) {
       const int k = jb + 2;
       bar_sync(kBarH, C::NT);  // ring block jb+1
+      MSTAMP(tid == C::NP, 2 + 3 * jb);  // block available
       if (MARCH_ON(1)) {
       // vertical rho-pass of output block j = k-2 from ring blocks j, j+1: this thread's column, output row
       // pairs 4*chalf .. +3, input ring row pairs 4*chalf .. 4*chalf + NIN - 1 (relative to block j)
@@ -532,6 +550,7 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
           }
       }
       }
+      MSTAMP(tid == C::NP, 3 + 3 * jb);  // vertical pass done
       if (jb + 2 <= NB) bar_arrive(kBarV, C::NT);  // ring slot jb&1 may be overwritten (block jb+2)
       if (MARCH_ON(0)) {
       // per-pixel chain + stores of output block j: rows y0 + 16j + 8*chalf + 2o (+1), column x0 + ccol
@@ -569,6 +588,7 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
     }
   }
 
+  MSTAMP(tid == C::NP, 4 + 3 * (NB - 1));  // last chain done
   // Deterministic loss reduction: block partial -> workspace; the last block to finish sums all
   // partials in a fixed order (double) and re-zeroes the workspace for the next call.
   lsum = warp_sum(lsum);

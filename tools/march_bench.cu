@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <algorithm>
 #include "st_march.cuh"
 using namespace srst;
 #ifndef MB_TW
@@ -90,5 +91,25 @@ int main(int argc, char** argv) {
     }
     printf("  mask %3d: %8.2f us\n", mask, best * 1e3f);
   }
+  // phase stamps of one launch (producer thread 0: slots 0..63, consumer thread 0: 64..127), median over CTAs
+#ifdef SRST_MARCH_STAMPS
+  if (getenv("MB_STAMPS")) {
+    long long* d; cudaMalloc(&d, (size_t)grid * 128 * 8); cudaMemset(d, 0, (size_t)grid * 128 * 8);
+    const int zero = getenv("MB_STAMP_MASK") ? atoi(getenv("MB_STAMP_MASK")) : 0; cudaMemcpyToSymbol(g_march_abl, &zero, sizeof(int));
+    cudaMemcpyToSymbol(g_march_stamp, &d, sizeof(d));
+    kern<<<grid, C::NT, C::SMEM_BYTES>>>(MPs[1]);
+    cudaDeviceSynchronize();
+    std::vector<long long> hst((size_t)grid * 128);
+    cudaMemcpy(hst.data(), d, hst.size() * 8, cudaMemcpyDeviceToHost);
+    long long t0 = 0; for (int c = 0; c < grid; ++c) if (hst[(size_t)c * 128] && (!t0 || hst[(size_t)c * 128] < t0)) t0 = hst[(size_t)c * 128];
+    for (int sl = 0; sl < 128; ++sl) {
+      std::vector<double> v;
+      for (int c = 0; c < grid; ++c) if (hst[(size_t)c * 128 + sl]) v.push_back((hst[(size_t)c * 128 + sl] - t0) * 1e-3);
+      if (v.empty()) continue;
+      std::sort(v.begin(), v.end());
+      printf("  %s slot %2d: median %7.2f us  min %7.2f  max %7.2f  (n=%zu)\n", sl < 64 ? "P" : "C", sl & 63, v[v.size() / 2], v.front(), v.back(), v.size());
+    }
+  }
+#endif
   return 0;
 }
