@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRST_VERSION 200 /* major*100 + minor: the major number changes whenever an argument list changes */
+#define SRST_VERSION 201 /* major*100 + minor: the major number changes whenever an argument list changes */
 
 #define SRST_E_INVALID (-1)     /* null pointer / non-positive size / bad enum */
 #define SRST_E_UNSUPPORTED (-2) /* filter radius or patch geometry not compiled in */
@@ -157,6 +157,10 @@ int srst_stpx_backward(const float* sr, const float* hr, const float* ixy, const
  * ------------------------------------------------------------------------------------------- */
 #define SRST_BB_L1 0
 #define SRST_BB_L2 1
+/* OR-ed into `criterion` of the three *_forward entry points below: search with dist_norm='l1'
+ * (utils.py:166-172: alpha * sum|x - y| + beta * sum|g - y|) instead of the default squared l2 distance.  Every pair is
+ * scored exactly then (no filter); the backward entry points ignore the flag (they only need the indices). */
+#define SRST_BB_DIST_L1 0x100
 
 size_t srst_bb_workspace_bytes(int B, int H, int W);
 

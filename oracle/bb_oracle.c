@@ -137,6 +137,8 @@ int bb_oracle_forward_mode(const float* sr, const float* gt, const float* gt2, c
                            float alpha, float beta, int criterion, int mode, int64_t* idx, double* loss_out,
                            float* best_out, float* second_out) {
   const int Dd = mode == 1 ? 9 : D;
+  const int dist_l1 = (criterion & 0x100) != 0; /* dist_norm='l1' (utils.py:166-172), flag as in include/srst.h */
+  criterion &= 0xff;
   const int n0x = W / 3, N0 = (H / 3) * n0x;
   const int H2 = H / 2, W2 = W / 2, n2x = W2 / 3, N2 = (H2 / 3) * n2x;
   const int H4 = H / 4, W4 = W / 4, n4x = W4 / 3, N4 = (H4 / 3) * n4x;
@@ -174,6 +176,13 @@ int bb_oracle_forward_mode(const float* sr, const float* gt, const float* gt2, c
         float d2 = fmaf(-2.0f, dotd(q2 + (size_t)i * Dd, y + (size_t)j * Dd, Dd), gn[i] + yn[j]);
         d1 = d1 < 0.f ? 0.f : d1; /* torch.clamp(min=0) keeps NaN (utils.py:187) */
         d2 = d2 < 0.f ? 0.f : d2;
+        if (dist_l1) { /* sum_k |x_k - y_k| accumulated in k order, fp32 (utils.py:172) */
+          d1 = 0.f; d2 = 0.f;
+          for (int k = 0; k < Dd; ++k) {
+            d1 = d1 + fabsf(q1[(size_t)i * Dd + k] - y[(size_t)j * Dd + k]);
+            d2 = d2 + fabsf(q2[(size_t)i * Dd + k] - y[(size_t)j * Dd + k]);
+          }
+        }
         const float a = alpha * d1, bb = beta * d2;
         const float s = a + bb;
         /* torch.min (loss.py:135): first minimum; a NaN beats every number and the first NaN wins */

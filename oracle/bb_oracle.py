@@ -85,9 +85,11 @@ def describe_c(img, mode="pst", taps=None):
     return out
 
 
-def bb_forward_c(sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion="l1", mode="patch", taps=None):
+def bb_forward_c(sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion="l1", mode="patch", taps=None,
+                 dist_norm="l2"):
     """mode="patch": BestBuddyLoss (27 raw values); mode="gram": GramLoss (3x3 Gram matrix, loss.py:146-225);
-    mode="pst": PatchwiseStructureTensorLoss (loss.py:292-375), taps = (g, dg, k) of utils.get_gaussian_kernel."""
+    mode="pst": PatchwiseStructureTensorLoss (loss.py:292-375), taps = (g, dg, k) of utils.get_gaussian_kernel.
+    dist_norm: 'l2' (default) or 'l1' (utils.py:166-172), the distance of the search."""
     if mode == "pst":
         _set_pst_taps(taps)
     sr = np.ascontiguousarray(sr, np.float32)
@@ -103,7 +105,8 @@ def bb_forward_c(sr, gt, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion="l1"
     second = np.empty((B, N), np.float32)
     loss = ctypes.c_double(0.0)
     rc = _load().bb_oracle_forward_mode(_fp(sr), _fp(gt), _fp(gt2), _fp(gt4), B, H, W, ctypes.c_float(alpha),
-                                   ctypes.c_float(beta), 0 if criterion == "l1" else 1, _MODES[mode],
+                                   ctypes.c_float(beta), (0 if criterion == "l1" else 1) | (0x100 if dist_norm == "l1" else 0),
+                                   _MODES[mode],
                                    idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), ctypes.byref(loss),
                                    _fp(best), _fp(second))
     assert rc == 0
@@ -118,13 +121,15 @@ def unfold3(img):
     return p.transpose(0, 2, 4, 1, 3, 5).reshape(B, ny * nx, C * 9)
 
 
-def bb_scores_f64(sr, gt, gt2, gt4, alpha=1.0, beta=1.0):
+def bb_scores_f64(sr, gt, gt2, gt4, alpha=1.0, beta=1.0, dist_norm="l2"):
     """[B,N,M] float64 scores, the exact-arithmetic version of loss.py:132-133."""
     p1 = unfold3(np.asarray(sr, np.float64))
     p2 = unfold3(np.asarray(gt, np.float64))
     cat = np.concatenate([p2, unfold3(np.asarray(gt2, np.float64)), unfold3(np.asarray(gt4, np.float64))], 1)
 
     def dist(x, y):
+        if dist_norm == "l1":   # utils.py:166-172
+            return np.abs(x[:, :, None, :] - y[:, None, :, :]).sum(3)
         d = (x ** 2).sum(2)[:, :, None] + (y ** 2).sum(2)[:, None, :] - 2.0 * np.einsum("bnd,bmd->bnm", x, y)
         return np.clip(d, 0.0, None)
 

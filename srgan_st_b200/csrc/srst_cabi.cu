@@ -608,6 +608,8 @@ static int bb_forward_impl(const float* sr, const float* gt, const float* gt2, c
                            size_t workspace_bytes, void* stream, const PstTaps& tp = PstTaps{}) {
   constexpr int D = BbDesc<MODE>::D;
   if (!sr || !gt || !idx_out || !loss_out || B <= 0) return SRST_E_INVALID;
+  const bool dist_l1 = (criterion & SRST_BB_DIST_L1) != 0;  // dist_norm of the search (utils.py:166-172)
+  criterion &= ~SRST_BB_DIST_L1;
   if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
   if (H < 12 || W < 12 || B > 65535) return SRST_E_SHAPE;
   if ((gt2 == nullptr) != (gt4 == nullptr)) return SRST_E_INVALID;
@@ -625,8 +627,12 @@ static int bb_forward_impl(const float* sr, const float* gt, const float* gt2, c
   SRST_LAUNCH(bb_pack_kernel<MODE>, dim3((npack + 255) / 256, B), dim3(256), 0, stream, sr, gt, gt2, gt4, w.mats,
               w.per_image, g, tp);
   if ((e = (int)cudaGetLastError()) != 0) return e;
-  SRST_LAUNCH((bb_search_kernel<D, MODE == 2>), dim3(g.Npad / BB_QT, B), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, alpha,
-              beta, idx_out);
+  if (dist_l1)
+    SRST_LAUNCH(bb_search_l1_kernel<D>, dim3(g.Npad / BB_QT, B), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, alpha, beta,
+                idx_out);
+  else
+    SRST_LAUNCH((bb_search_kernel<D, MODE == 2>), dim3(g.Npad / BB_QT, B), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, alpha,
+                beta, idx_out);
   if ((e = (int)cudaGetLastError()) != 0) return e;
   const unsigned nl = (unsigned)(((size_t)B * g.N + BB_NT - 1) / BB_NT);
   SRST_LAUNCH(bb_loss_kernel<D>, dim3(nl), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, idx_out, criterion,
@@ -685,6 +691,7 @@ int srst_pst_backward(const float* sr, const float* gt, const float* gt2, const 
                       const float* k, int r_rho, int criterion, float* d_sr, void* workspace, size_t workspace_bytes,
                       void* stream) {
   if (!sr || !gt || !idx || !grad_out || !d_sr || B <= 0) return SRST_E_INVALID;
+  criterion &= ~SRST_BB_DIST_L1;  // the search norm does not matter to the backward
   if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
   if (H < 12 || W < 12 || B > 65535) return SRST_E_SHAPE;
   if ((gt2 == nullptr) != (gt4 == nullptr)) return SRST_E_INVALID;
@@ -717,6 +724,7 @@ int srst_gram_backward(const float* sr, const float* gt, const float* gt2, const
                        const float* grad_out, int B, int H, int W, int criterion, float* d_sr, void* workspace,
                        size_t workspace_bytes, void* stream) {
   if (!sr || !gt || !idx || !grad_out || !d_sr || B <= 0) return SRST_E_INVALID;
+  criterion &= ~SRST_BB_DIST_L1;  // the search norm does not matter to the backward
   if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
   if (H < 12 || W < 12 || B > 65535) return SRST_E_SHAPE;
   if ((gt2 == nullptr) != (gt4 == nullptr)) return SRST_E_INVALID;
@@ -747,6 +755,7 @@ int srst_bb_backward(const float* sr, const float* gt, const float* gt2, const f
                      const float* grad_out, int B, int H, int W, int criterion, float* d_sr, void* workspace,
                      size_t workspace_bytes, void* stream) {
   if (!sr || !gt || !idx || !grad_out || !d_sr || B <= 0) return SRST_E_INVALID;
+  criterion &= ~SRST_BB_DIST_L1;  // the search norm does not matter to the backward
   if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
   if (H < 12 || W < 12 || B > 65535) return SRST_E_SHAPE;
   if ((gt2 == nullptr) != (gt4 == nullptr)) return SRST_E_INVALID;

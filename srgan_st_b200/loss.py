@@ -20,6 +20,7 @@ from torch.autograd.function import once_differentiable
 from . import _cabi, taps as _taps
 
 _WORKSPACES: Dict[Tuple[str, int, int], torch.Tensor] = {}
+_DIST_L1 = 0x100  # SRST_BB_DIST_L1 (include/srst.h): OR-ed into the criterion argument, search with dist_norm='l1' (utils.py:166-172)
 
 
 def _workspace(kind: str, device: torch.device, stream_ptr: int, nbytes: int) -> torch.Tensor:
@@ -387,8 +388,9 @@ class BestBuddyLoss(nn.Module):
 
     ``forward(x, gt)``: for every 3x3 SR patch pick the HR candidate patch (three pyramid levels)
     minimising ``alpha*|sr-cand|^2 + beta*|gt-cand|^2`` and return the L1 (or MSE) distance to it.
-    Only the reference's default patch geometry (ksize=3, pad=0, stride=3) and ``dist_norm='l2'``
-    have kernels; other values raise ``NotImplementedError``.
+    Only the reference's default patch geometry (ksize=3, pad=0, stride=3) has kernels; other values raise
+    ``NotImplementedError``.  ``dist_norm='l1'`` (utils.py:166-172) scores every pair exactly with
+    ``alpha*sum|sr-cand| + beta*sum|gt-cand|`` (the reference materialises a [B,N,M,27] tensor for it).
 
     ``pyramid``: "fused" (default) lets libsrst build the two HR pyramid levels with the cubic taps of
     ``F.interpolate(mode='bicubic', align_corners=False)`` (equal to 2e-7; 0.03 ms instead of 0.43 ms at
@@ -415,10 +417,11 @@ class BestBuddyLoss(nn.Module):
             raise NotImplementedError("%s criterion has not been implmented." % criterion)  # loss.py:113
         if dist_norm not in ("l1", "l2"):
             raise NotImplementedError("%s norm has not been supported." % dist_norm)        # utils.py:189
-        if dist_norm != "l2" or (ksize, pad, stride) != (3, 0, 3):
+        if (ksize, pad, stride) != (3, 0, 3):
             raise NotImplementedError(
-                "BestBuddyLoss: libsrst.so implements the reference default geometry only "
-                "(ksize=3, pad=0, stride=3, dist_norm='l2')")
+                "BestBuddyLoss: libsrst.so implements the reference default geometry only (ksize=3, pad=0, stride=3)")
+        if dist_norm == "l1":
+            self._crit |= _DIST_L1
         if pyramid not in ("aten", "fused"):
             raise ValueError("pyramid must be 'aten' or 'fused'")
         self.pyramid = pyramid
@@ -436,7 +439,7 @@ class BestBuddyLoss(nn.Module):
 class GramLoss(nn.Module):
     """Gram loss; same signature and semantics as reference loss.py:146-225: the best-buddy search
     and the final criterion run on the 3x3 Gram matrix of every 3x3x3 patch instead of its pixels.
-    Only ``ksize=3`` and ``dist_norm='l2'`` have kernels (the reference's defaults)."""
+    Only ``ksize=3`` has kernels (the reference's default); ``dist_norm`` may be 'l2' or 'l1'."""
 
     def __init__(self, alpha: float = 1.0, beta: float = 1.0, ksize: int = 3, dist_norm: str = "l2",
                  criterion: str = "l1", pyramid: str = "fused"):
@@ -455,8 +458,10 @@ class GramLoss(nn.Module):
             raise NotImplementedError("%s criterion has not been implmented." % criterion)  # loss.py:178
         if dist_norm not in ("l1", "l2"):
             raise NotImplementedError("%s norm has not been supported." % dist_norm)        # utils.py:189
-        if dist_norm != "l2" or ksize != 3:
-            raise NotImplementedError("GramLoss: libsrst.so implements ksize=3, dist_norm='l2' only")
+        if ksize != 3:
+            raise NotImplementedError("GramLoss: libsrst.so implements ksize=3 only")
+        if dist_norm == "l1":
+            self._crit |= _DIST_L1
         if pyramid not in ("aten", "fused"):
             raise ValueError("pyramid must be 'aten' or 'fused'")
         self.pyramid = pyramid
@@ -535,7 +540,7 @@ class PatchwiseStructureTensorLoss(nn.Module):
     """Patchwise structure-tensor loss; same signature and semantics as reference loss.py:292-375:
     the best-buddy search and the final criterion run on the det-normalised structure tensor of
     every 3x3 patch (seen as a 3x3 image, zero 'same' padding) instead of its pixels.
-    Only ``ksize=3`` and ``dist_norm='l2'`` have kernels (the reference's defaults)."""
+    Only ``ksize=3`` has kernels (the reference's default); ``dist_norm`` may be 'l2' or 'l1'."""
 
     def __init__(self, sigma: float = 0.5, rho: float = 2, alpha: float = 1.0, beta: float = 1.0, ksize: int = 3,
                  dist_norm: str = "l2", criterion: str = "l1", pyramid: str = "fused"):
@@ -556,8 +561,10 @@ class PatchwiseStructureTensorLoss(nn.Module):
             raise NotImplementedError("%s criterion has not been supported." % criterion)  # loss.py:323
         if dist_norm not in ("l1", "l2"):
             raise NotImplementedError("%s norm has not been supported." % dist_norm)       # utils.py:189
-        if dist_norm != "l2" or ksize != 3:
-            raise NotImplementedError("PatchwiseStructureTensorLoss: libsrst.so implements ksize=3, dist_norm='l2' only")
+        if ksize != 3:
+            raise NotImplementedError("PatchwiseStructureTensorLoss: libsrst.so implements ksize=3 only")
+        if dist_norm == "l1":
+            self._crit |= _DIST_L1
         if pyramid not in ("aten", "fused"):
             raise ValueError("pyramid must be 'aten' or 'fused'")
         self.pyramid = pyramid

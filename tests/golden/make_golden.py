@@ -183,10 +183,56 @@ def make_pst(ref_loss, ref_utils):
         print(f"{name}: loss={loss.item():.8g} N={p1.shape[1]} M={cat.shape[1]}")
 
 
+L1_CASES = [
+    # dist_norm='l1' (utils.py:166-172) for the three patch losses: name, module, kind, B, H, W, seed, alpha, beta, criterion
+    ("bbl1_rand_2x24x24", "bb", "rand", 2, 24, 24, 41, 1.0, 1.0, "l1"),
+    ("bbl1_srlike_2x48x36", "bb", "srlike", 2, 48, 36, 42, 0.5, 2.0, "l2"),
+    ("graml1_rand_1x36x36", "gram", "rand", 1, 36, 36, 43, 1.0, 1.0, "l1"),
+    ("pstl1_rand_2x24x24", "pst", "rand", 2, 24, 24, 44, 1.0, 1.0, "l1"),
+]
+
+
+def make_l1(ref_loss, ref_utils):
+    import torch.nn.functional as F
+    for name, which, kind, B, H, W, seed, alpha, beta, crit in L1_CASES:
+        sr, hr = _inputs(kind, B, H, W, seed)
+        sr.requires_grad_(True)
+        if which == "bb":
+            m = ref_loss.BestBuddyLoss(alpha=alpha, beta=beta, dist_norm="l1", criterion=crit)
+            desc = lambda t: F.unfold(t, kernel_size=3, padding=0, stride=3).permute(0, 2, 1).contiguous()
+        elif which == "gram":
+            m = ref_loss.GramLoss(alpha=alpha, beta=beta, dist_norm="l1", criterion=crit)
+            desc = m.compute_patches
+        else:
+            m = ref_loss.PatchwiseStructureTensorLoss(alpha=alpha, beta=beta, dist_norm="l1", criterion=crit)
+            desc = m.compute_patches
+        loss = m(sr, hr)
+        loss.backward()
+        with torch.no_grad():
+            p1, p2 = desc(sr), desc(hr)
+            hr2 = F.interpolate(hr, scale_factor=0.5, mode="bicubic", align_corners=False)
+            hr4 = F.interpolate(hr, scale_factor=0.25, mode="bicubic", align_corners=False)
+            cat = torch.cat([p2, desc(hr2), desc(hr4)], 1)
+            score = alpha * ref_utils.batch_pairwise_distance(p1, cat, "l1") \
+                + beta * ref_utils.batch_pairwise_distance(p2, cat, "l1")
+            _, ind = torch.min(score, dim=2)
+            top2 = torch.topk(score, 2, dim=2, largest=False).values
+        extra = {}
+        if which == "pst":
+            g, dg = ref_utils.get_gaussian_kernel(0.5, also_dg=True)
+            extra = dict(g=g.numpy(), dg=dg.numpy(), k=ref_utils.get_gaussian_kernel(2.0).numpy())
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            sr=sr.detach().numpy(), hr=hr.detach().numpy(), loss=np.float32(loss.item()),
+            d_sr=sr.grad.numpy(), ind=ind.numpy(), top2=top2.numpy(), hr2=hr2.numpy(), hr4=hr4.numpy(),
+            alpha=np.float64(alpha), beta=np.float64(beta), criterion=np.str_(crit), which=np.str_(which), **extra)
+        print(f"{name}: loss={loss.item():.8g} N={p1.shape[1]} M={cat.shape[1]}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # fixed summation order inside MKL for reproducible fixtures
     rl, ru = _import_reference()
-    which = sys.argv[1:] or ["st", "bb", "gram", "pst"]
+    which = sys.argv[1:] or ["st", "bb", "gram", "pst", "l1"]
     if "st" in which:
         make_st(rl, ru)
     if "bb" in which:
@@ -195,3 +241,5 @@ if __name__ == "__main__":
         make_gram(rl, ru)
     if "pst" in which:
         make_pst(rl, ru)
+    if "l1" in which:
+        make_l1(rl, ru)

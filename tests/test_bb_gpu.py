@@ -154,7 +154,7 @@ def test_rejects_unsupported_geometry():
     with pytest.raises(NotImplementedError):
         BestBuddyLoss(ksize=5)
     with pytest.raises(NotImplementedError):
-        BestBuddyLoss(dist_norm="l1")
+        BestBuddyLoss(dist_norm="cosine")  # utils.py:189 (l1 and l2 have kernels)
     with pytest.raises(RuntimeError):
         BestBuddyLoss()(torch.rand(1, 3, 24, 24), torch.rand(1, 3, 24, 24))
     with pytest.raises(NotImplementedError):  # the reference would differentiate the gathered candidates
