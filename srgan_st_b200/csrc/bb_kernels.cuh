@@ -415,6 +415,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
   // SHARE only: 2*tol of a pair is at most 2 kappa (ca_i + max over the chunk's valid candidates of yt_j)
   [[maybe_unused]] __shared__ __align__(16) float sCa[SHARE ? BB_QT : 4];   // |alpha||x|^2 + |beta||g|^2
   [[maybe_unused]] __shared__ __align__(16) float sYtm[2][4];               // per staging warp: max (|alpha|+|beta|)|y|^2
+  __shared__ int sW[BB_NT / 32][64];   // per warp: queued survivors (tile query << 8 | chunk candidate), then their exact scores
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y, qt = blockIdx.x;
@@ -578,20 +579,75 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
           if (!(acc[p][j].y > B[2 * p + 1])) hit |= 1ull << (8 * j + 2 * p + 1);
         }
     }
-    if (hit) {  // rare: exact re-scoring, ascending candidate order per query
+    // Survivors: exact re-scoring, warp-cooperative.  The survivors of all 32 lanes are numbered by a warp prefix sum
+    // (a lane's own ones in ascending bit order = ascending candidate order per query, which the first-minimum rule
+    // needs) and queued 64 at a time; every lane scores queue slots lane and lane+32, then each owner folds the results
+    // of its slots into its running minima in slot order.  Round 1 let every lane score its own survivors inside a
+    // divergent branch: the warp then serialised the UNION of all lanes' survivors (PatchwiseST: 15 % of the kernel's
+    // samples there and 27 % waiting for it at the chunk barrier; Gram likewise on its 9-dimensional descriptors).
+    {
+      constexpr int QCAP = 64;
+      const int lane = tid & 31, wrp = tid >> 5;
+      const int cnt = __popcll(hit);
+      int pre = cnt;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int cj = chunk + 4 * tx + (j & 3) + 64 * (j >> 2);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if ((hit >> (8 * j + i)) & 1ull) {
-            const int qi = qbase + 4 * ty + (i & 3) + 64 * (i >> 2);
-            const float s = bb_exact_score(P.q1, P.q2, P.y, P.xn, P.gn, P.yn, g.Npad, g.Mpad, D, qi, cj, alpha, beta);
-            // ascending cj per thread: first minimum kept; the first NaN beats every number (torch.min)
-            if (s < best[i] || (s != s && best[i] == best[i])) { best[i] = s; bidx[i] = cj; }
-            B[i] = fminf(B[i], s);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += up;
+      }
+      const int total = __shfl_sync(0xffffffffu, pre, 31);
+      const int first = pre - cnt;  // queue slot of this lane's first survivor
+      for (int w0 = 0; w0 < total; w0 += QCAP) {
+        {
+          unsigned long long h = hit;
+          for (int slot = first - w0; h; ++slot) {
+            const int e = __ffsll((long long)h) - 1;
+            h &= h - 1ull;
+            if (slot >= 0 && slot < QCAP) {
+              const int i = e & 7, j = e >> 3;
+              sW[wrp][slot] = ((4 * ty + (i & 3) + 64 * (i >> 2)) << 8) | (4 * tx + (j & 3) + 64 * (j >> 2));
+            }
           }
         }
+        __syncwarp();
+        const int n = min(QCAP, total - w0);
+        float sc[QCAP / 32];
+#pragma unroll
+        for (int u = 0; u < QCAP / 32; ++u) {
+          const int s0 = lane + 32 * u;
+          sc[u] = 0.f;
+          if (s0 < n) {
+            const int ent = sW[wrp][s0];
+            sc[u] = bb_exact_score(P.q1, P.q2, P.y, P.xn, P.gn, P.yn, g.Npad, g.Mpad, D, qbase + (ent >> 8), chunk + (ent & 255),
+                                   alpha, beta);
+          }
+        }
+        __syncwarp();  // every entry has been read
+#pragma unroll
+        for (int u = 0; u < QCAP / 32; ++u)
+          if (lane + 32 * u < n) sW[wrp][lane + 32 * u] = __float_as_int(sc[u]);
+        __syncwarp();
+        {
+          unsigned long long h = hit;
+          for (int slot = first - w0; h; ++slot) {
+            const int e = __ffsll((long long)h) - 1;
+            h &= h - 1ull;
+            if (slot >= 0 && slot < QCAP) {
+              const float s = __int_as_float(sW[wrp][slot]);
+              const int iq = e & 7, j = e >> 3;
+              const int cj = chunk + 4 * tx + (j & 3) + 64 * (j >> 2);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (i == iq) {
+                  // ascending cj per thread: first minimum kept; the first NaN beats every number (torch.min)
+                  if (s < best[i] || (s != s && best[i] == best[i])) { best[i] = s; bidx[i] = cj; }
+                  B[i] = fminf(B[i], s);
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();  // the queue is reused by the next window
       }
     }
     if (more) commit(buf ^ 1, chunk + BB_CT);  // buf^1 was last read before the previous barrier

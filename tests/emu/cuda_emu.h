@@ -124,6 +124,16 @@ inline T warp_exchange(T v, int src_lane) {
   c->warp_bar[w]->arrive_and_wait();
   return out;
 }
+inline unsigned warp_ballot(bool pred) {
+  BlockCtx* c = g_block;
+  unsigned w = t_linear_tid / 32, lane = t_linear_tid % 32;
+  c->warp_xchg[32 * w + lane] = pred ? 1u : 0u;
+  c->warp_bar[w]->arrive_and_wait();
+  unsigned lanes = std::min(32u, c->nthreads - 32 * w), mask = 0;
+  for (unsigned l = 0; l < lanes; ++l) mask |= (unsigned)(c->warp_xchg[32 * w + l] & 1u) << l;
+  c->warp_bar[w]->arrive_and_wait();
+  return mask;
+}
 }  // namespace emu
 
 #define threadIdx (emu::t_threadIdx)
@@ -149,6 +159,14 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) {
   return emu::warp_exchange(v, src < 32 ? src : -1);
 }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu::warp_exchange(v, src & 31); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) {
+  int src = int(emu::t_linear_tid % 32) - d;
+  return emu::warp_exchange(v, src >= 0 ? src : -1);
+}
+static inline unsigned __ballot_sync(unsigned, int pred) { return emu::warp_ballot(pred != 0); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
