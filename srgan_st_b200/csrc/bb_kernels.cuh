@@ -398,6 +398,15 @@ bb_exact_score(const float* q1, const float* q2, const float* y, const float* xn
   return bb_score(__ldg(xn + qi), __ldg(gn + qi), __ldg(yn + cj), dot1, dot2, alpha, beta);
 }
 
+// The filter compares lo' = yl_j - 2 acc_ij with Bc_i instead of cl_i + lo' with B_i.  With F = fl(B - cl),
+// Bc = F + 6e-7 |F| guarantees  lo' > Bc  =>  cl + yl - 2 acc > B  in real arithmetic on the fp32 operands (the two
+// roundings involved, of lo' and of F, are each below 1.2e-7 of max(|lo'|, |F|), and |lo'| > |F| only where the margin
+// is not needed).  B = -inf (padded queries: nothing is ever evaluated) stays -inf; a NaN bound stays NaN (= always hit).
+SRST_DEV float bb_shifted_bound(float B, float cl) {
+  const float F = B - cl;
+  return (B == __int_as_float(0xff800000)) ? B : fmaf(6e-7f, fabsf(F), F);
+}
+
 // SHARE: the 16 threads that own a query also pool their bound -- every chunk early on, every fourth
 // later, B_i is lowered to the smallest UPPER bound s'_ij + tol_ij any of them saw in the chunk (four
 // shuffle steps).  It costs ~8 % on descriptors whose co-located patch is already a tight seed
@@ -484,16 +493,16 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
   commit(0, 0);
   __syncthreads();  // queries, bounds and chunk 0 are in shared memory
 
-  float best[8], B[8];
+  float best[8], B[8], Bc[8], clq[8];
   int bidx[8];
-  float2 cl[4];
   {
     const float4 c0 = ld4(&sCl[4 * ty]), c1 = ld4(&sCl[64 + 4 * ty]);
     const float4 b0 = ld4(&sB0[4 * ty]), b1 = ld4(&sB0[64 + 4 * ty]);
-    cl[0] = make_float2(c0.x, c0.y); cl[1] = make_float2(c0.z, c0.w);
-    cl[2] = make_float2(c1.x, c1.y); cl[3] = make_float2(c1.z, c1.w);
+    clq[0] = c0.x; clq[1] = c0.y; clq[2] = c0.z; clq[3] = c0.w; clq[4] = c1.x; clq[5] = c1.y; clq[6] = c1.z; clq[7] = c1.w;
     B[0] = b0.x; B[1] = b0.y; B[2] = b0.z; B[3] = b0.w; B[4] = b1.x; B[5] = b1.y; B[6] = b1.z; B[7] = b1.w;
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Bc[i] = bb_shifted_bound(B[i], clq[i]);
 #pragma unroll
   for (int i = 0; i < 8; ++i) { best[i] = __int_as_float(0x7f800000); bidx[i] = 0x7fffffff; }
   const float2 m2 = make_float2(-2.0f, -2.0f);
@@ -526,57 +535,58 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
         for (int p = 0; p < 4; ++p) acc[p][j] = __ffma2_rn(up[p], w2, acc[p][j]);
       }
     }
-    // filter: lower bound of the exact score vs the running upper bound; survivors are flagged
+    // Filter: lower bound of the exact score vs the running upper bound; survivors are flagged.  The bound
+    // L_ij = cl_i + yl_j - 2 acc_ij is compared in the shifted form  lo'_ij = yl_j - 2 acc_ij  >  Bc_i ~ B_i - cl_i
+    // (one FFMA2 per pair, no add), and the per-pair compare is replaced by a per-query minimum (FMNMX3.NAN: a NaN
+    // anywhere still reaches the exact path) tested once against Bc_i: the 64 compares + mask updates only run in the
+    // rare chunks that hold a survivor.
     unsigned long long hit = 0ull;
     const float4 yla = ld4(&sYl[buf][4 * tx]), ylb = ld4(&sYl[buf][64 + 4 * tx]);
     const float yl[8] = {yla.x, yla.y, yla.z, yla.w, ylb.x, ylb.y, ylb.z, ylb.w};
-    if constexpr (!SHARE) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 y2 = make_float2(yl[j], yl[j]);
+    for (int j = 0; j < 8; ++j) {
+      const float2 y2 = make_float2(yl[j], yl[j]);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const float2 lo = __ffma2_rn(m2, acc[p][j], __fadd2_rn(cl[p], y2));
-          // !(lo > B): a NaN bound or a NaN candidate is a hit, so NaN inputs reach the exact path below
-          if (!(lo.x > B[2 * p])) hit |= 1ull << (8 * j + 2 * p);
-          if (!(lo.y > B[2 * p + 1])) hit |= 1ull << (8 * j + 2 * p + 1);
-        }
-      }
-    } else {
-      // lower bounds L_ij in place; an upper bound of the pair is L_ij + 2 tol_ij <= L_ij + delta_i with
-      // delta_i = 2 kappa (ca_i + max_chunk yt): pool min_j (L_ij) + delta_i over the half-warp into B_i first,
-      // then flag against the pooled bound
+      for (int p = 0; p < 4; ++p) acc[p][j] = __ffma2_rn(m2, acc[p][j], y2);
+    }
+    float mq[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 y2 = make_float2(yl[j], yl[j]);
-#pragma unroll
-        for (int p = 0; p < 4; ++p) acc[p][j] = __ffma2_rn(m2, acc[p][j], __fadd2_rn(cl[p], y2));
-      }
+    for (int p = 0; p < 4; ++p) {
+      float mx = min3_nan(acc[p][0].x, acc[p][1].x, acc[p][2].x), my = min3_nan(acc[p][0].y, acc[p][1].y, acc[p][2].y);
+      mx = min3_nan(mx, acc[p][3].x, acc[p][4].x); my = min3_nan(my, acc[p][3].y, acc[p][4].y);
+      mx = min3_nan(mx, acc[p][5].x, acc[p][6].x); my = min3_nan(my, acc[p][5].y, acc[p][6].y);
+      mq[2 * p] = min3_nan(mx, acc[p][7].x, acc[p][7].x);
+      mq[2 * p + 1] = min3_nan(my, acc[p][7].y, acc[p][7].y);
+    }
+    if constexpr (SHARE) {
+      // an upper bound of a pair is L_ij + 2 tol_ij <= L_ij + delta_i with delta_i = 2 kappa (ca_i + max over the
+      // chunk of yt): pool min_j L_ij + delta_i over the half-warp into B_i before the test
       const int cidx = chunk / BB_CT;
       if (cidx < 4 || (cidx & 3) == 0) {
         const float4 ym = ld4(&sYtm[buf][0]);
         const float ytmax = fmaxf(fmaxf(ym.x, ym.y), fmaxf(ym.z, ym.w));
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          float mx = acc[p][0].x, my = acc[p][0].y;
+        for (int i = 0; i < 8; ++i) {
+          float m = mq[i];
 #pragma unroll
-          for (int j = 1; j < 8; ++j) { mx = fminf(mx, acc[p][j].x); my = fminf(my, acc[p][j].y); }
-#pragma unroll
-          for (int o = 1; o <= 8; o <<= 1) {
-            mx = fminf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            my = fminf(my, __shfl_xor_sync(0xffffffffu, my, o));
-          }
-          // 1.0001: the three fp32 roundings of this expression stay far inside the slack of kappa
-          B[2 * p] = fminf(B[2 * p], mx + 2.0002f * kBbKappa * (ca[2 * p] + ytmax));
-          B[2 * p + 1] = fminf(B[2 * p + 1], my + 2.0002f * kBbKappa * (ca[2 * p + 1] + ytmax));
+          for (int o = 1; o <= 8; o <<= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          // the fp32 roundings of this expression stay far inside the slack of kappa
+          B[i] = fminf(B[i], (m + clq[i]) + 2.0002f * kBbKappa * (ca[i] + ytmax));
+          Bc[i] = bb_shifted_bound(B[i], clq[i]);
         }
       }
+    }
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) any |= !(mq[i] > Bc[i]);
+    if (any) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          if (!(acc[p][j].x > B[2 * p])) hit |= 1ull << (8 * j + 2 * p);
-          if (!(acc[p][j].y > B[2 * p + 1])) hit |= 1ull << (8 * j + 2 * p + 1);
+          // !(lo' > Bc): a NaN bound or a NaN candidate is a hit, so NaN inputs reach the exact path below
+          if (!(acc[p][j].x > Bc[2 * p])) hit |= 1ull << (8 * j + 2 * p);
+          if (!(acc[p][j].y > Bc[2 * p + 1])) hit |= 1ull << (8 * j + 2 * p + 1);
         }
     }
     // Survivors: exact re-scoring, warp-cooperative.  The survivors of all 32 lanes are numbered by a warp prefix sum
@@ -642,6 +652,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
                   // ascending cj per thread: first minimum kept; the first NaN beats every number (torch.min)
                   if (s < best[i] || (s != s && best[i] == best[i])) { best[i] = s; bidx[i] = cj; }
                   B[i] = fminf(B[i], s);
+                  Bc[i] = bb_shifted_bound(B[i], clq[i]);
                 }
               }
             }

@@ -99,6 +99,20 @@ SRST_DEV float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "
 SRST_DEV float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #endif
 
+// NaN-propagating minimum of three (one FMNMX3.NAN on sm_100a): any NaN operand gives NaN.
+#ifdef SRST_EMULATE
+SRST_DEV float min3_nan(float a, float b, float c) {
+  if (a != a || b != b || c != c) return std::nanf("");
+  return std::fmin(a, std::fmin(b, c));
+}
+#else
+SRST_DEV float min3_nan(float a, float b, float c) {
+  float d;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+#endif
+
 // 16-byte asynchronous global->shared copy (LDGSTS); `valid == false` zero-fills the destination
 // without reading `gsrc` (src-size 0), which implements the reference's zero padding for free.
 #ifdef SRST_EMULATE
