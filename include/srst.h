@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRST_VERSION 201 /* major*100 + minor: the major number changes whenever an argument list changes */
+#define SRST_VERSION 202 /* major*100 + minor: the major number changes whenever an argument list changes */
 
 #define SRST_E_INVALID (-1)     /* null pointer / non-positive size / bad enum */
 #define SRST_E_UNSUPPORTED (-2) /* filter radius or patch geometry not compiled in */
@@ -46,11 +46,15 @@ const char* srst_error_string(int code);
  *
  * g, dg: 2*r_sigma+1 host floats (utils.get_gaussian_kernel(sigma, also_dg=True), utils.py:194-208)
  * k    : 2*r_rho+1   host floats (utils.get_gaussian_kernel(rho))
- * Radii are padded with zero taps to the compiled classes r_sigma in {2,4}, r_rho in {4,8,12};
- * srst_st_supported() tells whether a pair fits.  The reference default (sigma=0.5, rho=2.0) is (2, 8).
+ * Radii are padded with zero taps to the compiled classes r_sigma in {2,4}, r_rho in {4,8,12} (shared-memory
+ * kernels; the reference default sigma=0.5, rho=2.0 is (2, 8)).  Larger radii, up to 64 each -- the reference's
+ * radius max(int(4 sigma + 0.5), 1) is unbounded, utils.py:198 -- run on the generic-radius path: the same passes,
+ * one thread per pixel, intermediates in global scratch planes (srst_st_workspace_bytes_r,
+ * srst_st_backward_workspace_bytes, srst_st_backward_ws).
  * ------------------------------------------------------------------------------------------- */
 
-/* 1 if the (r_sigma, r_rho) pair fits a compiled radius class, else 0. */
+/* 1 if the (r_sigma, r_rho) pair fits a compiled radius class, 2 if it takes the generic-radius path
+ * (srst_st_forward + srst_st_backward_ws only; not the fused Pixel variant, not srst_st_features), else 0. */
 int srst_st_supported(int r_sigma, int r_rho);
 
 /* Tile-shape override for tests and tuning sweeps: force compiled forward / backward tile configuration
@@ -70,6 +74,13 @@ int srst_st_force_chunk_blocks(int blocks);
  * so the buffer can be reused by later calls on the same stream; do not share one buffer between
  * streams, or between this entry point and the patch-loss entry points (they lay it out differently). */
 size_t srst_st_workspace_bytes(int B, int H, int W);
+/* Same, for a given radius pair: equal to srst_st_workspace_bytes() for the compiled classes; the generic-radius
+ * path adds eleven [B,H,W] fp32 scratch planes (smoothed tensors of both images, one pass buffer, Ix/Iy when they
+ * are not saved).  0 if the pair is not supported at all. */
+size_t srst_st_workspace_bytes_r(int B, int H, int W, int r_sigma, int r_rho);
+/* Scratch bytes srst_st_backward_ws needs: 0 for the compiled classes, five [B,H,W] fp32 planes on the
+ * generic-radius path (no zero-initialisation required). */
+size_t srst_st_backward_workspace_bytes(int B, int H, int W, int r_sigma, int r_rho);
 
 /* Number of floats of a saved-gradient buffer ("ixy") for a [B,3,H,W] problem: [B][2][ceil(H/2)][W][2],
  * plane 0 = Ix (derivative along H), plane 1 = Iy, rows 2p / 2p+1 of a column interleaved (the layout the
@@ -102,6 +113,14 @@ int srst_st_backward(const float* ixy, const float* ds, const float* grad_out,
                      const float* g, const float* dg, int r_sigma,
                      const float* k, int r_rho,
                      float* d_img, void* stream);
+/* Same with a scratch buffer: the only backward entry point of the generic-radius path (srst_st_backward returns
+ * SRST_E_WORKSPACE there); for the compiled classes `workspace` is ignored and may be NULL.  On the generic path
+ * the saved ixy buffer is planar [B][2][H][W] (written by srst_st_forward with the same radii). */
+int srst_st_backward_ws(const float* ixy, const float* ds, const float* grad_out,
+                        int B, int H, int W,
+                        const float* g, const float* dg, int r_sigma,
+                        const float* k, int r_rho,
+                        float* d_img, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Structure-tensor FEATURES of one image tensor (diagnostic output; BASELINE.json north_star: "closed-form 2x2
  * eigendecomposition giving orientation, coherence and eigenvalues").  The reference computes these only in an

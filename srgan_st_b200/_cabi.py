@@ -26,6 +26,8 @@ SIGNATURES = {
     "srst_st_force_cfg": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "srst_st_force_chunk_blocks": (ctypes.c_int, [ctypes.c_int]),
     "srst_st_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 3),
+    "srst_st_workspace_bytes_r": (ctypes.c_size_t, [ctypes.c_int] * 5),
+    "srst_st_backward_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] * 5),
     "srst_st_ixy_floats": (ctypes.c_size_t, [ctypes.c_int] * 3),
     "srst_st_forward": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
@@ -34,6 +36,9 @@ SIGNATURES = {
     "srst_st_backward": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
                                         vp, vp]),
+    "srst_st_backward_ws": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
+                                           vp, vp, ctypes.c_size_t, vp]),
     "srst_st_features": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                         c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int, vp, vp, vp, vp, vp]),
     "srst_stpx_forward": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,

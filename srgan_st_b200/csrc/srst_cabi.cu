@@ -13,6 +13,7 @@
 
 #include "st_kernels.cuh"
 #include "st_march.cuh"
+#include "st_generic.cuh"
 #include "bb_kernels.cuh"
 
 namespace srst {
@@ -334,7 +335,11 @@ const char* srst_error_string(int code) {
 // Compiled radius classes: r_sigma is padded up to 2 or 4, r_rho up to 4, 8 or 12 (zero taps).
 // (2, 8) -- the reference default sigma=0.5, rho=2.0 -- has the tuned tile shapes; the other
 // classes use one generic shape each.
-int srst_st_supported(int r_sigma, int r_rho) { return (r_sigma >= 1 && r_sigma <= 4 && r_rho >= 1 && r_rho <= 12) ? 1 : 0; }
+static bool st_compiled(int r_sigma, int r_rho) { return r_sigma >= 1 && r_sigma <= 4 && r_rho >= 1 && r_rho <= 12; }
+int srst_st_supported(int r_sigma, int r_rho) {
+  if (st_compiled(r_sigma, r_rho)) return 1;
+  return (r_sigma >= 1 && r_sigma <= kGenMaxR && r_rho >= 1 && r_rho <= kGenMaxR) ? 2 : 0;  // 2: generic-radius path
+}
 
 #if defined(SRST_TIMING) && !defined(SRST_EMULATE)
 // tools-only build: where the kernels write their phase time stamps (32 slots per CTA); NULL turns them off
@@ -366,6 +371,22 @@ static size_t st_partials_bytes(int B, int H, int W) {
 size_t srst_st_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
   return 2 * st_partials_bytes(B, H, W);  // ST partials + ticket | partials of the fused Pixel term
+}
+
+static size_t gen_plane_bytes(int B, int H, int W) { return ((size_t)B * H * W * sizeof(float) + 255) / 256 * 256; }
+constexpr int kGenFwdPlanes = 11, kGenBwdPlanes = 5;
+
+size_t srst_st_workspace_bytes_r(int B, int H, int W, int r_sigma, int r_rho) {
+  const size_t base = srst_st_workspace_bytes(B, H, W);
+  const int sup = srst_st_supported(r_sigma, r_rho);
+  if (base == 0 || sup == 0) return 0;
+  if (sup == 1) return base;
+  return base + kGenMaxPartials * sizeof(float) + kGenFwdPlanes * gen_plane_bytes(B, H, W);
+}
+
+size_t srst_st_backward_workspace_bytes(int B, int H, int W, int r_sigma, int r_rho) {
+  if (B <= 0 || H <= 0 || W <= 0 || srst_st_supported(r_sigma, r_rho) != 2) return 0;
+  return kGenBwdPlanes * gen_plane_bytes(B, H, W);
 }
 
 size_t srst_st_ixy_floats(int B, int H, int W) {
@@ -463,6 +484,81 @@ static int st_backward_rr(const StCall& c) {
   }
 }
 
+// ---- generic-radius path (st_generic.cuh): any radius up to kGenMaxR, scratch planes in the workspace ----
+static void gen_fill_taps(StGenTaps& t, const StCall& c) {
+  t.rs = c.rs; t.rk = c.rk;
+  std::memcpy(t.g, c.g, sizeof(float) * (2 * c.rs + 1));
+  std::memcpy(t.dg, c.dg, sizeof(float) * (2 * c.rs + 1));
+  std::memcpy(t.k, c.k, sizeof(float) * (2 * c.rk + 1));
+}
+
+static int st_forward_generic(const StCall& c, size_t workspace_bytes) {
+  if (workspace_bytes < srst_st_workspace_bytes_r(c.B, c.H, c.W, c.rs, c.rk)) return SRST_E_WORKSPACE;
+  const size_t npix = (size_t)c.B * c.H * c.W, pb = gen_plane_bytes(c.B, c.H, c.W);
+  if (npix > 0x7fffffffULL * (size_t)kGenNT) return SRST_E_SHAPE;
+  char* w = reinterpret_cast<char*>(c.workspace);
+  float* partials = reinterpret_cast<float*>(w + srst_st_workspace_bytes(c.B, c.H, c.W));
+  char* planes = reinterpret_cast<char*>(partials + kGenMaxPartials);
+  auto plane = [&](int i) { return reinterpret_cast<float*>(planes + (size_t)i * pb); };
+  float* S[2] = {plane(0), plane(3)};  // smoothed tensors of SR / HR (3 planes each); T1, T2 of an image live in its S first
+  float* V = plane(6);                 // vertical pass of the products (3 planes), shared by the two images
+  float* IXY = plane(9);               // Ix, Iy (2 planes) when the caller does not save them
+  static thread_local StGenParams P_tls;
+  StGenParams& P = P_tls;
+  P.B = c.B; P.H = c.H; P.W = c.W; P.scale = 0.f;
+  gen_fill_taps(P.taps, c);
+  const unsigned nblk = (unsigned)((npix + kGenNT - 1) / kGenNT);
+  for (int img = 0; img < 2; ++img) {
+    float* ixy = img ? c.ixy_hr : c.ixy_sr;
+    if (!ixy) ixy = IXY;
+    float* T1 = S[img];
+    float* T2 = S[img] + pb / sizeof(float);
+    P.in0 = img ? c.hr : c.sr; P.in1 = P.in2 = nullptr; P.out0 = T1; P.out1 = T2;
+    SRST_LAUNCH(gen_gray_v_kernel, dim3(nblk), dim3(kGenNT), 0, c.stream, P);
+    P.in0 = T1; P.in1 = T2; P.out0 = ixy; P.out1 = nullptr;
+    SRST_LAUNCH(gen_grad_h_kernel, dim3(nblk), dim3(kGenNT), 0, c.stream, P);
+    P.in0 = ixy; P.in1 = nullptr; P.out0 = V;
+    SRST_LAUNCH(gen_prod_v_kernel, dim3(nblk), dim3(kGenNT), 0, c.stream, P);
+    P.in0 = V; P.out0 = S[img];
+    SRST_LAUNCH(gen_smooth_h_kernel, dim3(nblk), dim3(kGenNT), 0, c.stream, P);
+  }
+  StGenChainParams Q;
+  Q.s1 = S[0]; Q.s2 = S[1]; Q.ds_sr = c.ds_sr; Q.ds_hr = c.ds_hr; Q.partials = partials;
+  Q.ticket = reinterpret_cast<unsigned int*>(c.workspace); Q.loss_out = c.loss_out;
+  Q.B = c.B; Q.H = c.H; Q.W = c.W; Q.normalize = c.normalize; Q.eps = c.eps;
+  Q.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
+  const unsigned ngrid = nblk < (unsigned)kGenMaxPartials ? nblk : (unsigned)kGenMaxPartials;
+  SRST_LAUNCH(gen_chain_kernel, dim3(ngrid), dim3(kGenNT), 0, c.stream, Q);
+  return (int)cudaGetLastError();
+}
+
+static int st_backward_generic(const StCall& c, void* workspace, size_t workspace_bytes) {
+  if (!workspace || !aligned16(workspace) ||
+      workspace_bytes < srst_st_backward_workspace_bytes(c.B, c.H, c.W, c.rs, c.rk))
+    return SRST_E_WORKSPACE;
+  const size_t npix = (size_t)c.B * c.H * c.W, pb = gen_plane_bytes(c.B, c.H, c.W);
+  if (npix > 0x7fffffffULL * (size_t)kGenNT) return SRST_E_SHAPE;
+  char* w = reinterpret_cast<char*>(workspace);
+  float* V = reinterpret_cast<float*>(w);            // Ch(k) ds: 3 planes; U1, U2 re-use its first two
+  float* DI = reinterpret_cast<float*>(w + 3 * pb);  // dIx, dIy
+  // the kernels index [B][n][H][W] densely: the plane stride inside a scratch region is H*W floats, not pb
+  static thread_local StGenParams P_tls;
+  StGenParams& P = P_tls;
+  P.B = c.B; P.H = c.H; P.W = c.W;
+  P.scale = (float)(1.0 / ((double)c.B * c.H * c.W));
+  gen_fill_taps(P.taps, c);
+  const unsigned nblk = (unsigned)((npix + kGenNT - 1) / kGenNT);
+  P.in0 = c.ds; P.in1 = P.in2 = nullptr; P.out0 = V; P.out1 = nullptr;
+  SRST_LAUNCH(gen_smooth_v_kernel, dim3(nblk), dim3(kGenNT), 0, c.stream, P);
+  P.in0 = V; P.in1 = c.ixy; P.out0 = DI;
+  SRST_LAUNCH(gen_bwd_prod_kernel, dim3(nblk), dim3(kGenNT), 0, c.stream, P);
+  P.in0 = DI; P.in1 = nullptr; P.out0 = V;
+  SRST_LAUNCH(gen_bwd_gh_kernel, dim3(nblk), dim3(kGenNT), 0, c.stream, P);
+  P.in0 = V; P.in1 = c.grad_out; P.out0 = c.d_img;
+  SRST_LAUNCH(gen_bwd_gv_kernel, dim3(nblk), dim3(kGenNT), 0, c.stream, P);
+  return (int)cudaGetLastError();
+}
+
 static int st_dispatch(const StCall& c, bool forward) {
   const int rg = c.rs <= 2 ? 2 : 4;
   const int rk = c.rk <= 4 ? 4 : (c.rk <= 8 ? 8 : 12);
@@ -491,12 +587,13 @@ int srst_st_forward(const float* sr, const float* hr, int B, int H, int W, const
   c.vec4 = (W % 4 == 0 && aligned16(sr) && aligned16(hr) && (!ds_sr || aligned16(ds_sr)) &&
             (!ds_hr || aligned16(ds_hr)) && (!ixy_sr || aligned16(ixy_sr)) && (!ixy_hr || aligned16(ixy_hr))) ? 1 : 0;
   c.workspace = workspace; c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;
+  if (!st_compiled(r_sigma, r_rho)) return st_forward_generic(c, workspace_bytes);
   return st_dispatch(c, true);
 }
 
-int srst_st_backward(const float* ixy, const float* ds, const float* grad_out, int B, int H, int W,
-                     const float* g, const float* dg, int r_sigma, const float* k, int r_rho, float* d_img,
-                     void* stream) {
+int srst_st_backward_ws(const float* ixy, const float* ds, const float* grad_out, int B, int H, int W,
+                        const float* g, const float* dg, int r_sigma, const float* k, int r_rho, float* d_img,
+                        void* workspace, size_t workspace_bytes, void* stream) {
   if (!ixy || !ds || !grad_out || !g || !dg || !k || !d_img || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
   if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
   StCall c;
@@ -504,14 +601,21 @@ int srst_st_backward(const float* ixy, const float* ds, const float* grad_out, i
   c.B = B; c.H = H; c.W = W;
   c.vec4 = (W % 4 == 0 && aligned16(d_img) && aligned16(ds)) ? 1 : 0;
   c.g = g; c.dg = dg; c.k = k; c.rs = r_sigma; c.rk = r_rho; c.stream = stream;
+  if (!st_compiled(r_sigma, r_rho)) return st_backward_generic(c, workspace, workspace_bytes);
   return st_dispatch(c, false);
+}
+
+int srst_st_backward(const float* ixy, const float* ds, const float* grad_out, int B, int H, int W,
+                     const float* g, const float* dg, int r_sigma, const float* k, int r_rho, float* d_img,
+                     void* stream) {
+  return srst_st_backward_ws(ixy, ds, grad_out, B, H, W, g, dg, r_sigma, k, r_rho, d_img, nullptr, 0, stream);
 }
 
 int srst_stpx_forward(const float* sr, const float* hr, int B, int H, int W, const float* g, const float* dg,
                       int r_sigma, const float* k, int r_rho, int normalize, float eps, float* loss2_out, float* ds_sr,
                       float* ixy_sr, void* workspace, size_t workspace_bytes, void* stream) {
   if (!sr || !hr || !g || !dg || !k || !loss2_out || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
-  if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
+  if (!st_compiled(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;  // the generic-radius path has no fused / feature variant
   if (!workspace || !aligned16(workspace) || workspace_bytes < srst_st_workspace_bytes(B, H, W))
     return SRST_E_WORKSPACE;
   StCall c;
@@ -528,7 +632,7 @@ int srst_stpx_backward(const float* sr, const float* hr, const float* ixy, const
                        const float* k, int r_rho, float* d_sr, void* stream) {
   if (!sr || !hr || !ixy || !ds || !grad_st || !grad_px || !g || !dg || !k || !d_sr || B <= 0 || H <= 0 || W <= 0)
     return SRST_E_INVALID;
-  if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
+  if (!st_compiled(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;  // the generic-radius path has no fused / feature variant
   StCall c;
   c.ixy = ixy; c.ds = ds; c.grad_out = grad_st; c.d_img = d_sr; c.px_img = sr; c.px_other = hr; c.grad_px = grad_px;
   c.B = B; c.H = H; c.W = W;
@@ -566,7 +670,7 @@ extern "C" int srst_st_features(const float* img, int B, int H, int W, const flo
                                 float* coher_out, void* stream) {
   if (!img || !g || !dg || !k || B <= 0 || H <= 0 || W <= 0) return SRST_E_INVALID;
   if (!J_out && !eig_out && !orient_out && !coher_out) return SRST_E_INVALID;
-  if (!srst_st_supported(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;
+  if (!st_compiled(r_sigma, r_rho)) return SRST_E_UNSUPPORTED;  // the generic-radius path has no fused / feature variant
   const int vec4 = (W % 4 == 0 && aligned16(img)) ? 1 : 0;
   const int rg = r_sigma <= 2 ? 2 : 4;
   const int rk = r_rho <= 4 ? 4 : (r_rho <= 8 ? 8 : 12);

@@ -71,16 +71,18 @@ def _raw_stream(device: torch.device) -> int:
     return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
 
 
-_SIZES: Dict[Tuple[int, int, int], Tuple[int, int, int]] = {}
+_SIZES: Dict[Tuple[int, int, int, int, int], Tuple[int, int, int, int]] = {}
 
 
-def _st_sizes(B: int, H: int, W: int) -> Tuple[int, int, int]:
-    """(ds floats padded to 16 bytes, ixy floats, workspace bytes) of a [B,3,H,W] problem, cached per shape."""
-    key = (B, H, W)
+def _st_sizes(B: int, H: int, W: int, rs: int = 2, rk: int = 8) -> Tuple[int, int, int, int]:
+    """(ds floats padded to 16 bytes, ixy floats, forward workspace bytes, backward workspace bytes) of a
+    [B,3,H,W] problem with filter radii (rs, rk), cached per shape.  The last one is 0 for the compiled classes."""
+    key = (B, H, W, rs, rk)
     v = _SIZES.get(key)
     if v is None:
         lib = _cabi.lib()
-        v = ((B * 3 * H * W + 3) // 4 * 4, lib.srst_st_ixy_floats(B, H, W), lib.srst_st_workspace_bytes(B, H, W))
+        v = ((B * 3 * H * W + 3) // 4 * 4, lib.srst_st_ixy_floats(B, H, W), lib.srst_st_workspace_bytes_r(B, H, W, rs, rk),
+             lib.srst_st_backward_workspace_bytes(B, H, W, rs, rk))
         _SIZES[key] = v
     return v
 
@@ -106,20 +108,27 @@ class _on_device:
 _ST_TAPS: Dict[Tuple[float, float], tuple] = {}
 
 
-def _st_taps(sigma: float, rho: float, who: str):
-    """(g*, dg*, r_sigma, k*, r_rho) as ready-made ctypes arguments, cached per (sigma, rho); raises for
-    radii outside the compiled classes."""
+def _st_taps(sigma: float, rho: float, who: str, compiled_only: bool = False):
+    """(g*, dg*, r_sigma, k*, r_rho, arrays, generic) as ready-made ctypes arguments, cached per (sigma, rho).
+    `generic` is True for radii beyond the compiled shared-memory classes (r_sigma > 4 or r_rho > 12, i.e.
+    sigma > 1.1 or rho > 3.1): they run on the library's generic-radius path, which needs scratch planes in the
+    workspace and has no fused Pixel / feature variant (`compiled_only`).  Radii above 64 raise."""
     key = (float(sigma), float(rho))
     t = _ST_TAPS.get(key)
     if t is None:
         g, dg = _taps.gaussian_taps(key[0])
         k, _ = _taps.gaussian_taps(key[1])
         rs, rk = len(g) // 2, len(k) // 2
-        if not _cabi.lib().srst_st_supported(rs, rk):
+        sup = _cabi.lib().srst_st_supported(rs, rk)
+        if not sup:
             raise NotImplementedError(
-                f"{who}: filter radii (sigma={sigma} -> {rs}, rho={rho} -> {rk}) are not compiled into libsrst.so")
-        t = (_taps.as_c(g), _taps.as_c(dg), rs, _taps.as_c(k), rk, (g, dg, k))  # keep the arrays alive
+                f"{who}: filter radii (sigma={sigma} -> {rs}, rho={rho} -> {rk}) exceed what libsrst.so handles (64)")
+        t = (_taps.as_c(g), _taps.as_c(dg), rs, _taps.as_c(k), rk, (g, dg, k), sup == 2)  # keep the arrays alive
         _ST_TAPS[key] = t
+    if compiled_only and t[6]:
+        raise NotImplementedError(
+            f"{who}: filter radii (sigma={sigma} -> {t[2]}, rho={rho} -> {t[4]}) are outside the compiled radius classes; "
+            "only StructureTensorLoss has a generic-radius path")
     return t
 
 
@@ -136,7 +145,7 @@ class _StructureTensorLossFn(torch.autograd.Function):
         B, _, H, W = sr.shape
         tp = _st_taps(sigma, rho, "StructureTensorLoss")
         need = ctx.needs_input_grad
-        n_ds, n_ixy, ws_bytes = _st_sizes(B, H, W)   # n_ds is padded: the ixy part stays 16-byte aligned
+        n_ds, n_ixy, ws_bytes, bws_bytes = _st_sizes(B, H, W, tp[2], tp[4])   # n_ds is padded: the ixy part stays 16-byte aligned
         with _on_device(sr.device):
             stream = _raw_stream(sr.device)
             loss = torch.empty((), dtype=torch.float32, device=sr.device)
@@ -150,14 +159,14 @@ class _StructureTensorLossFn(torch.autograd.Function):
         if rc:
             _cabi.check(rc, "srst_st_forward")
         ctx.save_for_backward(saved[0], saved[1])
-        ctx.meta = (tp, B, H, W, n_ds)
+        ctx.meta = (tp, B, H, W, n_ds, bws_bytes)
         return loss
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_out):
         lib = _cabi.lib()
-        tp, B, H, W, n_ds = ctx.meta
+        tp, B, H, W, n_ds, bws_bytes = ctx.meta
         if grad_out.dtype != torch.float32 or not grad_out.is_contiguous():
             grad_out = grad_out.to(torch.float32).contiguous()
         outs = [None, None]
@@ -168,8 +177,14 @@ class _StructureTensorLossFn(torch.autograd.Function):
                 if saved is None or not ctx.needs_input_grad[i]:
                     continue
                 d_img = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
-                rc = lib.srst_st_backward(saved.data_ptr() + 4 * n_ds, saved.data_ptr(), grad_out.data_ptr(), B, H, W,
-                                          tp[0], tp[1], tp[2], tp[3], tp[4], d_img.data_ptr(), stream)
+                if bws_bytes:  # generic-radius path: five scratch planes
+                    ws = _workspace("st_bwd", dev, stream, bws_bytes)
+                    rc = lib.srst_st_backward_ws(saved.data_ptr() + 4 * n_ds, saved.data_ptr(), grad_out.data_ptr(), B, H, W,
+                                                 tp[0], tp[1], tp[2], tp[3], tp[4], d_img.data_ptr(), ws.data_ptr(),
+                                                 ws.numel(), stream)
+                else:
+                    rc = lib.srst_st_backward(saved.data_ptr() + 4 * n_ds, saved.data_ptr(), grad_out.data_ptr(), B, H, W,
+                                              tp[0], tp[1], tp[2], tp[3], tp[4], d_img.data_ptr(), stream)
                 if rc:
                     _cabi.check(rc, "srst_st_backward")
                 outs[i] = d_img
@@ -215,7 +230,7 @@ def structure_tensor_features(img: torch.Tensor, sigma: float = 0.5, rho: float 
     lib = _cabi.lib()
     img = img.detach().contiguous()
     B, _, H, W = img.shape
-    tp = _st_taps(sigma, rho, "structure_tensor_features")
+    tp = _st_taps(sigma, rho, "structure_tensor_features", compiled_only=True)
     with _on_device(img.device):
         stream = _raw_stream(img.device)
         J = torch.empty((B, 3, H, W), dtype=torch.float32, device=img.device)
@@ -239,9 +254,9 @@ class _StructureTensorPixelLossFn(torch.autograd.Function):
         sr = sr.contiguous()
         hr = hr.contiguous()
         B, _, H, W = sr.shape
-        tp = _st_taps(sigma, rho, "StructureTensorPixelLoss")
+        tp = _st_taps(sigma, rho, "StructureTensorPixelLoss", compiled_only=True)
         need_sr = ctx.needs_input_grad[0]
-        n_ds, n_ixy, ws_bytes = _st_sizes(B, H, W)
+        n_ds, n_ixy, ws_bytes, _ = _st_sizes(B, H, W)
         with _on_device(sr.device):
             stream = _raw_stream(sr.device)
             both = torch.empty(2, dtype=torch.float32, device=sr.device)

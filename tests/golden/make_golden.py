@@ -56,6 +56,9 @@ ST_CASES = [
     ("st_rand_s1_r25_1x32x40", "rand", 1, 32, 40, 5, 1.0, 2.5, True),
     ("st_rand_nonorm_1x24x36", "rand", 1, 24, 36, 6, 0.5, 2.0, False),
     ("st_rand_ragged_1x37x53", "rand", 1, 37, 53, 7, 0.5, 2.0, True),
+    # radii beyond the compiled classes (r_sigma 6 / 8, r_rho 16 / 20): the generic-radius path
+    ("st_rand_s15_r4_1x40x52", "rand", 1, 40, 52, 8, 1.5, 4.0, True),
+    ("st_srlike_s2_r5_2x33x45", "srlike", 2, 33, 45, 9, 2.0, 5.0, True),
 ]
 
 BB_CASES = [

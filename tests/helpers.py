@@ -63,8 +63,14 @@ def emu_st(lib, sr, hr, taps, normalize=True, want_hr=False, grad_out=1.0):
     hr = np.ascontiguousarray(hr, np.float32)
     B, _, H, W = sr.shape
     g, dg, k = [np.ascontiguousarray(t, np.float32) for t in taps]
-    nb = lib.srst_st_workspace_bytes(B, H, W)
+    rs, rk = len(g) // 2, len(k) // 2
+    generic = lib.srst_st_supported(rs, rk) == 2   # radii beyond the compiled classes: scratch planes in the workspace
+    nb = lib.srst_st_workspace_bytes_r(B, H, W, rs, rk)
+    assert nb >= lib.srst_st_workspace_bytes(B, H, W) and (generic or nb == lib.srst_st_workspace_bytes(B, H, W))
     ws = np.zeros(nb // 4 + 4, np.float32)
+    nbb = lib.srst_st_backward_workspace_bytes(B, H, W, rs, rk)
+    assert (nbb > 0) == generic
+    bws = np.full(nbb // 4 + 4, np.nan, np.float32)
     loss = np.zeros(1, np.float32)
     n_ixy = lib.srst_st_ixy_floats(B, H, W)
     ds_sr = np.full_like(sr, np.nan)
@@ -76,18 +82,24 @@ def emu_st(lib, sr, hr, taps, normalize=True, want_hr=False, grad_out=1.0):
                              None)
     assert rc == 0, rc
     go = np.full(1, grad_out, np.float32)
-    out = dict(loss=float(loss[0]), ds_sr=ds_sr, ws=ws, ixy_sr=ixy_sr.reshape(B, 2, (H + 1) // 2, W, 2))
-    d_sr = np.full_like(sr, np.nan)
-    rc = lib.srst_st_backward(_p(ixy_sr), _p(ds_sr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
-                              len(k) // 2, _p(d_sr), None)
-    assert rc == 0, rc
-    out["d_sr"] = d_sr
-    if want_hr:
-        d_hr = np.full_like(sr, np.nan)
-        rc = lib.srst_st_backward(_p(ixy_hr), _p(ds_hr), _p(go), B, H, W, _fp(g), _fp(dg), len(g) // 2, _fp(k),
-                                  len(k) // 2, _p(d_hr), None)
+    # only the ticket header of the workspace is promised to come back zeroed (the generic path's planes are scratch)
+    out = dict(loss=float(loss[0]), ds_sr=ds_sr, ws=ws[:lib.srst_st_workspace_bytes(B, H, W) // 4] if not generic else ws[:4],
+               ixy_sr=ixy_sr.reshape(B, 2, (H + 1) // 2, W, 2))
+
+    def backward(ixy, ds):
+        d = np.full_like(sr, np.nan)
+        if generic:
+            assert lib.srst_st_backward(_p(ixy), _p(ds), _p(go), B, H, W, _fp(g), _fp(dg), rs, _fp(k), rk, _p(d), None) == -3
+            rc = lib.srst_st_backward_ws(_p(ixy), _p(ds), _p(go), B, H, W, _fp(g), _fp(dg), rs, _fp(k), rk, _p(d), _p(bws),
+                                         nbb, None)
+        else:
+            rc = lib.srst_st_backward(_p(ixy), _p(ds), _p(go), B, H, W, _fp(g), _fp(dg), rs, _fp(k), rk, _p(d), None)
         assert rc == 0, rc
-        out["d_hr"] = d_hr
+        return d
+
+    out["d_sr"] = backward(ixy_sr, ds_sr)
+    if want_hr:
+        out["d_hr"] = backward(ixy_hr, ds_hr)
     return out
 
 

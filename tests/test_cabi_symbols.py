@@ -38,7 +38,12 @@ def test_no_compute_entry_points_that_need_no_gpu():
     assert lib.srst_version() // 100 == _cabi.ABI_MAJOR == 2
     assert lib.srst_st_supported(2, 8) == 1
     assert lib.srst_st_supported(4, 12) == 1 and lib.srst_st_supported(1, 3) == 1   # padded radius classes
-    assert lib.srst_st_supported(5, 8) == 0 and lib.srst_st_supported(2, 13) == 0
+    assert lib.srst_st_supported(5, 8) == 2 and lib.srst_st_supported(2, 13) == 2   # generic-radius path
+    assert lib.srst_st_supported(65, 8) == 0 and lib.srst_st_supported(2, 65) == 0
+    assert lib.srst_st_workspace_bytes_r(16, 96, 96, 2, 8) == lib.srst_st_workspace_bytes(16, 96, 96)
+    assert lib.srst_st_workspace_bytes_r(16, 96, 96, 6, 16) > 11 * 16 * 96 * 96 * 4
+    assert lib.srst_st_backward_workspace_bytes(16, 96, 96, 2, 8) == 0
+    assert lib.srst_st_backward_workspace_bytes(16, 96, 96, 6, 16) >= 5 * 16 * 96 * 96 * 4
     assert lib.srst_st_workspace_bytes(16, 96, 96) >= 16 * 3 * 2 * 4
     assert lib.srst_st_workspace_bytes(0, 96, 96) == 0
     assert b"workspace" in lib.srst_error_string(-3)
@@ -49,6 +54,7 @@ def test_no_compute_entry_points_that_need_no_gpu():
     assert lib.srst_st_forward(None, None, 1, 8, 8, None, None, 2, None, 8, 1, 1e-12, None, None, None,
                                None, None, None, 0, None) == -1
     assert lib.srst_st_backward(None, None, None, 1, 8, 8, None, None, 2, None, 8, None, None) == -1
+    assert lib.srst_st_backward_ws(None, None, None, 1, 8, 8, None, None, 6, None, 16, None, None, 0, None) == -1
 
 
 def test_integration_md_binding_snippet_matches_the_abi():

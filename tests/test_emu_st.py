@@ -135,3 +135,42 @@ def test_emulated_tiny_and_degenerate_shapes(lib, shape):
     ref = O.st_loss(sr, hr, taps=taps, want_hr_grad=True)
     assert rel_err(out["loss"], ref["loss"]) < 1e-5
     assert maxnorm_err(out["d_sr"], ref["d_sr"]) < 1e-4 and maxnorm_err(out["d_hr"], ref["d_hr"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["st_rand_s15_r4_1x40x52", "st_srlike_s2_r5_2x33x45"])
+def test_emulated_generic_radius_matches_reference(lib, name):
+    """Radii beyond the compiled classes: the generic-radius kernels (st_generic.cuh) against the reference's outputs
+    and the fp64 oracle, both gradients, through srst_st_workspace_bytes_r / srst_st_backward_ws."""
+    z = golden(name)
+    taps = (z["g"], z["dg"], z["k"])
+    assert lib.srst_st_supported(len(z["g"]) // 2, len(z["k"]) // 2) == 2
+    out = emu_st(lib, z["sr"], z["hr"], taps, want_hr=True)
+    ref = O.st_loss(z["sr"], z["hr"], taps=taps, want_hr_grad=True)
+    assert rel_err(out["loss"], z["loss"]) < 1e-5 and rel_err(out["loss"], ref["loss"]) < 1e-5
+    for ours, orc, refg in ((out["d_sr"], ref["d_sr"], z["d_sr"]), (out["d_hr"], ref["d_hr"], z["d_hr"])):
+        assert maxnorm_err(ours, orc) < 1e-4
+        assert maxnorm_err(ours, refg) < 1e-4 + maxnorm_err(refg, orc)
+    assert np.all(out["ws"] == 0)   # ticket header handed back zeroed
+
+
+@pytest.mark.parametrize("sigma,rho,shape", [(2.0, 2.0, (1, 20, 28)), (0.5, 4.0, (2, 17, 19)), (3.0, 8.0, (1, 9, 13))])
+def test_emulated_generic_radius_one_sided_and_larger_than_image(lib, sigma, rho, shape):
+    rng = np.random.default_rng(int(10 * sigma + rho))
+    sr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+    hr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+    taps = (*O.gaussian_taps(sigma, True), O.gaussian_taps(rho))
+    out = emu_st(lib, sr, hr, taps, want_hr=True, grad_out=-0.5)
+    ref = O.st_loss(sr, hr, taps=taps, want_hr_grad=True)
+    assert rel_err(out["loss"], ref["loss"]) < 1e-5
+    assert maxnorm_err(out["d_sr"], -0.5 * ref["d_sr"]) < 1e-4 and maxnorm_err(out["d_hr"], -0.5 * ref["d_hr"]) < 1e-4
+
+
+def test_generic_radius_limits_and_workspace_sizes(lib):
+    assert lib.srst_st_supported(2, 8) == 1 and lib.srst_st_supported(4, 12) == 1
+    assert lib.srst_st_supported(5, 8) == 2 and lib.srst_st_supported(2, 13) == 2 and lib.srst_st_supported(64, 64) == 2
+    assert lib.srst_st_supported(65, 8) == 0 and lib.srst_st_supported(2, 65) == 0 and lib.srst_st_supported(0, 8) == 0
+    base = lib.srst_st_workspace_bytes(2, 30, 40)
+    assert lib.srst_st_workspace_bytes_r(2, 30, 40, 2, 8) == base and lib.srst_st_backward_workspace_bytes(2, 30, 40, 2, 8) == 0
+    assert lib.srst_st_workspace_bytes_r(2, 30, 40, 6, 16) >= base + 11 * 2 * 30 * 40 * 4
+    assert lib.srst_st_backward_workspace_bytes(2, 30, 40, 6, 16) >= 5 * 2 * 30 * 40 * 4
+    assert lib.srst_st_workspace_bytes_r(2, 30, 40, 65, 16) == 0

@@ -17,7 +17,8 @@ from tests.helpers import golden, golden_names, maxnorm_err, rel_err
 
 pytestmark = pytest.mark.gpu
 
-DEFAULT_CASES = [n for n in golden_names("st_") if "s1_r25" not in n]
+DEFAULT_CASES = [n for n in golden_names("st_") if "s1_r25" not in n and "s15_r4" not in n and "s2_r5" not in n]
+GENERIC_CASES = [("st_rand_s15_r4_1x40x52", 1.5, 4.0), ("st_srlike_s2_r5_2x33x45", 2.0, 5.0)]
 
 
 def _run(sr, hr, normalize=True, want_hr=True, sigma=0.5, rho=2.0):
@@ -204,10 +205,45 @@ def test_golden_sigma1_rho25_matches_reference():
     assert maxnorm_err(d_sr, z["d_sr"]) < 1e-4 + maxnorm_err(z["d_sr"], ref["d_sr"])
 
 
-def test_unsupported_radius_raises():
+@pytest.mark.parametrize("name,sigma,rho", GENERIC_CASES)
+def test_generic_radius_golden_matches_reference(name, sigma, rho):
+    """Radii beyond the compiled classes (utils.py:198 is unbounded) run on the generic-radius path: reference
+    outputs, fp64 oracle, both gradients."""
+    z = golden(name)
+    loss, d_sr, d_hr = _run(z["sr"], z["hr"], sigma=sigma, rho=rho)
+    ref = O.st_loss(z["sr"], z["hr"], taps=(z["g"], z["dg"], z["k"]), want_hr_grad=True)
+    assert rel_err(loss, z["loss"]) < 1e-5 and rel_err(loss, ref["loss"]) < 1e-5
+    for ours, orc, refg in ((d_sr, ref["d_sr"], z["d_sr"]), (d_hr, ref["d_hr"], z["d_hr"])):
+        assert maxnorm_err(ours, orc) < 1e-4, "grad vs fp64 oracle"
+        assert maxnorm_err(ours, refg) < 1e-4 + maxnorm_err(refg, orc), "grad vs reference"
+
+
+@pytest.mark.parametrize("sigma,rho,shape", [(2.0, 2.0, (2, 100, 152)), (0.5, 4.0, (1, 96, 96)), (3.0, 8.0, (1, 37, 53)),
+                                             (1.5, 16.0, (1, 130, 70))])
+def test_generic_radius_matches_oracle(sigma, rho, shape):
+    """Either radius alone beyond its class, radii larger than the image, the largest radius (rho = 16 -> 64)."""
+    rng = np.random.default_rng(int(10 * sigma + rho))
+    sr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+    hr = rng.random((shape[0], 3, shape[1], shape[2]), dtype=np.float32)
+    loss, d_sr, d_hr = _run(sr, hr, sigma=sigma, rho=rho)
+    ref = O.st_loss(sr, hr, sigma=sigma, rho=rho, want_hr_grad=True)
+    assert rel_err(loss, ref["loss"]) < 1e-5
+    assert maxnorm_err(d_sr, ref["d_sr"]) < 1e-4 and maxnorm_err(d_hr, ref["d_hr"]) < 1e-4
+    # no gradient wanted: nothing saved, same loss; and a second call re-uses the cached workspace
     from srgan_st_b200 import StructureTensorLoss
+    with torch.no_grad():
+        l2 = StructureTensorLoss(sigma=sigma, rho=rho)(torch.from_numpy(sr).cuda(), torch.from_numpy(hr).cuda())
+    assert l2.item() == loss
+
+
+def test_unsupported_radius_raises():
+    from srgan_st_b200 import StructureTensorLoss, StructureTensorPixelLoss, structure_tensor_features
     a = torch.rand(1, 3, 32, 32, device="cuda")
     with pytest.raises(NotImplementedError):
-        StructureTensorLoss(sigma=2.0)(a, a)      # radius 8 > 4
+        StructureTensorLoss(sigma=17.0)(a, a)     # radius 68 > 64
     with pytest.raises(NotImplementedError):
-        StructureTensorLoss(rho=4.0)(a, a)        # radius 16 > 12
+        StructureTensorLoss(rho=16.2)(a, a)       # radius 65 > 64
+    with pytest.raises(NotImplementedError):
+        StructureTensorPixelLoss(rho=4.0)(a, a)   # the fused variant exists for the compiled classes only
+    with pytest.raises(NotImplementedError):
+        structure_tensor_features(a, sigma=2.0)
