@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRST_VERSION 202 /* major*100 + minor: the major number changes whenever an argument list changes */
+#define SRST_VERSION 203 /* major*100 + minor: the major number changes whenever an argument list changes */
 
 #define SRST_E_INVALID (-1)     /* null pointer / non-positive size / bad enum */
 #define SRST_E_UNSUPPORTED (-2) /* filter radius or patch geometry not compiled in */
@@ -239,6 +239,21 @@ int srst_pst_backward(const float* sr, const float* gt, const float* gt2, const 
                       const float* g, const float* dg, int r_sigma, const float* k, int r_rho,
                       int criterion,
                       float* d_sr, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradient w.r.t. gt of the three patch losses: the reference's gather of the selected candidates is differentiable
+ * in p2_cat (loss.py:136-139, :219-222, :369-371), so a gt that requires grad receives, per query, minus the SR-side
+ * criterion gradient pushed through the descriptor of the SELECTED candidate, accumulated over the queries that chose
+ * it, and folded back through the bicubic pyramid taps for candidates of the two coarse levels.
+ *   mode: 0 = BestBuddyLoss, 1 = GramLoss, 2 = PatchwiseStructureTensorLoss (g, dg, k as for srst_pst_forward;
+ *         ignored, may be NULL, for modes 0 and 1).
+ *   d_gt [B,3,H,W] is overwritten.  Workspace: srst_bb_workspace_bytes (always required).  Sums over queries use
+ *   atomicAdd: the result can differ in the last bits from run to run. */
+int srst_patch_backward_gt(int mode, const float* sr, const float* gt, const float* gt2, const float* gt4,
+                           const int64_t* idx, const float* grad_out,
+                           int B, int H, int W,
+                           const float* g, const float* dg, int r_sigma, const float* k, int r_rho,
+                           int criterion,
+                           float* d_gt, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The HR pyramid on its own (exposed for tests): out2 [B,3,H/2,W/2], out4 [B,3,H/4,W/4]. */
 int srst_bb_pyramid(const float* gt, int B, int H, int W, float* out2, float* out4, void* stream);

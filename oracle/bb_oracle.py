@@ -231,3 +231,62 @@ def pst_backward(sr, sel_desc, taps, criterion="l1"):
     out = np.zeros_like(sr)
     out[:, :, :ny * 3, :nx * 3] = dF.reshape(B, ny, nx, C, 3, 3).transpose(0, 3, 1, 4, 2, 5).reshape(B, C, ny * 3, nx * 3)
     return out
+
+
+# ---- gradient w.r.t. gt (loss.py:136-139: the gather of the selected candidates is differentiable in p2_cat) ----
+def _fold3(p, H, W):
+    """inverse of unfold3 for non-overlapping 3x3 patches: [B,N,27] -> [B,3,H,W] (pixels outside every patch = 0)."""
+    B = p.shape[0]
+    ny, nx = H // 3, W // 3
+    out = np.zeros((B, 3, H, W), p.dtype)
+    out[:, :, :ny * 3, :nx * 3] = p.reshape(B, ny, nx, 3, 3, 3).transpose(0, 3, 1, 4, 2, 5).reshape(B, 3, ny * 3, nx * 3)
+    return out
+
+
+def _bicubic_adjoint(d, H, W, scale):
+    """adjoint of F.interpolate(gt, scale_factor=1/scale, mode='bicubic', align_corners=False) for scale 2 or 4:
+    taps (-0.09375, 0.59375, 0.59375, -0.09375) on source rows / columns 2i-1..2i+2 (x1/2) or 4i..4i+3 (x1/4), indices
+    clamped to the image (bb_oracle.c pyramid, F.interpolate)."""
+    w = np.array([-0.09375, 0.59375, 0.59375, -0.09375])
+    B, C, Ho, Wo = d.shape
+    out = np.zeros((B, C, H, W), np.float64)
+    ys = np.arange(Ho)[:, None] * scale + (0 if scale == 4 else -1) + np.arange(4)[None, :]
+    xs = np.arange(Wo)[:, None] * scale + (0 if scale == 4 else -1) + np.arange(4)[None, :]
+    ys, xs = np.clip(ys, 0, H - 1), np.clip(xs, 0, W - 1)
+    for i in range(4):
+        for k in range(4):
+            np.add.at(out, (slice(None), slice(None), ys[:, i][:, None], xs[:, k][None, :]), d * (w[i] * w[k]))
+    return out
+
+
+def patch_backward_gt(sr, gt, gt2, gt4, idx, mode="patch", taps=None, criterion="l1"):
+    """d loss / d gt of BestBuddyLoss / GramLoss / PatchwiseStructureTensorLoss given the argmin indices [B,N]
+    (float64).  The final criterion is symmetric, so the gradient w.r.t. a selected candidate is the SR-side formula
+    (bb_backward / gram_backward / pst_backward) with the two operands swapped; it is accumulated over the queries
+    that selected the candidate and folded back through the pyramid."""
+    sr = np.asarray(sr, np.float64)
+    gt = np.asarray(gt, np.float64)
+    gt2 = np.asarray(gt2, np.float64)
+    gt4 = np.asarray(gt4, np.float64)
+    B, _, H, W = sr.shape
+    ny, nx = H // 3, W // 3
+    N = ny * nx
+    cat = np.concatenate([unfold3(gt), unfold3(gt2), unfold3(gt4)], 1)             # [B,M,27] candidate patches
+    sel = np.take_along_axis(cat, idx[:, :, None].astype(np.int64), 1)            # [B,N,27]
+    sel_img = _fold3(sel, 3 * ny, 3 * nx)                                          # the selected candidates as an image
+    sr_c = sr[:, :, :3 * ny, :3 * nx]
+    if mode == "patch":
+        g_img = bb_backward(sel_img, unfold3(sr_c), criterion)
+    elif mode == "gram":
+        g_img = gram_backward(sel_img, gram_descriptors(sr_c), criterion)
+    else:
+        g_img = pst_backward(sel_img, pst_descriptors(sr_c, taps), taps, criterion)
+    g_sel = unfold3(g_img)                                                         # [B,N,27] per-query candidate gradients
+    g_cat = np.zeros_like(cat)
+    for b in range(B):
+        np.add.at(g_cat[b], idx[b], g_sel[b])
+    N0, N2 = N, (gt2.shape[2] // 3) * (gt2.shape[3] // 3)
+    d0 = _fold3(g_cat[:, :N0], H, W)
+    d2 = _fold3(g_cat[:, N0:N0 + N2], gt2.shape[2], gt2.shape[3])
+    d4 = _fold3(g_cat[:, N0 + N2:], gt4.shape[2], gt4.shape[3])
+    return d0 + _bicubic_adjoint(d2, H, W, 2) + _bicubic_adjoint(d4, H, W, 4)

@@ -64,6 +64,9 @@ SIGNATURES = {
     "srst_pst_backward": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
                                          ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
+    "srst_patch_backward_gt": (ctypes.c_int, [ctypes.c_int, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              c_float_p, c_float_p, ctypes.c_int, c_float_p, ctypes.c_int,
+                                              ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
     "srst_bb_pyramid": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
 }
 

@@ -841,25 +841,117 @@ bb_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt, c
   d_sr[t] = out;
 }
 
+// ---- gradient w.r.t. gt (loss.py:136-139: the gather of the selected candidates is differentiable in p2_cat) ----
+// The final criterion is symmetric in its two arguments, so d/d(candidate) is the SR-side formula with the roles of
+// the SR patch and the selected candidate swapped.  Several queries may select the same candidate: the 27 values of a
+// query are accumulated with atomicAdd into the gradient image of the candidate's pyramid level (level 0 = d_gt
+// itself), and bb_pyramid_adjoint_kernel then folds the two coarse levels back through the bicubic taps.
+struct BbLevel { float* img; int H, W, nx, p; };
+SRST_DEV BbLevel bb_locate(const BbGeom& g, int b, int j, float* d0, float* d2, float* d4) {
+  BbLevel L;
+  if (j < g.N0) { L.img = d0 + (size_t)b * 3 * g.H * g.W; L.H = g.H; L.W = g.W; L.nx = g.n0x; L.p = j; }
+  else if (j < g.N0 + g.N2) { L.img = d2 + (size_t)b * 3 * g.H2 * g.W2; L.H = g.H2; L.W = g.W2; L.nx = g.n2x; L.p = j - g.N0; }
+  else { L.img = d4 + (size_t)b * 3 * g.H4 * g.W4; L.H = g.H4; L.W = g.W4; L.nx = g.n4x; L.p = j - g.N0 - g.N2; }
+  return L;
+}
+SRST_DEV void bb_read_candidate(const float* gt, const float* gt2, const float* gt4, const BbGeom& g, int b, int j,
+                                float (&w)[BB_D]) {
+  if (j < g.N0) bb_read_patch(gt + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, j, w);
+  else if (j < g.N0 + g.N2) bb_read_patch(gt2 + (size_t)b * 3 * g.H2 * g.W2, g.H2, g.W2, g.n2x, j - g.N0, w);
+  else bb_read_patch(gt4 + (size_t)b * 3 * g.H4 * g.W4, g.H4, g.W4, g.n4x, j - g.N0 - g.N2, w);
+}
+// element c*9 + ky*3 + kx of `v` is added to pixel (c, 3 py + ky, 3 px + kx) of the level image
+SRST_DEV void bb_scatter_add_patch(const BbLevel& L, const float (&v)[BB_D]) {
+  const int py = L.p / L.nx, px = L.p - py * L.nx;
+#pragma unroll
+  for (int e = 0; e < BB_D; ++e) {
+    const int c = e / 9, ky = (e % 9) / 3, kx = e % 3;
+    atomicAdd(L.img + ((size_t)c * L.H + 3 * py + ky) * L.W + 3 * px + kx, v[e]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bb_fill_zero_kernel(float* __restrict__ p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
+}
+
+// BestBuddyLoss: one thread per query patch
+__global__ void __launch_bounds__(256)
+bb_backward_gt_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const float* __restrict__ gt2,
+                      const float* __restrict__ gt4, const int64_t* __restrict__ idx, const float* __restrict__ grad_out,
+                      BbGeom g, int criterion, float* __restrict__ d0, float* __restrict__ d2, float* __restrict__ d4) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)g.B * g.N) return;
+  const int b = (int)(t / g.N), i = (int)(t - (size_t)b * g.N);
+  const int j = (int)idx[t];
+  float v[BB_D], w[BB_D];
+  bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, i, v);
+  bb_read_candidate(gt, gt2, gt4, g, b, j, w);
+  const float scale = __ldg(grad_out) / ((float)g.B * (float)g.N * (float)BB_D);
+#pragma unroll
+  for (int e = 0; e < BB_D; ++e) {
+    const float d = w[e] - v[e];
+    w[e] = (criterion == 0) ? ((d > 0.f) ? scale : ((d < 0.f) ? -scale : 0.f)) : 2.0f * d * scale;
+  }
+  bb_scatter_add_patch(bb_locate(g, b, j, d0, d2, d4), w);
+}
+
+// Adjoint of bb_pyramid_kernel: every element of the two coarse gradient images is spread over its 4x4 source
+// taps (same constants, same clamped indices) into d_gt.
+__global__ void __launch_bounds__(256)
+bb_pyramid_adjoint_kernel(const float* __restrict__ d2, const float* __restrict__ d4, float* __restrict__ d_gt, int planes,
+                          int H, int W, int H2, int W2, int H4, int W4) {
+  const size_t n2 = (size_t)planes * H2 * W2, n4 = (size_t)planes * H4 * W4;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n2 + n4) return;
+  const bool lvl4 = t >= n2;
+  const size_t u = lvl4 ? t - n2 : t;
+  const float gv = lvl4 ? d4[u] : d2[u];
+  if (gv == 0.f) return;
+  const int Ho = lvl4 ? H4 : H2, Wo = lvl4 ? W4 : W2;
+  const int x = (int)(u % Wo);
+  const int y = (int)((u / Wo) % Ho);
+  const int pl = (int)(u / ((size_t)Wo * Ho));
+  const int sy = lvl4 ? 4 * y : 2 * y - 1;
+  const int sx = lvl4 ? 4 * x : 2 * x - 1;
+  float* dst = d_gt + (size_t)pl * H * W;
+  const float wt[4] = {-0.09375f, 0.59375f, 0.59375f, -0.09375f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int yy = min(max(sy + i, 0), H - 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xx = min(max(sx + k, 0), W - 1);
+      atomicAdd(dst + (size_t)yy * W + xx, gv * (wt[i] * wt[k]));
+    }
+  }
+}
+
 // ---- GramLoss backward --------------------------------------------------------------------------
 // loss = mean over B*N*9 of |G1 - Gsel| (or squared); G1 = F F^T / 27 of the SR patch.
 //   dL/dG1[a][b] = scale * sign(G1 - Gsel)[a][b]                 (or 2*diff)
 //   dL/dF[a][s]  = sum_b (dG[a][b] + dG[b][a]) F[b][s] / 27
 // One thread per patch; every pixel covered by a patch belongs to exactly one, the rest stay 0.
+// TO_GT: the same formula with the roles swapped (v = the selected candidate, differentiated; w = the SR patch), the
+// result accumulated into the candidate's level image (d_sr = level 0 = d_gt, d2, d4).
+template <bool TO_GT = false>
 __global__ void __launch_bounds__(256)
 gram_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const float* __restrict__ gt2,
                      const float* __restrict__ gt4, const int64_t* __restrict__ idx, const float* __restrict__ grad_out,
-                     BbGeom g, int criterion, float* __restrict__ d_sr) {
+                     BbGeom g, int criterion, float* __restrict__ d_sr, float* __restrict__ d2 = nullptr,
+                     float* __restrict__ d4 = nullptr) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)g.B * g.N) return;
   const int b = (int)(t / g.N), i = (int)(t - (size_t)b * g.N);
   float v[BB_D], w[BB_D], g1[9], gs[9];
-  bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, i, v);
-  bb_gram(v, g1);
   const int j = (int)idx[t];
-  if (j < g.N0) bb_read_patch(gt + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, j, w);
-  else if (j < g.N0 + g.N2) bb_read_patch(gt2 + (size_t)b * 3 * g.H2 * g.W2, g.H2, g.W2, g.n2x, j - g.N0, w);
-  else bb_read_patch(gt4 + (size_t)b * 3 * g.H4 * g.W4, g.H4, g.W4, g.n4x, j - g.N0 - g.N2, w);
+  if constexpr (TO_GT) {
+    bb_read_candidate(gt, gt2, gt4, g, b, j, v);
+    bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, i, w);
+  } else {
+    bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, i, v);
+    bb_read_candidate(gt, gt2, gt4, g, b, j, w);
+  }
+  bb_gram(v, g1);
   bb_gram(w, gs);
   const float scale = __ldg(grad_out) / ((float)g.B * (float)g.N * 9.0f);
   float dG[9];
@@ -870,6 +962,7 @@ gram_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt,
   }
   const int py = i / g.n0x, px = i - py * g.n0x;
   float* o = d_sr + (size_t)b * 3 * g.H * g.W;
+  [[maybe_unused]] float outv[BB_D];
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -877,8 +970,10 @@ gram_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt,
       float acc = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) acc = fmaf(dG[a * 3 + c] + dG[c * 3 + a], v[c * 9 + s9], acc);
-      o[((size_t)a * g.H + 3 * py + s9 / 3) * g.W + 3 * px + s9 % 3] = acc / 27.0f;
+      if constexpr (TO_GT) outv[a * 9 + s9] = acc / 27.0f;
+      else o[((size_t)a * g.H + 3 * py + s9 / 3) * g.W + 3 * px + s9 % 3] = acc / 27.0f;
     }
+  if constexpr (TO_GT) bb_scatter_add_patch(bb_locate(g, b, j, d_sr, d2, d4), outv);
 }
 
 // ---- PatchwiseStructureTensorLoss backward ------------------------------------------------------
@@ -887,20 +982,25 @@ gram_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt,
 //   dJxx = dDxx/q + ddet*Jyy , dJyy = dDyy/q + ddet*Jxx , dJxy = dDxy/q - 2 ddet*Jxy
 // then the adjoint 3x3 smoothing, the product rule dIx = 2 Ix dPxx + Iy dPxy, dIy = 2 Iy dPyy + Ix dPxy,
 // the adjoint derivative filters and the grayscale weights.  One thread per patch.
+template <bool TO_GT = false>  // TO_GT: roles swapped and scatter-add into the candidate's level image, as in gram_backward_kernel
 __global__ void __launch_bounds__(128)
 pst_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const float* __restrict__ gt2,
                     const float* __restrict__ gt4, const int64_t* __restrict__ idx, const float* __restrict__ grad_out,
-                    BbGeom g, PstTaps tp, int criterion, float* __restrict__ d_sr) {
+                    BbGeom g, PstTaps tp, int criterion, float* __restrict__ d_sr, float* __restrict__ d2 = nullptr,
+                    float* __restrict__ d4 = nullptr) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)g.B * g.N) return;
   const int b = (int)(t / g.N), i = (int)(t - (size_t)b * g.N);
   float v[BB_D], w[BB_D], dsel[BB_D];
   const int j = (int)idx[t];
-  if (j < g.N0) bb_read_patch(gt + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, j, w);
-  else if (j < g.N0 + g.N2) bb_read_patch(gt2 + (size_t)b * 3 * g.H2 * g.W2, g.H2, g.W2, g.n2x, j - g.N0, w);
-  else bb_read_patch(gt4 + (size_t)b * 3 * g.H4 * g.W4, g.H4, g.W4, g.n4x, j - g.N0 - g.N2, w);
+  if constexpr (TO_GT) {
+    bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, i, w);
+    bb_read_candidate(gt, gt2, gt4, g, b, j, v);
+  } else {
+    bb_read_candidate(gt, gt2, gt4, g, b, j, w);
+    bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, i, v);
+  }
   pst_descriptor(w, tp, dsel);
-  bb_read_patch(sr + (size_t)b * 3 * g.H * g.W, g.H, g.W, g.n0x, i, v);
   PstState S;
   pst_state(v, tp, S);
   const float scale = __ldg(grad_out) / ((float)g.B * (float)g.N * (float)BB_D);
@@ -937,11 +1037,15 @@ pst_backward_kernel(const float* __restrict__ sr, const float* __restrict__ gt, 
   const int py = i / g.n0x, px = i - py * g.n0x;
   float* o = d_sr + (size_t)b * 3 * g.H * g.W;
   const float coef[3] = {kGrayR, kGrayG, kGrayB};
+  [[maybe_unused]] float outv[BB_D];
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int p = 0; p < 9; ++p)
-      o[((size_t)c * g.H + 3 * py + p / 3) * g.W + 3 * px + p % 3] = coef[c] * (ga[p] + gb[p]);
+    for (int p = 0; p < 9; ++p) {
+      if constexpr (TO_GT) outv[c * 9 + p] = coef[c] * (ga[p] + gb[p]);
+      else o[((size_t)c * g.H + 3 * py + p / 3) * g.W + 3 * px + p % 3] = coef[c] * (ga[p] + gb[p]);
+    }
+  if constexpr (TO_GT) bb_scatter_add_patch(bb_locate(g, b, j, d_sr, d2, d4), outv);
 }
 
 }  // namespace srst

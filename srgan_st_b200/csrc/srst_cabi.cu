@@ -819,8 +819,8 @@ int srst_pst_backward(const float* sr, const float* gt, const float* gt2, const 
 #endif
   }
   const size_t total = (size_t)B * gm.N;
-  SRST_LAUNCH(pst_backward_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, stream, sr, gt, gt2, gt4, idx,
-              grad_out, gm, tp, criterion, d_sr);
+  SRST_LAUNCH(pst_backward_kernel<false>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, stream, sr, gt, gt2, gt4, idx,
+              grad_out, gm, tp, criterion, d_sr, nullptr, nullptr);
   return (int)cudaGetLastError();
 }
 
@@ -850,8 +850,54 @@ int srst_gram_backward(const float* sr, const float* gt, const float* gt2, const
 #endif
   }
   const size_t total = (size_t)B * g.N;
-  SRST_LAUNCH(gram_backward_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, sr, gt, gt2, gt4, idx,
-              grad_out, g, criterion, d_sr);
+  SRST_LAUNCH(gram_backward_kernel<false>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, sr, gt, gt2, gt4, idx,
+              grad_out, g, criterion, d_sr, nullptr, nullptr);
+  return (int)cudaGetLastError();
+}
+
+int srst_patch_backward_gt(int mode, const float* sr, const float* gt, const float* gt2, const float* gt4,
+                           const int64_t* idx, const float* grad_out, int B, int H, int W, const float* g, const float* dg,
+                           int r_sigma, const float* k, int r_rho, int criterion, float* d_gt, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (!sr || !gt || !idx || !grad_out || !d_gt || B <= 0 || mode < 0 || mode > 2) return SRST_E_INVALID;
+  criterion &= ~SRST_BB_DIST_L1;  // the search norm does not matter to the backward
+  if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
+  if (H < 12 || W < 12 || B > 65535) return SRST_E_SHAPE;
+  if ((gt2 == nullptr) != (gt4 == nullptr)) return SRST_E_INVALID;
+  PstTaps tp = {};
+  int e;
+  if (mode == 2) {
+    if (!g || !dg || !k) return SRST_E_INVALID;
+    if ((e = pst_taps(g, dg, r_sigma, k, r_rho, tp)) != 0) return e;
+  }
+  const BbGeom gm = bb_geom(B, H, W);
+  if (!workspace || !aligned16(workspace)) return SRST_E_WORKSPACE;
+  const BbWorkspace w = bb_carve(workspace, gm);
+  if (workspace_bytes < w.total_bytes) return SRST_E_WORKSPACE;
+  if (!gt2) {
+    if ((e = bb_launch_pyramid(gt, gm, w.pyr2, w.pyr4, stream)) != 0) return e;
+    gt2 = w.pyr2;
+    gt4 = w.pyr4;
+  }
+  // gradient images of the two coarse levels: in the descriptor-matrix region of the workspace (dead after the forward)
+  const size_t n0 = (size_t)B * 3 * H * W, n2 = (size_t)B * 3 * gm.H2 * gm.W2, n4 = (size_t)B * 3 * gm.H4 * gm.W4;
+  float* d2 = w.mats;
+  float* d4 = d2 + (n2 + 3) / 4 * 4;
+  if ((n2 + 3) / 4 * 4 + n4 > w.per_image * (size_t)B) return SRST_E_WORKSPACE;
+  SRST_LAUNCH(bb_fill_zero_kernel, dim3(592), dim3(256), 0, stream, d_gt, n0);
+  SRST_LAUNCH(bb_fill_zero_kernel, dim3(148), dim3(256), 0, stream, d2, (n2 + 3) / 4 * 4 + n4);
+  const size_t total = (size_t)B * gm.N;
+  if (mode == 0)
+    SRST_LAUNCH(bb_backward_gt_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, sr, gt, gt2, gt4, idx,
+                grad_out, gm, criterion, d_gt, d2, d4);
+  else if (mode == 1)
+    SRST_LAUNCH(gram_backward_kernel<true>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, sr, gt, gt2, gt4,
+                idx, grad_out, gm, criterion, d_gt, d2, d4);
+  else
+    SRST_LAUNCH(pst_backward_kernel<true>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, stream, sr, gt, gt2, gt4,
+                idx, grad_out, gm, tp, criterion, d_gt, d2, d4);
+  SRST_LAUNCH(bb_pyramid_adjoint_kernel, dim3((unsigned)((n2 + n4 + 255) / 256)), dim3(256), 0, stream, d2, d4, d_gt, B * 3,
+              H, W, gm.H2, gm.W2, gm.H4, gm.W4);
   return (int)cudaGetLastError();
 }
 

@@ -338,9 +338,27 @@ class StructureTensorPixelLoss(nn.Module):
                 f"pixel_weight={self.pixel_weight}")
 
 
+def _patch_backward_gt(mode: int, sr, gt, gt2, gt4, idx, grad_out, taps, criterion: int, stream: int):
+    """d loss / d gt of a patch loss (include/srst.h, srst_patch_backward_gt): the reference's gather of the selected
+    candidates is differentiable in p2_cat (loss.py:136-139), so a gt that requires grad gets one."""
+    lib = _cabi.lib()
+    B, _, H, W = sr.shape
+    d_gt = torch.empty_like(gt)
+    ws = _workspace("bb", sr.device, stream, lib.srst_bb_workspace_bytes(B, H, W))
+    if taps is not None:
+        g, dg, k = taps
+        tp = (_taps.as_c(g), _taps.as_c(dg), len(g) // 2, _taps.as_c(k), len(k) // 2)
+    else:
+        tp = (None, None, 0, None, 0)
+    rc = lib.srst_patch_backward_gt(mode, _ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
+                                    *tp, criterion, _ptr(d_gt), _ptr(ws), ws.numel(), stream)
+    _cabi.check(rc, "srst_patch_backward_gt")
+    return d_gt
+
+
 class _BestBuddyLossFn(torch.autograd.Function):
-    """autograd boundary of the Best-Buddy loss.  Only the final criterion is differentiable
-    (w.r.t. the SR patches): the argmin is not, and gt carries no gradient (reference loss.py:135-139)."""
+    """autograd boundary of the Best-Buddy loss.  Only the final criterion is differentiable: w.r.t. the SR patches
+    and, through the gather of the selected candidates, w.r.t. gt (reference loss.py:135-139); the argmin is not."""
 
     @staticmethod
     def forward(ctx, sr, gt, alpha, beta, criterion, pyramid, mode="patch"):
@@ -384,18 +402,23 @@ class _BestBuddyLossFn(torch.autograd.Function):
         sr, gt, gt2, gt4, idx = ctx.saved_tensors
         B, _, H, W = sr.shape
         bwd = lib.srst_bb_backward if ctx.mode == "patch" else lib.srst_gram_backward
-        if not ctx.needs_input_grad[0]:
+        if not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
             return None, None, None, None, None, None, None
         grad_out = grad_out.to(torch.float32).contiguous()
+        d_sr = d_gt = None
         with _on_device(sr.device):
             stream = _raw_stream(sr.device)
-            d_sr = torch.empty_like(sr)
-            nbytes = lib.srst_bb_workspace_bytes(B, H, W)
-            ws = _workspace("bb", sr.device, stream, nbytes)
-            rc = bwd(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
-                                      ctx.criterion, _ptr(d_sr), _ptr(ws), ws.numel(), stream)
-        _cabi.check(rc, "srst_bb_backward" if ctx.mode == "patch" else "srst_gram_backward")
-        return d_sr, None, None, None, None, None, None
+            if ctx.needs_input_grad[0]:
+                d_sr = torch.empty_like(sr)
+                nbytes = lib.srst_bb_workspace_bytes(B, H, W)
+                ws = _workspace("bb", sr.device, stream, nbytes)
+                rc = bwd(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
+                         ctx.criterion, _ptr(d_sr), _ptr(ws), ws.numel(), stream)
+                _cabi.check(rc, "srst_bb_backward" if ctx.mode == "patch" else "srst_gram_backward")
+            if ctx.needs_input_grad[1]:
+                d_gt = _patch_backward_gt(0 if ctx.mode == "patch" else 1, sr, gt, gt2, gt4, idx, grad_out, None,
+                                          ctx.criterion, stream)
+        return d_sr, d_gt, None, None, None, None, None
 
 
 class BestBuddyLoss(nn.Module):
@@ -445,7 +468,6 @@ class BestBuddyLoss(nn.Module):
 
     def forward(self, x, gt):
         _check_pair(x, gt, "BestBuddyLoss")
-        _no_gt_grad(gt, "BestBuddyLoss")
         loss, idx = _BestBuddyLossFn.apply(x, gt, self.alpha, self.beta, self._crit, self.pyramid)
         self.last_indices = idx
         return loss
@@ -485,7 +507,6 @@ class GramLoss(nn.Module):
 
     def forward(self, x, gt):
         _check_pair(x, gt, "GramLoss")
-        _no_gt_grad(gt, "GramLoss")
         loss, idx = _BestBuddyLossFn.apply(x, gt, self.alpha, self.beta, self._crit, self.pyramid, "gram")
         self.last_indices = idx
         return loss
@@ -493,7 +514,7 @@ class GramLoss(nn.Module):
 
 class _PatchwiseStLossFn(torch.autograd.Function):
     """autograd boundary of the patchwise structure-tensor loss: differentiable through the final
-    criterion and the SR patch descriptors only (argmin is not; gt carries no gradient, loss.py:366-371)."""
+    criterion and the descriptors of the SR patch and of the selected candidate (argmin is not; loss.py:366-371)."""
 
     @staticmethod
     def forward(ctx, sr, gt, sigma, rho, alpha, beta, criterion, pyramid):
@@ -537,18 +558,22 @@ class _PatchwiseStLossFn(torch.autograd.Function):
         sr, gt, gt2, gt4, idx = ctx.saved_tensors
         g, dg, k = ctx.taps
         B, _, H, W = sr.shape
-        if not ctx.needs_input_grad[0]:
+        if not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
             return (None,) * 8
         grad_out = grad_out.to(torch.float32).contiguous()
+        d_sr = d_gt = None
         with _on_device(sr.device):
             stream = _raw_stream(sr.device)
-            d_sr = torch.empty_like(sr)
-            ws = _workspace("bb", sr.device, stream, lib.srst_bb_workspace_bytes(B, H, W))
-            rc = lib.srst_pst_backward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
-                                       _taps.as_c(g), _taps.as_c(dg), len(g) // 2, _taps.as_c(k), len(k) // 2,
-                                       ctx.criterion, _ptr(d_sr), _ptr(ws), ws.numel(), stream)
-        _cabi.check(rc, "srst_pst_backward")
-        return (d_sr,) + (None,) * 7
+            if ctx.needs_input_grad[0]:
+                d_sr = torch.empty_like(sr)
+                ws = _workspace("bb", sr.device, stream, lib.srst_bb_workspace_bytes(B, H, W))
+                rc = lib.srst_pst_backward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
+                                           _taps.as_c(g), _taps.as_c(dg), len(g) // 2, _taps.as_c(k), len(k) // 2,
+                                           ctx.criterion, _ptr(d_sr), _ptr(ws), ws.numel(), stream)
+                _cabi.check(rc, "srst_pst_backward")
+            if ctx.needs_input_grad[1]:
+                d_gt = _patch_backward_gt(2, sr, gt, gt2, gt4, idx, grad_out, (g, dg, k), ctx.criterion, stream)
+        return (d_sr, d_gt) + (None,) * 6
 
 
 class PatchwiseStructureTensorLoss(nn.Module):
@@ -588,7 +613,6 @@ class PatchwiseStructureTensorLoss(nn.Module):
 
     def forward(self, x, gt):
         _check_pair(x, gt, "PatchwiseStructureTensorLoss")
-        _no_gt_grad(gt, "PatchwiseStructureTensorLoss")
         loss, idx = _PatchwiseStLossFn.apply(x, gt, self.sigma, self.rho, self.alpha, self.beta, self._crit,
                                              self.pyramid)
         self.last_indices = idx

@@ -186,6 +186,31 @@ def make_pst(ref_loss, ref_utils):
         print(f"{name}: loss={loss.item():.8g} N={p1.shape[1]} M={cat.shape[1]}")
 
 
+GT_GRAD_CASES = [
+    # gradient w.r.t. gt (loss.py:136-139): same inputs as the fixture named first; only d_gt (and the loss) is stored
+    ("bb_rand_2x24x24", "bb", "rand", 2, 24, 24, 11, dict(alpha=1.0, beta=1.0, criterion="l1")),
+    ("bb_srlike_2x48x48", "bb", "srlike", 2, 48, 48, 13, dict(alpha=1.0, beta=1.0, criterion="l1")),
+    ("bb_rand_ab_1x36x36", "bb", "rand", 1, 36, 36, 14, dict(alpha=0.5, beta=2.0, criterion="l2")),
+    ("gram_srlike_2x48x36", "gram", "srlike", 2, 48, 36, 22, dict(alpha=1.0, beta=1.0, criterion="l1")),
+    ("gram_rand_ab_1x36x36", "gram", "rand", 1, 36, 36, 23, dict(alpha=0.5, beta=2.0, criterion="l2")),
+    ("pst_rand_2x24x24", "pst", "rand", 2, 24, 24, 31, dict(sigma=0.5, rho=2.0, alpha=1.0, beta=1.0, criterion="l1")),
+    ("pst_rand_ab_s1_1x36x36", "pst", "rand", 1, 36, 36, 33, dict(sigma=1.0, rho=2.5, alpha=0.5, beta=2.0, criterion="l2")),
+]
+
+
+def make_gt_grad(ref_loss, ref_utils):
+    cls = {"bb": ref_loss.BestBuddyLoss, "gram": ref_loss.GramLoss, "pst": ref_loss.PatchwiseStructureTensorLoss}
+    for name, which, kind, B, H, W, seed, kw in GT_GRAD_CASES:
+        sr, hr = _inputs(kind, B, H, W, seed)
+        sr.requires_grad_(True)
+        hr.requires_grad_(True)
+        loss = cls[which](**kw)(sr, hr)
+        loss.backward()
+        np.savez_compressed(os.path.join(HERE, name + "_dgt.npz"), loss=np.float32(loss.item()), d_gt=hr.grad.numpy(),
+                            d_sr=sr.grad.numpy())
+        print(f"{name}_dgt: loss={loss.item():.8g} |d_gt|max={hr.grad.abs().max().item():.4g}")
+
+
 L1_CASES = [
     # dist_norm='l1' (utils.py:166-172) for the three patch losses: name, module, kind, B, H, W, seed, alpha, beta, criterion
     ("bbl1_rand_2x24x24", "bb", "rand", 2, 24, 24, 41, 1.0, 1.0, "l1"),
@@ -235,7 +260,7 @@ def make_l1(ref_loss, ref_utils):
 if __name__ == "__main__":
     torch.set_num_threads(1)  # fixed summation order inside MKL for reproducible fixtures
     rl, ru = _import_reference()
-    which = sys.argv[1:] or ["st", "bb", "gram", "pst", "l1"]
+    which = sys.argv[1:] or ["st", "bb", "gram", "pst", "l1", "gtgrad"]
     if "st" in which:
         make_st(rl, ru)
     if "bb" in which:
@@ -246,3 +271,5 @@ if __name__ == "__main__":
         make_pst(rl, ru)
     if "l1" in which:
         make_l1(rl, ru)
+    if "gtgrad" in which:
+        make_gt_grad(rl, ru)

@@ -17,8 +17,10 @@ def golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 
 
-def golden_names(prefix):
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
+def golden_names(prefix, suffix=""):
+    """Fixture names starting with `prefix`; the `_dgt` companions (gradient w.r.t. gt only) are listed on request."""
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, prefix + "*" + suffix + ".npz")))
+    return [n for n in names if suffix or not n.endswith("_dgt")]
 
 
 def rel_err(x, ref):
@@ -157,3 +159,26 @@ def emu_stpx(lib, sr, hr, taps, grad_st=1.0, grad_px=1.0):
                                 len(g) // 2, _fp(k), len(k) // 2, _p(d_sr), None)
     assert rc == 0, rc
     return dict(st=float(both[0]), px=float(both[1]), d_sr=d_sr, ws=ws)
+
+
+def emu_patch_gt(lib, sr, gt, idx, gt2=None, gt4=None, criterion=0, grad_out=1.0, mode="patch", taps=None):
+    """Run srst_patch_backward_gt of `lib` on host arrays (emulation library only): d loss / d gt."""
+    sr = np.ascontiguousarray(sr, np.float32)
+    gt = np.ascontiguousarray(gt, np.float32)
+    gt2 = np.ascontiguousarray(gt2, np.float32) if gt2 is not None else None
+    gt4 = np.ascontiguousarray(gt4, np.float32) if gt4 is not None else None
+    idx = np.ascontiguousarray(idx, np.int64)
+    B, _, H, W = sr.shape
+    nb = lib.srst_bb_workspace_bytes(B, H, W)
+    ws = np.zeros(nb // 4 + 4, np.float32)
+    go = np.full(1, grad_out, np.float32)
+    d_gt = np.full_like(gt, np.nan)
+    if taps is not None:
+        g, dg, k = [np.ascontiguousarray(t, np.float32) for t in taps]
+        tp = (_fp(g), _fp(dg), len(g) // 2, _fp(k), len(k) // 2)
+    else:
+        tp = (None, None, 0, None, 0)
+    rc = lib.srst_patch_backward_gt({"patch": 0, "gram": 1, "pst": 2}[mode], _p(sr), _p(gt), _p(gt2), _p(gt4), _p(idx), _p(go),
+                                    B, H, W, *tp, criterion, _p(d_gt), _p(ws), nb, None)
+    assert rc == 0, rc
+    return d_gt

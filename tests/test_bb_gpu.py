@@ -157,5 +157,7 @@ def test_rejects_unsupported_geometry():
         BestBuddyLoss(dist_norm="cosine")  # utils.py:189 (l1 and l2 have kernels)
     with pytest.raises(RuntimeError):
         BestBuddyLoss()(torch.rand(1, 3, 24, 24), torch.rand(1, 3, 24, 24))
-    with pytest.raises(NotImplementedError):  # the reference would differentiate the gathered candidates
-        BestBuddyLoss()(torch.rand(1, 3, 24, 24, device="cuda"), torch.rand(1, 3, 24, 24, device="cuda").requires_grad_())
+    # a gt that requires grad gets the gradient through the gathered candidates (loss.py:136-139; tests/test_gt_grad.py)
+    y = torch.rand(1, 3, 24, 24, device="cuda").requires_grad_()
+    BestBuddyLoss()(torch.rand(1, 3, 24, 24, device="cuda"), y).backward()
+    assert y.grad is not None and torch.isfinite(y.grad).all() and y.grad.abs().max() > 0
