@@ -419,6 +419,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
   __shared__ __align__(16) float sQ[D][BB_QT];      // alpha*x + beta*g
   __shared__ __align__(16) float sY[2][D][BB_CT];
   __shared__ __align__(16) float sYl[2][BB_CT];     // (alpha+beta)|y|^2 - kappa*(|alpha|+|beta|)|y|^2
+  [[maybe_unused]] __shared__ __align__(16) float sYn[2][(D > 9 && !SHARE) ? BB_CT : 4];   // |y|^2 as copied from the workspace (cp.async path)
   __shared__ __align__(16) float sCl[BB_QT];        // c_i - kappa*(|alpha||x|^2 + |beta||g|^2)
   __shared__ __align__(16) float sB0[BB_QT];        // exact score of the co-located candidate j = i
   // SHARE only: 2*tol of a pair is at most 2 kappa (ca_i + max over the chunk's valid candidates of yt_j)
@@ -449,33 +450,53 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
                           : __int_as_float(0xff800000);
   }
 
-  // candidate-chunk staging: D * BB_CT / 4 float4 elements over BB_NT threads
+  // Candidate-chunk staging: D * BB_CT / 4 16-byte pieces over BB_NT threads into the buffer the previous chunk used,
+  // while this chunk is being scored.  D = 27 (ASYNC): cp.async (LDGSTS) straight into shared memory -- staging
+  // through registers let the compiler sink the loads behind the FFMA2 block to save registers, and their L2 latency
+  // was then exposed in front of every chunk barrier (8 % long-scoreboard + 9 % barrier stalls; 1.95 -> 1.80 ms at
+  // batch 64 x 192x192).  D = 9: the chunk is short and the register path measured faster (Gram 1.48 vs 1.55 ms).
+  constexpr bool ASYNC = D > 9 && !SHARE;   // PatchwiseST (SHARE) also measured faster through registers: 2.84 vs 3.04 ms
   constexpr int NLD = (D * (BB_CT / 4) + BB_NT - 1) / BB_NT;
-  float4 pf[NLD];
-  float pfn = 0.f;
-  auto prefetch = [&](int chunk) {
-#pragma unroll
-    for (int u = 0; u < NLD; ++u) {
-      const int it = tid + u * BB_NT;
-      if (it < D * (BB_CT / 4)) {
+  [[maybe_unused]] float4 pf[ASYNC ? 1 : NLD];
+  [[maybe_unused]] float pfn_reg = 0.f;
+  auto prefetch = [&](int buf, int chunk) {
+    if constexpr (ASYNC) {
+      for (int it = tid; it < D * (BB_CT / 4); it += BB_NT) {
         const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
-        pf[u] = ldg4(P.y + (size_t)k * g.Mpad + chunk + 4 * c4);
+        cp_async16(&sY[buf][k][4 * c4], P.y + (size_t)k * g.Mpad + chunk + 4 * c4, true);
       }
-    }
-    if (tid < BB_CT) pfn = __ldg(P.yn + chunk + tid);
-  };
-  auto commit = [&](int buf, int chunk) {
+      if (tid < BB_CT) cp_async4(&sYn[buf][tid], P.yn + chunk + tid);
+      cp_async_commit();
+    } else {
 #pragma unroll
-    for (int u = 0; u < NLD; ++u) {
-      const int it = tid + u * BB_NT;
-      if (it < D * (BB_CT / 4)) {
-        const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
-        st4(&sY[buf][k][4 * c4], pf[u]);
+      for (int u = 0; u < NLD; ++u) {
+        const int it = tid + u * BB_NT;
+        if (it < D * (BB_CT / 4)) {
+          const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
+          pf[u] = ldg4(P.y + (size_t)k * g.Mpad + chunk + 4 * c4);
+        }
+      }
+      if (tid < BB_CT) pfn_reg = __ldg(P.yn + chunk + tid);
+    }
+  };
+  // the copies have landed (ASYNC) / are stored (registers); then the per-candidate part of the bound
+  auto commit = [&](int buf, int chunk) {
+    if constexpr (ASYNC) {
+      cp_async_wait_all();
+    } else {
+#pragma unroll
+      for (int u = 0; u < NLD; ++u) {
+        const int it = tid + u * BB_NT;
+        if (it < D * (BB_CT / 4)) {
+          const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
+          st4(&sY[buf][k][4 * c4], pf[u]);
+        }
       }
     }
     // padded candidates (|y|^2 = +inf in the workspace) get a lower bound of exactly +inf: it never passes the
     // filter, not even against a NaN-poisoned comparison (inf - inf would be NaN, which now counts as a hit)
     if (tid < BB_CT) {
+      const float pfn = ASYNC ? sYn[buf][tid] : pfn_reg;   // ASYNC: each thread reads back its own 4-byte copy
       sYl[buf][tid] = (chunk + tid < g.M) ? (alpha + beta) * pfn - kBbKappa * ((aa + ab) * pfn) : __int_as_float(0x7f800000);
       if constexpr (SHARE) {
         float m = (chunk + tid < g.M) ? (aa + ab) * pfn : 0.f;
@@ -489,7 +510,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
   const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads; a half-warp shares ty (its queries)
   // local query l (0..7) -> tile query ty*4 + (l&3) + 64*(l>>2); same for candidates with tx
 
-  prefetch(0);
+  prefetch(0, 0);
   commit(0, 0);
   __syncthreads();  // queries, bounds and chunk 0 are in shared memory
 
@@ -514,7 +535,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
 
   for (int chunk = 0, buf = 0; chunk < g.Mpad; chunk += BB_CT, buf ^= 1) {
     const bool more = chunk + BB_CT < g.Mpad;
-    if (more) prefetch(chunk + BB_CT);
+    if (more) prefetch(buf ^ 1, chunk + BB_CT);  // buf^1 was last read before the previous barrier
 
     float2 acc[4][8];  // [query pair][candidate]: .x = local query 2p, .y = 2p+1
 #pragma unroll
@@ -661,7 +682,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
         __syncwarp();  // the queue is reused by the next window
       }
     }
-    if (more) commit(buf ^ 1, chunk + BB_CT);  // buf^1 was last read before the previous barrier
+    if (more) commit(buf ^ 1, chunk + BB_CT);
     __syncthreads();
   }
 

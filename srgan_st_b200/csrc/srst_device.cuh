@@ -119,6 +119,7 @@ SRST_DEV float min3_nan(float a, float b, float c) {
 SRST_DEV void cp_async16(float* sdst, const float* gsrc, bool valid) {
   if (valid) std::memcpy(sdst, gsrc, 16); else std::memset(sdst, 0, 16);
 }
+SRST_DEV void cp_async4(float* sdst, const float* gsrc) { *sdst = *gsrc; }
 SRST_DEV void cp_async_commit() {}
 SRST_DEV void cp_async_wait_all() {}
 #else
@@ -126,6 +127,10 @@ SRST_DEV void cp_async16(float* sdst, const float* gsrc, bool valid) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
   const int sz = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gsrc), "r"(sz) : "memory");
+}
+SRST_DEV void cp_async4(float* sdst, const float* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
 }
 SRST_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 SRST_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
