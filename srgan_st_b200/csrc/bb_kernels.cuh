@@ -407,6 +407,29 @@ SRST_DEV float bb_shifted_bound(float B, float cl) {
   return (B == __int_as_float(0xff800000)) ? B : fmaf(6e-7f, fabsf(F), F);
 }
 
+// The same score with the descriptor length known at compile time: all 3 D operands are loaded up front (independent
+// loads: one L1/L2 round trip instead of D dependent ones), then the two sequential-fma chains run in the oracle's
+// order.  This is the survivors' path of the search kernel: a survivor used to cost D load-to-use latencies.
+template <int D>
+SRST_DEV float bb_exact_score_unrolled(const float* q1, const float* q2, const float* y, const float* xn, const float* gn,
+                                       const float* yn, int Npad, int Mpad, int qi, int cj, float alpha, float beta) {
+  float a[D], b[D], w[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    w[k] = __ldg(y + (size_t)k * Mpad + cj);
+    a[k] = __ldg(q1 + (size_t)k * Npad + qi);
+    b[k] = __ldg(q2 + (size_t)k * Npad + qi);
+  }
+  const float xq = __ldg(xn + qi), gq = __ldg(gn + qi), yc = __ldg(yn + cj);
+  float dot1 = 0.f, dot2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    dot1 = fmaf(a[k], w[k], dot1);
+    dot2 = fmaf(b[k], w[k], dot2);
+  }
+  return bb_score(xq, gq, yc, dot1, dot2, alpha, beta);
+}
+
 // SHARE: the 16 threads that own a query also pool their bound -- every chunk early on, every fourth
 // later, B_i is lowered to the smallest UPPER bound s'_ij + tol_ij any of them saw in the chunk (four
 // shuffle steps).  It costs ~8 % on descriptors whose co-located patch is already a tight seed
@@ -417,6 +440,13 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
                  int64_t* __restrict__ idx_out) {
   static_assert(BB_NT == 256 && BB_QT == 128 && BB_CT == 128, "search tile is 16x16 threads x (8 queries x 8 candidates)");
   __shared__ __align__(16) float sQ[D][BB_QT];      // alpha*x + beta*g
+  // short descriptors (Gram): the survivors' exact re-scoring reads x, g (and y from the chunk buffer) from shared
+  // memory -- with 9 dimensions nearly every chunk has a survivor per warp, and its global round trip was the chunk's
+  // longest latency
+  constexpr bool EXACT_SMEM = D <= 9;
+  [[maybe_unused]] __shared__ __align__(16) float sX1[EXACT_SMEM ? D : 1][EXACT_SMEM ? BB_QT : 4];
+  [[maybe_unused]] __shared__ __align__(16) float sX2[EXACT_SMEM ? D : 1][EXACT_SMEM ? BB_QT : 4];
+  [[maybe_unused]] __shared__ __align__(16) float sXn[EXACT_SMEM ? 2 : 1][EXACT_SMEM ? BB_QT : 4];   // |x|^2, |g|^2
   __shared__ __align__(16) float sY[2][D][BB_CT];
   __shared__ __align__(16) float sYl[2][BB_CT];     // (alpha+beta)|y|^2 - kappa*(|alpha|+|beta|)|y|^2
   [[maybe_unused]] __shared__ __align__(16) float sYn[2][(D > 9 && !SHARE) ? BB_CT : 4];   // |y|^2 as copied from the workspace (cp.async path)
@@ -439,10 +469,12 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     const float4 gg = ldg4(P.q2 + (size_t)k * g.Npad + qbase + 4 * c4);
     st4(&sQ[k][4 * c4], make_float4(fmaf(alpha, x.x, beta * gg.x), fmaf(alpha, x.y, beta * gg.y),
                                     fmaf(alpha, x.z, beta * gg.z), fmaf(alpha, x.w, beta * gg.w)));
+    if constexpr (EXACT_SMEM) { st4(&sX1[k][4 * c4], x); st4(&sX2[k][4 * c4], gg); }
   }
   if (tid < BB_QT) {
     const int qi = qbase + tid;
     const float xn = __ldg(P.xn + qi), gn = __ldg(P.gn + qi);
+    if constexpr (EXACT_SMEM) { sXn[0][tid] = xn; sXn[1][tid] = gn; }
     sCl[tid] = fmaf(alpha, xn, beta * gn) - kBbKappa * fmaf(aa, xn, ab * gn);
     if constexpr (SHARE) sCa[tid] = fmaf(aa, xn, ab * gn);
     // seed of the upper bound; padded queries get -inf so that nothing is ever evaluated for them
@@ -649,8 +681,20 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
           sc[u] = 0.f;
           if (s0 < n) {
             const int ent = sW[wrp][s0];
-            sc[u] = bb_exact_score(P.q1, P.q2, P.y, P.xn, P.gn, P.yn, g.Npad, g.Mpad, D, qbase + (ent >> 8), chunk + (ent & 255),
-                                   alpha, beta);
+            if constexpr (EXACT_SMEM) {
+              const int q = ent >> 8, c = ent & 255;
+              float dot1 = 0.f, dot2 = 0.f;
+#pragma unroll
+              for (int k = 0; k < D; ++k) {
+                const float w = sY[buf][k][c];
+                dot1 = fmaf(sX1[k][q], w, dot1);
+                dot2 = fmaf(sX2[k][q], w, dot2);
+              }
+              sc[u] = bb_score(sXn[0][q], sXn[1][q], __ldg(P.yn + chunk + c), dot1, dot2, alpha, beta);
+            } else {
+              sc[u] = bb_exact_score_unrolled<D>(P.q1, P.q2, P.y, P.xn, P.gn, P.yn, g.Npad, g.Mpad, qbase + (ent >> 8),
+                                                 chunk + (ent & 255), alpha, beta);
+            }
           }
         }
         __syncwarp();  // every entry has been read
