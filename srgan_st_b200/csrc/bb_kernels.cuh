@@ -434,11 +434,21 @@ SRST_DEV float bb_exact_score_unrolled(const float* q1, const float* q2, const f
 // later, B_i is lowered to the smallest UPPER bound s'_ij + tol_ij any of them saw in the chunk (four
 // shuffle steps).  It costs ~8 % on descriptors whose co-located patch is already a tight seed
 // (BestBuddy, Gram) and saves 25 % on PatchwiseST, whose noisy SR descriptors make the seed loose.
-template <int D, bool SHARE = false>
+// PIPE: the candidate chunks go through a four-stage shared-memory ring guarded by counting mbarriers ("full": every
+// thread's cp.async copies of the stage have landed; "empty": every thread is done reading it) instead of two buffers and
+// one CTA barrier per chunk.  A warp that has survivors to re-score no longer stalls the other seven at the end of every
+// chunk: warps may drift up to two chunks apart (Gram: 21 % of the warp time was spent at that barrier).
+constexpr int kBbStages = 4;
+template <int D>
+constexpr size_t bb_search_dyn_smem(bool pipe) { return pipe ? sizeof(float) * kBbStages * (D + 1) * BB_CT : 0; }
+
+template <int D, bool SHARE = false, bool PIPE = false>
 __global__ void __launch_bounds__(BB_NT, 1)
 bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, float alpha, float beta,
                  int64_t* __restrict__ idx_out) {
   static_assert(BB_NT == 256 && BB_QT == 128 && BB_CT == 128, "search tile is 16x16 threads x (8 queries x 8 candidates)");
+  SRST_DYN_SMEM(float, dyn);                          // PIPE: [stages][D][BB_CT] candidates, then [stages][BB_CT] |y|^2
+  __shared__ __align__(8) unsigned long long mb_full[kBbStages], mb_empty[kBbStages];
   __shared__ __align__(16) float sQ[D][BB_QT];      // alpha*x + beta*g
   // short descriptors (Gram): the survivors' exact re-scoring reads x, g (and y from the chunk buffer) from shared
   // memory -- with 9 dimensions nearly every chunk has a survivor per warp, and its global round trip was the chunk's
@@ -447,9 +457,11 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
   [[maybe_unused]] __shared__ __align__(16) float sX1[EXACT_SMEM ? D : 1][EXACT_SMEM ? BB_QT : 4];
   [[maybe_unused]] __shared__ __align__(16) float sX2[EXACT_SMEM ? D : 1][EXACT_SMEM ? BB_QT : 4];
   [[maybe_unused]] __shared__ __align__(16) float sXn[EXACT_SMEM ? 2 : 1][EXACT_SMEM ? BB_QT : 4];   // |x|^2, |g|^2
-  __shared__ __align__(16) float sY[2][D][BB_CT];
-  __shared__ __align__(16) float sYl[2][BB_CT];     // (alpha+beta)|y|^2 - kappa*(|alpha|+|beta|)|y|^2
-  [[maybe_unused]] __shared__ __align__(16) float sYn[2][(D > 9 && !SHARE) ? BB_CT : 4];   // |y|^2 as copied from the workspace (cp.async path)
+  __shared__ __align__(16) float sY2[PIPE ? 1 : 2][PIPE ? 1 : D][PIPE ? 4 : BB_CT];
+  float (*sY)[D][BB_CT] = PIPE ? reinterpret_cast<float (*)[D][BB_CT]>(dyn) : reinterpret_cast<float (*)[D][BB_CT]>(&sY2[0][0][0]);
+  [[maybe_unused]] float (*sYp)[BB_CT] = reinterpret_cast<float (*)[BB_CT]>(dyn + kBbStages * D * BB_CT);   // PIPE: |y|^2 per stage
+  __shared__ __align__(16) float sYl[2][PIPE ? 4 : BB_CT];     // (alpha+beta)|y|^2 - kappa*(|alpha|+|beta|)|y|^2
+  [[maybe_unused]] __shared__ __align__(16) float sYn[2][(D > 9 && !SHARE && !PIPE) ? BB_CT : 4];   // |y|^2 as copied from the workspace (cp.async path)
   __shared__ __align__(16) float sCl[BB_QT];        // c_i - kappa*(|alpha||x|^2 + |beta||g|^2)
   __shared__ __align__(16) float sB0[BB_QT];        // exact score of the co-located candidate j = i
   // SHARE only: 2*tol of a pair is at most 2 kappa (ca_i + max over the chunk's valid candidates of yt_j)
@@ -487,9 +499,9 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
   // through registers let the compiler sink the loads behind the FFMA2 block to save registers, and their L2 latency
   // was then exposed in front of every chunk barrier (8 % long-scoreboard + 9 % barrier stalls; 1.95 -> 1.80 ms at
   // batch 64 x 192x192).  D = 9: the chunk is short and the register path measured faster (Gram 1.48 vs 1.55 ms).
-  constexpr bool ASYNC = D > 9 && !SHARE;   // PatchwiseST (SHARE) also measured faster through registers: 2.84 vs 3.04 ms
+  constexpr bool ASYNC = D > 9 && !SHARE && !PIPE;   // PatchwiseST (SHARE) also measured faster through registers: 2.84 vs 3.04 ms
   constexpr int NLD = (D * (BB_CT / 4) + BB_NT - 1) / BB_NT;
-  [[maybe_unused]] float4 pf[ASYNC ? 1 : NLD];
+  [[maybe_unused]] float4 pf[(ASYNC || PIPE) ? 1 : NLD];
   [[maybe_unused]] float pfn_reg = 0.f;
   auto prefetch = [&](int buf, int chunk) {
     if constexpr (ASYNC) {
@@ -542,9 +554,29 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
   const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads; a half-warp shares ty (its queries)
   // local query l (0..7) -> tile query ty*4 + (l&3) + 64*(l>>2); same for candidates with tx
 
-  prefetch(0, 0);
-  commit(0, 0);
-  __syncthreads();  // queries, bounds and chunk 0 are in shared memory
+  const int nchunks = g.Mpad / BB_CT;
+  // PIPE: chunk c lives in stage c % kBbStages (its (c / kBbStages)-th use); every thread copies its share of the chunk
+  // and arrives on the stage's "full" barrier once its copies have landed
+  auto pipe_load = [&](int c) {
+    const int st = c % kBbStages, chunk = c * BB_CT;
+    for (int it = tid; it < D * (BB_CT / 4); it += BB_NT) {
+      const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
+      cp_async16(&sY[st][k][4 * c4], P.y + (size_t)k * g.Mpad + chunk + 4 * c4, true);
+    }
+    if (tid < BB_CT) cp_async4(&sYp[st][tid], P.yn + chunk + tid);
+    cp_async_mbar_arrive(&mb_full[st]);
+  };
+  if constexpr (PIPE) {
+    if (tid == 0)
+      for (int st = 0; st < kBbStages; ++st) { mbar_init(&mb_full[st], BB_NT); mbar_init(&mb_empty[st], BB_NT); }
+    __syncthreads();  // the barriers are initialised before anyone arrives on them
+    pipe_load(0);
+    if (nchunks > 1) pipe_load(1);
+  } else {
+    prefetch(0, 0);
+    commit(0, 0);
+  }
+  __syncthreads();  // queries and bounds (and chunk 0) are in shared memory
 
   float best[8], B[8], Bc[8], clq[8];
   int bidx[8];
@@ -565,9 +597,18 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
   }
 
-  for (int chunk = 0, buf = 0; chunk < g.Mpad; chunk += BB_CT, buf ^= 1) {
+  for (int chunk = 0, ci = 0, buf = 0; chunk < g.Mpad; chunk += BB_CT, ++ci, buf = PIPE ? (ci % kBbStages) : (buf ^ 1)) {
     const bool more = chunk + BB_CT < g.Mpad;
-    if (more) prefetch(buf ^ 1, chunk + BB_CT);  // buf^1 was last read before the previous barrier
+    if constexpr (PIPE) {
+      if (ci + 2 < nchunks) {
+        const int c2 = ci + 2, u2 = c2 / kBbStages;
+        if (u2 >= 1) mbar_wait(&mb_empty[c2 % kBbStages], (unsigned)((u2 - 1) & 1));  // chunk ci - 2 has been read by everyone
+        pipe_load(c2);
+      }
+      mbar_wait(&mb_full[buf], (unsigned)((ci / kBbStages) & 1));
+    } else {
+      if (more) prefetch(buf ^ 1, chunk + BB_CT);  // buf^1 was last read before the previous barrier
+    }
 
     float2 acc[4][8];  // [query pair][candidate]: .x = local query 2p, .y = 2p+1
 #pragma unroll
@@ -594,8 +635,23 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     // anywhere still reaches the exact path) tested once against Bc_i: the 64 compares + mask updates only run in the
     // rare chunks that hold a survivor.
     unsigned long long hit = 0ull;
-    const float4 yla = ld4(&sYl[buf][4 * tx]), ylb = ld4(&sYl[buf][64 + 4 * tx]);
-    const float yl[8] = {yla.x, yla.y, yla.z, yla.w, ylb.x, ylb.y, ylb.z, ylb.w};
+    float yl[8];
+    [[maybe_unused]] float ytloc = 0.f;   // PIPE + SHARE: max over this thread's valid candidates of (|alpha|+|beta|)|y|^2
+    if constexpr (PIPE) {
+      // the per-candidate part of the bound straight from |y|^2; padded candidates (|y|^2 = +inf in the workspace) get
+      // a lower bound of exactly +inf (inf - inf would be NaN, which counts as a hit)
+      const float4 na = ld4(&sYp[buf][4 * tx]), nb = ld4(&sYp[buf][64 + 4 * tx]);
+      const float yn8[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool valid = chunk + 4 * tx + (j & 3) + 64 * (j >> 2) < g.M;
+        yl[j] = valid ? (alpha + beta) * yn8[j] - kBbKappa * ((aa + ab) * yn8[j]) : __int_as_float(0x7f800000);
+        if constexpr (SHARE) ytloc = fmaxf(ytloc, valid ? (aa + ab) * yn8[j] : 0.f);
+      }
+    } else {
+      const float4 yla = ld4(&sYl[buf][4 * tx]), ylb = ld4(&sYl[buf][64 + 4 * tx]);
+      yl[0] = yla.x; yl[1] = yla.y; yl[2] = yla.z; yl[3] = yla.w; yl[4] = ylb.x; yl[5] = ylb.y; yl[6] = ylb.z; yl[7] = ylb.w;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float2 y2 = make_float2(yl[j], yl[j]);
@@ -616,8 +672,15 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
       // chunk of yt): pool min_j L_ij + delta_i over the half-warp into B_i before the test
       const int cidx = chunk / BB_CT;
       if (cidx < 4 || (cidx & 3) == 0) {
-        const float4 ym = ld4(&sYtm[buf][0]);
-        const float ytmax = fmaxf(fmaxf(ym.x, ym.y), fmaxf(ym.z, ym.w));
+        float ytmax;
+        if constexpr (PIPE) {   // the 16 lanes of a half-warp hold all 128 candidates of the chunk between them
+          ytmax = ytloc;
+#pragma unroll
+          for (int o = 1; o <= 8; o <<= 1) ytmax = fmaxf(ytmax, __shfl_xor_sync(0xffffffffu, ytmax, o));
+        } else {
+          const float4 ym = ld4(&sYtm[buf & 1][0]);
+          ytmax = fmaxf(fmaxf(ym.x, ym.y), fmaxf(ym.z, ym.w));
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float m = mq[i];
@@ -726,8 +789,12 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
         __syncwarp();  // the queue is reused by the next window
       }
     }
-    if (more) commit(buf ^ 1, chunk + BB_CT);
-    __syncthreads();
+    if constexpr (PIPE) {
+      mbar_arrive(&mb_empty[buf]);  // this thread is done with the stage
+    } else {
+      if (more) commit(buf ^ 1, chunk + BB_CT);
+      __syncthreads();
+    }
   }
 
   // argmin across the 16 threads (one half-warp) that share these queries: four shuffle steps

@@ -212,6 +212,54 @@ SRST_DEV void tma_wait(unsigned long long* mbar, unsigned parity = 0) {
 SRST_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
+// Counting mbarriers for multi-stage shared-memory pipelines (the patch-search kernel's candidate chunks): `count`
+// arrivals complete a phase; mbar_wait(parity) returns once the phase with that parity (0 for the first, then
+// alternating) has completed.  cp_async_mbar_arrive makes the calling thread's arrival wait for all of its earlier
+// cp.async copies.  The wait is bounded: a protocol error traps instead of hanging the GPU.
+#ifdef SRST_EMULATE
+// emulated state: pending arrivals (bits 0..19) | expected count (20..39) | completed phases (40..)
+SRST_DEV void mbar_init(unsigned long long* b, unsigned count) {
+  __atomic_store_n(b, (unsigned long long)count | ((unsigned long long)count << 20), __ATOMIC_SEQ_CST);
+}
+SRST_DEV void mbar_arrive(unsigned long long* b) {
+  unsigned long long v = __atomic_load_n(b, __ATOMIC_SEQ_CST), nv;
+  do {
+    const unsigned long long pending = (v & 0xFFFFFull) - 1, expected = (v >> 20) & 0xFFFFFull, phase = v >> 40;
+    nv = pending ? ((v & ~0xFFFFFull) | pending) : (expected | (expected << 20) | ((phase + 1) << 40));
+  } while (!__atomic_compare_exchange_n(b, &v, nv, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST));
+}
+SRST_DEV void cp_async_mbar_arrive(unsigned long long* b) { mbar_arrive(b); }  // emulated copies are synchronous
+SRST_DEV void mbar_wait(unsigned long long* b, unsigned parity) {
+  while (((__atomic_load_n(b, __ATOMIC_SEQ_CST) >> 40) & 1ull) == parity) std::this_thread::yield();
+}
+#else
+SRST_DEV void mbar_init(unsigned long long* b, unsigned count) {
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(b);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+SRST_DEV void mbar_arrive(unsigned long long* b) {
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(b);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+SRST_DEV void cp_async_mbar_arrive(unsigned long long* b) {
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(b);
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+SRST_DEV void mbar_wait(unsigned long long* b, unsigned parity) {
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(b);
+  unsigned done = 0;
+  for (int spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1 << 24)) __trap();
+  }
+}
+#endif
+
 // Named barriers for producer/consumer warp roles: `n` = number of participating threads.
 #ifdef SRST_EMULATE
 SRST_DEV void bar_sync(int id, int n) { emu_bar_sync(id, n); }
