@@ -437,23 +437,27 @@ SRST_DEV float bb_exact_score_unrolled(const float* q1, const float* q2, const f
 // PIPE: the candidate chunks go through a four-stage shared-memory ring guarded by counting mbarriers ("full": every
 // thread's cp.async copies of the stage have landed; "empty": every thread is done reading it) instead of two buffers and
 // one CTA barrier per chunk.  A warp that has survivors to re-score no longer stalls the other seven at the end of every
-// chunk: warps may drift up to two chunks apart (Gram: 21 % of the warp time was spent at that barrier).
-constexpr int kBbStages = 4;
+// chunk: warps may drift up to kBbAhead chunks apart (Gram: 21 % of the warp time was spent at that barrier).
+// stages of the ring: 4 for 27-dimensional descriptors, 8 for 9-dimensional ones (measured: Gram 1.23 -> 1.20 ms with 8,
+// BestBuddy / PatchwiseST 1-3 % slower); a thread copies kBbAhead = stages / 2 chunks ahead of the one it scores
+constexpr int kBbMaxStages = 8;
+template <int D> constexpr int bb_stages() { return D <= 9 ? 8 : 4; }
 template <int D>
-constexpr size_t bb_search_dyn_smem(bool pipe) { return pipe ? sizeof(float) * kBbStages * (D + 1) * BB_CT : 0; }
+constexpr size_t bb_search_dyn_smem(bool pipe) { return pipe ? sizeof(float) * bb_stages<D>() * (D + 1) * BB_CT : 0; }
 
 template <int D, bool SHARE = false, bool PIPE = false>
 __global__ void __launch_bounds__(BB_NT, 1)
 bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, float alpha, float beta,
                  int64_t* __restrict__ idx_out) {
   static_assert(BB_NT == 256 && BB_QT == 128 && BB_CT == 128, "search tile is 16x16 threads x (8 queries x 8 candidates)");
+  constexpr int kBbStages = bb_stages<D>(), kBbAhead = kBbStages / 2;
   SRST_DYN_SMEM(float, dyn);                          // PIPE: [stages][D][BB_CT] candidates, then [stages][BB_CT] |y|^2
-  __shared__ __align__(8) unsigned long long mb_full[kBbStages], mb_empty[kBbStages];
+  __shared__ __align__(8) unsigned long long mb_full[kBbMaxStages], mb_empty[kBbMaxStages];
   __shared__ __align__(16) float sQ[D][BB_QT];      // alpha*x + beta*g
   // short descriptors (Gram): the survivors' exact re-scoring reads x, g (and y from the chunk buffer) from shared
   // memory -- with 9 dimensions nearly every chunk has a survivor per warp, and its global round trip was the chunk's
   // longest latency
-  constexpr bool EXACT_SMEM = D <= 9;
+  constexpr bool EXACT_SMEM = D <= 9;   // (PatchwiseST, 27-dim: no gain measured from the shared-memory copy)
   [[maybe_unused]] __shared__ __align__(16) float sX1[EXACT_SMEM ? D : 1][EXACT_SMEM ? BB_QT : 4];
   [[maybe_unused]] __shared__ __align__(16) float sX2[EXACT_SMEM ? D : 1][EXACT_SMEM ? BB_QT : 4];
   [[maybe_unused]] __shared__ __align__(16) float sXn[EXACT_SMEM ? 2 : 1][EXACT_SMEM ? BB_QT : 4];   // |x|^2, |g|^2
@@ -570,8 +574,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     if (tid == 0)
       for (int st = 0; st < kBbStages; ++st) { mbar_init(&mb_full[st], BB_NT); mbar_init(&mb_empty[st], BB_NT); }
     __syncthreads();  // the barriers are initialised before anyone arrives on them
-    pipe_load(0);
-    if (nchunks > 1) pipe_load(1);
+    for (int c = 0; c < kBbAhead && c < nchunks; ++c) pipe_load(c);
   } else {
     prefetch(0, 0);
     commit(0, 0);
@@ -600,9 +603,9 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
   for (int chunk = 0, ci = 0, buf = 0; chunk < g.Mpad; chunk += BB_CT, ++ci, buf = PIPE ? (ci % kBbStages) : (buf ^ 1)) {
     const bool more = chunk + BB_CT < g.Mpad;
     if constexpr (PIPE) {
-      if (ci + 2 < nchunks) {
-        const int c2 = ci + 2, u2 = c2 / kBbStages;
-        if (u2 >= 1) mbar_wait(&mb_empty[c2 % kBbStages], (unsigned)((u2 - 1) & 1));  // chunk ci - 2 has been read by everyone
+      if (ci + kBbAhead < nchunks) {
+        const int c2 = ci + kBbAhead, u2 = c2 / kBbStages;
+        if (u2 >= 1) mbar_wait(&mb_empty[c2 % kBbStages], (unsigned)((u2 - 1) & 1));  // chunk c2 - kBbStages has been read by everyone
         pipe_load(c2);
       }
       mbar_wait(&mb_full[buf], (unsigned)((ci / kBbStages) & 1));
