@@ -434,24 +434,25 @@ SRST_DEV float bb_exact_score_unrolled(const float* q1, const float* q2, const f
 // later, B_i is lowered to the smallest UPPER bound s'_ij + tol_ij any of them saw in the chunk (four
 // shuffle steps).  It costs ~8 % on descriptors whose co-located patch is already a tight seed
 // (BestBuddy, Gram) and saves 25 % on PatchwiseST, whose noisy SR descriptors make the seed loose.
-// PIPE: the candidate chunks go through a four-stage shared-memory ring guarded by counting mbarriers ("full": every
-// thread's cp.async copies of the stage have landed; "empty": every thread is done reading it) instead of two buffers and
-// one CTA barrier per chunk.  A warp that has survivors to re-score no longer stalls the other seven at the end of every
-// chunk: warps may drift up to kBbAhead chunks apart (Gram: 21 % of the warp time was spent at that barrier).
-// stages of the ring: 4 for 27-dimensional descriptors, 8 for 9-dimensional ones (measured: Gram 1.23 -> 1.20 ms with 8,
-// BestBuddy / PatchwiseST 1-3 % slower); a thread copies kBbAhead = stages / 2 chunks ahead of the one it scores
+// Candidate chunks go through a shared-memory ring guarded by counting mbarriers ("full": every thread's cp.async
+// copies of the stage have landed; "empty": every thread is done reading it).  Round 1 used two buffers, register
+// staging and one CTA barrier per chunk: ptxas sank the prefetch loads below the FFMA2 block (their L2 latency sat in
+// front of every barrier) and a warp with survivors to re-score stalled the other seven (Gram: 21 % of the warp time at
+// that barrier).  Now there is no CTA barrier in the loop and warps may drift up to kBbAhead chunks apart.
+// Stages: 4 for 27-dimensional descriptors, 8 for 9-dimensional ones (measured: Gram 1.23 -> 1.21 ms with 8,
+// BestBuddy / PatchwiseST 1-3 % slower); a thread copies kBbAhead = stages / 2 chunks ahead of the one it scores.
 constexpr int kBbMaxStages = 8;
-template <int D> constexpr int bb_stages() { return D <= 9 ? 8 : 4; }
+template <int D> struct BbStages { static constexpr int value = D <= 9 ? 8 : 4; };
 template <int D>
-constexpr size_t bb_search_dyn_smem(bool pipe) { return pipe ? sizeof(float) * bb_stages<D>() * (D + 1) * BB_CT : 0; }
+constexpr size_t bb_search_dyn_smem() { return sizeof(float) * BbStages<D>::value * (D + 1) * BB_CT; }
 
-template <int D, bool SHARE = false, bool PIPE = false>
+template <int D, bool SHARE = false>
 __global__ void __launch_bounds__(BB_NT, 1)
 bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, float alpha, float beta,
                  int64_t* __restrict__ idx_out) {
   static_assert(BB_NT == 256 && BB_QT == 128 && BB_CT == 128, "search tile is 16x16 threads x (8 queries x 8 candidates)");
-  constexpr int kBbStages = bb_stages<D>(), kBbAhead = kBbStages / 2;
-  SRST_DYN_SMEM(float, dyn);                          // PIPE: [stages][D][BB_CT] candidates, then [stages][BB_CT] |y|^2
+  constexpr int kBbStages = BbStages<D>::value, kBbAhead = kBbStages / 2;
+  SRST_DYN_SMEM(float, dyn);                          // [stages][D][BB_CT] candidates, then [stages][BB_CT] |y|^2
   __shared__ __align__(8) unsigned long long mb_full[kBbMaxStages], mb_empty[kBbMaxStages];
   __shared__ __align__(16) float sQ[D][BB_QT];      // alpha*x + beta*g
   // short descriptors (Gram): the survivors' exact re-scoring reads x, g (and y from the chunk buffer) from shared
@@ -461,16 +462,12 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
   [[maybe_unused]] __shared__ __align__(16) float sX1[EXACT_SMEM ? D : 1][EXACT_SMEM ? BB_QT : 4];
   [[maybe_unused]] __shared__ __align__(16) float sX2[EXACT_SMEM ? D : 1][EXACT_SMEM ? BB_QT : 4];
   [[maybe_unused]] __shared__ __align__(16) float sXn[EXACT_SMEM ? 2 : 1][EXACT_SMEM ? BB_QT : 4];   // |x|^2, |g|^2
-  __shared__ __align__(16) float sY2[PIPE ? 1 : 2][PIPE ? 1 : D][PIPE ? 4 : BB_CT];
-  float (*sY)[D][BB_CT] = PIPE ? reinterpret_cast<float (*)[D][BB_CT]>(dyn) : reinterpret_cast<float (*)[D][BB_CT]>(&sY2[0][0][0]);
-  [[maybe_unused]] float (*sYp)[BB_CT] = reinterpret_cast<float (*)[BB_CT]>(dyn + kBbStages * D * BB_CT);   // PIPE: |y|^2 per stage
-  __shared__ __align__(16) float sYl[2][PIPE ? 4 : BB_CT];     // (alpha+beta)|y|^2 - kappa*(|alpha|+|beta|)|y|^2
-  [[maybe_unused]] __shared__ __align__(16) float sYn[2][(D > 9 && !SHARE && !PIPE) ? BB_CT : 4];   // |y|^2 as copied from the workspace (cp.async path)
+  float (*sY)[D][BB_CT] = reinterpret_cast<float (*)[D][BB_CT]>(dyn);
+  float (*sYp)[BB_CT] = reinterpret_cast<float (*)[BB_CT]>(dyn + kBbStages * D * BB_CT);   // |y|^2 per stage
   __shared__ __align__(16) float sCl[BB_QT];        // c_i - kappa*(|alpha||x|^2 + |beta||g|^2)
   __shared__ __align__(16) float sB0[BB_QT];        // exact score of the co-located candidate j = i
   // SHARE only: 2*tol of a pair is at most 2 kappa (ca_i + max over the chunk's valid candidates of yt_j)
   [[maybe_unused]] __shared__ __align__(16) float sCa[SHARE ? BB_QT : 4];   // |alpha||x|^2 + |beta||g|^2
-  [[maybe_unused]] __shared__ __align__(16) float sYtm[2][4];               // per staging warp: max (|alpha|+|beta|)|y|^2
   __shared__ int sW[BB_NT / 32][64];   // per warp: queued survivors (tile query << 8 | chunk candidate), then their exact scores
 
   const int tid = threadIdx.x;
@@ -498,69 +495,12 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
                           : __int_as_float(0xff800000);
   }
 
-  // Candidate-chunk staging: D * BB_CT / 4 16-byte pieces over BB_NT threads into the buffer the previous chunk used,
-  // while this chunk is being scored.  D = 27 (ASYNC): cp.async (LDGSTS) straight into shared memory -- staging
-  // through registers let the compiler sink the loads behind the FFMA2 block to save registers, and their L2 latency
-  // was then exposed in front of every chunk barrier (8 % long-scoreboard + 9 % barrier stalls; 1.95 -> 1.80 ms at
-  // batch 64 x 192x192).  D = 9: the chunk is short and the register path measured faster (Gram 1.48 vs 1.55 ms).
-  constexpr bool ASYNC = D > 9 && !SHARE && !PIPE;   // PatchwiseST (SHARE) also measured faster through registers: 2.84 vs 3.04 ms
-  constexpr int NLD = (D * (BB_CT / 4) + BB_NT - 1) / BB_NT;
-  [[maybe_unused]] float4 pf[(ASYNC || PIPE) ? 1 : NLD];
-  [[maybe_unused]] float pfn_reg = 0.f;
-  auto prefetch = [&](int buf, int chunk) {
-    if constexpr (ASYNC) {
-      for (int it = tid; it < D * (BB_CT / 4); it += BB_NT) {
-        const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
-        cp_async16(&sY[buf][k][4 * c4], P.y + (size_t)k * g.Mpad + chunk + 4 * c4, true);
-      }
-      if (tid < BB_CT) cp_async4(&sYn[buf][tid], P.yn + chunk + tid);
-      cp_async_commit();
-    } else {
-#pragma unroll
-      for (int u = 0; u < NLD; ++u) {
-        const int it = tid + u * BB_NT;
-        if (it < D * (BB_CT / 4)) {
-          const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
-          pf[u] = ldg4(P.y + (size_t)k * g.Mpad + chunk + 4 * c4);
-        }
-      }
-      if (tid < BB_CT) pfn_reg = __ldg(P.yn + chunk + tid);
-    }
-  };
-  // the copies have landed (ASYNC) / are stored (registers); then the per-candidate part of the bound
-  auto commit = [&](int buf, int chunk) {
-    if constexpr (ASYNC) {
-      cp_async_wait_all();
-    } else {
-#pragma unroll
-      for (int u = 0; u < NLD; ++u) {
-        const int it = tid + u * BB_NT;
-        if (it < D * (BB_CT / 4)) {
-          const int k = it / (BB_CT / 4), c4 = it - k * (BB_CT / 4);
-          st4(&sY[buf][k][4 * c4], pf[u]);
-        }
-      }
-    }
-    // padded candidates (|y|^2 = +inf in the workspace) get a lower bound of exactly +inf: it never passes the
-    // filter, not even against a NaN-poisoned comparison (inf - inf would be NaN, which now counts as a hit)
-    if (tid < BB_CT) {
-      const float pfn = ASYNC ? sYn[buf][tid] : pfn_reg;   // ASYNC: each thread reads back its own 4-byte copy
-      sYl[buf][tid] = (chunk + tid < g.M) ? (alpha + beta) * pfn - kBbKappa * ((aa + ab) * pfn) : __int_as_float(0x7f800000);
-      if constexpr (SHARE) {
-        float m = (chunk + tid < g.M) ? (aa + ab) * pfn : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((tid & 31) == 0) sYtm[buf][tid >> 5] = m;
-      }
-    }
-  };
-
   const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads; a half-warp shares ty (its queries)
   // local query l (0..7) -> tile query ty*4 + (l&3) + 64*(l>>2); same for candidates with tx
 
   const int nchunks = g.Mpad / BB_CT;
-  // PIPE: chunk c lives in stage c % kBbStages (its (c / kBbStages)-th use); every thread copies its share of the chunk
-  // and arrives on the stage's "full" barrier once its copies have landed
+  // chunk c lives in stage c % kBbStages (its (c / kBbStages)-th use); every thread copies its share of the chunk
+  // (D * BB_CT / 4 16-byte pieces over BB_NT threads) and arrives on the stage's "full" barrier once its copies have landed
   auto pipe_load = [&](int c) {
     const int st = c % kBbStages, chunk = c * BB_CT;
     for (int it = tid; it < D * (BB_CT / 4); it += BB_NT) {
@@ -570,16 +510,10 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     if (tid < BB_CT) cp_async4(&sYp[st][tid], P.yn + chunk + tid);
     cp_async_mbar_arrive(&mb_full[st]);
   };
-  if constexpr (PIPE) {
-    if (tid == 0)
-      for (int st = 0; st < kBbStages; ++st) { mbar_init(&mb_full[st], BB_NT); mbar_init(&mb_empty[st], BB_NT); }
-    __syncthreads();  // the barriers are initialised before anyone arrives on them
-    for (int c = 0; c < kBbAhead && c < nchunks; ++c) pipe_load(c);
-  } else {
-    prefetch(0, 0);
-    commit(0, 0);
-  }
-  __syncthreads();  // queries and bounds (and chunk 0) are in shared memory
+  if (tid == 0)
+    for (int st = 0; st < kBbStages; ++st) { mbar_init(&mb_full[st], BB_NT); mbar_init(&mb_empty[st], BB_NT); }
+  __syncthreads();  // the barriers are initialised before anyone arrives on them; queries and bounds are in shared memory
+  for (int c = 0; c < kBbAhead && c < nchunks; ++c) pipe_load(c);
 
   float best[8], B[8], Bc[8], clq[8];
   int bidx[8];
@@ -600,18 +534,14 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
   }
 
-  for (int chunk = 0, ci = 0, buf = 0; chunk < g.Mpad; chunk += BB_CT, ++ci, buf = PIPE ? (ci % kBbStages) : (buf ^ 1)) {
-    const bool more = chunk + BB_CT < g.Mpad;
-    if constexpr (PIPE) {
-      if (ci + kBbAhead < nchunks) {
-        const int c2 = ci + kBbAhead, u2 = c2 / kBbStages;
-        if (u2 >= 1) mbar_wait(&mb_empty[c2 % kBbStages], (unsigned)((u2 - 1) & 1));  // chunk c2 - kBbStages has been read by everyone
-        pipe_load(c2);
-      }
-      mbar_wait(&mb_full[buf], (unsigned)((ci / kBbStages) & 1));
-    } else {
-      if (more) prefetch(buf ^ 1, chunk + BB_CT);  // buf^1 was last read before the previous barrier
+  for (int ci = 0; ci < nchunks; ++ci) {
+    const int chunk = ci * BB_CT, buf = ci % kBbStages;
+    if (ci + kBbAhead < nchunks) {
+      const int c2 = ci + kBbAhead, u2 = c2 / kBbStages;
+      if (u2 >= 1) mbar_wait(&mb_empty[c2 % kBbStages], (unsigned)((u2 - 1) & 1));  // chunk c2 - kBbStages has been read by everyone
+      pipe_load(c2);
     }
+    mbar_wait(&mb_full[buf], (unsigned)((ci / kBbStages) & 1));
 
     float2 acc[4][8];  // [query pair][candidate]: .x = local query 2p, .y = 2p+1
 #pragma unroll
@@ -638,11 +568,11 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     // anywhere still reaches the exact path) tested once against Bc_i: the 64 compares + mask updates only run in the
     // rare chunks that hold a survivor.
     unsigned long long hit = 0ull;
+    // the per-candidate part of the bound straight from |y|^2; padded candidates (|y|^2 = +inf in the workspace) get a
+    // lower bound of exactly +inf (inf - inf would be NaN, which counts as a hit)
     float yl[8];
-    [[maybe_unused]] float ytloc = 0.f;   // PIPE + SHARE: max over this thread's valid candidates of (|alpha|+|beta|)|y|^2
-    if constexpr (PIPE) {
-      // the per-candidate part of the bound straight from |y|^2; padded candidates (|y|^2 = +inf in the workspace) get
-      // a lower bound of exactly +inf (inf - inf would be NaN, which counts as a hit)
+    [[maybe_unused]] float ytloc = 0.f;   // SHARE: max over this thread's valid candidates of (|alpha|+|beta|)|y|^2
+    {
       const float4 na = ld4(&sYp[buf][4 * tx]), nb = ld4(&sYp[buf][64 + 4 * tx]);
       const float yn8[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
 #pragma unroll
@@ -651,9 +581,6 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
         yl[j] = valid ? (alpha + beta) * yn8[j] - kBbKappa * ((aa + ab) * yn8[j]) : __int_as_float(0x7f800000);
         if constexpr (SHARE) ytloc = fmaxf(ytloc, valid ? (aa + ab) * yn8[j] : 0.f);
       }
-    } else {
-      const float4 yla = ld4(&sYl[buf][4 * tx]), ylb = ld4(&sYl[buf][64 + 4 * tx]);
-      yl[0] = yla.x; yl[1] = yla.y; yl[2] = yla.z; yl[3] = yla.w; yl[4] = ylb.x; yl[5] = ylb.y; yl[6] = ylb.z; yl[7] = ylb.w;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -675,15 +602,9 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
       // chunk of yt): pool min_j L_ij + delta_i over the half-warp into B_i before the test
       const int cidx = chunk / BB_CT;
       if (cidx < 4 || (cidx & 3) == 0) {
-        float ytmax;
-        if constexpr (PIPE) {   // the 16 lanes of a half-warp hold all 128 candidates of the chunk between them
-          ytmax = ytloc;
+        float ytmax = ytloc;   // the 16 lanes of a half-warp hold all 128 candidates of the chunk between them
 #pragma unroll
-          for (int o = 1; o <= 8; o <<= 1) ytmax = fmaxf(ytmax, __shfl_xor_sync(0xffffffffu, ytmax, o));
-        } else {
-          const float4 ym = ld4(&sYtm[buf & 1][0]);
-          ytmax = fmaxf(fmaxf(ym.x, ym.y), fmaxf(ym.z, ym.w));
-        }
+        for (int o = 1; o <= 8; o <<= 1) ytmax = fmaxf(ytmax, __shfl_xor_sync(0xffffffffu, ytmax, o));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float m = mq[i];
@@ -792,12 +713,7 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
         __syncwarp();  // the queue is reused by the next window
       }
     }
-    if constexpr (PIPE) {
-      mbar_arrive(&mb_empty[buf]);  // this thread is done with the stage
-    } else {
-      if (more) commit(buf ^ 1, chunk + BB_CT);
-      __syncthreads();
-    }
+    mbar_arrive(&mb_empty[buf]);  // this thread is done with the stage
   }
 
   // argmin across the 16 threads (one half-warp) that share these queries: four shuffle steps

@@ -735,18 +735,11 @@ static int bb_forward_impl(const float* sr, const float* gt, const float* gt2, c
     SRST_LAUNCH(bb_search_l1_kernel<D>, dim3(g.Npad / BB_QT, B), dim3(BB_NT), 0, stream, w.mats, w.per_image, g, alpha, beta,
                 idx_out);
   else {
-    // SRST_BB_PIPE (read once): 1 = the four-stage mbarrier ring, 0 = two buffers and a CTA barrier per chunk
-    static const bool pipe = env_int_once("SRST_BB_PIPE", 1) != 0;
-    if (pipe) {
-      struct SearchTag {};
-      constexpr size_t dyn = bb_search_dyn_smem<D>(true);
-      if ((e = ensure_smem<SearchTag>(bb_search_kernel<D, MODE == 2, true>, dyn)) != 0) return e;
-      SRST_LAUNCH((bb_search_kernel<D, MODE == 2, true>), dim3(g.Npad / BB_QT, B), dim3(BB_NT), dyn, stream, w.mats, w.per_image,
-                  g, alpha, beta, idx_out);
-    } else {
-      SRST_LAUNCH((bb_search_kernel<D, MODE == 2, false>), dim3(g.Npad / BB_QT, B), dim3(BB_NT), 0, stream, w.mats, w.per_image,
-                  g, alpha, beta, idx_out);
-    }
+    struct SearchTag {};
+    constexpr size_t dyn = bb_search_dyn_smem<D>();
+    if ((e = ensure_smem<SearchTag>(bb_search_kernel<D, MODE == 2>, dyn)) != 0) return e;
+    SRST_LAUNCH((bb_search_kernel<D, MODE == 2>), dim3(g.Npad / BB_QT, B), dim3(BB_NT), dyn, stream, w.mats, w.per_image, g,
+                alpha, beta, idx_out);
   }
   if ((e = (int)cudaGetLastError()) != 0) return e;
   const unsigned nl = (unsigned)(((size_t)B * g.N + BB_NT - 1) / BB_NT);
