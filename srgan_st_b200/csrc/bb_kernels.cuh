@@ -381,23 +381,6 @@ SRST_DEV void bb_argmin_merge(float& s, int& i, float so, int io) {
 // argmin is four warp-shuffle steps.
 constexpr float kBbKappa = 2e-5f;
 
-// Exact reference-order score of (query qi, candidate cj) of one image: the rare path.
-#ifdef SRST_EMULATE
-static float
-#else
-__device__ __noinline__ float
-#endif
-bb_exact_score(const float* q1, const float* q2, const float* y, const float* xn, const float* gn, const float* yn,
-               int Npad, int Mpad, int D, int qi, int cj, float alpha, float beta) {
-  float dot1 = 0.f, dot2 = 0.f;
-  for (int k = 0; k < D; ++k) {
-    const float w = __ldg(y + (size_t)k * Mpad + cj);
-    dot1 = fmaf(__ldg(q1 + (size_t)k * Npad + qi), w, dot1);
-    dot2 = fmaf(__ldg(q2 + (size_t)k * Npad + qi), w, dot2);
-  }
-  return bb_score(__ldg(xn + qi), __ldg(gn + qi), __ldg(yn + cj), dot1, dot2, alpha, beta);
-}
-
 // The filter compares lo' = yl_j - 2 acc_ij with Bc_i instead of cl_i + lo' with B_i.  With F = fl(B - cl),
 // Bc = F + 6e-7 |F| guarantees  lo' > Bc  =>  cl + yl - 2 acc > B  in real arithmetic on the fp32 operands (the two
 // roundings involved, of lo' and of F, are each below 1.2e-7 of max(|lo'|, |F|), and |lo'| > |F| only where the margin
@@ -407,9 +390,9 @@ SRST_DEV float bb_shifted_bound(float B, float cl) {
   return (B == __int_as_float(0xff800000)) ? B : fmaf(6e-7f, fabsf(F), F);
 }
 
-// The same score with the descriptor length known at compile time: all 3 D operands are loaded up front (independent
-// loads: one L1/L2 round trip instead of D dependent ones), then the two sequential-fma chains run in the oracle's
-// order.  This is the survivors' path of the search kernel: a survivor used to cost D load-to-use latencies.
+// Exact reference-order score of (query qi, candidate cj) of one image (the seed of the bound and the survivors' path):
+// all 3 D operands are loaded up front (independent loads: one L1/L2 round trip instead of D dependent ones), then the
+// two sequential-fma chains run in the oracle's order.
 template <int D>
 SRST_DEV float bb_exact_score_unrolled(const float* q1, const float* q2, const float* y, const float* xn, const float* gn,
                                        const float* yn, int Npad, int Mpad, int qi, int cj, float alpha, float beta) {
@@ -491,7 +474,8 @@ bb_search_kernel(const float* __restrict__ mats, size_t per_image, BbGeom g, flo
     sCl[tid] = fmaf(alpha, xn, beta * gn) - kBbKappa * fmaf(aa, xn, ab * gn);
     if constexpr (SHARE) sCa[tid] = fmaf(aa, xn, ab * gn);
     // seed of the upper bound; padded queries get -inf so that nothing is ever evaluated for them
-    sB0[tid] = (qi < g.N) ? bb_exact_score(P.q1, P.q2, P.y, P.xn, P.gn, P.yn, g.Npad, g.Mpad, D, qi, qi, alpha, beta)
+    // (unrolled: all operands in flight at once -- the rolled loop paid D dependent L2 round trips, ~8 us per CTA)
+    sB0[tid] = (qi < g.N) ? bb_exact_score_unrolled<D>(P.q1, P.q2, P.y, P.xn, P.gn, P.yn, g.Npad, g.Mpad, qi, qi, alpha, beta)
                           : __int_as_float(0xff800000);
   }
 
