@@ -63,7 +63,8 @@ int srst_st_supported(int r_sigma, int r_rho);
  * (read once). */
 int srst_st_num_cfgs(int backward);
 int srst_st_force_cfg(int fwd_cfg, int bwd_cfg);
-/* Forward cfgs 6 and 7 are the row-marching kernel (96- / 128-column strips).  It cuts a strip into row chunks so
+/* Forward cfgs 0-2 are tiled shapes (32x64, 24x96 with two or three CTAs per SM), 3 and 4 the row-marching kernel
+ * (96- / 112-column strips); backward cfgs: 0 = 28x56 tiles, 1 = 12x96 strips (both persistent).  The marching kernel cuts a strip into row chunks so
  * that small batches fill the machine; `blocks` > 0 forces the chunk height to blocks*16 rows (tests), <= 0 hands
  * the choice back to the library.  Process-wide; SRST_ST_CHUNK_BLOCKS sets the initial value. */
 int srst_st_force_chunk_blocks(int blocks);

@@ -42,28 +42,21 @@ static int forced_bwd() {
 }
 
 // ---- compiled structure-tensor tile configurations (reference default radii: r_sigma 2, r_rho 8) ----
+// Only shapes the dispatcher can pick are compiled (the sweeps that selected them: profiles/r02_tile_sweep.log; the
+// round-1 shapes that lost them are gone).  Forward cfg ids: 0-2 tiled (unaligned tensors / fall-back), 3-4 marching.
 //                       TH  TW  RS CSB RG RK MINB CHU
-using Fwd0 = StFwdCfg<48, 48, 12, 4, 2, 8, 2>;     // square quarter of a 96x96 crop, 288 threads, rolled
-using Fwd1 = StFwdCfg<32, 64, 16, 4, 2, 8, 3, 0, true>;  // large images, 256 threads, unrolled: three CTAs per SM; plane-split vertical items
-using Fwd2 = StFwdCfg<24, 96, 8, 4, 2, 8, 2>;      // full-width strip of a 96-wide crop (no horizontal halo), 288 threads, rolled
-using Fwd3 = StFwdCfg<24, 96, 8, 4, 2, 8, 2, 0>;   // Fwd2 unrolled
-using Fwd4 = StFwdCfg<24, 96, 8, 4, 2, 8, 3, 0>;   // Fwd3 with three CTAs per SM (72 registers): multi-wave batches of 96-wide crops
-using Fwd5 = StFwdCfg<40, 64, 10, 4, 2, 8, 2, 0>;  // taller unrolled tile, 320 threads, two CTAs per SM
-// cfg 6, 7: the row-marching kernel (st_march.cuh), 96- and 112-column strips -- the default whenever TMA can
+using Fwd0 = StFwdCfg<32, 64, 16, 4, 2, 8, 3, 0, true>;  // large images, 256 threads, unrolled: three CTAs per SM; plane-split vertical items
+using Fwd1 = StFwdCfg<24, 96, 8, 4, 2, 8, 2, 0>;   // full-width strip of a 96-wide crop (no horizontal halo), 288 threads, unrolled
+using Fwd2 = StFwdCfg<24, 96, 8, 4, 2, 8, 3, 0>;   // Fwd1 with three CTAs per SM (72 registers): multi-wave batches of 96-wide crops
+// cfg 3, 4: the row-marching kernel (st_march.cuh), 96- and 112-column strips -- the default whenever TMA can
 // fetch the images; the tiled shapes above remain for unaligned tensors and as the fall-back
 using March96 = StMarchCfg<96, 2, 8>;
 using March112 = StMarchCfg<112, 2, 8>;
-constexpr int kNumFwdCfg = 8;
-//                       TH  TW  RS   NT RG RK MINB CSD
-using Bwd0 = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8>;  // large images: 16 row pairs per horizontal-pass column
-using Bwd1 = StBwdCfg<16, 96, 10, 288, 2, 8, 2, 8>;  // full-width strips of 96-wide crops
-using Bwd2 = StBwdCfg<12, 96, 8, 224, 2, 8, 2, 8>;   // shorter strips for small batches (more CTAs)
-using Bwd3 = StBwdCfg<20, 56, 12, 192, 2, 8, 3, 8>;  // three CTAs per SM
-using Bwd4 = StBwdCfg<24, 64, 14, 256, 2, 8, 2, 8>;
-using Bwd5 = StBwdCfg<28, 96, 16, 384, 2, 8, 1, 8>;  // 96-wide crops, one large CTA per SM
-using Bwd6 = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8, true>;  // Bwd0, persistent with the next tile's boxes prefetched
-using Bwd7 = StBwdCfg<12, 96, 8, 224, 2, 8, 2, 8, true>;   // Bwd2, persistent with the next tile's boxes prefetched
-constexpr int kNumBwdCfg = 8;
+constexpr int kNumFwdCfg = 5, kFwdMarch96 = 3, kFwdMarch112 = 4;
+//                       TH  TW  RS   NT RG RK MINB CSD PIPE
+using Bwd0 = StBwdCfg<28, 56, 16, 256, 2, 8, 2, 8, true>;  // large images: persistent CTAs, the next tile's boxes prefetched
+using Bwd1 = StBwdCfg<12, 96, 8, 224, 2, 8, 2, 8, true>;   // full-width strips of 96-wide crops, persistent
+constexpr int kNumBwdCfg = 2;
 
 constexpr int kMinFwdTH = 16, kMinFwdTW = 48;  // finest forward work split (workspace sizing): 16-row chunks, 48-wide tiles
 
@@ -286,27 +279,26 @@ static int pick_fwd_cfg(int B, int H, int W) {
   // measured on B200 (profiles/r02_tile_sweep.log): full-width 24x96 strips win on 96-wide crops -- two CTAs per SM
   // while the batch is a single wave, the 72-register variant (three CTAs per SM) once there are several waves of
   // strips; the 32x64 tile with three CTAs per SM wins on large images (all unrolled kernels)
-  if (W <= 96) return ((long long)B * ((H + 23) / 24) >= 6LL * sm_count()) ? 4 : 3;
-  return 1;
+  if (W <= 96) return ((long long)B * ((H + 23) / 24) >= 6LL * sm_count()) ? 2 : 1;
+  return 0;
 }
 // Strip width of the marching kernel: the one that pads the image width least (cost = strips * (TW + 2 RK) columns
-// of gradient work); cfg 6 = 96 columns, cfg 7 = 112 (15 warps: four per scheduler, 128 registers).
+// of gradient work); 96 columns or 112 (15 warps: four per scheduler, 128 registers).
 static int pick_march_cfg(int W) {
   const int forced = forced_fwd();
-  if (forced == 6 || forced == 7) return forced;
+  if (forced == kFwdMarch96 || forced == kFwdMarch112) return forced;
   if (forced >= 0) return -1;  // a tiled shape was asked for
   static const bool off = env_int_once("SRST_ST_MARCH", 1) == 0;
   if (off) return -1;
   const long long c96 = (long long)((W + 95) / 96) * (96 + 16), c112 = (long long)((W + 111) / 112) * (112 + 16);
-  return c96 <= c112 ? 6 : 7;
+  return c96 <= c112 ? kFwdMarch96 : kFwdMarch112;
 }
 static int pick_bwd_cfg(int B, int H, int W) {
   const int forced = forced_bwd();
   if (forced >= 0 && forced < kNumBwdCfg) return forced;
-  // measured on B200 (profiles/r02_tile_sweep.log): the persistent, prefetching kernels win everywhere -- full-width
-  // 12x96 strips on 96-wide crops, the 28x56 tile on large images
+  // measured on B200 (profiles/r02_tile_sweep.log): full-width 12x96 strips on 96-wide crops, the 28x56 tile on large images
   (void)B; (void)H;
-  return W <= 96 ? 7 : 6;
+  return W <= 96 ? 1 : 0;
 }
 
 }  // namespace srst
@@ -429,23 +421,20 @@ static int st_forward_rr(const StCall& c) {
     const int mcfg = pick_march_cfg(c.W);
     if (mcfg >= 0) {
       int e;
-      if (mcfg == 6) e = c.px ? launch_st_march<March96, true>(P, c.stream) : launch_st_march<March96>(P, c.stream);
+      if (mcfg == kFwdMarch96) e = c.px ? launch_st_march<March96, true>(P, c.stream) : launch_st_march<March96>(P, c.stream);
       else e = c.px ? launch_st_march<March112, true>(P, c.stream) : launch_st_march<March112>(P, c.stream);
       if (e != kMarchUnusable) return e;
     }
     int cfg = pick_fwd_cfg(c.B, c.H, c.W);
-    if (cfg >= 6) cfg = (c.W <= 96) ? 3 : 1;  // a marching shape was forced but TMA cannot fetch these tensors
+    if (cfg >= kFwdMarch96) cfg = (c.W <= 96) ? 1 : 0;  // a marching shape was forced but TMA cannot fetch these tensors
     if (c.px) {  // the fused Pixel term is compiled into the two default tile shapes only
-      if (cfg != 1 && c.W <= 96) return launch_st_forward<Fwd3, true>(P, c.stream);
-      return launch_st_forward<Fwd1, true>(P, c.stream);
+      if (cfg != 0 && c.W <= 96) return launch_st_forward<Fwd1, true>(P, c.stream);
+      return launch_st_forward<Fwd0, true>(P, c.stream);
     }
     switch (cfg) {
-      case 0: return launch_st_forward<Fwd0>(P, c.stream);
+      case 1: return launch_st_forward<Fwd1>(P, c.stream);
       case 2: return launch_st_forward<Fwd2>(P, c.stream);
-      case 3: return launch_st_forward<Fwd3>(P, c.stream);
-      case 4: return launch_st_forward<Fwd4>(P, c.stream);
-      case 5: return launch_st_forward<Fwd5>(P, c.stream);
-      default: return launch_st_forward<Fwd1>(P, c.stream);
+      default: return launch_st_forward<Fwd0>(P, c.stream);
     }
   } else {
     using G = StFwdCfg<32, 64, 16, 4, RG, RK, (RK <= 8 ? 2 : 1), 0>;
@@ -464,20 +453,12 @@ static int st_backward_rr(const StCall& c) {
   P.inv_count = (float)(1.0 / ((double)c.B * c.H * c.W));
   P.taps = cached_taps<RG, RK>(c.g, c.dg, c.rs, c.k, c.rk);
   if constexpr (RG == 2 && RK == 8) {
-    if (c.px_other) {  // the fused Pixel term is compiled into the two default tile shapes only
-      if (c.W <= 96) return launch_st_backward<Bwd7, true>(P, c.stream);
-      return launch_st_backward<Bwd6, true>(P, c.stream);
+    if (c.px_other) {  // the fused Pixel term is compiled into the two default tile shapes
+      if (c.W <= 96) return launch_st_backward<Bwd1, true>(P, c.stream);
+      return launch_st_backward<Bwd0, true>(P, c.stream);
     }
-    switch (pick_bwd_cfg(c.B, c.H, c.W)) {
-      case 1: return launch_st_backward<Bwd1>(P, c.stream);
-      case 2: return launch_st_backward<Bwd2>(P, c.stream);
-      case 3: return launch_st_backward<Bwd3>(P, c.stream);
-      case 4: return launch_st_backward<Bwd4>(P, c.stream);
-      case 5: return launch_st_backward<Bwd5>(P, c.stream);
-      case 6: return launch_st_backward<Bwd6>(P, c.stream);
-      case 7: return launch_st_backward<Bwd7>(P, c.stream);
-      default: return launch_st_backward<Bwd0>(P, c.stream);
-    }
+    if (pick_bwd_cfg(c.B, c.H, c.W) == 1) return launch_st_backward<Bwd1>(P, c.stream);
+    return launch_st_backward<Bwd0>(P, c.stream);
   } else {
     using G = StBwdCfg<24, 64, (24 + 2 * RG) / 2, 256, RG, RK, (RK <= 8 ? 2 : 1), 4>;
     return c.px_other ? launch_st_backward<G, true>(P, c.stream) : launch_st_backward<G>(P, c.stream);

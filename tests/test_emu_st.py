@@ -15,16 +15,16 @@ def lib():
     return emu_lib()
 
 
-@pytest.fixture(params=[0, 1, 2, 3, 4, 5, 6, 7])  # forward shape = backward shape = param
+@pytest.fixture(params=[(0, 0), (1, 1), (2, 0), (3, 1), (4, 0)], ids=lambda p: f"fwd{p[0]}-bwd{p[1]}")
 def tile_cfg(request, lib):
-    """Every compiled forward shape (0-5 tiled, 6-7 row-marching), paired with a backward shape (srst_st_force_cfg)."""
-    assert lib.srst_st_num_cfgs(0) >= 8 and lib.srst_st_num_cfgs(1) >= 8
-    assert lib.srst_st_force_cfg(request.param, request.param) == 0
+    """Every compiled forward shape (0-2 tiled, 3-4 row-marching), paired with a backward shape (srst_st_force_cfg)."""
+    assert lib.srst_st_num_cfgs(0) == 5 and lib.srst_st_num_cfgs(1) == 2
+    assert lib.srst_st_force_cfg(*request.param) == 0
     yield request.param
     lib.srst_st_force_cfg(-1, -1)
 
 
-@pytest.mark.parametrize("cfg", [6, 7])
+@pytest.mark.parametrize("cfg", [3, 4])
 @pytest.mark.parametrize("chunk_blocks", [1, 2, 3])
 @pytest.mark.parametrize("shape", [(1, 100, 152), (2, 96, 96), (1, 37, 52), (1, 52, 204)])
 def test_emulated_marching_forward_row_chunks(lib, cfg, chunk_blocks, shape):

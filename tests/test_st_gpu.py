@@ -32,16 +32,14 @@ def _run(sr, hr, normalize=True, want_hr=True, sigma=0.5, rho=2.0):
     return loss.item(), x.grad.cpu().numpy(), (y.grad.cpu().numpy() if want_hr else None)
 
 
-N_FWD, N_BWD = 8, 8   # compiled tile shapes exercised per direction (srst_st_num_cfgs() >= these)
-
-
-@pytest.fixture(params=[-1, 0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.fixture(params=[(-1, -1), (0, 0), (1, 1), (2, 0), (3, 1), (4, 0), (3, 0), (4, 1)], ids=lambda p: f"fwd{p[0]}-bwd{p[1]}")
 def tile_cfg(request):
-    """-1 = the library's own choice; 0.. force a compiled forward / backward tile shape (srst_st_force_cfg)."""
+    """(-1, -1) = the library's own choice; otherwise force a compiled forward (0-2 tiled, 3-4 marching) and backward
+    (0-1) tile shape (srst_st_force_cfg)."""
     from srgan_st_b200 import _cabi
     lib = _cabi.lib()
-    assert lib.srst_st_num_cfgs(0) >= N_FWD and lib.srst_st_num_cfgs(1) >= N_BWD
-    assert lib.srst_st_force_cfg(request.param % N_FWD if request.param >= 0 else -1, request.param) == 0
+    assert lib.srst_st_num_cfgs(0) == 5 and lib.srst_st_num_cfgs(1) == 2
+    assert lib.srst_st_force_cfg(*request.param) == 0
     yield request.param
     lib.srst_st_force_cfg(-1, -1)
 
@@ -108,7 +106,7 @@ def test_matches_oracle_on_larger_shapes(shape):
     assert maxnorm_err(d_hr, ref["d_hr"]) < 1e-4
 
 
-@pytest.mark.parametrize("cfg", [6, 7])
+@pytest.mark.parametrize("cfg", [3, 4])
 @pytest.mark.parametrize("chunk_blocks", [1, 2, 5])
 @pytest.mark.parametrize("shape", [(2, 96, 96), (1, 100, 152), (1, 333, 516)])
 def test_marching_forward_row_chunks(cfg, chunk_blocks, shape):
