@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SRST_VERSION 203 /* major*100 + minor: the major number changes whenever an argument list changes */
+#define SRST_VERSION 204 /* major*100 + minor: the major number changes whenever an argument list changes */
 
 #define SRST_E_INVALID (-1)     /* null pointer / non-positive size / bad enum */
 #define SRST_E_UNSUPPORTED (-2) /* filter radius or patch geometry not compiled in */
@@ -255,6 +255,35 @@ int srst_patch_backward_gt(int mode, const float* sr, const float* gt, const flo
                            const float* g, const float* dg, int r_sigma, const float* k, int r_rho,
                            int criterion,
                            float* d_gt, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Best-Buddy loss with an arbitrary patch geometry: BestBuddyLoss(ksize, pad, stride) of the reference
+ * (loss.py:86; F.unfold(kernel_size=ksize, padding=pad, stride=stride) at loss.py:116-129) for everything
+ * but the default (3, 0, 3), which the tuned entry points above serve.  1 <= ksize <= 8, pad >= 0, stride >= 1;
+ * patches may overlap (stride < ksize), leave gaps (stride > ksize) and reach into the zero padding.
+ *   N = ny*nx, ny = (H + 2 pad - ksize)/stride + 1 (srst_bbg_num_patches); every pyramid level must hold at least
+ *   one patch (F.unfold raises otherwise): SRST_E_SHAPE.  D = 3*ksize*ksize elements per patch.
+ * Every (query, candidate) pair is scored exactly (no filter); criterion / SRST_BB_DIST_L1, gt2 / gt4 and the
+ * first-minimum rule as for srst_bb_forward.  Workspace: srst_bbg_workspace_bytes (always required; 0 = geometry or
+ * shape not usable).
+ * Backward: d_sr [B,3,H,W] sums, per pixel and in a fixed order, the criterion gradients grad_out/(B*N*D) *
+ * sign(sr_patch - cand[idx]) (or 2*diff) of the patches that cover the pixel; d_gt [B,3,H,W] is the gradient through
+ * the gather of the selected candidates (loss.py:136-139; atomicAdd, then the bicubic pyramid adjoint).  Either of
+ * d_sr / d_gt may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+int srst_bbg_supported(int ksize, int pad, int stride);
+size_t srst_bbg_workspace_bytes(int B, int H, int W, int ksize, int pad, int stride);
+long long srst_bbg_num_patches(int H, int W, int ksize, int pad, int stride);
+int srst_bbg_forward(const float* sr, const float* gt, const float* gt2, const float* gt4,
+                     int B, int H, int W, int ksize, int pad, int stride,
+                     float alpha, float beta, int criterion,
+                     int64_t* idx_out, float* loss_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int srst_bbg_backward(const float* sr, const float* gt, const float* gt2, const float* gt4,
+                      const int64_t* idx, const float* grad_out,
+                      int B, int H, int W, int ksize, int pad, int stride, int criterion,
+                      float* d_sr, float* d_gt,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* The HR pyramid on its own (exposed for tests): out2 [B,3,H/2,W/2], out4 [B,3,H/4,W/4]. */
 int srst_bb_pyramid(const float* gt, int B, int H, int W, float* out2, float* out4, void* stream);

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsrst.so")
 SOURCES = ["srst_cabi.cu"]
-DEPS = ["srst_cabi.cu", "st_kernels.cuh", "st_march.cuh", "st_generic.cuh", "bb_kernels.cuh", "srst_device.cuh", os.path.join("..", "..", "include", "srst.h")]
+DEPS = ["srst_cabi.cu", "st_kernels.cuh", "st_march.cuh", "st_generic.cuh", "bb_kernels.cuh", "bb_generic.cuh", "srst_device.cuh", os.path.join("..", "..", "include", "srst.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -13,6 +13,7 @@
 
 #include "st_kernels.cuh"
 #include "st_march.cuh"
+#include "bb_generic.cuh"
 #include "st_generic.cuh"
 #include "bb_kernels.cuh"
 
@@ -671,6 +672,12 @@ size_t srst_bb_workspace_bytes(int B, int H, int W) {
   return bb_carve(nullptr, bb_geom(B, H, W)).total_bytes;
 }
 
+// grid of the grid-stride zero-fill: never more CTAs than the buffer has 256-element slices
+static unsigned fill_grid(size_t n, unsigned cap) {
+  const size_t want = (n + 255) / 256;
+  return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
 static int bb_launch_pyramid(const float* gt, const BbGeom& g, float* o2, float* o4, void* stream) {
   const size_t n = (size_t)g.B * 3 * ((size_t)g.H2 * g.W2 + (size_t)g.H4 * g.W4);
   const unsigned nblk = (unsigned)((n + 255) / 256);
@@ -869,8 +876,8 @@ int srst_patch_backward_gt(int mode, const float* sr, const float* gt, const flo
   float* d2 = w.mats;
   float* d4 = d2 + (n2 + 3) / 4 * 4;
   if ((n2 + 3) / 4 * 4 + n4 > w.per_image * (size_t)B) return SRST_E_WORKSPACE;
-  SRST_LAUNCH(bb_fill_zero_kernel, dim3(592), dim3(256), 0, stream, d_gt, n0);
-  SRST_LAUNCH(bb_fill_zero_kernel, dim3(148), dim3(256), 0, stream, d2, (n2 + 3) / 4 * 4 + n4);
+  SRST_LAUNCH(bb_fill_zero_kernel, dim3(fill_grid(n0, 592)), dim3(256), 0, stream, d_gt, n0);
+  SRST_LAUNCH(bb_fill_zero_kernel, dim3(fill_grid((n2 + 3) / 4 * 4 + n4, 148)), dim3(256), 0, stream, d2, (n2 + 3) / 4 * 4 + n4);
   const size_t total = (size_t)B * gm.N;
   if (mode == 0)
     SRST_LAUNCH(bb_backward_gt_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, sr, gt, gt2, gt4, idx,
@@ -908,6 +915,97 @@ int srst_bb_backward(const float* sr, const float* gt, const float* gt2, const f
   SRST_LAUNCH(bb_backward_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, sr, gt, gt2, gt4, idx,
               grad_out, g, criterion, d_sr);
   return (int)cudaGetLastError();
+}
+
+}  // extern "C"
+
+// ---- Best-Buddy loss, arbitrary patch geometry (bb_generic.cuh) -----------------------------------------------
+static int bbg_prepare(const float* gt, const float*& gt2, const float*& gt4, int B, int H, int W, const BbgGeom& g,
+                       void* workspace, size_t workspace_bytes, BbgWorkspace& w, void* stream) {
+  if (!workspace || !aligned16(workspace)) return SRST_E_WORKSPACE;
+  w = bbg_carve(workspace, g);
+  if (workspace_bytes < w.total_bytes) return SRST_E_WORKSPACE;
+  if ((gt2 == nullptr) != (gt4 == nullptr)) return SRST_E_INVALID;
+  if (!gt2) {
+    const int e = bb_launch_pyramid(gt, bb_geom(B, H, W), w.pyr2, w.pyr4, stream);
+    if (e) return e;
+    gt2 = w.pyr2;
+    gt4 = w.pyr4;
+  }
+  return 0;
+}
+
+extern "C" {
+
+int srst_bbg_supported(int ksize, int pad, int stride) {
+  return (ksize >= 1 && ksize <= BBG_MAXK && pad >= 0 && pad <= 64 && stride >= 1 && stride <= 4096) ? 1 : 0;
+}
+
+size_t srst_bbg_workspace_bytes(int B, int H, int W, int ksize, int pad, int stride) {
+  if (!bbg_geom_ok(B, H, W, ksize, pad, stride)) return 0;
+  return bbg_carve(nullptr, bbg_geom(B, H, W, ksize, pad, stride)).total_bytes;
+}
+
+long long srst_bbg_num_patches(int H, int W, int ksize, int pad, int stride) {
+  if (!bbg_geom_ok(1, H, W, ksize, pad, stride)) return 0;
+  return bbg_geom(1, H, W, ksize, pad, stride).N;
+}
+
+int srst_bbg_forward(const float* sr, const float* gt, const float* gt2, const float* gt4, int B, int H, int W, int ksize,
+                     int pad, int stride, float alpha, float beta, int criterion, int64_t* idx_out, float* loss_out,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (!sr || !gt || !idx_out || !loss_out || B <= 0) return SRST_E_INVALID;
+  const int dist_l1 = (criterion & SRST_BB_DIST_L1) ? 1 : 0;
+  criterion &= ~SRST_BB_DIST_L1;
+  if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
+  if (!srst_bbg_supported(ksize, pad, stride)) return SRST_E_UNSUPPORTED;
+  if (!bbg_geom_ok(B, H, W, ksize, pad, stride)) return SRST_E_SHAPE;
+  const BbgGeom g = bbg_geom(B, H, W, ksize, pad, stride);
+  BbgWorkspace w;
+  int e = bbg_prepare(gt, gt2, gt4, B, H, W, g, workspace, workspace_bytes, w, stream);
+  if (e) return e;
+  struct BbgSearchTag {};
+  const size_t dyn = bbg_search_smem(3 * BBG_MAXK * BBG_MAXK);  // one opt-in covers every ksize
+  if ((e = ensure_smem<BbgSearchTag>(bbg_search_kernel, dyn)) != 0) return e;
+  SRST_LAUNCH(bbg_search_kernel, dim3((unsigned)((g.N + BBG_QT - 1) / BBG_QT), (unsigned)B), dim3(BBG_NT),
+              bbg_search_smem(g.D), stream, sr, gt, gt2, gt4, g, alpha, beta, dist_l1, idx_out);
+  if ((e = (int)cudaGetLastError()) != 0) return e;
+  const unsigned nl = (unsigned)(((size_t)B * g.N + BBG_NT - 1) / BBG_NT);
+  SRST_LAUNCH(bbg_loss_kernel, dim3(nl), dim3(BBG_NT), 0, stream, sr, gt, gt2, gt4, g, idx_out, criterion, w.partials,
+              w.ticket, loss_out);
+  return (int)cudaGetLastError();
+}
+
+int srst_bbg_backward(const float* sr, const float* gt, const float* gt2, const float* gt4, const int64_t* idx,
+                      const float* grad_out, int B, int H, int W, int ksize, int pad, int stride, int criterion,
+                      float* d_sr, float* d_gt, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!sr || !gt || !idx || !grad_out || (!d_sr && !d_gt) || B <= 0) return SRST_E_INVALID;
+  criterion &= ~SRST_BB_DIST_L1;  // the search norm does not matter to the backward
+  if (criterion != SRST_BB_L1 && criterion != SRST_BB_L2) return SRST_E_INVALID;
+  if (!srst_bbg_supported(ksize, pad, stride)) return SRST_E_UNSUPPORTED;
+  if (!bbg_geom_ok(B, H, W, ksize, pad, stride)) return SRST_E_SHAPE;
+  const BbgGeom g = bbg_geom(B, H, W, ksize, pad, stride);
+  BbgWorkspace w;
+  int e = bbg_prepare(gt, gt2, gt4, B, H, W, g, workspace, workspace_bytes, w, stream);
+  if (e) return e;
+  const size_t n0 = (size_t)B * 3 * H * W;
+  if (d_sr) {
+    SRST_LAUNCH(bbg_backward_kernel, dim3((unsigned)((n0 + 255) / 256)), dim3(256), 0, stream, sr, gt, gt2, gt4, idx,
+                grad_out, g, criterion, d_sr);
+    if ((e = (int)cudaGetLastError()) != 0) return e;
+  }
+  if (d_gt) {
+    const size_t n2 = (size_t)B * 3 * g.L[1].H * g.L[1].W, n4 = (size_t)B * 3 * g.L[2].H * g.L[2].W;
+    SRST_LAUNCH(bb_fill_zero_kernel, dim3(fill_grid(n0, 592)), dim3(256), 0, stream, d_gt, n0);
+    SRST_LAUNCH(bb_fill_zero_kernel, dim3(fill_grid((n2 + 3) / 4 * 4 + n4, 148)), dim3(256), 0, stream, w.d2, (n2 + 3) / 4 * 4 + n4);
+    const size_t total = (size_t)B * g.N * 3;
+    SRST_LAUNCH(bbg_backward_gt_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, sr, gt, gt2, gt4, idx,
+                grad_out, g, criterion, d_gt, w.d2, w.d4);
+    SRST_LAUNCH(bb_pyramid_adjoint_kernel, dim3((unsigned)((n2 + n4 + 255) / 256)), dim3(256), 0, stream, w.d2, w.d4, d_gt,
+                B * 3, H, W, g.L[1].H, g.L[1].W, g.L[2].H, g.L[2].W);
+    if ((e = (int)cudaGetLastError()) != 0) return e;
+  }
+  return 0;
 }
 
 }  // extern "C"

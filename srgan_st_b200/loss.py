@@ -421,13 +421,75 @@ class _BestBuddyLossFn(torch.autograd.Function):
         return d_sr, d_gt, None, None, None, None, None
 
 
+class _BestBuddyGeometryFn(torch.autograd.Function):
+    """BestBuddyLoss with a non-default (ksize, pad, stride): the exact all-pairs path of libsrst (include/srst.h,
+    srst_bbg_forward / srst_bbg_backward).  Differentiable w.r.t. the SR patches (folded back over overlapping patches)
+    and, through the gather of the selected candidates, w.r.t. gt (loss.py:135-139); the argmin is not."""
+
+    @staticmethod
+    def forward(ctx, sr, gt, alpha, beta, criterion, pyramid, geom):
+        lib = _cabi.lib()
+        sr = sr.contiguous()
+        gt = gt.contiguous()
+        B, _, H, W = sr.shape
+        ks, pad, st = geom
+        N = lib.srst_bbg_num_patches(H, W, ks, pad, st)
+        nbytes = lib.srst_bbg_workspace_bytes(B, H, W, ks, pad, st)
+        if N <= 0 or nbytes == 0:
+            raise ValueError(f"BestBuddyLoss: a {H}x{W} image has a pyramid level without a single "
+                             f"ksize={ks}, pad={pad}, stride={st} patch (F.unfold would raise too)")
+        with _on_device(sr.device):
+            stream = _raw_stream(sr.device)
+            if pyramid == "aten":
+                with torch.no_grad():
+                    gt2 = torch.nn.functional.interpolate(gt, scale_factor=0.5, mode="bicubic",
+                                                          align_corners=False).contiguous()
+                    gt4 = torch.nn.functional.interpolate(gt, scale_factor=0.25, mode="bicubic",
+                                                          align_corners=False).contiguous()
+            else:
+                gt2 = gt4 = None
+            idx = torch.empty((B, N), dtype=torch.int64, device=sr.device)
+            loss = torch.empty((), dtype=torch.float32, device=sr.device)
+            ws = _workspace("bbg", sr.device, stream, nbytes)
+            rc = lib.srst_bbg_forward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), B, H, W, ks, pad, st, float(alpha),
+                                      float(beta), int(criterion), _ptr(idx), _ptr(loss), _ptr(ws), ws.numel(), stream)
+        _cabi.check(rc, "srst_bbg_forward")
+        ctx.save_for_backward(sr, gt, gt2, gt4, idx)
+        ctx.criterion = int(criterion)
+        ctx.geom = geom
+        ctx.mark_non_differentiable(idx)
+        return loss, idx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out, _grad_idx):
+        lib = _cabi.lib()
+        sr, gt, gt2, gt4, idx = ctx.saved_tensors
+        if not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            return None, None, None, None, None, None, None
+        B, _, H, W = sr.shape
+        ks, pad, st = ctx.geom
+        grad_out = grad_out.to(torch.float32).contiguous()
+        with _on_device(sr.device):
+            stream = _raw_stream(sr.device)
+            d_sr = torch.empty_like(sr) if ctx.needs_input_grad[0] else None
+            d_gt = torch.empty_like(gt) if ctx.needs_input_grad[1] else None
+            ws = _workspace("bbg", sr.device, stream, lib.srst_bbg_workspace_bytes(B, H, W, ks, pad, st))
+            rc = lib.srst_bbg_backward(_ptr(sr), _ptr(gt), _ptr(gt2), _ptr(gt4), _ptr(idx), _ptr(grad_out), B, H, W,
+                                       ks, pad, st, ctx.criterion, _ptr(d_sr), _ptr(d_gt), _ptr(ws), ws.numel(), stream)
+        _cabi.check(rc, "srst_bbg_backward")
+        return d_sr, d_gt, None, None, None, None, None
+
+
 class BestBuddyLoss(nn.Module):
     """Best-Buddy loss; same signature and semantics as reference loss.py:78-141.
 
     ``forward(x, gt)``: for every 3x3 SR patch pick the HR candidate patch (three pyramid levels)
     minimising ``alpha*|sr-cand|^2 + beta*|gt-cand|^2`` and return the L1 (or MSE) distance to it.
-    Only the reference's default patch geometry (ksize=3, pad=0, stride=3) has kernels; other values raise
-    ``NotImplementedError``.  ``dist_norm='l1'`` (utils.py:166-172) scores every pair exactly with
+    The reference's default patch geometry (ksize=3, pad=0, stride=3) runs the tuned filter + exact re-scoring search;
+    any other ``ksize`` (1..8), ``pad`` and ``stride`` -- overlapping patches, gaps, zero padding (F.unfold semantics,
+    loss.py:116-129) -- runs an exact all-pairs search kernel.  ``dist_norm='l1'`` (utils.py:166-172) scores every pair
+    exactly with
     ``alpha*sum|sr-cand| + beta*sum|gt-cand|`` (the reference materialises a [B,N,M,27] tensor for it).
 
     ``pyramid``: "fused" (default) lets libsrst build the two HR pyramid levels with the cubic taps of
@@ -455,9 +517,15 @@ class BestBuddyLoss(nn.Module):
             raise NotImplementedError("%s criterion has not been implmented." % criterion)  # loss.py:113
         if dist_norm not in ("l1", "l2"):
             raise NotImplementedError("%s norm has not been supported." % dist_norm)        # utils.py:189
+        self._geom = None   # None: the tuned (3, 0, 3) kernels; else the generic-geometry path
         if (ksize, pad, stride) != (3, 0, 3):
-            raise NotImplementedError(
-                "BestBuddyLoss: libsrst.so implements the reference default geometry only (ksize=3, pad=0, stride=3)")
+            if not all(isinstance(v, int) and not isinstance(v, bool) for v in (ksize, pad, stride)):
+                raise TypeError("BestBuddyLoss: ksize, pad and stride must be ints")
+            if not _cabi.lib().srst_bbg_supported(ksize, pad, stride):
+                raise NotImplementedError(
+                    f"BestBuddyLoss: libsrst.so has kernels for 1 <= ksize <= 8, pad >= 0, stride >= 1 "
+                    f"(got ksize={ksize}, pad={pad}, stride={stride})")
+            self._geom = (ksize, pad, stride)
         if dist_norm == "l1":
             self._crit |= _DIST_L1
         if pyramid not in ("aten", "fused"):
@@ -468,7 +536,10 @@ class BestBuddyLoss(nn.Module):
 
     def forward(self, x, gt):
         _check_pair(x, gt, "BestBuddyLoss")
-        loss, idx = _BestBuddyLossFn.apply(x, gt, self.alpha, self.beta, self._crit, self.pyramid)
+        if self._geom is not None:
+            loss, idx = _BestBuddyGeometryFn.apply(x, gt, self.alpha, self.beta, self._crit, self.pyramid, self._geom)
+        else:
+            loss, idx = _BestBuddyLossFn.apply(x, gt, self.alpha, self.beta, self._crit, self.pyramid)
         self.last_indices = idx
         return loss
 

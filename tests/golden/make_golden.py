@@ -257,10 +257,48 @@ def make_l1(ref_loss, ref_utils):
         print(f"{name}: loss={loss.item():.8g} N={p1.shape[1]} M={cat.shape[1]}")
 
 
+GEOM_CASES = [
+    # BestBuddyLoss with a non-default patch geometry (loss.py:116-129 use self.ksize / self.pad / self.stride):
+    # name, kind, B, H, W, seed, ksize, pad, stride, alpha, beta, dist_norm, criterion
+    ("bbg_k4p1s2_rand_2x24x28", "rand", 2, 24, 28, 51, 4, 1, 2, 1.0, 1.0, "l2", "l1"),     # overlapping, zero-padded
+    ("bbg_k3p1s1_srlike_1x20x24", "srlike", 1, 20, 24, 52, 3, 1, 1, 0.5, 2.0, "l2", "l2"),  # every pixel in nine patches
+    ("bbg_k5p0s5_rand_2x40x45", "rand", 2, 40, 45, 53, 5, 0, 5, 1.0, 1.0, "l2", "l1"),     # 75-dim patches, ragged levels
+    ("bbg_k2p0s3_rand_1x24x24", "rand", 1, 24, 24, 54, 2, 0, 3, 1.0, 1.0, "l1", "l1"),     # gaps between patches, l1 search
+]
+
+
+def make_geom(ref_loss, ref_utils):
+    import torch.nn.functional as F
+    for name, kind, B, H, W, seed, ks, pad, st, alpha, beta, dn, crit in GEOM_CASES:
+        sr, hr = _inputs(kind, B, H, W, seed)
+        sr.requires_grad_(True)
+        hr.requires_grad_(True)   # the gather of the selected candidates is differentiable in gt (loss.py:136-139)
+        m = ref_loss.BestBuddyLoss(alpha=alpha, beta=beta, ksize=ks, pad=pad, stride=st, dist_norm=dn, criterion=crit)
+        loss = m(sr, hr)
+        loss.backward()
+        with torch.no_grad():
+            unf = lambda t: F.unfold(t, kernel_size=ks, padding=pad, stride=st).permute(0, 2, 1).contiguous()
+            p1, p2 = unf(sr), unf(hr)
+            hr2 = F.interpolate(hr, scale_factor=0.5, mode="bicubic", align_corners=False)
+            hr4 = F.interpolate(hr, scale_factor=0.25, mode="bicubic", align_corners=False)
+            cat = torch.cat([p2, unf(hr2), unf(hr4)], 1)
+            score = alpha * ref_utils.batch_pairwise_distance(p1, cat, dn) \
+                + beta * ref_utils.batch_pairwise_distance(p2, cat, dn)
+            _, ind = torch.min(score, dim=2)
+            top2 = torch.topk(score, 2, dim=2, largest=False).values
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            sr=sr.detach().numpy(), hr=hr.detach().numpy(), loss=np.float32(loss.item()),
+            d_sr=sr.grad.numpy(), d_gt=hr.grad.numpy(), ind=ind.numpy(), top2=top2.numpy(), hr2=hr2.numpy(), hr4=hr4.numpy(),
+            alpha=np.float64(alpha), beta=np.float64(beta), criterion=np.str_(crit), dist_norm=np.str_(dn),
+            ksize=np.int64(ks), pad=np.int64(pad), stride=np.int64(st))
+        print(f"{name}: loss={loss.item():.8g} N={p1.shape[1]} M={cat.shape[1]} D={p1.shape[2]}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # fixed summation order inside MKL for reproducible fixtures
     rl, ru = _import_reference()
-    which = sys.argv[1:] or ["st", "bb", "gram", "pst", "l1", "gtgrad"]
+    which = sys.argv[1:] or ["st", "bb", "gram", "pst", "l1", "gtgrad", "geom"]
     if "st" in which:
         make_st(rl, ru)
     if "bb" in which:
@@ -273,3 +311,5 @@ if __name__ == "__main__":
         make_l1(rl, ru)
     if "gtgrad" in which:
         make_gt_grad(rl, ru)
+    if "geom" in which:
+        make_geom(rl, ru)

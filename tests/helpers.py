@@ -182,3 +182,29 @@ def emu_patch_gt(lib, sr, gt, idx, gt2=None, gt4=None, criterion=0, grad_out=1.0
                                     B, H, W, *tp, criterion, _p(d_gt), _p(ws), nb, None)
     assert rc == 0, rc
     return d_gt
+
+
+def emu_bbg(lib, sr, gt, ksize, pad, stride, gt2=None, gt4=None, alpha=1.0, beta=1.0, criterion=0, grad_out=1.0,
+            want_gt=False):
+    """Run srst_bbg_forward + srst_bbg_backward (arbitrary patch geometry) of `lib` on host arrays (emulation only)."""
+    sr = np.ascontiguousarray(sr, np.float32)
+    gt = np.ascontiguousarray(gt, np.float32)
+    gt2 = np.ascontiguousarray(gt2, np.float32) if gt2 is not None else None
+    gt4 = np.ascontiguousarray(gt4, np.float32) if gt4 is not None else None
+    B, _, H, W = sr.shape
+    N = lib.srst_bbg_num_patches(H, W, ksize, pad, stride)
+    nb = lib.srst_bbg_workspace_bytes(B, H, W, ksize, pad, stride)
+    assert N > 0 and nb > 0
+    ws = np.zeros(nb // 4 + 4, np.float32)
+    idx = np.full((B, N), -1, np.int64)
+    loss = np.zeros(1, np.float32)
+    go = np.full(1, grad_out, np.float32)
+    d_sr = np.full_like(sr, np.nan)
+    d_gt = np.full_like(sr, np.nan) if want_gt else None
+    rc = lib.srst_bbg_forward(_p(sr), _p(gt), _p(gt2), _p(gt4), B, H, W, ksize, pad, stride, alpha, beta, criterion,
+                              _p(idx), _p(loss), _p(ws), nb, None)
+    assert rc == 0, rc
+    rc = lib.srst_bbg_backward(_p(sr), _p(gt), _p(gt2), _p(gt4), _p(idx), _p(go), B, H, W, ksize, pad, stride, criterion,
+                               _p(d_sr), _p(d_gt), _p(ws), nb, None)
+    assert rc == 0, rc
+    return dict(loss=float(loss[0]), idx=idx, d_sr=d_sr, d_gt=d_gt)
