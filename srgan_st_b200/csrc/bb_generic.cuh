@@ -14,8 +14,10 @@
 //   bbg_backward_gt_kernel : d_gt through the gather of the selected candidates (loss.py:136-139): scattered with
 //                         atomicAdd into per-level gradient images, folded back by bb_pyramid_adjoint_kernel
 //
-// A 32-query x 32-candidate tile per CTA step, one query x four candidates per thread: 2 LDS + 1 LDS.128 per 8 FMA.
-// This path is sized for correctness at any geometry, not tuned like the (3, 0, 3) search.
+// A 64-query x 64-candidate tile per CTA step, four queries x four candidates per thread: 3 LDS.128 per 32 FMA
+// (the first version, one query x four candidates, was bound by the shared-memory pipe: 14 TFLOP/s algorithmic at
+// (3, 0, 3), profiles/r02_bb_geometry.log).  Both dot products of every pair are evaluated -- no filter as in the
+// tuned (3, 0, 3) search.
 // oracle/bbg_oracle.c restates the same order; tests/test_bb_geometry.py pins both on outputs of the reference.
 #pragma once
 #include "bb_kernels.cuh"
@@ -23,7 +25,7 @@
 namespace srst {
 
 constexpr int BBG_MAXK = 8;                 // ksize 1..8: D = 3 k^2 <= 192
-constexpr int BBG_QT = 32, BBG_CT = 32, BBG_NT = 256;
+constexpr int BBG_QT = 64, BBG_CT = 64, BBG_NT = 256;
 
 struct BbgLevel { int H, W, ny, nx, n; };
 struct BbgGeom {
@@ -108,15 +110,20 @@ bbg_search_kernel(const float* __restrict__ sr, const float* __restrict__ gt, co
                   const float* __restrict__ gt4, BbgGeom g, float alpha, float beta, int dist_l1,
                   int64_t* __restrict__ idx_out) {
   SRST_DYN_SMEM(float, smem);
+  constexpr int NQG = BBG_QT / 4, NCG = BBG_CT / 4;  // 16 x 16 threads, each 4 queries x 4 candidates
+  static_assert(NQG * NCG == BBG_NT && BBG_QT == BBG_CT && BBG_NT % BBG_QT == 0, "bbg: tile");
+  constexpr int NEG = BBG_NT / BBG_QT;               // element groups of the gather (a thread owns one patch)
   const int D = g.D;
   float* sX = smem;                         // [D][QT]  SR query patches
   float* sG = sX + (size_t)D * BBG_QT;      // [D][QT]  gt query patches
   float* sY = sG + (size_t)D * BBG_QT;      // [D][CT]  candidate chunk
   int* sE = reinterpret_cast<int*>(sY + (size_t)D * BBG_CT);  // element e -> c << 16 | ky << 8 | kx
   __shared__ float s_xn[BBG_QT], s_gn[BBG_QT], s_yn[BBG_CT];
-  __shared__ float s_best[BBG_NT / 32][BBG_QT];
-  __shared__ int s_bidx[BBG_NT / 32][BBG_QT];
-  const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
+  __shared__ float s_best[NCG][BBG_QT];
+  __shared__ int s_bidx[NCG][BBG_QT];
+  const int tid = threadIdx.x;
+  const int pslot = tid % BBG_QT, egrp = tid / BBG_QT;  // gather: patch slot, element group
+  const int qg = tid % NQG, cg = tid / NQG;             // scoring: queries 4 qg .., candidates 4 cg .. of the chunk
   const int b = blockIdx.y, qbase = blockIdx.x * BBG_QT;
   const int kk = g.k * g.k;
   for (int e = tid; e < D; e += BBG_NT) {
@@ -125,17 +132,17 @@ bbg_search_kernel(const float* __restrict__ sr, const float* __restrict__ gt, co
   }
   __syncthreads();
   {
-    // queries: this thread gathers elements grp, grp + 8, .. of query `lane` (SR and gt patch at the same place)
-    const int i = qbase + lane;
+    // queries: this thread gathers elements egrp, egrp + NEG, .. of query `pslot` (SR and gt patch at the same place)
+    const int i = qbase + pslot;
     const bool ok = i < g.N;
     const BbgPatch P1 = bbg_patch_of(sr + (size_t)b * 3 * g.L[0].H * g.L[0].W, g.L[0], g.p, g.s, ok ? i : 0);
     BbgPatch P2 = P1;
     P2.img = gt + (size_t)b * 3 * g.L[0].H * g.L[0].W;
-    for (int e = grp; e < D; e += BBG_NT / 32) {
+    for (int e = egrp; e < D; e += NEG) {
       const int code = sE[e];
       const int c = code >> 16, ky = (code >> 8) & 255, kx = code & 255;
-      sX[e * BBG_QT + lane] = ok ? bbg_value(P1, c, ky, kx) : 0.f;
-      sG[e * BBG_QT + lane] = ok ? bbg_value(P2, c, ky, kx) : 0.f;
+      sX[e * BBG_QT + pslot] = ok ? bbg_value(P1, c, ky, kx) : 0.f;
+      sG[e * BBG_QT + pslot] = ok ? bbg_value(P2, c, ky, kx) : 0.f;
     }
   }
   __syncthreads();
@@ -149,17 +156,19 @@ bbg_search_kernel(const float* __restrict__ sr, const float* __restrict__ gt, co
     s_xn[tid] = xn;
     s_gn[tid] = gn;
   }
-  float best = __int_as_float(0x7f800000);
-  int bidx = 0x7fffffff;
+  float best[4];
+  int bidx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { best[i] = __int_as_float(0x7f800000); bidx[i] = 0x7fffffff; }
   for (int chunk = 0; chunk < g.M; chunk += BBG_CT) {
     __syncthreads();  // the previous chunk has been consumed (first pass: query norms are in place)
     {
-      const int j = chunk + lane;
+      const int j = chunk + pslot;
       const bool ok = j < g.M;
       const BbgPatch Pc = bbg_candidate(gt, gt2, gt4, g, b, ok ? j : 0);
-      for (int e = grp; e < D; e += BBG_NT / 32) {
+      for (int e = egrp; e < D; e += NEG) {
         const int code = sE[e];
-        sY[e * BBG_CT + lane] = ok ? bbg_value(Pc, code >> 16, (code >> 8) & 255, code & 255) : 0.f;
+        sY[e * BBG_CT + pslot] = ok ? bbg_value(Pc, code >> 16, (code >> 8) & 255, code & 255) : 0.f;
       }
     }
     __syncthreads();
@@ -169,48 +178,63 @@ bbg_search_kernel(const float* __restrict__ sr, const float* __restrict__ gt, co
       s_yn[tid] = yn;
     }
     __syncthreads();
-    // query `lane`, candidates 4 grp .. 4 grp + 3 of the chunk
-    float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
-    if (dist_l1) {
-      for (int e = 0; e < D; ++e) {
-        const float x = sX[e * BBG_QT + lane], q = sG[e * BBG_QT + lane];
-        const float4 yv = ld4(sY + e * BBG_CT + 4 * grp);
-        const float y[4] = {yv.x, yv.y, yv.z, yv.w};
+    float d1[4][4], d2[4][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          d1[u] = __fadd_rn(d1[u], fabsf(__fsub_rn(x, y[u])));
-          d2[u] = __fadd_rn(d2[u], fabsf(__fsub_rn(q, y[u])));
-        }
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { d1[i][u] = 0.f; d2[i][u] = 0.f; }
+    if (dist_l1) {
+#pragma unroll 2
+      for (int e = 0; e < D; ++e) {
+        const float4 xv = ld4(sX + e * BBG_QT + 4 * qg), qv = ld4(sG + e * BBG_QT + 4 * qg);
+        const float4 yv = ld4(sY + e * BBG_CT + 4 * cg);
+        const float x[4] = {xv.x, xv.y, xv.z, xv.w}, q[4] = {qv.x, qv.y, qv.z, qv.w}, y[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            d1[i][u] = __fadd_rn(d1[i][u], fabsf(__fsub_rn(x[i], y[u])));
+            d2[i][u] = __fadd_rn(d2[i][u], fabsf(__fsub_rn(q[i], y[u])));
+          }
       }
     } else {
+#pragma unroll 2
       for (int e = 0; e < D; ++e) {
-        const float x = sX[e * BBG_QT + lane], q = sG[e * BBG_QT + lane];
-        const float4 yv = ld4(sY + e * BBG_CT + 4 * grp);
-        const float y[4] = {yv.x, yv.y, yv.z, yv.w};
+        const float4 xv = ld4(sX + e * BBG_QT + 4 * qg), qv = ld4(sG + e * BBG_QT + 4 * qg);
+        const float4 yv = ld4(sY + e * BBG_CT + 4 * cg);
+        const float x[4] = {xv.x, xv.y, xv.z, xv.w}, q[4] = {qv.x, qv.y, qv.z, qv.w}, y[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          d1[u] = fmaf(x, y[u], d1[u]);
-          d2[u] = fmaf(q, y[u], d2[u]);
-        }
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            d1[i][u] = fmaf(x[i], y[u], d1[i][u]);
+            d2[i][u] = fmaf(q[i], y[u], d2[i][u]);
+          }
       }
     }
-    const float xn = s_xn[lane], gn = s_gn[lane];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int cj = chunk + 4 * grp + u;
+    for (int u = 0; u < 4; ++u) {   // ascending candidate index per thread
+      const int cj = chunk + 4 * cg + u;
       if (cj >= g.M) continue;
-      const float sc = dist_l1 ? __fadd_rn(__fmul_rn(alpha, d1[u]), __fmul_rn(beta, d2[u]))
-                               : bb_score(xn, gn, s_yn[4 * grp + u], d1[u], d2[u], alpha, beta);
-      if (bb_score_before(sc, cj, best, bidx)) { best = sc; bidx = cj; }
+      const float yn = s_yn[4 * cg + u];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float sc = dist_l1 ? __fadd_rn(__fmul_rn(alpha, d1[i][u]), __fmul_rn(beta, d2[i][u]))
+                                 : bb_score(s_xn[4 * qg + i], s_gn[4 * qg + i], yn, d1[i][u], d2[i][u], alpha, beta);
+        if (bb_score_before(sc, cj, best[i], bidx[i])) { best[i] = sc; bidx[i] = cj; }
+      }
     }
   }
-  s_best[grp][lane] = best;
-  s_bidx[grp][lane] = bidx;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    s_best[cg][4 * qg + i] = best[i];
+    s_bidx[cg][4 * qg + i] = bidx[i];
+  }
   __syncthreads();
   if (tid < BBG_QT && qbase + tid < g.N) {
     float sb = s_best[0][tid];
     int ib = s_bidx[0][tid];
-    for (int w = 1; w < BBG_NT / 32; ++w) bb_argmin_merge(sb, ib, s_best[w][tid], s_bidx[w][tid]);
+    for (int w = 1; w < NCG; ++w) bb_argmin_merge(sb, ib, s_best[w][tid], s_bidx[w][tid]);
     if (ib < 0 || ib >= g.M) ib = 0;  // unreachable (M >= 1 and (score, index) order is total); keeps later reads in range
     idx_out[(size_t)b * g.N + qbase + tid] = ib;
   }

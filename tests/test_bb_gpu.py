@@ -152,7 +152,7 @@ def test_rejects_unsupported_geometry():
     with pytest.raises(NotImplementedError):
         BestBuddyLoss(criterion="huber")
     with pytest.raises(NotImplementedError):
-        BestBuddyLoss(ksize=5)
+        BestBuddyLoss(ksize=9)             # 1 <= ksize <= 8 have kernels (tests/test_bb_geometry.py)
     with pytest.raises(NotImplementedError):
         BestBuddyLoss(dist_norm="cosine")  # utils.py:189 (l1 and l2 have kernels)
     with pytest.raises(RuntimeError):
