@@ -246,3 +246,78 @@ def test_reference_warmup_loop_with_our_criteria(ref):
     _record("warmup_step_16x96x96", st_loss_vs_ref=rel_err(lv_o["ST"], lv_r["ST"]), total_vs_ref=rel_err(l_o, l_r),
             generator_grad_vs_ref=gerr)
     assert gerr < 1e-3   # generator weights' gradients: the loss gradient (1e-4) pushed through 37 conv layers of cuDNN
+
+
+def test_reference_train_loop_step_with_our_criteria(ref):
+    """BASELINE configs[2] at its per-GPU batch (128 / 8 = 16): the reference's GAN-phase loop body (train.py:121-164:
+    generator update over config.MODEL.G_LOSS.CRITERIONS with the 'Adversarial' special case, then the discriminator
+    update) with model.Generator and model.Discriminator, once with our ST + BestBuddy criteria registered through
+    config.add_g_criterion (config.py:122-125) and once with the reference's own.  Loss values, generator gradients and
+    the discriminator step must agree.  The VGG content criterion needs downloaded weights (no network here) and is
+    not registered -- it does not touch the loss path under test."""
+    import copy
+    import srgan_st_b200 as pkg
+    torch.manual_seed(1)
+    dev = torch.device("cuda:0")
+    base = ref.config.Config()
+    base.DEVICE = "cuda:0"
+    gen0 = ref.model.Generator(base).to(dev)
+    disc0 = ref.model.Discriminator(base).to(dev)
+    B = 16
+    gt, _ = _pair("srlike", B, 96, 96, 5)
+    lr = F.interpolate(gt, scale_factor=0.25, mode="bicubic", align_corners=False).clamp(0, 1)
+    results = []
+    for ours in (True, False):
+        config = ref.config.Config()
+        config.DEVICE = "cuda:0"
+        config.DATA.BATCH_SIZE = B
+        config.MODEL.G_LOSS.CRITERIONS = {"Adversarial": torch.nn.BCEWithLogitsLoss()}
+        config.add_g_criterion("Pixel", torch.nn.MSELoss(), 1.0)
+        config.add_g_criterion("ST", pkg.StructureTensorLoss() if ours else ref.loss.StructureTensorLoss(), 1.0 / 3.0)
+        config.add_g_criterion("BestBuddy", pkg.BestBuddyLoss() if ours else ref.loss.BestBuddyLoss(), 50.0)
+        generator, discriminator = copy.deepcopy(gen0), copy.deepcopy(disc0)
+        generator.train()
+        discriminator.train()
+        g_optimizer = torch.optim.Adam(generator.parameters(), lr=1e-4)
+        d_optimizer = torch.optim.Adam(discriminator.parameters(), lr=1e-4)
+        adversarial_criterion = torch.nn.BCEWithLogitsLoss().to(config.DEVICE)
+        real_label = torch.full([config.DATA.BATCH_SIZE, 1], 1.0 - config.EXP.LABEL_SMOOTHING, dtype=torch.float, device=config.DEVICE)
+        fake_label = torch.full([config.DATA.BATCH_SIZE, 1], 0.0, dtype=torch.float, device=config.DEVICE)
+        loss_values = {}
+        # ---- train.py:121-164, verbatim control flow ----
+        for p in discriminator.parameters():
+            p.requires_grad = False
+        generator.zero_grad()
+        sr = generator(lr)
+        g_loss = torch.tensor(0.0, device=config.DEVICE)
+        for name, criterion in config.MODEL.G_LOSS.CRITERIONS.items():
+            weight = config.MODEL.G_LOSS.CRITERION_WEIGHTS[name]
+            if name == 'Adversarial':
+                loss = criterion(discriminator(sr), real_label)
+            else:
+                loss = criterion(sr, gt)
+            g_loss = g_loss + (loss * weight)
+            loss_values[name] = (loss * weight).item()
+        g_loss.backward()
+        g_grads = torch.cat([p.grad.flatten() for p in generator.parameters()])
+        g_optimizer.step()
+        for p in discriminator.parameters():
+            p.requires_grad = True
+        discriminator.zero_grad()
+        pred_gt = discriminator(gt)
+        loss_real = adversarial_criterion(pred_gt, real_label)
+        pred_sr = discriminator(sr.detach().clone())
+        loss_fake = adversarial_criterion(pred_sr, fake_label)
+        d_loss = loss_real + loss_fake
+        d_loss.backward()
+        d_optimizer.step()
+        results.append((loss_values, g_grads, g_loss.item(), d_loss.item()))
+    (lv_o, g_o, gl_o, dl_o), (lv_r, g_r, gl_r, dl_r) = results
+    e = dict(st_vs_ref=rel_err(lv_o["ST"], lv_r["ST"]), bb_vs_ref=rel_err(lv_o["BestBuddy"], lv_r["BestBuddy"]),
+             g_loss_vs_ref=rel_err(gl_o, gl_r), d_loss_vs_ref=rel_err(dl_o, dl_r),
+             generator_grad_vs_ref=maxnorm_err(g_o.cpu().numpy(), g_r.cpu().numpy()))
+    _record("train_step_16x96x96", **e)
+    assert e["st_vs_ref"] < 1e-5 and e["bb_vs_ref"] < 1e-4 and e["g_loss_vs_ref"] < 1e-4
+    assert rel_err(lv_o["Pixel"], lv_r["Pixel"]) < 1e-6 and rel_err(lv_o["Adversarial"], lv_r["Adversarial"]) < 1e-5
+    assert e["d_loss_vs_ref"] < 1e-5
+    assert e["generator_grad_vs_ref"] < 1e-3   # the loss gradients (1e-4) pushed through the generator's cuDNN layers
