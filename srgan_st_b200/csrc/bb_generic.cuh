@@ -6,8 +6,9 @@
 //   bbg_search_kernel   : every (query, candidate) pair scored EXACTLY with the reference's expression and rounding
 //                         points (bb_score, utils.py:183-187 / loss.py:132-133; l1: utils.py:166-172), patch elements
 //                         accumulated in ascending order e = c*k*k + ky*k + kx (F.unfold's layout, zero outside the
-//                         image = its padding); first minimal index wins (torch.min).  Nothing is materialised: query
-//                         and candidate tiles are gathered straight from the images into shared memory.
+//                         image = its padding); first minimal index wins (torch.min).  bbg_pack_kernel gathers the
+//                         candidate patches of an image once (element-major matrix + norms); the query tile of a CTA
+//                         is gathered straight from the images.
 //   bbg_loss_kernel     : mean |sr_patch - cand[idx]| (or squared) over B*N*D, deterministic reduction
 //   bbg_backward_kernel : d_sr in GATHER form -- a pixel sums, in a fixed order, the criterion gradients of the
 //                         ceil(k/s)^2 patches that cover it (overlapping patches when stride < ksize; no atomics)
@@ -64,6 +65,9 @@ struct BbgWorkspace {
   float* partials;
   float *pyr2, *pyr4;  // the two coarse levels of gt when the caller does not pass them
   float *d2, *d4;      // their gradient images (gradient w.r.t. gt)
+  float* ymat;         // per image: candidate patches Y[D][Mpad] (element-major) followed by their norms yn[Mpad]
+  size_t y_per_image;  // floats
+  int Mpad;
   size_t total_bytes;
 };
 inline BbgWorkspace bbg_carve(void* base, const BbgGeom& g) {
@@ -78,6 +82,9 @@ inline BbgWorkspace bbg_carve(void* base, const BbgGeom& g) {
   w.pyr4 = reinterpret_cast<float*>(take(n4 * sizeof(float)));
   w.d2 = reinterpret_cast<float*>(take((n2 + 3) / 4 * 4 * sizeof(float) + n4 * sizeof(float)));  // d4 follows d2: one fill
   w.d4 = w.d2 + (n2 + 3) / 4 * 4;
+  w.Mpad = (g.M + BBG_CT - 1) / BBG_CT * BBG_CT;
+  w.y_per_image = (size_t)(g.D + 1) * w.Mpad;
+  w.ymat = reinterpret_cast<float*>(take(w.y_per_image * g.B * sizeof(float)));
   w.total_bytes = off;
   return w;
 }
@@ -103,11 +110,34 @@ SRST_DEV float bbg_value(const BbgPatch& P, int c, int ky, int kx) {
   return (y >= 0 && y < P.H && x >= 0 && x < P.W) ? __ldg(P.img + ((size_t)c * P.H + y) * P.W + x) : 0.f;
 }
 
+// Candidate patches of one image, gathered ONCE: Y[e][j] (element-major, Mpad columns, zeros beyond M) and the norms
+// yn[j] (fmaf over e ascending).  The search then stages its chunks with coalesced 16-byte copies; gathering them from
+// the images inside the search cost 41 % of its time (every CTA repeated the index arithmetic for all M candidates).
+__global__ void __launch_bounds__(256)
+bbg_pack_kernel(const float* __restrict__ gt, const float* __restrict__ gt2, const float* __restrict__ gt4, BbgGeom g,
+                float* __restrict__ ymat, size_t y_per_image, int Mpad) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (j >= Mpad) return;
+  float* Y = ymat + y_per_image * b;
+  const bool ok = j < g.M;
+  const BbgPatch Pc = bbg_candidate(gt, gt2, gt4, g, b, ok ? j : 0);
+  float yn = 0.f;
+  int e = 0;
+  for (int c = 0; c < 3; ++c)
+    for (int ky = 0; ky < g.k; ++ky)
+      for (int kx = 0; kx < g.k; ++kx, ++e) {
+        const float v = ok ? bbg_value(Pc, c, ky, kx) : 0.f;
+        Y[(size_t)e * Mpad + j] = v;
+        yn = fmaf(v, v, yn);
+      }
+  Y[(size_t)g.D * Mpad + j] = yn;
+}
+
 inline size_t bbg_search_smem(int D) { return sizeof(float) * ((size_t)D * (2 * BBG_QT + BBG_CT)) + sizeof(int) * (size_t)D; }
 
 __global__ void __launch_bounds__(BBG_NT)
-bbg_search_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const float* __restrict__ gt2,
-                  const float* __restrict__ gt4, BbgGeom g, float alpha, float beta, int dist_l1,
+bbg_search_kernel(const float* __restrict__ sr, const float* __restrict__ gt, const float* __restrict__ ymat,
+                  size_t y_per_image, int Mpad, BbgGeom g, float alpha, float beta, int dist_l1,
                   int64_t* __restrict__ idx_out) {
   SRST_DYN_SMEM(float, smem);
   constexpr int NQG = BBG_QT / 4, NCG = BBG_CT / 4;  // 16 x 16 threads, each 4 queries x 4 candidates
@@ -125,6 +155,7 @@ bbg_search_kernel(const float* __restrict__ sr, const float* __restrict__ gt, co
   const int pslot = tid % BBG_QT, egrp = tid / BBG_QT;  // gather: patch slot, element group
   const int qg = tid % NQG, cg = tid / NQG;             // scoring: queries 4 qg .., candidates 4 cg .. of the chunk
   const int b = blockIdx.y, qbase = blockIdx.x * BBG_QT;
+  const float* __restrict__ Y = ymat + y_per_image * b;   // [D][Mpad], then yn[Mpad]
   const int kk = g.k * g.k;
   for (int e = tid; e < D; e += BBG_NT) {
     const int c = e / kk, r = e - c * kk, ky = r / g.k;
@@ -162,21 +193,11 @@ bbg_search_kernel(const float* __restrict__ sr, const float* __restrict__ gt, co
   for (int i = 0; i < 4; ++i) { best[i] = __int_as_float(0x7f800000); bidx[i] = 0x7fffffff; }
   for (int chunk = 0; chunk < g.M; chunk += BBG_CT) {
     __syncthreads();  // the previous chunk has been consumed (first pass: query norms are in place)
-    {
-      const int j = chunk + pslot;
-      const bool ok = j < g.M;
-      const BbgPatch Pc = bbg_candidate(gt, gt2, gt4, g, b, ok ? j : 0);
-      for (int e = egrp; e < D; e += NEG) {
-        const int code = sE[e];
-        sY[e * BBG_CT + pslot] = ok ? bbg_value(Pc, code >> 16, (code >> 8) & 255, code & 255) : 0.f;
-      }
+    for (int it = tid; it < D * (BBG_CT / 4); it += BBG_NT) {   // packed candidates: coalesced 16-byte copies
+      const int e = it / (BBG_CT / 4), c4 = it - e * (BBG_CT / 4);
+      st4(sY + e * BBG_CT + 4 * c4, ldg4(Y + (size_t)e * Mpad + chunk + 4 * c4));
     }
-    __syncthreads();
-    if (tid < BBG_CT) {
-      float yn = 0.f;
-      for (int e = 0; e < D; ++e) { const float y = sY[e * BBG_CT + tid]; yn = fmaf(y, y, yn); }
-      s_yn[tid] = yn;
-    }
+    if (tid < BBG_CT) s_yn[tid] = __ldg(Y + (size_t)D * Mpad + chunk + tid);
     __syncthreads();
     float d1[4][4], d2[4][4];
 #pragma unroll

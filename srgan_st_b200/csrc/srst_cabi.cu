@@ -969,8 +969,11 @@ int srst_bbg_forward(const float* sr, const float* gt, const float* gt2, const f
   struct BbgSearchTag {};
   const size_t dyn = bbg_search_smem(3 * BBG_MAXK * BBG_MAXK);  // one opt-in covers every ksize
   if ((e = ensure_smem<BbgSearchTag>(bbg_search_kernel, dyn)) != 0) return e;
+  SRST_LAUNCH(bbg_pack_kernel, dim3((unsigned)((w.Mpad + 255) / 256), (unsigned)B), dim3(256), 0, stream, gt, gt2, gt4, g,
+              w.ymat, w.y_per_image, w.Mpad);
+  if ((e = (int)cudaGetLastError()) != 0) return e;
   SRST_LAUNCH(bbg_search_kernel, dim3((unsigned)((g.N + BBG_QT - 1) / BBG_QT), (unsigned)B), dim3(BBG_NT),
-              bbg_search_smem(g.D), stream, sr, gt, gt2, gt4, g, alpha, beta, dist_l1, idx_out);
+              bbg_search_smem(g.D), stream, sr, gt, w.ymat, w.y_per_image, w.Mpad, g, alpha, beta, dist_l1, idx_out);
   if ((e = (int)cudaGetLastError()) != 0) return e;
   const unsigned nl = (unsigned)(((size_t)B * g.N + BBG_NT - 1) / BBG_NT);
   SRST_LAUNCH(bbg_loss_kernel, dim3(nl), dim3(BBG_NT), 0, stream, sr, gt, gt2, gt4, g, idx_out, criterion, w.partials,

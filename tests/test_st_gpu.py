@@ -17,6 +17,20 @@ from tests.helpers import golden, golden_names, maxnorm_err, rel_err
 
 pytestmark = pytest.mark.gpu
 
+
+def _record(key, **vals):
+    import json
+    import os
+    from tests.helpers import ROOT
+    path = os.path.join(ROOT, "gpurun_out", "r02_parity.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    try:
+        data = json.load(open(path))
+    except Exception:
+        data = {}
+    data[key] = {k: float(v) for k, v in vals.items()}
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+
 DEFAULT_CASES = [n for n in golden_names("st_") if "s1_r25" not in n and "s15_r4" not in n and "s2_r5" not in n]
 GENERIC_CASES = [("st_rand_s15_r4_1x40x52", 1.5, 4.0), ("st_srlike_s2_r5_2x33x45", 2.0, 5.0)]
 
@@ -59,9 +73,16 @@ def test_matches_reference_golden(name, tile_cfg):
     if "nonorm" in name:
         assert np.abs(d_sr).max() == 0.0
         return
-    for ours, orc, refg in ((d_sr, ref["d_sr"], z["d_sr"]), (d_hr, ref["d_hr"], z["d_hr"])):
-        assert maxnorm_err(ours, orc) < 1e-4, "grad vs fp64 oracle"
-        assert maxnorm_err(ours, refg) < 1e-4 + maxnorm_err(refg, orc), "grad vs reference"
+    # Gradients vs the reference's own: strict 1e-4 on every fixture but st_rand_1x96x96, where the reference's fp32
+    # gradient itself sits 4.2e-4 from the float64 truth (ill-conditioned pixels) and the bound is
+    # widened by exactly that distance.  The measured errors go to gpurun_out/r02_parity.json.
+    rec = {}
+    for tag, ours, orc, refg in (("dsr", d_sr, ref["d_sr"], z["d_sr"]), ("dhr", d_hr, ref["d_hr"], z["d_hr"])):
+        e_orc, e_ref, ref_orc = maxnorm_err(ours, orc), maxnorm_err(ours, refg), maxnorm_err(refg, orc)
+        rec.update({f"{tag}_vs_fp64": e_orc, f"{tag}_vs_ref": e_ref, f"{tag}_ref_vs_fp64": ref_orc})
+        assert e_orc < 1e-4, "grad vs fp64 oracle"
+        assert e_ref < (1e-4 + ref_orc if "st_rand_1x96x96" in name else 1e-4), "grad vs reference"
+    _record("golden_" + name, loss_vs_ref=rel_err(loss, z["loss"]), loss_vs_fp64=rel_err(loss, ref["loss"]), **rec)
 
 
 def test_hr_without_grad_and_no_grad_mode():
@@ -211,9 +232,15 @@ def test_generic_radius_golden_matches_reference(name, sigma, rho):
     loss, d_sr, d_hr = _run(z["sr"], z["hr"], sigma=sigma, rho=rho)
     ref = O.st_loss(z["sr"], z["hr"], taps=(z["g"], z["dg"], z["k"]), want_hr_grad=True)
     assert rel_err(loss, z["loss"]) < 1e-5 and rel_err(loss, ref["loss"]) < 1e-5
-    for ours, orc, refg in ((d_sr, ref["d_sr"], z["d_sr"]), (d_hr, ref["d_hr"], z["d_hr"])):
-        assert maxnorm_err(ours, orc) < 1e-4, "grad vs fp64 oracle"
-        assert maxnorm_err(ours, refg) < 1e-4 + maxnorm_err(refg, orc), "grad vs reference"
+    # Gradients vs the reference's own: 1e-4 widened by the reference's own distance from the float64 truth (the SR-like
+    # fixture with sigma 2 / rho 5 is smooth enough that its fp32 gradient wanders; the measured errors are recorded).
+    rec = {}
+    for tag, ours, orc, refg in (("dsr", d_sr, ref["d_sr"], z["d_sr"]), ("dhr", d_hr, ref["d_hr"], z["d_hr"])):
+        e_orc, e_ref, ref_orc = maxnorm_err(ours, orc), maxnorm_err(ours, refg), maxnorm_err(refg, orc)
+        rec.update({f"{tag}_vs_fp64": e_orc, f"{tag}_vs_ref": e_ref, f"{tag}_ref_vs_fp64": ref_orc})
+        assert e_orc < 1e-4, "grad vs fp64 oracle"
+        assert e_ref < 1e-4 + ref_orc, "grad vs reference"
+    _record("golden_" + name, loss_vs_ref=rel_err(loss, z["loss"]), loss_vs_fp64=rel_err(loss, ref["loss"]), **rec)
 
 
 @pytest.mark.parametrize("sigma,rho,shape", [(2.0, 2.0, (2, 100, 152)), (0.5, 4.0, (1, 96, 96)), (3.0, 8.0, (1, 37, 53)),
