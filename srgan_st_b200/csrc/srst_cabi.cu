@@ -239,8 +239,6 @@ static int launch_st_march(const StFwdParams<C::RG, C::RK>& F, void* stream) {
   if (forced_chunk() > 0) cb = forced_chunk() < nblk ? forced_chunk() : nblk;
   MP.chunk_blocks = cb;
   MP.nchunks = (nblk + cb - 1) / cb;
-  static const int coop_fill = env_int_once("SRST_MARCH_COOP", 1);  // A/B switch: the consumers share the fill steps
-  MP.coop_fill = coop_fill;
   const long long grid = base * MP.nchunks;
   if (grid <= 0 || grid > 0x7fffffffLL) return SRST_E_SHAPE;
   int e;

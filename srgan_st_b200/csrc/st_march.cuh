@@ -57,7 +57,6 @@ struct StMarchParams {
   SrstTmap hr_map;
   StFwdParams<RG, RK> F;
   int nstrips, nchunks, chunk_blocks;  // grid = B * nchunks * nstrips; a chunk = chunk_blocks * 16 rows
-  int coop_fill;                       // 1: the consumers share the two fill steps of a chunk (gray conversion, 4-column horizontal items)
 };
 
 template <int TW_, int RG_, int RK_, int CR_ = 8>
@@ -228,10 +227,10 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
   };
   [[maybe_unused]] float pxsum = 0.f;
   // raw box of block k -> gray row pairs RG .. RG+7 of gray buffer k&1; item = image x row pair x 4 columns
-  auto convert = [&](int k, int t0, int nthr) {
+  auto convert = [&](int k) {
     constexpr int C4 = C::GW / 4;
     float* gbuf = sGray + (k & 1) * 2 * C::GRAY_IMG;
-    for (int it = t0; it < 2 * NQ * C4; it += nthr) {
+    for (int it = tid; it < 2 * NQ * C4; it += C::NP) {
       const int c4 = it % C4, rr = it / C4;
       const int q = rr % NQ, img = rr / NQ;
       const float* r0 = sRaw + img * C::RAW_IMG + (2 * q) * C::GW + 4 * c4;
@@ -247,7 +246,7 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
       // fused Pixel term: squared RGB difference over the rows of this raw block that belong to the chunk
       constexpr int C2 = C::TW / 2;
       const int ry0 = hb(k) + RG;
-      for (int it = t0; it < C::RS * C2; it += nthr) {
+      for (int it = tid; it < C::RS * C2; it += C::NP) {
         const int c2 = it % C2, r = it / C2;
         const int gy = ry0 + r, gx = x0 + 2 * c2;
         if (gy < y0 || gy >= y1 || gx >= W) continue;
@@ -337,55 +336,7 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
   // Named barriers (0 is __syncthreads): kBarP among the producers; kBarH "ring block complete" (producers arrive,
   // consumers wait); kBarV "ring slot free" (consumers arrive, producers wait).  The two groups are coupled by these
   // hand-shakes only, so the latency-bound chain of the consumers overlaps whatever the producers are doing.
-  constexpr int kBarP = 1, kBarH = 2, kBarV = 3, kBarD = 4;
-  // Fill steps (k = 0, 1: the consumers have no ring block to read yet).  With coop_fill the consumers convert the gray
-  // rows of block k+1 while the producers compute the gradients of block k, and the horizontal pass of the block is cut
-  // into 4-column items (20-column window; same taps in the same order per output, so the ring rows are bit-identical)
-  // spread over producers AND consumers: NH4 = 2 NH items on NH + NC threads.  kBarD: "Ix, Iy of block k and the gray
-  // rows of block k+1 are complete" (all threads); ring block k complete = a full kBarH rendezvous in these two steps.
-  const bool coop = MP.coop_fill != 0;
-  static_assert(C::NC == C::NH, "march: 4-column fill items map one to one onto the horizontal producers + the consumers");
-  auto horiz4 = [&](int item, int k) {
-    constexpr int NSEG4 = C::TW / 4, W4 = 4 + 2 * RK;
-    const int q = item & 7, rest = item >> 3;
-    const int seg = rest % NSEG4, img = rest / NSEG4;
-    const float* pix = sD + (img * 2) * C::D_PLANE + q * C::PD + 2 * (4 * seg);
-    const float* piy = pix + C::D_PLANE;
-    float2 acc[3][4];
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int o = 0; o < 4; ++o) acc[c][o] = make_float2(0.f, 0.f);
-    const int gyh = hb(k) + 2 * q;
-    if (gyh + 1 >= 0 && gyh < H && MARCH_ON(2)) {
-#pragma unroll
-      for (int m = 0; m < W4 / 2; ++m) {
-        const float4 xv = ld4(pix + 4 * m), yv = ld4(piy + 4 * m);
-#pragma unroll
-        for (int hcol = 0; hcol < 2; ++hcol) {
-          const int j = 2 * m + hcol;
-          const float2 ix = hcol ? make_float2(xv.z, xv.w) : make_float2(xv.x, xv.y);
-          const float2 iy = hcol ? make_float2(yv.z, yv.w) : make_float2(yv.x, yv.y);
-          const float2 pxx = mul2(ix, ix), pyy = mul2(iy, iy), pxy = mul2(ix, iy);
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            const int tap = j - o;
-            if (tap >= 0 && tap <= 2 * RK) {
-              acc[0][o] = ffma2(pxx, bcast2(tp.k[tap]), acc[0][o]);
-              acc[1][o] = ffma2(pyy, bcast2(tp.k[tap]), acc[1][o]);
-              acc[2][o] = ffma2(pxy, bcast2(tp.k[tap]), acc[2][o]);
-            }
-          }
-        }
-      }
-    }
-    float* o = sH + (img * 3) * C::H_PLANE + (8 * (k & 1) + q) * C::PH + 2 * (4 * seg);
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int jj = 0; jj < 4; jj += 2)
-        st4(o + c * C::H_PLANE + 2 * jj, make_float4(acc[c][jj].x, acc[c][jj].y, acc[c][jj + 1].x, acc[c][jj + 1].y));
-  };
+  constexpr int kBarP = 1, kBarH = 2, kBarV = 3;
   MSTAMP(tid == 0, 1);        // prologue done
   MSTAMP(tid == C::NP, 1);
   if (producer) {
@@ -425,20 +376,16 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
         }
         MSTAMP(tid == 0, 2 + 6 * k);  // gradients done
         // gray rows of block k+1 into the other gray buffer (its box was requested one half-step ago)
-        if (k + 1 <= NB && !(coop && k < 2)) {  // (fill steps with coop_fill: the consumers convert)
+        if (k + 1 <= NB) {
           if (MARCH_ON(7)) tma_wait(&s_mbar, (unsigned)(k & 1));  // box of block k+1 is the k-th use of the barrier
           MSTAMP(tid == 0, 3 + 6 * k);  // box arrived
-          if (MARCH_ON(4)) convert(k + 1, tid, C::NP);
+          if (MARCH_ON(4)) convert(k + 1);
           MSTAMP(tid == 0, 4 + 6 * k);  // converted
         }
       }
-      const bool fill = coop && k < 2;
-      // Ix, Iy of block k and the gray rows of block k+1 are complete; the raw box is free
-      if (fill) bar_sync(kBarD, C::NT);
-      else bar_sync(kBarP, C::NP);
+      bar_sync(kBarP, C::NP);  // Ix, Iy of block k and the gray rows of block k+1 are complete; the raw box is free
       MSTAMP(tid == 0, 5 + 6 * k);
-      // without coop_fill, k == 1: the consumers have seen block 0; k >= 2: they are done with block k-2
-      if (k >= (coop ? 2 : 1)) bar_sync(kBarV, C::NT);
+      if (k >= 1) bar_sync(kBarV, C::NT);  // k == 1: the consumers have seen block 0; k >= 2: they are done with block k-2
       MSTAMP(tid == 0, 6 + 6 * k);
       {
         if (tid >= C::NH) {
@@ -508,9 +455,7 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
         }
         // products + horizontal rho-pass of block k -> ring row pairs 8*(k&1) ..; item = image x row pair x 8 columns.
         // Scatter form: window column j contributes k[j - o] to output column o, so Ix, Iy are read once.
-        if (tid < C::NH && fill) {
-          horiz4(tid, k);
-        } else if (tid < C::NH && MARCH_ON(2)) {
+        if (tid < C::NH && MARCH_ON(2)) {
           const int q = tid & 7, rest = tid >> 3;
           const int seg = rest % C::NSEGH, img = rest / C::NSEGH;
           const float* pix = sD + (img * 2) * C::D_PLANE + q * C::PD + 2 * (8 * seg);
@@ -553,31 +498,16 @@ st_forward_march_kernel(const __grid_constant__ StMarchParams<C::RG, C::RK> MP) 
       }
       MSTAMP(tid == 0, 7 + 6 * k);  // horizontal pass done
       __threadfence_block();
-      if (fill) bar_sync(kBarH, C::NT);   // ring block k is complete; the consumers are done with Ix, Iy of block k too
-      else bar_arrive(kBarH, C::NT);      // ring block k is complete
+      bar_arrive(kBarH, C::NT);  // ring block k is complete
       bar_sync(kBarP, C::NP);    // every producer is done with Ix, Iy of block k; the carried gray rows are in place
     }
   } else {
-    if (coop) {
-#pragma unroll 1
-      for (int kf = 0; kf < 2; ++kf) {  // H blocks 0 and 1 always exist (NB >= 1)
-        if (kf + 1 <= NB) {
-          if (MARCH_ON(7)) tma_wait(&s_mbar, (unsigned)(kf & 1));
-          if (MARCH_ON(4)) convert(kf + 1, ct, C::NC);
-        }
-        bar_sync(kBarD, C::NT);
-        horiz4(C::NH + ct, kf);
-        __threadfence_block();
-        bar_sync(kBarH, C::NT);
-      }
-    } else {
-      bar_sync(kBarH, C::NT);    // ring block 0
-      bar_arrive(kBarV, C::NT);
-    }
+    bar_sync(kBarH, C::NT);    // ring block 0
+    bar_arrive(kBarV, C::NT);
 #pragma unroll 1
     for (int jb = 0; jb < NB; ++jb) {
       const int k = jb + 2;
-      if (!(coop && jb == 0)) bar_sync(kBarH, C::NT);  // ring block jb+1
+      bar_sync(kBarH, C::NT);  // ring block jb+1
       MSTAMP(tid == C::NP, 2 + 3 * jb);  // block available
       if (MARCH_ON(1)) {
       // vertical rho-pass of output block j = k-2 from ring blocks j, j+1: this thread's column, output row

@@ -68,7 +68,6 @@ int main(int argc, char** argv) {
     int cb = (int)((nblk + nch - 1) / nch);
     if (cb_forced > 0) cb = cb_forced < nblk ? cb_forced : nblk;
     MP.chunk_blocks = cb; MP.nchunks = (nblk + cb - 1) / cb;
-    MP.coop_fill = getenv("SRST_MARCH_COOP") ? atoi(getenv("SRST_MARCH_COOP")) : 1;
   }
   auto kern = st_forward_march_kernel<C, false, false>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
