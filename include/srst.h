@@ -259,7 +259,8 @@ int srst_patch_backward_gt(int mode, const float* sr, const float* gt, const flo
 /* ---------------------------------------------------------------------------------------------
  * Best-Buddy loss with an arbitrary patch geometry: BestBuddyLoss(ksize, pad, stride) of the reference
  * (loss.py:86; F.unfold(kernel_size=ksize, padding=pad, stride=stride) at loss.py:116-129) for everything
- * but the default (3, 0, 3), which the tuned entry points above serve.  1 <= ksize <= 8, pad >= 0, stride >= 1;
+ * but the default (3, 0, 3), which the tuned entry points above serve.  1 <= ksize <= 8, 0 <= pad <= 64, 1 <= stride <= 4096
+ * (srst_bbg_supported);
  * patches may overlap (stride < ksize), leave gaps (stride > ksize) and reach into the zero padding.
  *   N = ny*nx, ny = (H + 2 pad - ksize)/stride + 1 (srst_bbg_num_patches); every pyramid level must hold at least
  *   one patch (F.unfold raises otherwise): SRST_E_SHAPE.  D = 3*ksize*ksize elements per patch.
