@@ -52,7 +52,7 @@ def test_losses_register_and_train_like_the_reference_loop():
 
 
 def test_every_loss_module_trains_in_the_loop_and_under_a_cuda_graph():
-    """All five modules registered at once (incl. the fused ST+Pixel criterion replacing "Pixel" + "ST"), then the
+    """All five modules (BestBuddy twice: default and a non-default patch geometry) registered at once (incl. the fused ST+Pixel criterion replacing "Pixel" + "ST"), then the
     whole generator step replayed from ONE CUDA graph without any per-criterion .item(): the
     loss objects neither allocate outside torch's caching allocator nor synchronise."""
     from srgan_st_b200 import (BestBuddyLoss, GramLoss, PatchwiseStructureTensorLoss, StructureTensorLoss,
@@ -61,7 +61,8 @@ def test_every_loss_module_trains_in_the_loop_and_under_a_cuda_graph():
     dev = torch.device("cuda:0")
     crits = {"ST+Pixel": (StructureTensorPixelLoss(st_weight=1 / 3, pixel_weight=1.0), 1.0),
              "BestBuddy": (BestBuddyLoss(), 50.0), "Gram": (GramLoss(), 10.0),
-             "PatchST": (PatchwiseStructureTensorLoss(), 1.0), "ST": (StructureTensorLoss(rho=1.0), 0.1)}
+             "PatchST": (PatchwiseStructureTensorLoss(), 1.0), "ST": (StructureTensorLoss(rho=1.0), 0.1),
+             "BestBuddy4": (BestBuddyLoss(ksize=4, pad=1, stride=2), 20.0)}   # overlapping patches: the all-pairs path
     gen = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.PReLU(),
                               torch.nn.Conv2d(8, 3, 3, padding=1)).to(dev)
     opt = torch.optim.SGD(gen.parameters(), lr=1e-3)
