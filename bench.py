@@ -703,6 +703,23 @@ def run_gpu(args):
                            "reference_tflops_equiv": 4.0 * Nq * Mc * 27 * Bb / (tf * 1e-3) / 1e12,
                            "note": "reference work = two [N,M,27] SGEMMs (utils.py:183); the search kernel does ONE "
                                    "filtered dot product per pair and re-scores survivors exactly (bit-identical indices)"}
+        # the same crops with a non-default patch geometry (BestBuddyLoss(ksize=4, stride=4), loss.py:86): the exact
+        # all-pairs path (bb_generic.cuh) -- both dot products of every pair, no filter
+        mg = BestBuddyLoss(ksize=4, pad=0, stride=4, pyramid="fused")
+        for _ in range(2):
+            mg(xb, gtb).backward()
+        torch.cuda.synchronize()
+        tfg = tbg = 0.0
+        for _ in range(nb):
+            ev[0].record(); lb = mg(xb, gtb); ev[1].record(); lb.backward(); ev[2].record()
+            torch.cuda.synchronize()
+            tfg += ev[0].elapsed_time(ev[1]) / nb; tbg += ev[1].elapsed_time(ev[2]) / nb
+        Ng = (Hb // 4) * (Wb // 4)
+        Mg = Ng + ((Hb // 2) // 4) * ((Wb // 2) // 4) + ((Hb // 4) // 4) * ((Wb // 4) // 4)
+        others["bb_k4s4"] = {"workload": "Best-Buddy loss fwd+bwd with ksize=4, pad=0, stride=4 (48-dim patches), batch 64 x "
+                                         "3x192x192 per GPU, exact all-pairs kernels through the nn.Module",
+                             "images_per_s_per_gpu": Bb / ((tfg + tbg) * 1e-3), "ms_fwd": tfg, "ms_bwd": tbg,
+                             "reference_tflops_equiv": 4.0 * Ng * Mg * 48 * Bb / (tfg * 1e-3) / 1e12}
         del gtb, xb
 
     if not args.no_extra:
